@@ -1,0 +1,234 @@
+/* jiminy_b200 -- C ABI of the B200-native batched rigid-body stepping library.
+ *
+ * This header is the drop-in boundary for ONE path of duburcqa/jiminy: the per-step rigid-body
+ * pipeline of `jiminy::Engine::step` (core/src/engine/engine.cc:1724-2417) and the ODE
+ * right-hand side it integrates, `Engine::computeRobotsDynamics` (engine.cc:3585-3708).
+ * Every entry point cites the reference interface it replaces.  Plain C: pointers, sizes and
+ * int status codes only.  No exception ever crosses this boundary: failures return a negative
+ * status and `jb_last_error()` gives the message (the reference throws, python/jiminy_pywrap
+ * maps C++ exceptions to Python ones, module.cc:98-102; the Python host layer in
+ * `jiminy_b200/core.py` re-raises the matching Python exception class).
+ *
+ * Memory convention: all host arrays are env-major, C-contiguous, fp64 (`[n_env][width]`), which
+ * is what the reference exposes per robot through `RobotState.{q,v,a,command,...}` numpy views
+ * (python/jiminy_pywrap/src/engine.cc:175-187), stacked along a leading env axis.  On the device
+ * the state is structure-of-arrays `[width][n_env_padded]` (env fastest) so that one warp reads
+ * 128-byte-aligned coalesced lines.
+ */
+#ifndef JIMINY_B200_H
+#define JIMINY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- status codes -------- */
+#define JB_OK 0
+#define JB_ERR_INVALID_ARGUMENT (-1) /* reference: std::invalid_argument -> ValueError      */
+#define JB_ERR_BAD_CONTROL_FLOW (-2) /* reference: jiminy::bad_control_flow                 */
+#define JB_ERR_RUNTIME (-3)          /* reference: std::runtime_error -> RuntimeError       */
+#define JB_ERR_NOT_IMPLEMENTED (-4)  /* reference: jiminy::not_implemented_error            */
+#define JB_ERR_CUDA (-5)             /* no CUDA device / CUDA runtime failure (never a CPU fallback) */
+
+/* Per-env status bits written by the device scheduler (jb_get_status).  The reference raises
+ * from Engine::step for the first three (engine.cc:1742-1747, :2341-2378). */
+#define JB_ENV_OK 0
+#define JB_ENV_NAN 1              /* NaN in (q, v, a): "Low-level ode solver failed"                */
+#define JB_ENV_ITER_FAILED 2      /* too many successive failed inner iterations                    */
+#define JB_ENV_DT_UNDERFLOW 4     /* "The internal time step is getting too small"                  */
+#define JB_ENV_JOINT_LIMIT 8      /* a bounded joint left [lo, hi]: the reference would switch this
+                                     env to the JointConstraint/PGS path (engine.cc:3285-3293), which
+                                     this round does not implement; the env keeps integrating with
+                                     ABA and is flagged                                             */
+#define JB_ENV_NOT_STARTED 16     /* env has never been started (jb_start not called on it)         */
+#define JB_ENV_CONTACT_FORCE 32   /* jb_start: initial contact force > 1e5 N (engine.cc:1338-1345)  */
+
+/* ---------------------------------------------------------------- joint model types --- */
+/* Pinocchio 2.7 joint models produced by its URDF parser. */
+enum {
+    JB_JOINT_UNIVERSE = 0,
+    JB_JOINT_RX = 1, JB_JOINT_RY = 2, JB_JOINT_RZ = 3,      /* JointModelRX/RY/RZ                  */
+    JB_JOINT_RU = 4,                                        /* JointModelRevoluteUnaligned         */
+    JB_JOINT_RUBX = 5, JB_JOINT_RUBY = 6, JB_JOINT_RUBZ = 7,/* JointModelRUBX/Y/Z  (nq=2: cos,sin) */
+    JB_JOINT_RUBU = 8,                                      /* RevoluteUnboundedUnaligned          */
+    JB_JOINT_PX = 9, JB_JOINT_PY = 10, JB_JOINT_PZ = 11,    /* JointModelPX/PY/PZ                  */
+    JB_JOINT_PU = 12,                                       /* JointModelPrismaticUnaligned        */
+    JB_JOINT_FREEFLYER = 13                                 /* JointModelFreeFlyer (nq=7, nv=6)    */
+};
+
+enum { JB_SOLVER_EULER_EXPLICIT = 0, JB_SOLVER_RUNGE_KUTTA_4 = 1, JB_SOLVER_RUNGE_KUTTA_DOPRI = 2 };
+
+/* ---------------------------------------------------------------- model description --- */
+/* Flat, read-only description of one robot: what `jiminy::Model`/`jiminy::Robot` yield to the
+ * engine (core/src/robot/model.cc, robot.cc) -- tree topology, joint placements, body inertias,
+ * rotor inertias, limits, motors, contact frames, sensors -- with Pinocchio's joint / q / v
+ * indexing.  All pointers are borrowed for the duration of the call that receives the struct.
+ *
+ * SE3 placements are 12 doubles: rotation row-major (9) then translation (3), mapping child
+ * coordinates to parent coordinates (Pinocchio `SE3`).  Inertias are 10 doubles:
+ * mass, lever[3], then the symmetric rotational inertia about the centre of mass in Pinocchio
+ * `Symmetric3` order (xx, xy, yy, xz, yz, zz). */
+typedef struct JbModelDesc {
+    int32_t njoints;              /* including the universe, index 0                              */
+    int32_t nq, nv;
+    const int32_t* joint_type;    /* [njoints] JB_JOINT_*                                         */
+    const int32_t* parent;        /* [njoints] parent joint index (parents precede children)      */
+    const int32_t* idx_q;         /* [njoints]                                                    */
+    const int32_t* idx_v;         /* [njoints]                                                    */
+    const double* placement;      /* [njoints][12] model.jointPlacements                          */
+    const double* axis;           /* [njoints][3]  unit axis of 1-dof joints (also set for aligned)*/
+    const double* inertia;        /* [njoints][10] model.inertias                                 */
+    const double* rotor_inertia;  /* [nv] model.rotorInertia (robot.cc:243-246)                   */
+    const double* q_lower;        /* [nq] model.lowerPositionLimit (model.cc:1371-1440)           */
+    const double* q_upper;        /* [nq]                                                         */
+
+    /* SimpleMotor table, attach order (robot.cc:249; basic_motors.cc:83-143).  Per motor 10
+     * doubles: reduction, effort_limit, velocity_limit, velocity_effort_inv_slope,
+     * friction_viscous_pos, friction_viscous_neg, friction_dry_pos, friction_dry_neg,
+     * friction_dry_slope, reserved.  Per motor flags: bit0 enableEffortLimit,
+     * bit1 enableVelocityLimit, bit2 enableFriction. */
+    int32_t nmotors;
+    const int32_t* motor_joint;   /* [nmotors] joint index                                        */
+    const int32_t* motor_flags;   /* [nmotors]                                                    */
+    const double* motor_params;   /* [nmotors][10]                                                */
+
+    /* Contact frames (robot->getContactFrameIndices(), sorted by name, robot.py:717). */
+    int32_t ncontacts;
+    const int32_t* contact_joint;     /* [ncontacts] parent joint                                 */
+    const double* contact_placement;  /* [ncontacts][12] frame placement in parent joint           */
+
+    /* Sensors, attach order per type (basic_sensors.cc). */
+    int32_t nimu;
+    const int32_t* imu_joint;         /* [nimu]                                                   */
+    const double* imu_placement;      /* [nimu][12]                                               */
+    int32_t nforce;
+    const int32_t* force_joint;       /* [nforce]                                                 */
+    const double* force_placement;    /* [nforce][12]                                             */
+    int32_t nencoder;
+    const int32_t* encoder_joint;     /* [nencoder]                                               */
+    const double* encoder_reduction;  /* [nencoder] 1.0 when joint side (basic_sensors.cc:529-537) */
+    int32_t neffort;
+    const int32_t* effort_motor;      /* [neffort] motor index                                    */
+    int32_t ncontact_sensor;
+    const int32_t* contact_sensor_index; /* [ncontact_sensor] index into the contact frame list   */
+} JbModelDesc;
+
+/* ---------------------------------------------------------------- engine options ------ */
+/* The subset of `Engine::EngineOptions` (core/include/jiminy/core/engine/engine.h:260-353) the
+ * step path reads.  Defaults: jb_default_options(). */
+typedef struct JbOptions {
+    int32_t ode_solver;               /* stepper.odeSolver, JB_SOLVER_*                           */
+    int32_t successive_iter_failed_max; /* stepper.successiveIterFailedMax (1000)                 */
+    int32_t iter_max;                 /* stepper.iterMax (0 = unlimited), reserved                */
+    int32_t reserved0;
+    double tol_abs, tol_rel;          /* stepper.tolAbs / tolRel                                  */
+    double dt_max;                    /* stepper.dtMax                                            */
+    double dt_restore_threshold_rel;  /* stepper.dtRestoreThresholdRel                            */
+    double sensors_update_period;     /* stepper.sensorsUpdatePeriod                              */
+    double controller_update_period;  /* stepper.controllerUpdatePeriod                           */
+    double contact_stiffness;         /* contacts.stiffness                                       */
+    double contact_damping;           /* contacts.damping                                         */
+    double contact_friction;          /* contacts.friction                                        */
+    double contact_transition_eps;    /* contacts.transitionEps                                   */
+    double contact_transition_velocity; /* contacts.transitionVelocity                            */
+    double gravity[6];                /* world.gravity (only the linear part acts)                */
+} JbOptions;
+
+typedef struct JbBatch JbBatch;
+
+/* Layout of one row of the sensor/observation matrix returned by jb_get_sensors: the reference's
+ * per-type shared storage matrices `[fields x sensors]` (abstract_sensor.hxx:445-522) flattened
+ * field-major per type, concatenated in the order IMU, Force, Encoder, Effort, Contact. */
+typedef struct JbSensorLayout {
+    int32_t imu_offset, force_offset, encoder_offset, effort_offset, contact_offset;
+    int32_t width;
+} JbSensorLayout;
+
+/* Message of the last failing call on this thread. */
+const char* jb_last_error(void);
+
+/* Library / build identification ("jiminy_b200 <ver> sm_100a"). */
+const char* jb_version(void);
+
+/* Engine option defaults, engine.h:260-341. */
+void jb_default_options(JbOptions* out);
+
+/* Replaces: Engine::addRobot + the robot lock taken by Engine::start (engine.cc:952-1533).
+ * Uploads the model tables and allocates SoA state for `n_env` lockstep environments on CUDA
+ * device `device`.  Fails with JB_ERR_CUDA when no device is usable. */
+int jb_batch_create(const JbModelDesc* model, const JbOptions* options, int32_t n_env, int32_t device,
+                    JbBatch** out);
+int jb_batch_destroy(JbBatch* batch);
+
+/* Replaces: Engine::setOptions (engine.cc:2654-2795).  Only allowed while no env is running,
+ * except the contact/gravity values which the reference also allows between episodes. */
+int jb_set_options(JbBatch* batch, const JbOptions* options);
+
+/* Replaces: Engine::start(q, v) (engine.cc:952-1533) for every env with mask[i] != 0 (NULL mask =
+ * all).  q0 is [n_env][nq], v0 is [n_env][nv] (rows of unmasked envs are ignored).  Normalises q,
+ * runs forward kinematics, the initial contact-force guard, the INIT_ITERATIONS fixed-point loop
+ * and the first sensor refresh; sets t = 0, dt = SIMULATION_MIN_TIMESTEP. */
+int jb_start(JbBatch* batch, const uint8_t* mask, const double* q0, const double* v0);
+
+/* Replaces: the command buffer written by AbstractController::computeCommand through the
+ * FunctionalController callback (engine.cc:3240-3251; controller_functor.h:27-80).  The command is
+ * zero-order held until the next call.  cmd is [n_env][nmotors]. */
+int jb_set_command(JbBatch* batch, const double* cmd);
+/* Same, with `cmd_dev` a device pointer (same layout) on the batch's device: no host copy. */
+int jb_set_command_device(JbBatch* batch, const double* cmd_dev);
+
+/* Replaces: Engine::step(stepSize) (engine.cc:1724-2417), all envs in lockstep, one launch.
+ * step_dt < EPS selects the reference's default step size rule (engine.cc:1758-1777). */
+int jb_step(JbBatch* batch, double step_dt);
+
+/* Replaces: one call of Engine::computeRobotsDynamics (engine.cc:3585-3708) as exposed for parity
+ * through `jiminy_py.core.aba`-style helpers (python/jiminy_pywrap/src/helpers.cc:423-477):
+ * evaluates a = f(q, v, command) for every env without touching the running state.
+ * q [n_env][nq], v [n_env][nv], cmd [n_env][nmotors] -> a [n_env][nv],
+ * fext [n_env][njoints][6] (may be NULL), u [n_env][nv] (may be NULL). */
+int jb_compute_dynamics(JbBatch* batch, const double* q, const double* v, const double* cmd,
+                        double* a, double* fext, double* u);
+
+/* Replaces: the numpy views StepperState.{t,q,v,a} (pywrap engine.cc:134-143).  Any pointer may
+ * be NULL.  t [n_env], q [n_env][nq], v/a [n_env][nv]. */
+int jb_get_state(JbBatch* batch, double* t, double* q, double* v, double* a);
+
+/* Replaces: RobotState.{u, u_motor, command, f_external} views (pywrap engine.cc:175-187).
+ * u [n_env][nv], u_motor [n_env][nmotors], command [n_env][nmotors], fext [n_env][njoints][6]. */
+int jb_get_efforts(JbBatch* batch, double* u, double* u_motor, double* command, double* fext);
+
+/* Replaces: robot.sensor_measurements (Robot::computeSensorMeasurements, robot.cc:952) as
+ * refreshed by the engine at each sensor breakpoint (engine.cc:2386-2410).  out [n_env][width]. */
+int jb_get_sensors(JbBatch* batch, double* out);
+int jb_sensor_layout(JbBatch* batch, JbSensorLayout* out);
+
+/* Replaces: the quantities Engine::computeExtraTerms leaves in pinocchio::Data after each
+ * successful step (engine.cc:800-905): per env kinetic+potential energy `energy` [n_env][2],
+ * joint spatial accelerations `joint_a` [n_env][njoints][6] (data.a) and joint internal wrenches
+ * `joint_f` [n_env][njoints][6] (data.f).  Any pointer may be NULL. */
+int jb_get_extra_terms(JbBatch* batch, double* energy, double* joint_a, double* joint_f);
+
+/* Replaces: the exceptions Engine::step raises per robot; here one word per env (JB_ENV_*). */
+int jb_get_status(JbBatch* batch, int32_t* status);
+
+/* Replaces: StepperState.{iter, iter_failed} (pywrap engine.cc:134-143). iter/iter_failed [n_env]. */
+int jb_get_iters(JbBatch* batch, int64_t* iter, int64_t* iter_failed);
+
+/* Device-resident views for zero-copy consumers (policy networks on the same GPU): the sensor
+ * matrix `[n_env][width]` and the stacked (q, v) `[n_env][nq+nv]`, refreshed by jb_step.  This
+ * is the buffer a multi-GPU rollout all-gathers. */
+int jb_device_views(JbBatch* batch, double** sensors_dev, double** qv_dev);
+
+/* Stream the batch launches on (a `cudaStream_t` cast to void*), for CUDA-event timing. */
+int jb_get_stream(JbBatch* batch, void** stream);
+/* Number of kernel launches issued by this batch so far (bench.py `gpu_launches`). */
+int64_t jb_launch_count(JbBatch* batch);
+/* Block until all work queued on the batch stream has completed. */
+int jb_synchronize(JbBatch* batch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JIMINY_B200_H */

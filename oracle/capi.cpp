@@ -1,0 +1,152 @@
+// TEST INFRASTRUCTURE -- CPU oracle, not product code.  See oracle/README.md.
+//
+// C entry points over orc::Engine for ctypes (tests/, __graft_entry__.smoke, bench.py cpu_baseline).
+// A "batch" is a plain array of independent single-robot engines, stepped sequentially or with an
+// OpenMP `parallel for` over envs (the reference engine itself has no threading; N reference
+// processes on N cores is what this mirrors).
+#include <cstring>
+#include <memory>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "engine.hpp"
+
+using orc::Engine;
+
+struct OrcBatch {
+    std::vector<std::unique_ptr<Engine>> envs;
+    int nq, nv, nmotors, njoints, width;
+};
+
+extern "C" {
+
+int orc_max_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+OrcBatch* orc_create(const JbModelDesc* model, const JbOptions* opt, int n_env) {
+    auto* b = new OrcBatch;
+    for (int i = 0; i < n_env; ++i) b->envs.emplace_back(new Engine(*model, *opt));
+    b->nq = model->nq; b->nv = model->nv; b->nmotors = model->nmotors; b->njoints = model->njoints;
+    b->width = b->envs[0]->model.layout.width;
+    return b;
+}
+void orc_destroy(OrcBatch* b) { delete b; }
+int orc_sensor_width(OrcBatch* b) { return b->width; }
+void orc_sensor_layout(OrcBatch* b, JbSensorLayout* out) { *out = b->envs[0]->model.layout; }
+
+void orc_set_options(OrcBatch* b, const JbOptions* opt) {
+    for (auto& e : b->envs) e->set_options(*opt);
+}
+void orc_set_callbacks(OrcBatch* b, int env, orc::ControllerFn c, orc::InternalDynFn d, void* ctx) {
+    b->envs[env]->controller = c; b->envs[env]->internalDyn = d; b->envs[env]->ctx = ctx;
+}
+void orc_set_springs(OrcBatch* b, const double* k, const double* d) {
+    for (auto& e : b->envs) { e->spring_k.assign(k, k + b->nv); e->spring_d.assign(d, d + b->nv); }
+}
+
+// returns the number of envs whose start failed; rc[i] receives the per-env return code
+int orc_start(OrcBatch* b, const uint8_t* mask, const double* q0, const double* v0, int* rc) {
+    int bad = 0;
+    for (size_t i = 0; i < b->envs.size(); ++i) {
+        if (mask && !mask[i]) { if (rc) rc[i] = 0; continue; }
+        int r = b->envs[i]->start(q0 + i * b->nq, v0 + i * b->nv);
+        if (rc) rc[i] = r;
+        bad += (r != 0);
+    }
+    return bad;
+}
+void orc_set_command(OrcBatch* b, const double* cmd) {
+    for (size_t i = 0; i < b->envs.size(); ++i)
+        std::memcpy(b->envs[i]->state.command.data(), cmd + i * b->nmotors, sizeof(double) * b->nmotors);
+}
+int orc_step(OrcBatch* b, double step_dt, int parallel, int* rc) {
+    const int n = static_cast<int>(b->envs.size());
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(+ : bad) if (parallel)
+    for (int i = 0; i < n; ++i) {
+        int r = b->envs[i]->step(step_dt);
+        if (rc) rc[i] = r;
+        bad += (r != 0);
+    }
+    return bad;
+}
+void orc_get_state(OrcBatch* b, double* t, double* q, double* v, double* a) {
+    for (size_t i = 0; i < b->envs.size(); ++i) {
+        Engine& e = *b->envs[i];
+        if (t) t[i] = e.t;
+        if (q) std::memcpy(q + i * b->nq, e.q.data(), sizeof(double) * b->nq);
+        if (v) std::memcpy(v + i * b->nv, e.v.data(), sizeof(double) * b->nv);
+        if (a) std::memcpy(a + i * b->nv, e.a.data(), sizeof(double) * b->nv);
+    }
+}
+void orc_get_efforts(OrcBatch* b, double* u, double* u_motor, double* command, double* fext) {
+    for (size_t i = 0; i < b->envs.size(); ++i) {
+        Engine& e = *b->envs[i];
+        if (u) std::memcpy(u + i * b->nv, e.state.u.data(), sizeof(double) * b->nv);
+        if (u_motor) std::memcpy(u_motor + i * b->nmotors, e.state.uMotor.data(), sizeof(double) * b->nmotors);
+        if (command) std::memcpy(command + i * b->nmotors, e.state.command.data(), sizeof(double) * b->nmotors);
+        if (fext)
+            for (int j = 0; j < b->njoints; ++j) orc::to6(e.state.fExternal[j], fext + (i * b->njoints + j) * 6);
+    }
+}
+void orc_get_sensors(OrcBatch* b, double* out) {
+    for (size_t i = 0; i < b->envs.size(); ++i)
+        std::memcpy(out + i * b->width, b->envs[i]->sensors.data(), sizeof(double) * b->width);
+}
+void orc_get_extra_terms(OrcBatch* b, double* energy, double* joint_a, double* joint_f) {
+    for (size_t i = 0; i < b->envs.size(); ++i) {
+        Engine& e = *b->envs[i];
+        if (energy) { energy[2 * i] = e.data.kinetic_energy; energy[2 * i + 1] = e.data.potential_energy; }
+        for (int j = 0; j < b->njoints; ++j) {
+            if (joint_a) orc::to6(e.data.a[j], joint_a + (i * b->njoints + j) * 6);
+            if (joint_f) orc::to6(e.data.f[j], joint_f + (i * b->njoints + j) * 6);
+        }
+    }
+}
+void orc_get_status(OrcBatch* b, int32_t* status) {
+    for (size_t i = 0; i < b->envs.size(); ++i) status[i] = b->envs[i]->status;
+}
+void orc_get_iters(OrcBatch* b, int64_t* iter, int64_t* iter_failed) {
+    for (size_t i = 0; i < b->envs.size(); ++i) {
+        if (iter) iter[i] = b->envs[i]->iter;
+        if (iter_failed) iter_failed[i] = b->envs[i]->iterFailed;
+    }
+}
+int64_t orc_rhs_count(OrcBatch* b) {
+    int64_t s = 0;
+    for (auto& e : b->envs) s += e->rhs_count;
+    return s;
+}
+
+// One evaluation of Engine::computeRobotsDynamics on an arbitrary (q, v, command), per env, on a
+// scratch engine state: FK -> contacts -> motors -> ABA.  Used for per-RHS parity.
+void orc_compute_dynamics(OrcBatch* b, const double* q, const double* v, const double* cmd, double* a,
+                          double* fext, double* u) {
+    for (size_t i = 0; i < b->envs.size(); ++i) {
+        Engine& e = *b->envs[i];
+        const bool was = e.running;
+        e.running = true;
+        std::memcpy(e.state.command.data(), cmd + i * b->nmotors, sizeof(double) * b->nmotors);
+        std::vector<double> zeros(b->nv, 0.0), aout(b->nv);
+        e.statePrev.a = zeros;
+        e.computeRobotsDynamics(0.0, q + i * b->nq, v + i * b->nv, aout, false);
+        std::memcpy(a + i * b->nv, aout.data(), sizeof(double) * b->nv);
+        if (u) std::memcpy(u + i * b->nv, e.state.u.data(), sizeof(double) * b->nv);
+        if (fext)
+            for (int j = 0; j < b->njoints; ++j) orc::to6(e.state.fExternal[j], fext + (i * b->njoints + j) * 6);
+        e.running = was;
+    }
+}
+
+// Lie-group helpers exposed for unit tests (pinocchio::integrate / difference)
+void orc_integrate(OrcBatch* b, const double* q, const double* v, double* out) { b->envs[0]->integrate(q, v, out); }
+void orc_difference(OrcBatch* b, const double* q0, const double* q1, double* out) { b->envs[0]->difference(q0, q1, out); }
+
+}  // extern "C"

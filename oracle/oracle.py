@@ -1,0 +1,220 @@
+"""TEST INFRASTRUCTURE -- Python binding of the CPU oracle (`oracle/liboracle.so`).
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may
+import this module.  The product (`jiminy_b200/`) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+from typing import Callable, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+
+from jiminy_b200._ctypes_abi import (JbModelDesc, JbOptions, JbSensorLayout, ModelDescHolder,  # noqa: E402
+                                     c_double_p, c_int32_p, c_int64_p, c_uint8_p, dptr, make_options)
+from jiminy_b200.model import RobotTable  # noqa: E402
+
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in ("engine.cpp", "capi.cpp", "engine.hpp", "spatial.hpp")]
+    srcs.append(os.path.join(_HERE, "..", "include", "jiminy_b200.h"))
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-s", "-B", "liboracle.so"], check=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+CONTROLLER_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double, c_double_p, c_double_p, c_double_p, c_double_p)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.POINTER(JbModelDesc), C.POINTER(JbOptions), C.c_int]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_sensor_width.argtypes = [C.c_void_p]
+        L.orc_sensor_layout.argtypes = [C.c_void_p, C.POINTER(JbSensorLayout)]
+        L.orc_set_options.argtypes = [C.c_void_p, C.POINTER(JbOptions)]
+        L.orc_set_callbacks.argtypes = [C.c_void_p, C.c_int, CONTROLLER_FN, CONTROLLER_FN, C.c_void_p]
+        L.orc_set_springs.argtypes = [C.c_void_p, c_double_p, c_double_p]
+        L.orc_start.argtypes = [C.c_void_p, c_uint8_p, c_double_p, c_double_p, c_int32_p]
+        L.orc_set_command.argtypes = [C.c_void_p, c_double_p]
+        L.orc_step.argtypes = [C.c_void_p, C.c_double, C.c_int, c_int32_p]
+        L.orc_get_state.argtypes = [C.c_void_p] + [c_double_p] * 4
+        L.orc_get_efforts.argtypes = [C.c_void_p] + [c_double_p] * 4
+        L.orc_get_sensors.argtypes = [C.c_void_p, c_double_p]
+        L.orc_get_extra_terms.argtypes = [C.c_void_p] + [c_double_p] * 3
+        L.orc_get_status.argtypes = [C.c_void_p, c_int32_p]
+        L.orc_get_iters.argtypes = [C.c_void_p, c_int64_p, c_int64_p]
+        L.orc_rhs_count.argtypes = [C.c_void_p]
+        L.orc_rhs_count.restype = C.c_int64
+        L.orc_compute_dynamics.argtypes = [C.c_void_p] + [c_double_p] * 6
+        L.orc_integrate.argtypes = [C.c_void_p] + [c_double_p] * 3
+        L.orc_difference.argtypes = [C.c_void_p] + [c_double_p] * 3
+        _lib = L
+    return _lib
+
+
+class OracleBatch:
+    """N independent single-robot engines (restated `jiminy::Engine`) stepped on the host CPU."""
+
+    def __init__(self, robot: RobotTable, options: dict, n_env: int = 1):
+        self.robot, self.n = robot, int(n_env)
+        self._holder = ModelDescHolder(robot)
+        self._opt = make_options(options)
+        self._h = lib().orc_create(C.byref(self._holder.desc), C.byref(self._opt), self.n)
+        self.nq, self.nv, self.nm, self.nj = robot.nq, robot.nv, robot.nmotors, robot.njoints
+        self.width = lib().orc_sensor_width(self._h)
+        self._cbs = []
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_destroy(self._h)
+            self._h = None
+
+    @staticmethod
+    def max_threads() -> int:
+        return lib().orc_max_threads()
+
+    def set_options(self, options: dict) -> None:
+        self._opt = make_options(options)
+        lib().orc_set_options(self._h, C.byref(self._opt))
+
+    def set_springs(self, k, d) -> None:
+        k, d = np.ascontiguousarray(k, dtype=np.float64), np.ascontiguousarray(d, dtype=np.float64)
+        lib().orc_set_springs(self._h, dptr(k), dptr(d))
+
+    def set_callbacks(self, env: int, controller: Optional[Callable] = None,
+                      internal_dynamics: Optional[Callable] = None) -> None:
+        """`controller(t, q, v, sensors, out)` / `internal_dynamics(t, q, v, sensors, out)` write `out`
+        in place, like `jiminy.FunctionalController` (controller_functor.h:15-20)."""
+        nq, nv, nm, w = self.nq, self.nv, self.nm, self.width
+
+        def wrap(fn, nout):
+            if fn is None:
+                return C.cast(None, CONTROLLER_FN)
+
+            def tramp(_ctx, t, q, v, s, out):
+                fn(t, np.ctypeslib.as_array(q, (nq,)), np.ctypeslib.as_array(v, (nv,)),
+                   np.ctypeslib.as_array(s, (max(w, 1),))[:w], np.ctypeslib.as_array(out, (nout,)))
+            return CONTROLLER_FN(tramp)
+        c, d = wrap(controller, nm), wrap(internal_dynamics, nv)
+        self._cbs.append((c, d))
+        lib().orc_set_callbacks(self._h, env, c, d, None)
+
+    def start(self, q0, v0, mask=None) -> np.ndarray:
+        q0 = np.ascontiguousarray(np.broadcast_to(q0, (self.n, self.nq)), dtype=np.float64)
+        v0 = np.ascontiguousarray(np.broadcast_to(v0, (self.n, self.nv)), dtype=np.float64)
+        rc = np.zeros(self.n, dtype=np.int32)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        lib().orc_start(self._h, None if m is None else m.ctypes.data_as(c_uint8_p), dptr(q0), dptr(v0),
+                        rc.ctypes.data_as(c_int32_p))
+        return rc
+
+    def set_command(self, cmd) -> None:
+        cmd = np.ascontiguousarray(np.broadcast_to(cmd, (self.n, self.nm)), dtype=np.float64)
+        if self.nm:
+            lib().orc_set_command(self._h, dptr(cmd))
+
+    def step(self, step_dt: float, parallel: bool = False) -> np.ndarray:
+        rc = np.zeros(self.n, dtype=np.int32)
+        lib().orc_step(self._h, float(step_dt), int(parallel), rc.ctypes.data_as(c_int32_p))
+        return rc
+
+    def get_state(self):
+        t = np.zeros(self.n)
+        q, v, a = np.zeros((self.n, self.nq)), np.zeros((self.n, self.nv)), np.zeros((self.n, self.nv))
+        lib().orc_get_state(self._h, dptr(t), dptr(q), dptr(v), dptr(a))
+        return t, q, v, a
+
+    def get_efforts(self):
+        u, um = np.zeros((self.n, self.nv)), np.zeros((self.n, max(self.nm, 1)))
+        cmd, fext = np.zeros((self.n, max(self.nm, 1))), np.zeros((self.n, self.nj, 6))
+        lib().orc_get_efforts(self._h, dptr(u), dptr(um), dptr(cmd), dptr(fext))
+        return u, um[:, :self.nm], cmd[:, :self.nm], fext
+
+    def get_sensors(self) -> np.ndarray:
+        out = np.zeros((self.n, max(self.width, 1)))
+        if self.width:
+            lib().orc_get_sensors(self._h, dptr(out))
+        return out[:, :self.width]
+
+    def get_extra_terms(self):
+        e, ja, jf = np.zeros((self.n, 2)), np.zeros((self.n, self.nj, 6)), np.zeros((self.n, self.nj, 6))
+        lib().orc_get_extra_terms(self._h, dptr(e), dptr(ja), dptr(jf))
+        return e, ja, jf
+
+    def get_status(self) -> np.ndarray:
+        s = np.zeros(self.n, dtype=np.int32)
+        lib().orc_get_status(self._h, s.ctypes.data_as(c_int32_p))
+        return s
+
+    def get_iters(self):
+        it, itf = np.zeros(self.n, dtype=np.int64), np.zeros(self.n, dtype=np.int64)
+        lib().orc_get_iters(self._h, it.ctypes.data_as(c_int64_p), itf.ctypes.data_as(c_int64_p))
+        return it, itf
+
+    def rhs_count(self) -> int:
+        return int(lib().orc_rhs_count(self._h))
+
+    def compute_dynamics(self, q, v, cmd):
+        q = np.ascontiguousarray(np.broadcast_to(q, (self.n, self.nq)), dtype=np.float64)
+        v = np.ascontiguousarray(np.broadcast_to(v, (self.n, self.nv)), dtype=np.float64)
+        cmd = np.ascontiguousarray(np.broadcast_to(cmd, (self.n, max(self.nm, 1))), dtype=np.float64)
+        a, fext, u = np.zeros((self.n, self.nv)), np.zeros((self.n, self.nj, 6)), np.zeros((self.n, self.nv))
+        lib().orc_compute_dynamics(self._h, dptr(q), dptr(v), dptr(cmd), dptr(a), dptr(fext), dptr(u))
+        return a, fext, u
+
+    def integrate(self, q, v):
+        q, v = np.ascontiguousarray(q, dtype=np.float64), np.ascontiguousarray(v, dtype=np.float64)
+        out = np.zeros(self.nq)
+        lib().orc_integrate(self._h, dptr(q), dptr(v), dptr(out))
+        return out
+
+    def difference(self, q0, q1):
+        q0, q1 = np.ascontiguousarray(q0, dtype=np.float64), np.ascontiguousarray(q1, dtype=np.float64)
+        out = np.zeros(self.nv)
+        lib().orc_difference(self._h, dptr(q0), dptr(q1), dptr(out))
+        return out
+
+    def simulate(self, t_end: float, q0, v0, step_dt: Optional[float] = None, log: bool = True):
+        """`Engine::simulate` (engine.cc:1614-1699): start, then step(min(period or dtMax, tEnd - t))."""
+        rc = self.start(q0, v0)
+        if rc.any():
+            raise ValueError(f"start failed: {rc}")
+        st = self._opt
+        period = min([p for p in (st.sensors_update_period, st.controller_update_period) if p > 2.3e-16],
+                     default=np.inf)
+        ts, qs, vs, as_ = [], [], [], []
+
+        def snap():
+            t, q, v, a = self.get_state()
+            ts.append(t[0]); qs.append(q[0].copy()); vs.append(v[0].copy()); as_.append(a[0].copy())
+        if log:
+            snap()
+        while True:
+            t = self.get_state()[0][0]
+            if t_end - t < 1e-6:
+                break
+            h = min(period if np.isfinite(period) else st.dt_max, t_end - t) if step_dt is None else \
+                min(step_dt, t_end - t)
+            rc = self.step(h)
+            if rc.any():
+                raise RuntimeError(f"step failed rc={rc} status={self.get_status()}")
+            if log:
+                snap()
+        return np.array(ts), np.array(qs), np.array(vs), np.array(as_)
