@@ -166,6 +166,27 @@ int jb_batch_destroy(JbBatch* batch);
  * except the contact/gravity values which the reference also allows between episodes. */
 int jb_set_options(JbBatch* batch, const JbOptions* options);
 
+/* Replaces: the `internalDynamics` functor of FunctionalController (controller_functor.h:27-80,
+ * invoked at engine.cc:3690-3691) for the linear case the reference's analytical tests use
+ * (`u_custom = -k q - d v` on 1-dof joints).  k, d are [nv]; NULL disables. */
+int jb_set_joint_springs(JbBatch* batch, const double* k, const double* d);
+
+/* Replaces: the PD controller block that `gym_jiminy` pipelines run inside the controller callback,
+ * `gym_jiminy.common.blocks.pd_controller` (python/gym_jiminy/common/gym_jiminy/common/blocks/
+ * proportional_derivative_controller.py:101-165), for zero-order-held position targets with zero
+ * target velocity: at every controller breakpoint
+ *     command = clip(kp * ((target - q_enc) + kd * (0 - v_enc)), +-motor.effort_limit).
+ * While enabled, jb_set_command uploads *targets* (motor-side positions) instead of efforts.
+ * kp, kd are [nmotors]; NULL disables.  Requires a discrete controllerUpdatePeriod. */
+int jb_set_pd_controller(JbBatch* batch, const double* kp, const double* kd);
+
+/* One-line description of the lane plan / shared-memory footprint chosen for this batch. */
+int jb_describe(JbBatch* batch, char* buf, int32_t len);
+
+/* Host-only planner introspection (no device needed): fills `buf` like jb_describe and, when
+ * non-NULL, joint_lane[njoints] (-1 = trunk joint shared by all lanes).  lanes = 0: automatic. */
+int jb_plan_describe(const JbModelDesc* model, int32_t lanes, char* buf, int32_t len, int32_t* joint_lane);
+
 /* Replaces: Engine::start(q, v) (engine.cc:952-1533) for every env with mask[i] != 0 (NULL mask =
  * all).  q0 is [n_env][nq], v0 is [n_env][nv] (rows of unmasked envs are ignored).  Normalises q,
  * runs forward kinematics, the initial contact-force guard, the INIT_ITERATIONS fixed-point loop

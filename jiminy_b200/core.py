@@ -1,0 +1,277 @@
+"""Python host layer over the C ABI of `libjiminy_b200.so` (`include/jiminy_b200.h`).
+
+Mirrors the part of `jiminy_py.core` that sits on the step path (Boost.Python bindings,
+`python/jiminy_pywrap/src/engine.cc:587-787` in the reference): `Engine.start / step / stop /
+simulate`, `RobotState`, `StepperState`, option dicts -- for one env (`Engine`) and for N lockstep
+envs (`BatchedEngine`).  All physics runs in the CUDA library; there is no CPU path here: if the
+library or a CUDA device is missing the constructors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Any, Dict, Optional, Sequence
+
+import numpy as np
+
+from . import model as M
+from ._ctypes_abi import (JbModelDesc, JbOptions, JbSensorLayout, ModelDescHolder, c_double_p, c_int32_p,
+                          c_int64_p, c_uint8_p, dptr, make_options)
+
+JB_OK = 0
+JB_ERR_INVALID_ARGUMENT, JB_ERR_BAD_CONTROL_FLOW, JB_ERR_RUNTIME, JB_ERR_NOT_IMPLEMENTED, JB_ERR_CUDA = -1, -2, -3, -4, -5
+JB_ENV_OK, JB_ENV_NAN, JB_ENV_ITER_FAILED, JB_ENV_DT_UNDERFLOW = 0, 1, 2, 4
+JB_ENV_JOINT_LIMIT, JB_ENV_NOT_STARTED, JB_ENV_CONTACT_FORCE = 8, 16, 32
+
+
+class BadControlFlow(RuntimeError):
+    """`jiminy::bad_control_flow` (python/jiminy_pywrap/src/module.cc:98-102)."""
+
+
+class CudaUnavailable(RuntimeError):
+    """No CUDA device / runtime failure.  jiminy_b200 never falls back to a CPU implementation."""
+
+
+_EXC = {JB_ERR_INVALID_ARGUMENT: ValueError, JB_ERR_BAD_CONTROL_FLOW: BadControlFlow, JB_ERR_RUNTIME: RuntimeError,
+        JB_ERR_NOT_IMPLEMENTED: NotImplementedError, JB_ERR_CUDA: CudaUnavailable}
+
+_LIB_NAME = "libjiminy_b200.so"
+
+
+def library_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+
+
+class Api:
+    """Typed view of the C ABI exported by a loaded library (every symbol of include/jiminy_b200.h)."""
+
+    SYMBOLS = ("jb_last_error", "jb_version", "jb_default_options", "jb_batch_create", "jb_batch_destroy",
+               "jb_set_options", "jb_start", "jb_set_command", "jb_set_command_device", "jb_step",
+               "jb_compute_dynamics", "jb_get_state", "jb_get_efforts", "jb_get_sensors", "jb_sensor_layout",
+               "jb_get_extra_terms", "jb_get_status", "jb_get_iters", "jb_device_views", "jb_get_stream",
+               "jb_launch_count", "jb_synchronize", "jb_set_joint_springs", "jb_set_pd_controller", "jb_describe",
+               "jb_plan_describe")
+
+    def __init__(self, cdll: C.CDLL):
+        self.dll = L = cdll
+        missing = [s for s in self.SYMBOLS if not hasattr(L, s)]
+        if missing:
+            raise ImportError(f"{L._name} does not export: {missing}")
+        vp = C.c_void_p
+        L.jb_last_error.restype = C.c_char_p
+        L.jb_version.restype = C.c_char_p
+        L.jb_default_options.argtypes = [C.POINTER(JbOptions)]
+        L.jb_default_options.restype = None
+        L.jb_batch_create.argtypes = [C.POINTER(JbModelDesc), C.POINTER(JbOptions), C.c_int32, C.c_int32, C.POINTER(vp)]
+        L.jb_batch_destroy.argtypes = [vp]
+        L.jb_set_options.argtypes = [vp, C.POINTER(JbOptions)]
+        L.jb_start.argtypes = [vp, c_uint8_p, c_double_p, c_double_p]
+        L.jb_set_command.argtypes = [vp, c_double_p]
+        L.jb_set_command_device.argtypes = [vp, vp]
+        L.jb_step.argtypes = [vp, C.c_double]
+        L.jb_compute_dynamics.argtypes = [vp] + [c_double_p] * 6
+        L.jb_get_state.argtypes = [vp] + [c_double_p] * 4
+        L.jb_get_efforts.argtypes = [vp] + [c_double_p] * 4
+        L.jb_get_sensors.argtypes = [vp, c_double_p]
+        L.jb_sensor_layout.argtypes = [vp, C.POINTER(JbSensorLayout)]
+        L.jb_get_extra_terms.argtypes = [vp] + [c_double_p] * 3
+        L.jb_get_status.argtypes = [vp, c_int32_p]
+        L.jb_get_iters.argtypes = [vp, c_int64_p, c_int64_p]
+        L.jb_device_views.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+        L.jb_get_stream.argtypes = [vp, C.POINTER(vp)]
+        L.jb_launch_count.argtypes = [vp]
+        L.jb_launch_count.restype = C.c_int64
+        L.jb_synchronize.argtypes = [vp]
+        L.jb_set_joint_springs.argtypes = [vp, c_double_p, c_double_p]
+        L.jb_set_pd_controller.argtypes = [vp, c_double_p, c_double_p]
+        L.jb_describe.argtypes = [vp, C.c_char_p, C.c_int32]
+        L.jb_plan_describe.argtypes = [C.POINTER(JbModelDesc), C.c_int32, C.c_char_p, C.c_int32, c_int32_p]
+
+    def check(self, rc: int) -> None:
+        if rc != JB_OK:
+            msg = (self.dll.jb_last_error() or b"").decode()
+            raise _EXC.get(rc, RuntimeError)(msg)
+
+
+_api: Optional[Api] = None
+
+
+def api() -> Api:
+    """The product library.  Raises ImportError if it has not been built (`__graft_entry__.build()`)."""
+    global _api
+    if _api is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise ImportError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                              "jiminy_b200 has no fallback implementation.")
+        _api = Api(C.CDLL(path))
+    return _api
+
+
+def plan_describe(robot: M.RobotTable, lanes: int = 0, api_: Optional[Api] = None):
+    """Host-only: how the lane planner lays the robot's tree over the lanes of a warp."""
+    a = api_ or api()
+    holder = ModelDescHolder(robot)
+    buf = C.create_string_buffer(512)
+    jl = np.zeros(robot.njoints, dtype=np.int32)
+    a.check(a.dll.jb_plan_describe(C.byref(holder.desc), lanes, buf, 512, jl.ctypes.data_as(c_int32_p)))
+    return buf.value.decode(), jl
+
+
+class BatchedEngine:
+    """N lockstep copies of one robot stepped by one kernel launch per `step`.
+
+    Per-env semantics are those of `jiminy::Engine` with a zero-order-held command
+    (`Engine::start` engine.cc:952, `Engine::step` engine.cc:1724); arrays are env-major.
+    """
+
+    def __init__(self, robot: M.RobotTable, options: Dict[str, Any], n_env: int, device: int = 0,
+                 api_: Optional[Api] = None):
+        self._api = api_ or api()
+        self.robot, self.n_env, self.device = robot, int(n_env), int(device)
+        self.options = options
+        M.validate_options(options)
+        self._holder = ModelDescHolder(robot)
+        self._opt = make_options(options)
+        h = C.c_void_p()
+        self._api.check(self._api.dll.jb_batch_create(C.byref(self._holder.desc), C.byref(self._opt), self.n_env,
+                                                       self.device, C.byref(h)))
+        self._h = h
+        self.nq, self.nv, self.nm, self.nj = robot.nq, robot.nv, robot.nmotors, robot.njoints
+        lay = JbSensorLayout()
+        self._api.check(self._api.dll.jb_sensor_layout(self._h, C.byref(lay)))
+        self.sensor_layout, self.width = lay, lay.width
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._api.dll.jb_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def describe(self) -> str:
+        buf = C.create_string_buffer(512)
+        self._api.check(self._api.dll.jb_describe(self._h, buf, 512))
+        return buf.value.decode()
+
+    def set_options(self, options: Dict[str, Any]) -> None:
+        M.validate_options(options)
+        self.options, self._opt = options, make_options(options)
+        self._api.check(self._api.dll.jb_set_options(self._h, C.byref(self._opt)))
+
+    def set_joint_springs(self, stiffness: Optional[Sequence[float]], damping: Optional[Sequence[float]]) -> None:
+        if stiffness is None:
+            self._api.check(self._api.dll.jb_set_joint_springs(self._h, None, None))
+            return
+        k = np.ascontiguousarray(stiffness, dtype=np.float64)
+        d = np.ascontiguousarray(damping, dtype=np.float64)
+        assert k.shape == (self.nv,) and d.shape == (self.nv,)
+        self._api.check(self._api.dll.jb_set_joint_springs(self._h, dptr(k), dptr(d)))
+
+    def set_pd_controller(self, kp, kd) -> None:
+        """Device-side `PDController` block (position targets, zero target velocity); `set_command` then
+        uploads targets.  `kp=None` disables it."""
+        if kp is None:
+            self._api.check(self._api.dll.jb_set_pd_controller(self._h, None, None))
+            return
+        kp = np.ascontiguousarray(np.broadcast_to(kp, (self.nm,)), dtype=np.float64)
+        kd = np.ascontiguousarray(np.broadcast_to(kd, (self.nm,)), dtype=np.float64)
+        self._api.check(self._api.dll.jb_set_pd_controller(self._h, dptr(kp), dptr(kd)))
+
+    def start(self, q0, v0, mask=None) -> None:
+        q0 = np.ascontiguousarray(np.broadcast_to(q0, (self.n_env, self.nq)), dtype=np.float64)
+        v0 = np.ascontiguousarray(np.broadcast_to(v0, (self.n_env, self.nv)), dtype=np.float64)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self._api.check(self._api.dll.jb_start(self._h, None if m is None else m.ctypes.data_as(c_uint8_p),
+                                               dptr(q0), dptr(v0)))
+
+    def set_command(self, cmd) -> None:
+        if not self.nm:
+            return
+        cmd = np.ascontiguousarray(np.broadcast_to(cmd, (self.n_env, self.nm)), dtype=np.float64)
+        self._api.check(self._api.dll.jb_set_command(self._h, dptr(cmd)))
+        self._api.check(self._api.dll.jb_synchronize(self._h))  # `cmd` may be a temporary
+
+    def set_command_device(self, dev_ptr: int) -> None:
+        self._api.check(self._api.dll.jb_set_command_device(self._h, C.c_void_p(dev_ptr)))
+
+    def step(self, step_dt: float = -1.0) -> None:
+        self._api.check(self._api.dll.jb_step(self._h, float(step_dt)))
+
+    def synchronize(self) -> None:
+        self._api.check(self._api.dll.jb_synchronize(self._h))
+
+    def get_state(self):
+        t = np.zeros(self.n_env)
+        q, v, a = np.zeros((self.n_env, self.nq)), np.zeros((self.n_env, self.nv)), np.zeros((self.n_env, self.nv))
+        self._api.check(self._api.dll.jb_get_state(self._h, dptr(t), dptr(q), dptr(v), dptr(a)))
+        return t, q, v, a
+
+    def get_efforts(self):
+        u, um = np.zeros((self.n_env, self.nv)), np.zeros((self.n_env, max(self.nm, 1)))
+        cmd, fext = np.zeros((self.n_env, max(self.nm, 1))), np.zeros((self.n_env, self.nj, 6))
+        self._api.check(self._api.dll.jb_get_efforts(self._h, dptr(u), dptr(um), dptr(cmd), dptr(fext)))
+        return u, um[:, :self.nm], cmd[:, :self.nm], fext
+
+    def get_sensors(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.zeros((self.n_env, max(self.width, 1)))
+        self._api.check(self._api.dll.jb_get_sensors(self._h, dptr(out)))
+        return out[:, :self.width]
+
+    def get_status(self) -> np.ndarray:
+        s = np.zeros(self.n_env, dtype=np.int32)
+        self._api.check(self._api.dll.jb_get_status(self._h, s.ctypes.data_as(c_int32_p)))
+        return s
+
+    def get_iters(self):
+        it, itf = np.zeros(self.n_env, dtype=np.int64), np.zeros(self.n_env, dtype=np.int64)
+        self._api.check(self._api.dll.jb_get_iters(self._h, it.ctypes.data_as(c_int64_p), itf.ctypes.data_as(c_int64_p)))
+        return it, itf
+
+    def compute_dynamics(self, q, v, cmd=None):
+        q = np.ascontiguousarray(np.broadcast_to(q, (self.n_env, self.nq)), dtype=np.float64)
+        v = np.ascontiguousarray(np.broadcast_to(v, (self.n_env, self.nv)), dtype=np.float64)
+        cmd = np.zeros((self.n_env, max(self.nm, 1))) if cmd is None else \
+            np.ascontiguousarray(np.broadcast_to(cmd, (self.n_env, max(self.nm, 1))), dtype=np.float64)
+        a, fext, u = np.zeros((self.n_env, self.nv)), np.zeros((self.n_env, self.nj, 6)), np.zeros((self.n_env, self.nv))
+        self._api.check(self._api.dll.jb_compute_dynamics(self._h, dptr(q), dptr(v), dptr(cmd), dptr(a), dptr(fext), dptr(u)))
+        return a, fext, u
+
+    def device_views(self):
+        s, qv = C.c_void_p(), C.c_void_p()
+        self._api.check(self._api.dll.jb_device_views(self._h, C.byref(s), C.byref(qv)))
+        return s.value, qv.value
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        self._api.check(self._api.dll.jb_get_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    def launch_count(self) -> int:
+        return int(self._api.dll.jb_launch_count(self._h))
+
+    def simulate(self, t_end: float, q0, v0, log: bool = True):
+        """`Engine::simulate` (engine.cc:1614-1699) for every env; returns logged (t, q, v, a) of env 0..N-1."""
+        self.start(q0, v0)
+        st = self._opt
+        period = min([p for p in (st.sensors_update_period, st.controller_update_period) if p > 2.3e-16], default=np.inf)
+        ts, qs, vs, as_ = [], [], [], []
+
+        def snap():
+            t, q, v, a = self.get_state()
+            ts.append(t.copy()); qs.append(q.copy()); vs.append(v.copy()); as_.append(a.copy())
+        if log:
+            snap()
+        t = 0.0
+        while t_end - t >= 1e-6:
+            h = min(period if np.isfinite(period) else st.dt_max, t_end - t)
+            self.step(h)
+            t = float(self.get_state()[0][0])
+            if log:
+                snap()
+        return np.array(ts), np.array(qs), np.array(vs), np.array(as_)

@@ -1,0 +1,467 @@
+// C ABI of libjiminy_b200.so (declared in include/jiminy_b200.h): batch life-cycle, uploads,
+// kernel launches and env-major host views.  No CPU compute path exists: every entry point that
+// needs the device fails with JB_ERR_CUDA when CUDA is unavailable.
+#ifndef JB_HOST_EMUL
+#include <cuda_runtime.h>
+#endif
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/jiminy_b200.h"
+#include "jb_kernel.cuh"
+#include "jb_plan.h"
+
+using namespace jb;
+
+#ifndef JB_HOST_EMUL
+#define JB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) return fail(JB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));  \
+    } while (0)
+
+struct JbBatch {
+    int device = 0;
+    int n_env = 0, n_pad = 0;
+    Plan plan;
+    KParams kp{};
+    cudaStream_t stream = nullptr;
+    int nq = 0, nv = 0, nmotors = 0, njoints = 0, width = 0;
+    std::vector<double> q_lower, q_upper;
+    std::vector<void*> allocs;
+    // device buffers
+    double *d_q = nullptr, *d_v = nullptr, *d_a = nullptr, *d_sched = nullptr;
+    long long* d_iters = nullptr;
+    int32_t* d_status = nullptr;
+    double *d_cmd = nullptr, *d_sensors = nullptr, *d_qv = nullptr;
+    double *d_qin = nullptr, *d_vin = nullptr, *d_aout = nullptr, *d_fext = nullptr, *d_u = nullptr, *d_umotor = nullptr;
+    double* d_springs = nullptr;
+    double *d_pd = nullptr, *d_cmd_torque = nullptr;
+    uint8_t* d_mask = nullptr;
+    double* d_stage = nullptr;  // staging for SoA -> AoS getters
+    // pinned host staging
+    double* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    int64_t launches = 0;
+    bool any_started = false;
+    size_t smem_bytes = 0;
+};
+
+template <typename T>
+static int dev_alloc(JbBatch* b, T** p, size_t count) {
+    void* raw = nullptr;
+    CU(cudaMalloc(&raw, std::max<size_t>(count, 1) * sizeof(T)));
+    CU(cudaMemsetAsync(raw, 0, std::max<size_t>(count, 1) * sizeof(T), b->stream));
+    b->allocs.push_back(raw);
+    *p = static_cast<T*>(raw);
+    return JB_OK;
+}
+
+// SoA [k][n_pad] -> AoS [env][width]
+__global__ void soa_to_aos_kernel(const double* __restrict__ in, double* __restrict__ out, int n_env, int n_pad, int width) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= static_cast<size_t>(n_env) * width) return;
+    const size_t env = i / width, k = i % width;
+    out[i] = in[k * n_pad + env];
+}
+
+static int ensure_host_stage(JbBatch* b, size_t bytes) {
+    if (bytes <= b->h_stage_bytes) return JB_OK;
+    if (b->h_stage) cudaFreeHost(b->h_stage);
+    b->h_stage = nullptr; b->h_stage_bytes = 0;
+    CU(cudaMallocHost(reinterpret_cast<void**>(&b->h_stage), bytes));
+    b->h_stage_bytes = bytes;
+    return JB_OK;
+}
+
+static int launch(JbBatch* b, int mode, double step_dt) {
+    KParams kp = b->kp;
+    kp.mode = mode;
+    kp.step_dt = step_dt;
+    const int epw = 32 / b->plan.L;
+    const int nblocks = (b->n_env + epw - 1) / epw;
+#ifdef JB_HOST_EMUL
+    emul::current_L = b->plan.L;
+#endif
+    JB_LAUNCH(env_step_kernel, nblocks, 32, b->smem_bytes, b->stream, kp);
+    CU(cudaGetLastError());
+    ++b->launches;
+    return JB_OK;
+}
+
+extern "C" {
+
+const char* jb_last_error(void) { return g_err.c_str(); }
+const char* jb_version(void) { return "jiminy_b200 0.1 (sm_100a, fp64 lane-planned ABA)"; }
+
+void jb_default_options(JbOptions* o) {
+    std::memset(o, 0, sizeof *o);
+    o->ode_solver = JB_SOLVER_RUNGE_KUTTA_DOPRI;
+    o->successive_iter_failed_max = 1000;
+    o->iter_max = 0;
+    o->tol_abs = 1e-5; o->tol_rel = 1e-4; o->dt_max = 0.02; o->dt_restore_threshold_rel = 0.2;
+    o->sensors_update_period = 0.0; o->controller_update_period = 0.0;
+    o->contact_stiffness = 1e6; o->contact_damping = 2e3; o->contact_friction = 1.0;
+    o->contact_transition_eps = 1e-3; o->contact_transition_velocity = 1e-2;
+    o->gravity[2] = -9.81;
+}
+
+static int check_options(const JbOptions* o) {
+    if (o->ode_solver != JB_SOLVER_EULER_EXPLICIT && o->ode_solver != JB_SOLVER_RUNGE_KUTTA_4)
+        return fail(JB_ERR_NOT_IMPLEMENTED, "only 'euler_explicit' and 'runge_kutta_4' run on the device in this build "
+                                            "('runge_kutta_dopri' is a later scope row)");
+    if (!(o->dt_max >= 1e-6 - 1e-16 && o->dt_max <= 0.02 + 1e-16)) return fail(JB_ERR_INVALID_ARGUMENT, "'dtMax' option is out of range.");
+    for (double p : {o->sensors_update_period, o->controller_update_period})
+        if ((p > 2.3e-16 && p < 1e-6) || p > 0.02) return fail(JB_ERR_INVALID_ARGUMENT, "update period out of range");
+    if (o->contact_transition_velocity < 2.3e-16) return fail(JB_ERR_INVALID_ARGUMENT, "'transitionVelocity' must be strictly positive.");
+    if (o->contact_transition_eps < 0.0) return fail(JB_ERR_INVALID_ARGUMENT, "'transitionEps' must be positive.");
+    const double sp = o->sensors_update_period, cp = o->controller_update_period;
+    if (sp > 2.3e-16 && cp > 2.3e-16) {
+        const double lo = std::min(sp, cp), hi = std::max(sp, cp);
+        const double r = std::fmod(hi, lo);
+        if (std::min(r, lo - r) > 1e-12) return fail(JB_ERR_INVALID_ARGUMENT, "controller and sensor update periods must be multiple of each other");
+    }
+    return JB_OK;
+}
+
+static void apply_options(JbBatch* b, const JbOptions* o) {
+    b->kp.opt = *o;
+    double supd = INFINITY;
+    if (o->sensors_update_period > 2.3e-16) supd = std::min(supd, o->sensors_update_period);
+    if (o->controller_update_period > 2.3e-16) supd = std::min(supd, o->controller_update_period);
+    b->kp.stepper_update_period = std::isfinite(supd) ? supd : 1e308;
+}
+
+int jb_batch_destroy(JbBatch* b) {
+    if (!b) return JB_OK;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (void* p : b->allocs) cudaFree(p);
+    if (b->h_stage) cudaFreeHost(b->h_stage);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+    return JB_OK;
+}
+
+int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, int32_t device, JbBatch** out) {
+    if (!m || !opt || !out) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (n_env < 1) return fail(JB_ERR_INVALID_ARGUMENT, "n_env must be >= 1");
+    int rc = check_options(opt);
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(JB_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); jiminy_b200 has no CPU path");
+    if (device < 0 || device >= ndev) return fail(JB_ERR_INVALID_ARGUMENT, "invalid device index");
+    CU(cudaSetDevice(device));
+    JbBatch* b = new JbBatch;
+    b->device = device;
+    b->n_env = n_env;
+    b->n_pad = (n_env + 31) / 32 * 32;
+    try {
+        int lanes = 0;
+        if (const char* s = std::getenv("JB_LANES")) lanes = std::atoi(s);
+        b->plan = build_plan(*m, lanes, 0);
+    } catch (const std::exception& ex) {
+        delete b;
+        return fail(JB_ERR_INVALID_ARGUMENT, std::string("lane planner: ") + ex.what());
+    }
+    const Plan& P = b->plan;
+    if (P.nrec > MAX_REC) { delete b; return fail(JB_ERR_NOT_IMPLEMENTED, "too many records per lane"); }
+    b->nq = m->nq; b->nv = m->nv; b->nmotors = m->nmotors; b->njoints = m->njoints;
+    b->q_lower.assign(m->q_lower, m->q_lower + m->nq);
+    b->q_upper.assign(m->q_upper, m->q_upper + m->nq);
+    if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) { delete b; return fail(JB_ERR_CUDA, "stream creation failed"); }
+
+    KParams& kp = b->kp;
+    kp.n_env = n_env; kp.n_pad = b->n_pad;
+    kp.L = P.L; kp.nrec = P.nrec; kp.ntrunk = P.ntrunk; kp.npool = P.npool; kp.ncslot = P.ncslot; kp.nimuslot = P.nimuslot;
+    kp.nfields = P.nfields; kp.pool_off = P.pool_off; kp.cslot_off = P.cslot_off; kp.imu_off = P.imu_off;
+    kp.nq = m->nq; kp.nv = m->nv; kp.nmotors = m->nmotors; kp.njoints = m->njoints; kp.n_hist = 0;
+    kp.nimu = m->nimu; kp.nforce = m->nforce; kp.nenc = m->nencoder; kp.neff = m->neffort; kp.ncs = m->ncontact_sensor;
+    for (int r = 0; r < P.nrec; ++r) { kp.rec_off[r] = P.rec_off[r]; kp.rec_free[r] = P.rec_free[r]; kp.trunk_reduce[r] = P.trunk_reduce[r]; }
+    JbSensorLayout& L = kp.lay;
+    L.imu_offset = 0;
+    L.force_offset = 6 * m->nimu;
+    L.encoder_offset = L.force_offset + 6 * m->nforce;
+    L.effort_offset = L.encoder_offset + 2 * m->nencoder;
+    L.contact_offset = L.effort_offset + m->neffort;
+    L.width = L.contact_offset + 3 * m->ncontact_sensor;
+    b->width = L.width;
+    // one force sensor per joint at most (the per-contact table keeps a single sensor index)
+    for (int f = 0; f < m->nforce; ++f)
+        for (int g = f + 1; g < m->nforce; ++g)
+            if (m->force_joint[f] == m->force_joint[g]) { jb_batch_destroy(b); return fail(JB_ERR_NOT_IMPLEMENTED, "several force sensors on one joint"); }
+    apply_options(b, opt);
+
+#define ALLOC(ptr, count) do { int rc_ = dev_alloc(b, &(ptr), (count)); if (rc_) { jb_batch_destroy(b); return rc_; } } while (0)
+    RecInt* d_rint; RecDbl* d_rdbl; ContactSlot* d_cs; double* d_imu;
+    ALLOC(d_rint, P.rint.size()); ALLOC(d_rdbl, P.rdbl.size()); ALLOC(d_cs, P.cslots.size()); ALLOC(d_imu, 12 * static_cast<size_t>(m->nimu));
+    const size_t N = b->n_pad;
+    ALLOC(b->d_q, N * m->nq); ALLOC(b->d_v, N * m->nv); ALLOC(b->d_a, N * m->nv); ALLOC(b->d_sched, N * SCH_N);
+    ALLOC(b->d_iters, 2 * N); ALLOC(b->d_status, N);
+    ALLOC(b->d_cmd, static_cast<size_t>(n_env) * m->nmotors); ALLOC(b->d_sensors, static_cast<size_t>(n_env) * L.width);
+    ALLOC(b->d_qv, static_cast<size_t>(n_env) * (m->nq + m->nv));
+    ALLOC(b->d_qin, static_cast<size_t>(n_env) * m->nq); ALLOC(b->d_vin, static_cast<size_t>(n_env) * m->nv);
+    ALLOC(b->d_aout, static_cast<size_t>(n_env) * m->nv); ALLOC(b->d_fext, static_cast<size_t>(n_env) * m->njoints * 6);
+    ALLOC(b->d_u, static_cast<size_t>(n_env) * m->nv); ALLOC(b->d_umotor, static_cast<size_t>(n_env) * m->nmotors);
+    ALLOC(b->d_springs, 2 * static_cast<size_t>(m->nv)); ALLOC(b->d_mask, n_env);
+    ALLOC(b->d_pd, 2 * static_cast<size_t>(m->nmotors)); ALLOC(b->d_cmd_torque, static_cast<size_t>(n_env) * m->nmotors);
+    ALLOC(b->d_stage, static_cast<size_t>(n_env) * std::max(std::max(m->nq, m->nv), SCH_N + 0));
+#undef ALLOC
+    cudaMemcpyAsync(d_rint, P.rint.data(), P.rint.size() * sizeof(RecInt), cudaMemcpyHostToDevice, b->stream);
+    cudaMemcpyAsync(d_rdbl, P.rdbl.data(), P.rdbl.size() * sizeof(RecDbl), cudaMemcpyHostToDevice, b->stream);
+    if (!P.cslots.empty()) cudaMemcpyAsync(d_cs, P.cslots.data(), P.cslots.size() * sizeof(ContactSlot), cudaMemcpyHostToDevice, b->stream);
+    if (m->nimu) cudaMemcpyAsync(d_imu, m->imu_placement, 12 * sizeof(double) * m->nimu, cudaMemcpyHostToDevice, b->stream);
+    std::vector<int32_t> st(N, JB_ENV_NOT_STARTED);
+    cudaMemcpyAsync(b->d_status, st.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream);
+    kp.rint = d_rint; kp.rdbl = d_rdbl; kp.cslots = d_cs; kp.imu_placement = d_imu; kp.springs = nullptr;
+    kp.pd_gains = nullptr; kp.cmd_torque = b->d_cmd_torque;
+    kp.q = b->d_q; kp.v = b->d_v; kp.a = b->d_a; kp.sched = b->d_sched; kp.iters = b->d_iters; kp.status = b->d_status;
+    kp.command = b->d_cmd; kp.sensors = b->d_sensors; kp.qv_out = b->d_qv;
+    kp.q_in = b->d_qin; kp.v_in = b->d_vin; kp.mask = nullptr;
+    kp.a_out = b->d_aout; kp.fext_out = b->d_fext; kp.u_out = b->d_u;
+    kp.eff_u = b->d_u; kp.eff_umotor = b->d_umotor; kp.eff_fext = b->d_fext;
+    kp.extra_energy = nullptr; kp.extra_a = nullptr; kp.extra_f = nullptr;
+
+    b->smem_bytes = static_cast<size_t>(P.nfields) * 32 * sizeof(double);
+    if (b->smem_bytes > 227 * 1024) { jb_batch_destroy(b); return fail(JB_ERR_NOT_IMPLEMENTED, "robot too large: per-warp working set exceeds shared memory (" + P.describe() + ")"); }
+    e = cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(b->smem_bytes));
+    if (e != cudaSuccess) { jb_batch_destroy(b); return fail(JB_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
+    e = cudaStreamSynchronize(b->stream);
+    if (e != cudaSuccess) { jb_batch_destroy(b); return fail(JB_ERR_CUDA, std::string("upload failed: ") + cudaGetErrorString(e)); }
+    *out = b;
+    return JB_OK;
+}
+
+int jb_describe(JbBatch* b, char* buf, int32_t len) {
+    if (!b || !buf) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    std::snprintf(buf, len, "%s", b->plan.describe().c_str());
+    return JB_OK;
+}
+
+int jb_set_options(JbBatch* b, const JbOptions* o) {
+    if (!b || !o) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = check_options(o);
+    if (rc) return rc;
+    apply_options(b, o);
+    return JB_OK;
+}
+
+// Linear internal dynamics u_custom = -k q - d v on 1-dof joints: the device-side stand-in for the
+// `internalDynamics` functor of FunctionalController (controller_functor.h:27-80).
+int jb_set_joint_springs(JbBatch* b, const double* k, const double* d) {
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(b->device));
+    if (!k || !d) { b->kp.springs = nullptr; return JB_OK; }
+    CU(cudaMemcpyAsync(b->d_springs, k, sizeof(double) * b->nv, cudaMemcpyHostToDevice, b->stream));
+    CU(cudaMemcpyAsync(b->d_springs + b->nv, d, sizeof(double) * b->nv, cudaMemcpyHostToDevice, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    b->kp.springs = b->d_springs;
+    return JB_OK;
+}
+
+// Device-side PD controller block (see update_pd_commands in jb_kernel.cuh).
+int jb_set_pd_controller(JbBatch* b, const double* kp, const double* kd) {
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(b->device));
+    if (!kp || !kd) { b->kp.pd_gains = nullptr; return JB_OK; }
+    if (!b->nmotors) return fail(JB_ERR_INVALID_ARGUMENT, "the robot has no motor");
+    const JbOptions& o = b->kp.opt;
+    if (!(o.controller_update_period > 2.3e-16))
+        return fail(JB_ERR_NOT_IMPLEMENTED, "the device PD controller needs a discrete controllerUpdatePeriod");
+    if (o.sensors_update_period > 2.3e-16 && std::fabs(o.sensors_update_period - o.controller_update_period) > 1e-12)
+        return fail(JB_ERR_NOT_IMPLEMENTED, "the device PD controller needs sensorsUpdatePeriod == controllerUpdatePeriod (or 0)");
+    CU(cudaMemcpyAsync(b->d_pd, kp, sizeof(double) * b->nmotors, cudaMemcpyHostToDevice, b->stream));
+    CU(cudaMemcpyAsync(b->d_pd + b->nmotors, kd, sizeof(double) * b->nmotors, cudaMemcpyHostToDevice, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    b->kp.pd_gains = b->d_pd;
+    return JB_OK;
+}
+
+int jb_start(JbBatch* b, const uint8_t* mask, const double* q0, const double* v0) {
+    if (!b || !q0 || !v0) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(b->device));
+    // Engine::start input validation (engine.cc:1007-1037)
+    for (int i = 0; i < b->n_env; ++i) {
+        if (mask && !mask[i]) continue;
+        for (int k = 0; k < b->nq; ++k) {
+            const double x = q0[static_cast<size_t>(i) * b->nq + k];
+            if (!(x == x)) return fail(JB_ERR_INVALID_ARGUMENT, "Initial configuration contains NaN (env " + std::to_string(i) + ").");
+            if (2.220446049250313e-16 < x - b->q_upper[k] || 2.220446049250313e-16 < b->q_lower[k] - x)
+                return fail(JB_ERR_INVALID_ARGUMENT, "Initial configuration out-of-bounds (env " + std::to_string(i) + ").");
+        }
+        for (int k = 0; k < b->nv; ++k) {
+            const double x = v0[static_cast<size_t>(i) * b->nv + k];
+            if (!(x == x)) return fail(JB_ERR_INVALID_ARGUMENT, "Initial velocity contains NaN (env " + std::to_string(i) + ").");
+        }
+    }
+    CU(cudaMemcpyAsync(b->d_qin, q0, sizeof(double) * b->n_env * b->nq, cudaMemcpyHostToDevice, b->stream));
+    CU(cudaMemcpyAsync(b->d_vin, v0, sizeof(double) * b->n_env * b->nv, cudaMemcpyHostToDevice, b->stream));
+    if (mask) {
+        CU(cudaMemcpyAsync(b->d_mask, mask, b->n_env, cudaMemcpyHostToDevice, b->stream));
+        b->kp.mask = b->d_mask;
+    } else b->kp.mask = nullptr;
+    int rc = launch(b, MODE_START, 0.0);
+    b->kp.mask = nullptr;
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(b->stream));
+    b->any_started = true;
+    return JB_OK;
+}
+
+int jb_set_command(JbBatch* b, const double* cmd) {
+    if (!b || (!cmd && b->nmotors)) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!b->nmotors) return JB_OK;
+    CU(cudaSetDevice(b->device));
+    CU(cudaMemcpyAsync(b->d_cmd, cmd, sizeof(double) * b->n_env * b->nmotors, cudaMemcpyHostToDevice, b->stream));
+    return JB_OK;
+}
+
+int jb_set_command_device(JbBatch* b, const double* cmd_dev) {
+    if (!b || (!cmd_dev && b->nmotors)) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!b->nmotors) return JB_OK;
+    CU(cudaSetDevice(b->device));
+    CU(cudaMemcpyAsync(b->d_cmd, cmd_dev, sizeof(double) * b->n_env * b->nmotors, cudaMemcpyDeviceToDevice, b->stream));
+    return JB_OK;
+}
+
+int jb_step(JbBatch* b, double step_dt) {
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!b->any_started) return fail(JB_ERR_BAD_CONTROL_FLOW, "No simulation running. Please start one before using step method.");
+    if (step_dt > 2.220446049250313e-16 && step_dt < 1e-6) return fail(JB_ERR_INVALID_ARGUMENT, "Step size out of bounds.");
+    CU(cudaSetDevice(b->device));
+    return launch(b, MODE_STEP, step_dt);
+}
+
+int jb_compute_dynamics(JbBatch* b, const double* q, const double* v, const double* cmd, double* a, double* fext, double* u) {
+    if (!b || !q || !v || !a) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(b->device));
+    CU(cudaMemcpyAsync(b->d_qin, q, sizeof(double) * b->n_env * b->nq, cudaMemcpyHostToDevice, b->stream));
+    CU(cudaMemcpyAsync(b->d_vin, v, sizeof(double) * b->n_env * b->nv, cudaMemcpyHostToDevice, b->stream));
+    if (cmd && b->nmotors) CU(cudaMemcpyAsync(b->d_cmd, cmd, sizeof(double) * b->n_env * b->nmotors, cudaMemcpyHostToDevice, b->stream));
+    int rc = launch(b, MODE_DYNAMICS, 0.0);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(a, b->d_aout, sizeof(double) * b->n_env * b->nv, cudaMemcpyDeviceToHost, b->stream));
+    if (fext) CU(cudaMemcpyAsync(fext, b->d_fext, sizeof(double) * b->n_env * b->njoints * 6, cudaMemcpyDeviceToHost, b->stream));
+    if (u) CU(cudaMemcpyAsync(u, b->d_u, sizeof(double) * b->n_env * b->nv, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return JB_OK;
+}
+
+static int fetch_soa(JbBatch* b, const double* d_src, int width, double* host_dst) {
+    const size_t total = static_cast<size_t>(b->n_env) * width;
+    if (!total) return JB_OK;
+    JB_LAUNCH(soa_to_aos_kernel, static_cast<unsigned>((total + 255) / 256), 256, 0, b->stream, d_src, b->d_stage, b->n_env, b->n_pad, width);
+    CU(cudaGetLastError());
+    ++b->launches;
+    CU(cudaMemcpyAsync(host_dst, b->d_stage, total * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return JB_OK;
+}
+
+int jb_get_state(JbBatch* b, double* t, double* q, double* v, double* a) {
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(b->device));
+    int rc;
+    if (t) { CU(cudaMemcpyAsync(t, b->d_sched + static_cast<size_t>(SCH_T) * b->n_pad, sizeof(double) * b->n_env, cudaMemcpyDeviceToHost, b->stream)); CU(cudaStreamSynchronize(b->stream)); }
+    if (q && (rc = fetch_soa(b, b->d_q, b->nq, q))) return rc;
+    if (v && (rc = fetch_soa(b, b->d_v, b->nv, v))) return rc;
+    if (a && (rc = fetch_soa(b, b->d_a, b->nv, a))) return rc;
+    return JB_OK;
+}
+
+int jb_get_efforts(JbBatch* b, double* u, double* u_motor, double* command, double* fext) {
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(b->device));
+    if (u) CU(cudaMemcpyAsync(u, b->d_u, sizeof(double) * b->n_env * b->nv, cudaMemcpyDeviceToHost, b->stream));
+    if (u_motor && b->nmotors) CU(cudaMemcpyAsync(u_motor, b->d_umotor, sizeof(double) * b->n_env * b->nmotors, cudaMemcpyDeviceToHost, b->stream));
+    if (command && b->nmotors) CU(cudaMemcpyAsync(command, b->d_cmd, sizeof(double) * b->n_env * b->nmotors, cudaMemcpyDeviceToHost, b->stream));
+    if (fext) CU(cudaMemcpyAsync(fext, b->d_fext, sizeof(double) * b->n_env * b->njoints * 6, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return JB_OK;
+}
+
+int jb_get_sensors(JbBatch* b, double* out) {
+    if (!b || !out) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(b->device));
+    if (b->width) CU(cudaMemcpyAsync(out, b->d_sensors, sizeof(double) * b->n_env * b->width, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return JB_OK;
+}
+
+int jb_sensor_layout(JbBatch* b, JbSensorLayout* out) {
+    if (!b || !out) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    *out = b->kp.lay;
+    return JB_OK;
+}
+
+int jb_get_extra_terms(JbBatch* b, double* energy, double* joint_a, double* joint_f) {
+    (void)energy; (void)joint_a; (void)joint_f;
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    return fail(JB_ERR_NOT_IMPLEMENTED, "computeExtraTerms outputs (energy, data.a, data.f) are not produced by this build");
+}
+
+int jb_get_status(JbBatch* b, int32_t* status) {
+    if (!b || !status) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(b->device));
+    CU(cudaMemcpyAsync(status, b->d_status, sizeof(int32_t) * b->n_env, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return JB_OK;
+}
+
+int jb_get_iters(JbBatch* b, int64_t* iter, int64_t* iter_failed) {
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(b->device));
+    if (iter) CU(cudaMemcpyAsync(iter, b->d_iters, sizeof(int64_t) * b->n_env, cudaMemcpyDeviceToHost, b->stream));
+    if (iter_failed) CU(cudaMemcpyAsync(iter_failed, b->d_iters + b->n_pad, sizeof(int64_t) * b->n_env, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return JB_OK;
+}
+
+int jb_device_views(JbBatch* b, double** sensors_dev, double** qv_dev) {
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (sensors_dev) *sensors_dev = b->d_sensors;
+    if (qv_dev) *qv_dev = b->d_qv;
+    return JB_OK;
+}
+
+int jb_get_stream(JbBatch* b, void** stream) {
+    if (!b || !stream) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    *stream = b->stream;
+    return JB_OK;
+}
+
+int64_t jb_launch_count(JbBatch* b) { return b ? b->launches : 0; }
+
+int jb_synchronize(JbBatch* b) {
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(b->device));
+    CU(cudaStreamSynchronize(b->stream));
+    return JB_OK;
+}
+
+// Host-side introspection of the lane planner (no device needed): used by the CPU test-suite.
+int jb_plan_describe(const JbModelDesc* m, int32_t lanes, char* buf, int32_t len, int32_t* joint_lane) {
+    if (!m || !buf) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    try {
+        Plan P = build_plan(*m, lanes, 0);
+        std::snprintf(buf, len, "%s", P.describe().c_str());
+        if (joint_lane) for (int j = 0; j < m->njoints; ++j) joint_lane[j] = P.joint_lane[j];
+    } catch (const std::exception& ex) {
+        return fail(JB_ERR_INVALID_ARGUMENT, ex.what());
+    }
+    return JB_OK;
+}
+
+}  // extern "C"

@@ -63,8 +63,17 @@ int orc_start(OrcBatch* b, const uint8_t* mask, const double* q0, const double* 
     return bad;
 }
 void orc_set_command(OrcBatch* b, const double* cmd) {
-    for (size_t i = 0; i < b->envs.size(); ++i)
-        std::memcpy(b->envs[i]->state.command.data(), cmd + i * b->nmotors, sizeof(double) * b->nmotors);
+    for (size_t i = 0; i < b->envs.size(); ++i) {
+        Engine& e = *b->envs[i];
+        if (e.pd_enabled) e.pd_target.assign(cmd + i * b->nmotors, cmd + (i + 1) * b->nmotors);
+        else std::memcpy(e.state.command.data(), cmd + i * b->nmotors, sizeof(double) * b->nmotors);
+    }
+}
+void orc_set_pd(OrcBatch* b, const double* kp, const double* kd) {
+    for (auto& e : b->envs) {
+        e->pd_enabled = kp != nullptr;
+        if (kp) { e->pd_kp.assign(kp, kp + b->nmotors); e->pd_kd.assign(kd, kd + b->nmotors); e->pd_target.assign(b->nmotors, 0.0); }
+    }
 }
 int orc_step(OrcBatch* b, double step_dt, int parallel, int* rc) {
     const int n = static_cast<int>(b->envs.size());

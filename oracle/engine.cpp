@@ -252,6 +252,21 @@ void Engine::computeAllTerms(double /*t*/, const double* qv, const double* vv, b
 // Engine::computeCommand (engine.cc:3240-3251).  Without a functor the command buffer is a
 // zero-order hold of what the caller wrote (the batched boundary).
 void Engine::computeCommand(double tt, const double* qv, const double* vv, std::vector<double>& command) {
+    if (pd_enabled) {
+        // gym_jiminy.common.blocks.pd_controller (python/gym_jiminy/common/gym_jiminy/common/blocks/
+        // proportional_derivative_controller.py:101-165) with a zero-order-held position target and zero
+        // target velocity: tau = clip(kp * ((q_des - q_enc) + kd * (0 - v_enc)), +-effort_limit).
+        // Encoder data = motor-side position / velocity at the last sensor refresh (same instant).
+        for (int m = 0; m < model.nmotors; ++m) {
+            const int j = model.motor_joint[m];
+            const double red = model.motor_params[10 * m], lim = model.motor_params[10 * m + 1];
+            double pos = Model::is_unbounded(model.jtype[j]) ? std::atan2(qv[model.idx_q[j] + 1], qv[model.idx_q[j]]) : qv[model.idx_q[j]];
+            const double q_enc = pos * red, v_enc = vv[model.idx_v[j]] * red;
+            const double tau = pd_kp[m] * ((pd_target[m] - q_enc) + pd_kd[m] * (0.0 - v_enc));
+            command[m] = std::min(std::max(tau, -lim), lim);
+        }
+        return;
+    }
     if (!controller) return;
     std::fill(command.begin(), command.end(), 0.0);
     controller(ctx, tt, qv, vv, sensors.data(), command.data());
@@ -686,8 +701,12 @@ double Engine::computeErrorDopri(double dtt) {
     difference(qBuf.data(), qOther.data(), scale.v.data());  // initialState.difference(otherSolution_, scale_)
     for (int k = 0; k < nv; ++k) scale.a[k] = vBuf[k] - vOther[k];
     for (int k = 0; k < nv; ++k) {
-        scale.v[k] = std::fabs(scale.v[k]) * opt.tol_rel + opt.tol_abs;
-        scale.a[k] = std::fabs(scale.a[k]) * opt.tol_rel + opt.tol_abs;
+        // NB: Engine::start builds `RungeKuttaDOPRIStepper(robotOde, robots, stepper.tolAbs, stepper.tolRel)`
+        // (engine.cc:1161-1163) while the constructor takes (tolRel, tolAbs): the two options reach the
+        // error scale swapped.  Restated as the reference behaves, not as the option names suggest.
+        const double tolRel_ = opt.tol_abs, tolAbs_ = opt.tol_rel;
+        scale.v[k] = std::fabs(scale.v[k]) * tolRel_ + tolAbs_;
+        scale.a[k] = std::fabs(scale.a[k]) * tolRel_ + tolAbs_;
     }
     std::fill(inc.v.begin(), inc.v.end(), 0.0);
     std::fill(inc.a.begin(), inc.a.end(), 0.0);

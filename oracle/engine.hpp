@@ -136,6 +136,9 @@ struct Engine {
     InternalDynFn internalDyn = nullptr;    // internalDynamics functor
     void* ctx = nullptr;
     std::vector<double> spring_k, spring_d; // built-in linear internal dynamics u = -k q - d v (1-dof joints)
+    // built-in discrete PD controller (gym_jiminy PDController, order-0 target): command buffer = targets
+    bool pd_enabled = false;
+    std::vector<double> pd_kp, pd_kd, pd_target;
     int64_t rhs_count = 0;
 
     // stepper buffers

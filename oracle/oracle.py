@@ -51,6 +51,7 @@ def lib():
         L.orc_set_options.argtypes = [C.c_void_p, C.POINTER(JbOptions)]
         L.orc_set_callbacks.argtypes = [C.c_void_p, C.c_int, CONTROLLER_FN, CONTROLLER_FN, C.c_void_p]
         L.orc_set_springs.argtypes = [C.c_void_p, c_double_p, c_double_p]
+        L.orc_set_pd.argtypes = [C.c_void_p, c_double_p, c_double_p]
         L.orc_start.argtypes = [C.c_void_p, c_uint8_p, c_double_p, c_double_p, c_int32_p]
         L.orc_set_command.argtypes = [C.c_void_p, c_double_p]
         L.orc_step.argtypes = [C.c_void_p, C.c_double, C.c_int, c_int32_p]
@@ -98,6 +99,14 @@ class OracleBatch:
         k, d = np.ascontiguousarray(k, dtype=np.float64), np.ascontiguousarray(d, dtype=np.float64)
         lib().orc_set_springs(self._h, dptr(k), dptr(d))
 
+    def set_pd_controller(self, kp, kd) -> None:
+        if kp is None:
+            lib().orc_set_pd(self._h, None, None)
+            return
+        kp = np.ascontiguousarray(np.broadcast_to(kp, (self.nm,)), dtype=np.float64)
+        kd = np.ascontiguousarray(np.broadcast_to(kd, (self.nm,)), dtype=np.float64)
+        lib().orc_set_pd(self._h, dptr(kp), dptr(kd))
+
     def set_callbacks(self, env: int, controller: Optional[Callable] = None,
                       internal_dynamics: Optional[Callable] = None) -> None:
         """`controller(t, q, v, sensors, out)` / `internal_dynamics(t, q, v, sensors, out)` write `out`
@@ -109,8 +118,9 @@ class OracleBatch:
                 return C.cast(None, CONTROLLER_FN)
 
             def tramp(_ctx, t, q, v, s, out):
-                fn(t, np.ctypeslib.as_array(q, (nq,)), np.ctypeslib.as_array(v, (nv,)),
-                   np.ctypeslib.as_array(s, (max(w, 1),))[:w], np.ctypeslib.as_array(out, (nout,)))
+                sens = np.ctypeslib.as_array(s, (w,)) if (w and s) else np.zeros(0)
+                fn(t, np.ctypeslib.as_array(q, (nq,)), np.ctypeslib.as_array(v, (nv,)), sens,
+                   np.ctypeslib.as_array(out, (nout,)))
             return CONTROLLER_FN(tramp)
         c, d = wrap(controller, nm), wrap(internal_dynamics, nv)
         self._cbs.append((c, d))

@@ -1,0 +1,37 @@
+"""TEST INFRASTRUCTURE ONLY: builds / loads tests/emul/libjiminy_b200_emul.so (the product's C ABI
+and device code compiled for the host, warp lanes emulated by threads -- see jb_emul_shim.h) so
+that CPU-only tests can run the kernel source against the oracle.  Never imported by jiminy_b200/."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+sys.path.insert(0, _ROOT)
+from jiminy_b200.core import Api  # noqa: E402
+
+_LIB = os.path.join(_HERE, "libjiminy_b200_emul.so")
+_SRCS = [os.path.join(_HERE, f) for f in ("jb_emul.cpp", "jb_emul_shim.h")] + \
+        [os.path.join(_ROOT, "jiminy_b200", "csrc", f) for f in
+         ("jb_capi.cu", "jb_kernel.cuh", "jb_device.cuh", "jb_plan.cpp", "jb_plan.h")] + \
+        [os.path.join(_ROOT, "include", "jiminy_b200.h")]
+
+
+def build(force=False):
+    stale = not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in _SRCS)
+    if force or stale:
+        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-pthread", "-DJB_HOST_EMUL=1",
+                        "-ffp-contract=off", "-I", _HERE, "-x", "c++", os.path.join(_HERE, "jb_emul.cpp"),
+                        os.path.join(_ROOT, "jiminy_b200", "csrc", "jb_plan.cpp"), "-o", _LIB], check=True)
+    return _LIB
+
+
+_api = None
+
+
+def emul_api() -> Api:
+    global _api
+    if _api is None:
+        _api = Api(C.CDLL(build()))
+    return _api

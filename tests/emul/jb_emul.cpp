@@ -1,0 +1,39 @@
+// TEST INFRASTRUCTURE ONLY -- see jb_emul_shim.h.  Builds tests/emul/libjiminy_b200_emul.so: the
+// product's C ABI (jiminy_b200/csrc/jb_capi.cu + jb_plan.cpp, unchanged) on top of the thread
+// emulation of a warp.
+#include "jb_emul_shim.h"
+
+thread_local EmulDim3 threadIdx, blockIdx, blockDim, gridDim;
+thread_local double* emul_smem = nullptr;
+namespace emul {
+thread_local Warp* warp = nullptr;
+thread_local int lane_id = 0;
+int current_L = 1;
+
+void launch(unsigned grid, unsigned block, size_t smem_bytes, int L, const std::function<void()>& body) {
+    std::vector<double> smem((smem_bytes + 7) / 8 + 1, 0.0);
+    const unsigned nwarps = (block + 31) / 32;
+    for (unsigned bi = 0; bi < grid; ++bi) {
+        std::vector<Warp> warps(nwarps);
+        for (auto& w : warps) {
+            w.L = L;
+            for (int g = 0; g < 32 / L; ++g) w.bars.emplace_back(new std::barrier<>(L));
+        }
+        std::vector<std::thread> threads;
+        threads.reserve(block);
+        for (unsigned ti = 0; ti < block; ++ti) {
+            threads.emplace_back([&, ti]() {
+                threadIdx.x = ti; blockIdx.x = bi; blockDim.x = block; gridDim.x = grid;
+                emul_smem = smem.data();
+                warp = &warps[ti / 32];
+                lane_id = static_cast<int>(ti % 32);
+                body();
+            });
+        }
+        for (auto& t : threads) t.join();
+    }
+}
+}  // namespace emul
+
+#define JB_HOST_EMUL 1
+#include "../../jiminy_b200/csrc/jb_capi.cu"

@@ -1,0 +1,109 @@
+// TEST INFRASTRUCTURE ONLY -- never part of the product, never loaded by jiminy_b200/.
+//
+// Compiles the device code of jiminy_b200/csrc unchanged for the host and runs every CUDA thread
+// of a block as a std::thread, with warp shuffles / votes / __syncwarp implemented as rendez-vous
+// between the lanes named in the mask.  This lets the CPU test-suite (no GPU in the build
+// container) exercise the *same* kernel source -- lane plan, trunk all-reduce, scheduler -- against
+// the oracle before any GPU time is spent.  The numbers it produces are not performance data and
+// are never reported as such.
+#pragma once
+#include <atomic>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __noinline__
+#define __restrict__
+#define __grid_constant__
+#define __launch_bounds__(...)
+
+struct EmulDim3 { unsigned x = 1, y = 1, z = 1; };
+extern thread_local EmulDim3 threadIdx, blockIdx, blockDim, gridDim;
+extern thread_local double* emul_smem;
+
+// `extern __shared__ double smem[];` inside the kernel
+#define __shared__
+#define EMUL_SHARED_DECL
+namespace emul {
+struct Warp {
+    // exchange slots for the 32 lanes + one barrier per distinct mask in flight; masks used by the
+    // kernels are contiguous aligned groups, so a barrier per (group size, group index) suffices.
+    double dslot[32];
+    int islot[32];
+    std::vector<std::unique_ptr<std::barrier<>>> bars;   // indexed by group id for the current L
+    int L = 1;
+};
+extern thread_local Warp* warp;
+extern thread_local int lane_id;
+inline int group_of(unsigned mask) { return __builtin_ctz(mask) / warp->L; }
+inline void sync_group(unsigned mask) { warp->bars[group_of(mask)]->arrive_and_wait(); }
+}  // namespace emul
+
+inline void __syncwarp(unsigned mask = 0xffffffffu) { emul::sync_group(mask); }
+inline double __shfl_xor_sync(unsigned mask, double x, int o) {
+    emul::warp->dslot[emul::lane_id] = x;
+    emul::sync_group(mask);
+    const double r = emul::warp->dslot[emul::lane_id ^ o];
+    emul::sync_group(mask);
+    return r;
+}
+inline int __shfl_xor_sync(unsigned mask, int x, int o) {
+    emul::warp->islot[emul::lane_id] = x;
+    emul::sync_group(mask);
+    const int r = emul::warp->islot[emul::lane_id ^ o];
+    emul::sync_group(mask);
+    return r;
+}
+inline bool __any_sync(unsigned mask, bool p) {
+    emul::warp->islot[emul::lane_id] = p ? 1 : 0;
+    emul::sync_group(mask);
+    bool r = false;
+    for (int l = 0; l < 32; ++l)
+        if (mask & (1u << l)) r = r || (emul::warp->islot[l] != 0);
+    emul::sync_group(mask);
+    return r;
+}
+inline double __longlong_as_double(long long x) { double d; std::memcpy(&d, &x, sizeof d); return d; }
+inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
+
+// ---- minimal CUDA runtime stand-ins (host memory, synchronous "streams")
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum { cudaStreamNonBlocking = 1 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::calloc(1, n); return cudaSuccess; }
+inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = std::calloc(1, n); return cudaSuccess; }
+inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) { *s = reinterpret_cast<void*>(1); return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+template <typename F>
+inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+
+namespace emul {
+// Runs `body()` for every thread of every block, 32 lanes of a warp concurrently.
+void launch(unsigned grid, unsigned block, size_t smem_bytes, int lanes_per_group, const std::function<void()>& body);
+extern int current_L;   // lanes per env of the batch being launched (set by the launch macro)
+}  // namespace emul
+
+#define JB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    emul::launch((grid), (block), (smem), emul::current_L, [&]() { kernel(__VA_ARGS__); })

@@ -1,0 +1,169 @@
+"""CPU-only checks of the *kernel source* (jiminy_b200/csrc) against the oracle, by running it under
+the warp emulator of tests/emul (threads stand for lanes; shuffles are rendez-vous).  This is test
+infrastructure: it proves the lane plan, the trunk all-reduce, the scheduler and the sensor code
+before GPU time is spent.  The real parity gate is tests/test_gpu_parity.py (-m gpu)."""
+import os
+
+import numpy as np
+import pytest
+
+from jiminy_b200 import model as M
+from jiminy_b200 import robots as R
+from jiminy_b200 import scenarios
+from jiminy_b200.core import BatchedEngine, plan_describe
+from oracle.oracle import OracleBatch
+
+from conftest import DATA
+from emul import emul_api
+import parity_common as pc
+
+
+@pytest.fixture(scope="module")
+def api():
+    return emul_api()
+
+
+def _lanes(n):
+    os.environ["JB_LANES"] = str(n)
+
+
+@pytest.mark.parametrize("name,lanes", [("anymal", 0), ("anymal", 1), ("anymal", 2), ("atlas", 0), ("atlas", 8),
+                                        ("cartpole", 0), ("double_pendulum", 0)])
+def test_single_rhs_matches_oracle(api, name, lanes):
+    """One Engine::computeRobotsDynamics evaluation (FK + contacts + motors + ABA) on random states."""
+    _lanes(lanes)
+    robot, opt = R.load_robot(name)
+    opt = R.baseline_options(name, opt)
+    rng = np.random.default_rng(3)
+    n = 3
+    q, v = pc.random_states(robot, n, rng)
+    cmd = rng.uniform(-20, 20, size=(n, max(robot.nmotors, 1)))
+    a0, f0, u0 = OracleBatch(robot, opt, n).compute_dynamics(q, v, cmd)
+    eng = BatchedEngine(robot, opt, n, api_=api)
+    a1, f1, u1 = eng.compute_dynamics(q, v, cmd)
+    _lanes(0)
+    np.testing.assert_allclose(a1, a0, rtol=0, atol=1e-12 * max(1.0, np.abs(a0).max()))
+    np.testing.assert_allclose(f1, f0, rtol=0, atol=1e-12 * max(1.0, np.abs(f0).max()))
+    np.testing.assert_allclose(u1, u0, rtol=0, atol=1e-12)
+
+
+def test_all_joint_models_and_internal_branching(api):
+    """Every joint model of the path (RX/RY/RZ/RU, RUB*, PZ/PU, free-flyer) on a branched tree, with a
+    contact, an IMU, a force sensor and encoders; lanes = 1, 2 and automatic."""
+    robot = M.build_robot_table(os.path.join(DATA, "branched_arm.urdf"), True)
+    robot.add_contact_points(["b_sole", "a_tool"])
+    for jn in ("a_shoulder", "a_elbow", "a_spin", "b_hip", "b_slide", "b_skew_slide", "b_ankle_z", "c_spin_skew"):
+        M.attach_motor(robot, jn, jn, enableVelocityLimit=(jn == "b_hip"), velocityEffortInvSlope=0.05,
+                       enableArmature=True, armature=0.01, enableFriction=(jn == "a_elbow"),
+                       frictionViscousPositive=-0.1, frictionViscousNegative=-0.2, frictionDryPositive=-0.05,
+                       frictionDryNegative=-0.07, frictionDrySlope=3.0)
+        M.attach_sensor(robot, "EncoderSensor", jn, motor_name=jn)
+        M.attach_sensor(robot, "EffortSensor", jn, motor_name=jn)
+    M.attach_sensor(robot, "ImuSensor", "imu", frame_name="a_hand")
+    M.attach_sensor(robot, "ForceSensor", "sole", frame_name="b_toe")
+    M.attach_sensor(robot, "ContactSensor", "sole_c", frame_name="b_sole")
+    opt = M.default_engine_options()
+    opt["contacts"].update(model="spring_damper", stiffness=1e5, damping=5e2)
+    opt["stepper"].update(odeSolver="runge_kutta_4", dtMax=5e-4, sensorsUpdatePeriod=2e-3, controllerUpdatePeriod=4e-3)
+    rng = np.random.default_rng(5)
+    n = 2
+    q, v = pc.random_states(robot, n, rng, base_height=0.55)
+    cmd = rng.uniform(-5, 5, size=(n, robot.nmotors))
+    for lanes in (0, 1, 2):
+        _lanes(lanes)
+        orc = OracleBatch(robot, opt, n)
+        eng = BatchedEngine(robot, opt, n, api_=api)
+        for e in (orc, eng):
+            e.set_command(cmd)
+        a0, f0, u0 = orc.compute_dynamics(q, v, cmd)
+        a1, f1, u1 = eng.compute_dynamics(q, v, cmd)
+        np.testing.assert_allclose(a1, a0, rtol=0, atol=1e-11 * max(1.0, np.abs(a0).max()))
+        np.testing.assert_allclose(u1, u0, rtol=0, atol=1e-12)
+        assert not orc.start(q, v).any()
+        eng.start(q, v)
+        pc.compare(eng, orc, 1e-13, 1e-11)
+        for _ in range(3):
+            eng.step(0.01)
+            assert not orc.step(0.01).any()
+            pc.compare(eng, orc, 1e-10, 1e-8)
+    _lanes(0)
+
+
+def test_anymal_pd_env_steps(api):
+    pc.run_scenario("anymal", 3, 2, api=api)
+
+
+def test_anymal_torque_mode_euler(api):
+    """Zero-order-held effort commands, explicit Euler at 1e-4 (the alternative profile of SURVEY.md 8d)."""
+    sc = scenarios.make("anymal", 2, dt_max=1e-4, solver="euler_explicit")
+    sc.kp = None
+    rng = np.random.default_rng(2)
+    sc.target0 = rng.uniform(-10, 10, size=(2, 12))
+    eng, orc = pc.make_pair(sc, api)
+    eng.step(0.005)
+    assert not orc.step(0.005).any()
+    pc.compare(eng, orc, 1e-10, 1e-8)
+
+
+def test_atlas_pd_env_step(api):
+    pc.run_scenario("atlas", 2, 1, api=api)
+
+
+def test_cartpole_and_double_pendulum(api):
+    pc.run_scenario("cartpole", 5, 6, api=api, tol_state=1e-13, tol_sens=1e-12)
+    pc.run_scenario("double_pendulum", 2, 20, api=api, tol_state=1e-13, tol_sens=1e-12)
+
+
+def test_masked_restart_and_odd_env_count(api):
+    """jb_start with a mask restarts only the selected envs (batched reset); n_env not a multiple of a warp."""
+    sc = scenarios.make("anymal", 9)
+    eng, orc = pc.make_pair(sc, api)
+    eng.step(sc.step_dt)
+    orc.step(sc.step_dt, parallel=True)
+    mask = np.zeros(9, dtype=np.uint8)
+    mask[[1, 8]] = 1
+    eng.start(sc.q0, sc.v0, mask=mask)
+    orc.start(sc.q0, sc.v0, mask=mask)
+    t = eng.get_state()[0]
+    assert t[1] == 0.0 and t[8] == 0.0 and t[0] == pytest.approx(0.04)
+    pc.compare(eng, orc, 1e-9, 1e-7)
+    eng.step(sc.step_dt)
+    orc.step(sc.step_dt, parallel=True)
+    pc.compare(eng, orc, 1e-9, 1e-7)
+    it = eng.get_iters()[0]
+    assert it[1] == 41 and it[0] == 81       # restarted envs do the 1 us first step again
+
+
+def test_status_flags(api):
+    """Joint bound violation raises JB_ENV_JOINT_LIMIT on both sides; step before start is a control-flow error."""
+    from jiminy_b200.core import BadControlFlow, JB_ENV_JOINT_LIMIT
+    robot, opt = R.load_robot("anymal")
+    opt = R.baseline_options("anymal", opt)
+    eng = BatchedEngine(robot, opt, 1, api_=api)
+    with pytest.raises(BadControlFlow):
+        eng.step(0.04)
+    q = R.ground_base_height(robot, robot.neutral())
+    q[robot.idx_q[robot.joint_index("LF_HAA")]] = 0.48      # upper bound 0.49
+    v = np.zeros(robot.nv)
+    v[robot.idx_v[robot.joint_index("LF_HAA")]] = 3.0
+    orc = OracleBatch(robot, opt, 1)
+    eng.start(q, v)
+    orc.start(q, v)
+    eng.step(0.01)
+    orc.step(0.01)
+    assert eng.get_status()[0] & JB_ENV_JOINT_LIMIT and orc.get_status()[0] & JB_ENV_JOINT_LIMIT
+    bad = q.copy()
+    bad[robot.idx_q[robot.joint_index("LF_HAA")]] = 0.6
+    with pytest.raises(ValueError):
+        eng.start(bad, v)
+
+
+def test_lane_plans(api):
+    for name, lanes, expect in (("anymal", 0, 4), ("atlas", 0, 4), ("cartpole", 0, 1)):
+        robot, _ = R.load_robot(name)
+        text, joint_lane = plan_describe(robot, lanes, api)
+        assert f"lanes={expect}" in text
+    robot, _ = R.load_robot("anymal")
+    _, jl = plan_describe(robot, 0, api)
+    assert jl[1] == -1 and sorted(set(jl[2:].tolist())) == [0, 1, 2, 3]     # root is trunk, one leg per lane
+    assert len({int(jl[robot.joint_index(f"LF_{s}")]) for s in ("HAA", "HFE", "KFE")}) == 1

@@ -1,0 +1,225 @@
+"""Pins the CPU oracle with the reference's own analytical tests, re-implemented on
+hand-written fixtures:
+  1. core/unit/engine_sanity_check.cc:47-165 ......... double-pendulum energy conservation
+  2. unit_py/test_simple_pendulum.py:100-141 .......... rotor inertia (armature) + spring vs expm
+  3. unit_py/test_simple_pendulum.py:240-267 .......... non-linear pendulum vs scipy dopri5
+  4. unit_py/test_double_spring_mass.py:85-130 ........ two prismatic masses vs expm (continuous, discrete)
+  5. unit_py/test_simple_mass.py:113-176, :248-344 .... spring-damper contact equilibrium, friction steady state
+  6. unit_py/test_simple_mass.py:183-246 .............. contact / force sensor == external force in frame
+  7. unit_py/test_simulator.py:26-109 ................. Euler finite difference of v equals a; IMU reads g at rest
+The reference binary itself cannot run here, so these analytical pins are what anchors the oracle.
+"""
+import os
+
+import numpy as np
+import pytest
+import scipy.integrate
+import scipy.linalg
+
+from jiminy_b200 import model as M
+from jiminy_b200 import robots as R
+from oracle.oracle import OracleBatch
+
+from conftest import DATA
+
+TOL = 1e-7
+
+
+def _opt(**stepper):
+    opt = M.default_engine_options()
+    opt["contacts"]["model"] = "spring_damper"
+    opt["stepper"].update(stepper)
+    return opt
+
+
+def _pendulum(armature=None):
+    r = M.build_robot_table(os.path.join(DATA, "simple_pendulum.urdf"), False)
+    kw = dict(enableVelocityLimit=False, enableEffortLimit=False)
+    if armature is not None:
+        kw.update(enableArmature=True, armature=armature)
+    M.attach_motor(r, "PendulumJoint", "PendulumJoint", **kw)
+    return r
+
+
+def test_armature_spring_vs_expm():
+    J, k = 0.1, 500.0
+    r = _pendulum(J)
+    opt = _opt(tolAbs=TOL * 0.1, tolRel=TOL * 0.1)
+    opt["world"]["gravity"] = [0.0] * 6
+    o = OracleBatch(r, opt)
+    o.set_springs([k], [0.0])
+    ts, qs, vs, _ = o.simulate(2.0, [0.1], [0.0])
+    I_eq = 5.0 * 1.0 ** 2 + J
+    A = np.array([[0.0, 1.0], [-k / I_eq, 0.0]])
+    xa = np.stack([scipy.linalg.expm(A * t) @ np.array([0.1, 0.0]) for t in ts])
+    np.testing.assert_allclose(np.c_[qs, vs], xa, atol=TOL)
+
+
+def test_pendulum_vs_scipy_dopri5():
+    r = _pendulum()
+    o = OracleBatch(r, _opt(tolAbs=1e-10, tolRel=1e-10))
+    ts, qs, vs, _ = o.simulate(2.0, [0.3], [0.0])
+    g, l = 9.81, 1.0
+    # joint axis +Y, mass at +z: q is measured from the upright position
+    sol = scipy.integrate.solve_ivp(lambda t, x: [x[1], g / l * np.sin(x[0])], (0.0, 2.0), [0.3, 0.0], method="DOP853",
+                                    t_eval=ts, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(qs[:, 0], sol.y[0], atol=TOL)
+    np.testing.assert_allclose(vs[:, 0], sol.y[1], atol=TOL)
+
+
+@pytest.mark.parametrize("period", [0.0, 1e-3])
+def test_two_masses_vs_expm(period):
+    r = M.build_robot_table(os.path.join(DATA, "linear_two_masses.urdf"), False)
+    o = OracleBatch(r, _opt(tolAbs=TOL * 0.1, tolRel=TOL * 0.1, sensorsUpdatePeriod=period, controllerUpdatePeriod=period))
+    k, nu, m = np.array([200.0, 20.0]), np.array([0.1, 0.2]), np.array([1.0, 2.5])
+    o.set_springs(k, nu)
+    Iq = 1.0 / m[1] + 1.0 / m[0]
+    A = np.array([[0, 0, 1, 0], [0, 0, 0, 1],
+                  [-k[0] / m[0], k[1] / m[0], -nu[0] / m[0], nu[1] / m[0]],
+                  [k[0] / m[0], -k[1] * Iq, nu[0] / m[0], -nu[1] * Iq]])
+    x0 = np.array([0.1, -0.1, 0.0, 0.0])
+    ts, qs, vs, _ = o.simulate(4.0, x0[:2], x0[2:])
+    idx = np.linspace(0, len(ts) - 1, 60).astype(int)
+    xa = np.stack([scipy.linalg.expm(A * t) @ x0 for t in ts[idx]])
+    np.testing.assert_allclose(np.c_[qs, vs][idx], xa, rtol=1e-5, atol=TOL)   # == np.allclose(.., atol=TOL) of the reference test
+
+
+def test_two_masses_python_controller_callback():
+    """Same system driven through the FunctionalController-style callback instead of built-in springs."""
+    r = M.build_robot_table(os.path.join(DATA, "linear_two_masses.urdf"), False)
+    for j in ("FirstJoint", "SecondJoint"):
+        M.attach_motor(r, j, j, enableVelocityLimit=False, enableEffortLimit=False)
+    k, nu = np.array([200.0, 20.0]), np.array([0.1, 0.2])
+    a, b = OracleBatch(r, _opt(tolAbs=1e-9, tolRel=1e-9)), OracleBatch(r, _opt(tolAbs=1e-9, tolRel=1e-9))
+    a.set_callbacks(0, controller=lambda t, q, v, s, out: out.__setitem__(slice(None), -k * q - nu * v))
+    b.set_springs(k, nu)
+    ta, qa, va, _ = a.simulate(0.5, [0.1, -0.1], [0.0, 0.0])
+    tb, qb, vb, _ = b.simulate(0.5, [0.1, -0.1], [0.0, 0.0])
+    np.testing.assert_allclose(qa, qb, atol=1e-12)
+
+
+def _point_mass(**contacts):
+    r = M.build_robot_table(os.path.join(DATA, "point_mass.urdf"), True)
+    r.add_contact_points(["MassBody"])
+    M.attach_sensor(r, "ContactSensor", "MassBody", frame_name="MassBody")
+    r.add_frame("Sensor", "MassBody", M.SE3(M.rpy_to_matrix([0.3, -0.2, 0.5]), np.array([0.1, 0.2, -0.05])))
+    M.attach_sensor(r, "ForceSensor", "F", frame_name="Sensor")
+    opt = _opt(dtMax=1e-5, controllerUpdatePeriod=1e-5)
+    opt["contacts"].update(stiffness=1e6, damping=2e3, transitionEps=1e-6, **contacts)
+    return r, opt
+
+
+def test_contact_equilibrium_and_sensors():
+    r, opt = _point_mass()
+    o = OracleBatch(r, opt)
+    q0 = r.neutral()
+    q0[2] = 1.0
+    assert not o.start(q0, np.zeros(6)).any()
+    energies = []
+    for _ in range(150):
+        assert not o.step(0.01).any()
+        energies.append(o.get_extra_terms()[0][0].sum())
+    _, q, v, _ = o.get_state()
+    weight = 9.81
+    np.testing.assert_allclose(-q[0, 2], weight / 1e6, atol=TOL)          # equilibrium depth = weight / k
+    fext = o.get_efforts()[3]
+    np.testing.assert_allclose(fext[0, 1, 2], weight, atol=TOL)           # f_external on the parent joint
+    s = o.get_sensors()[0]
+    lay = r.sensor_layout()
+    cont = s[lay["ContactSensor"][0]:lay["ContactSensor"][0] + 3]
+    np.testing.assert_allclose(cont, [0, 0, weight], atol=TOL)
+    # force sensor = same wrench expressed in the (rotated, shifted) sensor frame
+    F = s[lay["ForceSensor"][0]:lay["ForceSensor"][0] + 6]
+    P = r.frames["Sensor"].placement
+    f_expected = P.R.T @ np.array([0, 0, weight])
+    t_expected = P.R.T @ np.cross(-P.p, np.array([0, 0, weight]))
+    np.testing.assert_allclose(F[:3], f_expected, atol=TOL)
+    np.testing.assert_allclose(F[3:], t_expected, atol=TOL)
+    # mechanical energy (robot + contact spring) never increases beyond numerical noise while settling
+    assert energies[-1] < energies[0]
+
+
+def test_friction_steady_state_velocity():
+    """v_steady = Fx / (mu * weight): pins the un-normalised tangential velocity of engine.cc:3218-3222."""
+    r, opt = _point_mass(friction=2.0, transitionVelocity=5e-2)
+    Fx = 5.0
+    opt["world"]["gravity"] = [Fx, 0.0, -9.81, 0.0, 0.0, 0.0]   # horizontal gravity = constant push on the unit mass
+    o = OracleBatch(r, opt)
+    q0 = r.neutral()
+    assert not o.start(q0, np.zeros(6)).any()
+    for _ in range(80):
+        assert not o.step(0.01).any()
+    _, _, v, a = o.get_state()
+    np.testing.assert_allclose(v[0, 0], Fx / (2.0 * 9.81), atol=TOL)
+    assert abs(a[0, 0]) < 1e-5
+
+
+def test_double_pendulum_energy_conservation():
+    robot, opt = R.load_robot("double_pendulum")
+    opt = R.baseline_options("double_pendulum", opt)
+    opt["stepper"].update(sensorsUpdatePeriod=0.0, controllerUpdatePeriod=0.0, dtMax=1e-3)
+    o = OracleBatch(robot, opt)
+    assert not o.start([0.0, 0.1], [0.0, 0.0]).any()
+    e0 = o.get_extra_terms()[0][0].sum()
+    drift = 0.0
+    for _ in range(300):
+        assert not o.step(0.01).any()
+        drift = max(drift, abs(o.get_extra_terms()[0][0].sum() - e0))
+    assert drift < 1e-6, drift     # fixed-step RK4 at 1 ms: O(dt^4) energy error
+    # the reference test: DOPRI with tolAbs = tolRel = 1e-11, continuous then discrete 1 ms, drift < 1e-9
+    for period, h in ((0.0, 0.02), (1e-3, 0.02)):
+        opt["stepper"].update(odeSolver="runge_kutta_dopri", tolAbs=1e-11, tolRel=1e-11, dtMax=0.02,
+                              sensorsUpdatePeriod=period, controllerUpdatePeriod=period)
+        o = OracleBatch(robot, opt)
+        o.start([0.0, 0.1], [0.0, 0.0])
+        e0 = o.get_extra_terms()[0][0].sum()
+        for _ in range(150):
+            assert not o.step(h).any()
+        assert abs(o.get_extra_terms()[0][0].sum() - e0) < 1e-9
+
+
+def test_euler_finite_difference_and_imu_at_rest():
+    r = _pendulum()
+    r.add_frame("ImuFrame", "PendulumLink", M.SE3(M.rpy_to_matrix([0.1, 0.2, 0.3]), np.zeros(3)))
+    M.attach_sensor(r, "ImuSensor", "imu", frame_name="ImuFrame")
+    opt = _opt(odeSolver="euler_explicit", dtMax=1e-3, controllerUpdatePeriod=1e-3, sensorsUpdatePeriod=1e-3)
+    o = OracleBatch(r, opt)
+    ts, qs, vs, as_ = o.simulate(0.05, [0.2], [0.0])
+    fd = np.diff(vs[:, 0]) / np.diff(ts)
+    np.testing.assert_allclose(fd[1:], as_[1:-1, 0], atol=1e-9)           # v' - v = dt * a(previous)
+    # hanging at rest (stable equilibrium, q = pi): accelerometer measures |g|, gyro zero
+    opt2 = _opt(odeSolver="runge_kutta_4", dtMax=1e-3)
+    o = OracleBatch(r, opt2)
+    o.set_springs([0.0], [50.0])
+    o.start([np.pi], [0.0])
+    o.step(0.01)
+    s = o.get_sensors()[0]
+    np.testing.assert_allclose(np.linalg.norm(s[3:6]), 9.81, atol=1e-9)
+    np.testing.assert_allclose(s[:3], 0.0, atol=1e-9)
+
+
+def test_lie_group_integrate_difference_roundtrip():
+    r = M.build_robot_table(os.path.join(DATA, "branched_arm.urdf"), True)
+    o = OracleBatch(r, _opt())
+    rng = np.random.default_rng(0)
+    q = r.neutral()
+    for _ in range(20):
+        v = rng.normal(size=r.nv) * 0.3
+        q1 = o.integrate(q, v)
+        np.testing.assert_allclose(o.difference(q, q1), v, atol=1e-12)
+        np.testing.assert_allclose(np.linalg.norm(q1[3:7]), 1.0, atol=1e-12)
+        q = q1
+
+
+def test_step_scheduler_microsecond_first_step_and_iters():
+    """First sub-step of an episode is 1 us (engine.cc:1176); afterwards dtMax steps snapped to the us grid."""
+    robot, opt = R.load_robot("anymal")
+    opt = R.baseline_options("anymal", opt)
+    o = OracleBatch(robot, opt)
+    q0 = R.ground_base_height(robot, robot.neutral())
+    assert not o.start(q0, np.zeros(robot.nv)).any()
+    o.step(0.04)
+    assert o.get_iters()[0][0] == 41           # 1 us + 4 x 1 ms + 0.999 ms, then 7 x 5 x 1 ms
+    o.step(0.04)
+    assert o.get_iters()[0][0] == 81
+    np.testing.assert_allclose(o.get_state()[0][0], 0.08, atol=1e-15)
