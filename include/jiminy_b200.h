@@ -242,6 +242,10 @@ int jb_get_iters(JbBatch* batch, int64_t* iter, int64_t* iter_failed);
  * is the buffer a multi-GPU rollout all-gathers. */
 int jb_device_views(JbBatch* batch, double** sensors_dev, double** qv_dev);
 
+/* Asynchronous device-to-device copy (on the batch stream) of the sensor matrix `[n_env][width]` into a
+ * caller-owned device buffer, e.g. the send buffer of the observation all-gather. */
+int jb_copy_sensors_device(JbBatch* batch, double* dst_dev);
+
 /* Stream the batch launches on (a `cudaStream_t` cast to void*), for CUDA-event timing. */
 int jb_get_stream(JbBatch* batch, void** stream);
 /* Number of kernel launches issued by this batch so far (bench.py `gpu_launches`). */

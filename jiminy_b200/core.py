@@ -49,7 +49,7 @@ class Api:
                "jb_set_options", "jb_start", "jb_set_command", "jb_set_command_device", "jb_step",
                "jb_compute_dynamics", "jb_get_state", "jb_get_efforts", "jb_get_sensors", "jb_sensor_layout",
                "jb_get_extra_terms", "jb_get_status", "jb_get_iters", "jb_device_views", "jb_get_stream",
-               "jb_launch_count", "jb_synchronize", "jb_set_joint_springs", "jb_set_pd_controller", "jb_describe",
+               "jb_launch_count", "jb_synchronize", "jb_set_joint_springs", "jb_set_pd_controller", "jb_copy_sensors_device", "jb_describe",
                "jb_plan_describe")
 
     def __init__(self, cdll: C.CDLL):
@@ -84,6 +84,7 @@ class Api:
         L.jb_synchronize.argtypes = [vp]
         L.jb_set_joint_springs.argtypes = [vp, c_double_p, c_double_p]
         L.jb_set_pd_controller.argtypes = [vp, c_double_p, c_double_p]
+        L.jb_copy_sensors_device.argtypes = [vp, vp]
         L.jb_describe.argtypes = [vp, C.c_char_p, C.c_int32]
         L.jb_plan_describe.argtypes = [C.POINTER(JbModelDesc), C.c_int32, C.c_char_p, C.c_int32, c_int32_p]
 
@@ -195,6 +196,16 @@ class BatchedEngine:
         cmd = np.ascontiguousarray(np.broadcast_to(cmd, (self.n_env, self.nm)), dtype=np.float64)
         self._api.check(self._api.dll.jb_set_command(self._h, dptr(cmd)))
         self._api.check(self._api.dll.jb_synchronize(self._h))  # `cmd` may be a temporary
+
+    def set_command_pinned(self, cmd: np.ndarray) -> None:
+        """Asynchronous upload from a caller-owned (ideally pinned) C-contiguous fp64 buffer of shape
+        (n_env, nmotors); the buffer must stay alive until the stream has consumed it."""
+        assert cmd.dtype == np.float64 and cmd.flags.c_contiguous and cmd.size == self.n_env * max(self.nm, 1)
+        if self.nm:
+            self._api.check(self._api.dll.jb_set_command(self._h, dptr(cmd)))
+
+    def copy_sensors_to(self, dev_ptr: int) -> None:
+        self._api.check(self._api.dll.jb_copy_sensors_device(self._h, C.c_void_p(dev_ptr)))
 
     def set_command_device(self, dev_ptr: int) -> None:
         self._api.check(self._api.dll.jb_set_command_device(self._h, C.c_void_p(dev_ptr)))

@@ -436,6 +436,13 @@ int jb_device_views(JbBatch* b, double** sensors_dev, double** qv_dev) {
     return JB_OK;
 }
 
+int jb_copy_sensors_device(JbBatch* b, double* dst_dev) {
+    if (!b || !dst_dev) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(b->device));
+    if (b->width) CU(cudaMemcpyAsync(dst_dev, b->d_sensors, sizeof(double) * b->n_env * b->width, cudaMemcpyDeviceToDevice, b->stream));
+    return JB_OK;
+}
+
 int jb_get_stream(JbBatch* b, void** stream) {
     if (!b || !stream) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
     *stream = b->stream;

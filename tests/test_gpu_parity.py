@@ -1,0 +1,98 @@
+"""Parity gate on the B200 (`pytest -m gpu`): the CUDA path, called through the C ABI, against the
+oracle on the same seeded inputs (sizes the oracle finishes in seconds), then size-independent
+properties at the BASELINE batch size (4096 envs)."""
+import numpy as np
+import pytest
+
+from jiminy_b200 import robots as R
+from jiminy_b200 import scenarios
+from jiminy_b200.core import BatchedEngine
+from oracle.oracle import OracleBatch
+
+import parity_common as pc
+
+pytestmark = pytest.mark.gpu
+
+# fp64 tolerances: a single RHS agrees to ~1e-15 relative; over an env-step the stiff contact
+# (k = 4e6 N/m) amplifies rounding differences, hence the looser trajectory bounds (north-star: 1e-10
+# relative on state trajectories).
+RHS_TOL = 1e-12
+TRAJ_TOL = 1e-9
+
+
+@pytest.mark.parametrize("name", R.ROBOT_NAMES)
+def test_rhs_matches_oracle(name):
+    robot, opt = R.load_robot(name)
+    opt = R.baseline_options(name, opt)
+    rng = np.random.default_rng(11)
+    n = 100
+    q, v = pc.random_states(robot, n, rng)
+    cmd = rng.uniform(-20, 20, size=(n, max(robot.nmotors, 1)))
+    a0, f0, u0 = OracleBatch(robot, opt, n).compute_dynamics(q, v, cmd)
+    a1, f1, u1 = BatchedEngine(robot, opt, n).compute_dynamics(q, v, cmd)
+    np.testing.assert_allclose(a1, a0, rtol=0, atol=RHS_TOL * max(1.0, np.abs(a0).max()))
+    np.testing.assert_allclose(f1, f0, rtol=0, atol=RHS_TOL * max(1.0, np.abs(f0).max()))
+    np.testing.assert_allclose(u1, u0, rtol=0, atol=RHS_TOL)
+
+
+@pytest.mark.parametrize("name,n_env,n_steps", [("anymal", 96, 5), ("atlas", 40, 3), ("cartpole", 512, 50),
+                                               ("double_pendulum", 1, 300)])
+def test_env_steps_match_oracle(name, n_env, n_steps):
+    tol = 1e-13 if name in ("cartpole", "double_pendulum") else TRAJ_TOL
+    pc.run_scenario(name, n_env, n_steps, tol_state=tol, tol_sens=max(tol, 1e-7) if tol > 1e-12 else 1e-11)
+
+
+def test_masked_restart():
+    sc = scenarios.make("anymal", 70)
+    eng, orc = pc.make_pair(sc)
+    for k in range(2):
+        eng.step(sc.step_dt)
+        orc.step(sc.step_dt, parallel=True)
+    mask = (np.arange(70) % 3 == 0).astype(np.uint8)
+    eng.start(sc.q0, sc.v0, mask=mask)
+    orc.start(sc.q0, sc.v0, mask=mask)
+    eng.step(sc.step_dt)
+    orc.step(sc.step_dt, parallel=True)
+    pc.compare(eng, orc, TRAJ_TOL, 1e-6)
+
+
+def test_full_size_properties():
+    """4096 ANYmal envs: (i) bit-determinism across runs, (ii) env permutation invariance -- an env's
+    trajectory does not depend on its position in the batch or on its warp neighbours, (iii) no env
+    leaves the well-posed regime, (iv) a sampled subset agrees with the oracle."""
+    n = 4096
+    sc = scenarios.make("anymal", n)
+    perm = np.random.default_rng(0).permutation(n)
+
+    def run(order):
+        eng = BatchedEngine(sc.robot, sc.options, n)
+        eng.set_pd_controller(sc.kp, sc.kd)
+        eng.set_command(sc.target0[order])
+        eng.start(sc.q0[order], sc.v0[order])
+        for k in range(3):
+            eng.set_command(sc.sample_targets(k)[order])
+            eng.step(sc.step_dt)
+        return eng.get_state(), eng.get_sensors().copy(), eng.get_status()
+    (t1, q1, v1, a1), s1, st1 = run(np.arange(n))
+    (t2, q2, v2, a2), s2, st2 = run(np.arange(n))
+    assert np.array_equal(q1, q2) and np.array_equal(v1, v2) and np.array_equal(s1, s2)       # (i)
+    (t3, q3, v3, a3), s3, st3 = run(perm)
+    assert np.array_equal(q3, q1[perm]) and np.array_equal(v3, v1[perm]) and np.array_equal(s3, s1[perm])   # (ii)
+    assert (st1 == 0).all() and np.isfinite(q1).all()                                         # (iii)
+    np.testing.assert_allclose(t1, 0.12, atol=1e-15)
+    idx = np.arange(0, n, 64)                                                                 # (iv)
+    orc = OracleBatch(sc.robot, sc.options, len(idx))
+    orc.set_pd_controller(sc.kp, sc.kd)
+    orc.set_command(sc.target0[idx])
+    assert not orc.start(sc.q0[idx], sc.v0[idx]).any()
+    for k in range(3):
+        orc.set_command(sc.sample_targets(k)[idx])
+        orc.step(sc.step_dt, parallel=True)
+    _, q0, v0, _ = orc.get_state()
+    np.testing.assert_allclose(q1[idx], q0, rtol=0, atol=TRAJ_TOL)
+    np.testing.assert_allclose(v1[idx], v0, rtol=0, atol=TRAJ_TOL * max(1.0, np.abs(v0).max()))
+
+
+def test_graft_smoke():
+    import __graft_entry__ as g
+    g.smoke()

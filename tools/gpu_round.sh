@@ -1,0 +1,26 @@
+#!/bin/bash
+# One GPU session: parity tests, smoke, bench, launch list and one full ncu capture of the step kernel.
+# Usage (from the repo root, on the GPU box): bash tools/gpu_round.sh [tag]
+TAG=${1:-r01}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+export PYTHONUNBUFFERED=1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit,memory.total --format=csv > $OUT/gpu.csv 2>&1
+nproc > $OUT/nproc.txt
+echo "== pytest -m gpu" | tee $OUT/pytest_gpu.log
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -40 | tee -a $OUT/pytest_gpu.log
+echo "== bench" | tee $OUT/bench.log
+timeout 600 python bench.py --gpus 1 --steps 20 --warmup 3 2> $OUT/bench.err | tee -a $OUT/bench.log
+tail -5 $OUT/bench.err
+for W in atlas cartpole; do
+  timeout 300 python bench.py --workload $W --steps 10 --warmup 3 --no-cpu-baseline 2>> $OUT/bench.err | tee -a $OUT/bench_$W.log
+done
+echo "== reference arm" | tee $OUT/bench_ref.log
+timeout 300 python bench.py --impl reference --steps 5 --warmup 1 2>> $OUT/bench.err | tee -a $OUT/bench_ref.log
+echo "== ncu launch list"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches.csv \
+    python bench.py --steps 3 --warmup 1 --no-cpu-baseline > $OUT/ncu_launch_run.log 2>&1
+echo "== ncu full capture of env_step_kernel"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:env_step_kernel -s 3 -c 2 -f -o $OUT/prof_step \
+    python bench.py --steps 3 --warmup 1 --no-cpu-baseline > $OUT/ncu_full_run.log 2>&1
+ls -la $OUT
