@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -21,6 +22,12 @@ using namespace jb;
 #define JB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
+#ifdef JB_HOST_EMUL
+namespace jb { KParams g_kp_host; }
+#else
+static std::mutex g_launch_mutex;
+static cudaEvent_t g_last_launch[64] = {};
+#endif
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
@@ -93,7 +100,21 @@ static int launch(JbBatch* b, int mode, double step_dt) {
 #ifdef JB_HOST_EMUL
     emul::current_L = b->plan.L;
 #endif
-    JB_LAUNCH(env_step_kernel, nblocks, 32, b->smem_bytes, b->stream, kp);
+#ifdef JB_HOST_EMUL
+    g_kp_host = kp;
+    JB_LAUNCH(env_step_kernel, nblocks, 32, b->smem_bytes, b->stream);
+#else
+    {
+        // one constant-memory parameter block per device: order this launch after the previous one
+        std::lock_guard<std::mutex> lock(g_launch_mutex);
+        cudaEvent_t& evt = g_last_launch[b->device];
+        if (!evt) CU(cudaEventCreateWithFlags(&evt, cudaEventDisableTiming));
+        else CU(cudaStreamWaitEvent(b->stream, evt, 0));
+        CU(cudaMemcpyToSymbolAsync(g_kp, &kp, sizeof kp, 0, cudaMemcpyHostToDevice, b->stream));
+        JB_LAUNCH(env_step_kernel, nblocks, 32, b->smem_bytes, b->stream);
+        CU(cudaEventRecord(evt, b->stream));
+    }
+#endif
     CU(cudaGetLastError());
     ++b->launches;
     return JB_OK;

@@ -267,6 +267,11 @@ Plan build_plan(const JbModelDesc& m, int lanes, int n_hist) {
                     ri.motor = mm;
                     ri.motor_flags = m.motor_flags[mm];
                     std::memcpy(rd.motor, m.motor_params + 10 * mm, sizeof rd.motor);
+                    {   // reciprocal of the velocity taper span of SimpleMotor::computeEffort (basic_motors.cc:110-118)
+                        const double effLim = rd.motor[1], velLim = rd.motor[2], velocityDelta = effLim * rd.motor[3];
+                        const double thr = std::max(velLim - velocityDelta, 0.0);
+                        rd.motor[9] = 1.0 / (velLim - thr);
+                    }
                 }
             for (int e = 0; e < m.nencoder; ++e)
                 if (m.encoder_joint[e] == j && ri.encoder < 0) { ri.encoder = e; rd.enc_reduction = m.encoder_reduction[e]; }

@@ -75,6 +75,7 @@ inline bool __any_sync(unsigned mask, bool p) {
 }
 inline double __longlong_as_double(long long x) { double d; std::memcpy(&d, &x, sizeof d); return d; }
 inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
+inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 
 // ---- minimal CUDA runtime stand-ins (host memory, synchronous "streams")
 typedef int cudaError_t;
