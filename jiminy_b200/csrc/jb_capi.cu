@@ -211,6 +211,21 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
     kp.nq = m->nq; kp.nv = m->nv; kp.nmotors = m->nmotors; kp.njoints = m->njoints; kp.n_hist = 0;
     kp.nimu = m->nimu; kp.nforce = m->nforce; kp.nenc = m->nencoder; kp.neff = m->neffort; kp.ncs = m->ncontact_sensor;
     for (int r = 0; r < P.nrec; ++r) { kp.rec_off[r] = P.rec_off[r]; kp.rec_free[r] = P.rec_free[r]; kp.trunk_reduce[r] = P.trunk_reduce[r]; }
+    // lane-uniform descriptors: usable when everything the dynamics evaluation branches on is identical on all lanes
+    kp.all_uniform = 1;
+    for (int r = 0; r < P.nrec; ++r) {
+        const RecInt& a = P.rint[static_cast<size_t>(r) * P.L];
+        for (int s = 1; s < P.L; ++s) {
+            const RecInt& o = P.rint[static_cast<size_t>(r) * P.L + s];
+            if (a.kind != o.kind || a.parent_rec != o.parent_rec || a.carry_in != o.carry_in || a.pool != o.pool ||
+                a.parent_pool != o.parent_pool || a.carry_out != o.carry_out || a.take_carry != o.take_carry ||
+                (a.motor >= 0) != (o.motor >= 0) || a.motor_flags != o.motor_flags || a.ncontact != o.ncontact ||
+                a.contact0 != o.contact0 || a.imu_slot != o.imu_slot || a.has_limit != o.has_limit)
+                kp.all_uniform = 0;
+        }
+        kp.rint_u[r] = a;
+    }
+    if (const char* s = std::getenv("JB_FORCE_PER_LANE")) if (std::atoi(s)) kp.all_uniform = 0;
     JbSensorLayout& L = kp.lay;
     L.imu_offset = 0;
     L.force_offset = 6 * m->nimu;
