@@ -167,3 +167,25 @@ def test_lane_plans(api):
     _, jl = plan_describe(robot, 0, api)
     assert jl[1] == -1 and sorted(set(jl[2:].tolist())) == [0, 1, 2, 3]     # root is trunk, one leg per lane
     assert len({int(jl[robot.joint_index(f"LF_{s}")]) for s in ("HAA", "HFE", "KFE")}) == 1
+
+
+def test_batched_env_reset_step_autoreset(api):
+    """BatchedJiminyEnv: gym-style reset/step over N envs with automatic masked restart of finished envs."""
+    from jiminy_b200.envs import BatchedJiminyEnv
+    sc = scenarios.make("anymal", 4)
+    env = BatchedJiminyEnv(sc, api_=api, simulation_duration_max=0.16)
+    obs, _ = env.reset()
+    assert obs["states"]["agent"]["q"].shape == (4, 19) and obs["measurements"]["ImuSensor"].shape == (4, 6, 1)
+    assert obs["measurements"]["EncoderSensor"].shape == (4, 2, 12)
+    obs, rew, term, trunc, info = env.step(sc.sample_targets(0))
+    assert rew.shape == (4,) and not term.any() and not trunc.any()
+    np.testing.assert_allclose(obs["t"], 0.04)
+    for k in (1, 2):
+        obs, rew, term, trunc, info = env.step(sc.sample_targets(k))
+    # settled on the ground after 0.12 s: the foot force sensors see a push of the order of the weight
+    fz = np.abs(obs["measurements"]["ForceSensor"][:, :3, :]).sum(axis=(1, 2))
+    assert np.all(fz > 0.2 * sc.robot.mass * 9.81)
+    obs, rew, term, trunc, info = env.step(sc.sample_targets(3))
+    assert trunc.all()                              # duration limit reached -> every env is restarted
+    np.testing.assert_allclose(env.engine.get_state()[0], 0.0)
+    env.close()
