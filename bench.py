@@ -193,6 +193,11 @@ def run_gpu(args):
             ev.record(stream)
             torch.cuda.current_stream().wait_event(ev)
             dist.all_gather_into_tensor(gather_out, gather_in)
+            # the step kernel fills every SM's shared memory (4 CTAs x 55 KB): a concurrent NCCL kernel
+            # would push CTAs into a second wave, so the next step is ordered after the gather
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream())
+            stream.wait_event(done)
 
     # ---------------- HBM-resident arm: `value`
     for k in range(args.warmup):

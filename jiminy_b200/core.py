@@ -234,6 +234,14 @@ class BatchedEngine:
         self._api.check(self._api.dll.jb_get_sensors(self._h, dptr(out)))
         return out[:, :self.width]
 
+    def get_extra_terms(self):
+        """(energy [n, 2] = kinetic, potential; joint accelerations [n, njoints, 6]; joint wrenches [n, njoints, 6])
+        of the accepted state: what `computeExtraTerms` leaves in `pinocchio_data` (engine.cc:800-905)."""
+        e = np.zeros((self.n_env, 2))
+        ja, jf = np.zeros((self.n_env, self.nj, 6)), np.zeros((self.n_env, self.nj, 6))
+        self._api.check(self._api.dll.jb_get_extra_terms(self._h, dptr(e), dptr(ja), dptr(jf)))
+        return e, ja, jf
+
     def get_status(self) -> np.ndarray:
         s = np.zeros(self.n_env, dtype=np.int32)
         self._api.check(self._api.dll.jb_get_status(self._h, s.ctypes.data_as(c_int32_p)))

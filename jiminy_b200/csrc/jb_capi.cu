@@ -138,9 +138,8 @@ void jb_default_options(JbOptions* o) {
 }
 
 static int check_options(const JbOptions* o) {
-    if (o->ode_solver != JB_SOLVER_EULER_EXPLICIT && o->ode_solver != JB_SOLVER_RUNGE_KUTTA_4)
-        return fail(JB_ERR_NOT_IMPLEMENTED, "only 'euler_explicit' and 'runge_kutta_4' run on the device in this build "
-                                            "('runge_kutta_dopri' is a later scope row)");
+    if (o->ode_solver < JB_SOLVER_EULER_EXPLICIT || o->ode_solver > JB_SOLVER_RUNGE_KUTTA_DOPRI)
+        return fail(JB_ERR_INVALID_ARGUMENT, "unknown ODE solver");
     if (!(o->dt_max >= 1e-6 - 1e-16 && o->dt_max <= 0.02 + 1e-16)) return fail(JB_ERR_INVALID_ARGUMENT, "'dtMax' option is out of range.");
     for (double p : {o->sensors_update_period, o->controller_update_period})
         if ((p > 2.3e-16 && p < 1e-6) || p > 0.02) return fail(JB_ERR_INVALID_ARGUMENT, "update period out of range");
@@ -192,7 +191,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
     try {
         int lanes = 0;
         if (const char* s = std::getenv("JB_LANES")) lanes = std::atoi(s);
-        b->plan = build_plan(*m, lanes, 0);
+        b->plan = build_plan(*m, lanes, opt->ode_solver == JB_SOLVER_RUNGE_KUTTA_DOPRI ? 7 : 0);
     } catch (const std::exception& ex) {
         delete b;
         return fail(JB_ERR_INVALID_ARGUMENT, std::string("lane planner: ") + ex.what());
@@ -208,7 +207,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
     kp.n_env = n_env; kp.n_pad = b->n_pad;
     kp.L = P.L; kp.nrec = P.nrec; kp.ntrunk = P.ntrunk; kp.npool = P.npool; kp.ncslot = P.ncslot; kp.nimuslot = P.nimuslot;
     kp.nfields = P.nfields; kp.pool_off = P.pool_off; kp.cslot_off = P.cslot_off; kp.imu_off = P.imu_off;
-    kp.nq = m->nq; kp.nv = m->nv; kp.nmotors = m->nmotors; kp.njoints = m->njoints; kp.n_hist = 0;
+    kp.nq = m->nq; kp.nv = m->nv; kp.nmotors = m->nmotors; kp.njoints = m->njoints; kp.n_hist = (opt->ode_solver == JB_SOLVER_RUNGE_KUTTA_DOPRI) ? 7 : 0;
     kp.nimu = m->nimu; kp.nforce = m->nforce; kp.nenc = m->nencoder; kp.neff = m->neffort; kp.ncs = m->ncontact_sensor;
     for (int r = 0; r < P.nrec; ++r) { kp.rec_off[r] = P.rec_off[r]; kp.rec_free[r] = P.rec_free[r]; kp.trunk_reduce[r] = P.trunk_reduce[r]; }
     // lane-uniform descriptors: usable when everything the dynamics evaluation branches on is identical on all lanes
@@ -254,7 +253,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
     ALLOC(b->d_springs, 2 * static_cast<size_t>(m->nv)); ALLOC(b->d_mask, n_env);
     ALLOC(b->d_pd, 2 * static_cast<size_t>(m->nmotors)); ALLOC(b->d_cmd_torque, static_cast<size_t>(n_env) * m->nmotors);
     ALLOC(b->d_stage, static_cast<size_t>(n_env) * std::max(std::max(m->nq, m->nv), SCH_N + 0));
-#undef ALLOC
+#define ALLOC2 ALLOC
     cudaMemcpyAsync(d_rint, P.rint.data(), P.rint.size() * sizeof(RecInt), cudaMemcpyHostToDevice, b->stream);
     cudaMemcpyAsync(d_rdbl, P.rdbl.data(), P.rdbl.size() * sizeof(RecDbl), cudaMemcpyHostToDevice, b->stream);
     if (!P.cslots.empty()) cudaMemcpyAsync(d_cs, P.cslots.data(), P.cslots.size() * sizeof(ContactSlot), cudaMemcpyHostToDevice, b->stream);
@@ -268,7 +267,12 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
     kp.q_in = b->d_qin; kp.v_in = b->d_vin; kp.mask = nullptr;
     kp.a_out = b->d_aout; kp.fext_out = b->d_fext; kp.u_out = b->d_u;
     kp.eff_u = b->d_u; kp.eff_umotor = b->d_umotor; kp.eff_fext = b->d_fext;
-    kp.extra_energy = nullptr; kp.extra_a = nullptr; kp.extra_f = nullptr;
+    {
+        double *d_en, *d_ea, *d_ef;
+        ALLOC2(d_en, 2 * static_cast<size_t>(n_env)); ALLOC2(d_ea, static_cast<size_t>(n_env) * m->njoints * 6);
+        ALLOC2(d_ef, static_cast<size_t>(n_env) * m->njoints * 6);
+        kp.extra_energy = d_en; kp.extra_a = d_ea; kp.extra_f = d_ef;
+    }
 
     b->smem_bytes = static_cast<size_t>(P.nfields) * 32 * sizeof(double);
     if (b->smem_bytes > 227 * 1024) { jb_batch_destroy(b); return fail(JB_ERR_NOT_IMPLEMENTED, "robot too large: per-warp working set exceeds shared memory (" + P.describe() + ")"); }
@@ -290,6 +294,8 @@ int jb_set_options(JbBatch* b, const JbOptions* o) {
     if (!b || !o) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
     int rc = check_options(o);
     if (rc) return rc;
+    if (o->ode_solver == JB_SOLVER_RUNGE_KUTTA_DOPRI && b->kp.n_hist == 0)
+        return fail(JB_ERR_BAD_CONTROL_FLOW, "switching to 'runge_kutta_dopri' changes the working-set layout: create a new batch");
     apply_options(b, o);
     return JB_OK;
 }
@@ -443,9 +449,14 @@ int jb_sensor_layout(JbBatch* b, JbSensorLayout* out) {
 }
 
 int jb_get_extra_terms(JbBatch* b, double* energy, double* joint_a, double* joint_f) {
-    (void)energy; (void)joint_a; (void)joint_f;
     if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
-    return fail(JB_ERR_NOT_IMPLEMENTED, "computeExtraTerms outputs (energy, data.a, data.f) are not produced by this build");
+    CU(cudaSetDevice(b->device));
+    const size_t nj6 = static_cast<size_t>(b->n_env) * b->njoints * 6;
+    if (energy) CU(cudaMemcpyAsync(energy, b->kp.extra_energy, sizeof(double) * 2 * b->n_env, cudaMemcpyDeviceToHost, b->stream));
+    if (joint_a) CU(cudaMemcpyAsync(joint_a, b->kp.extra_a, sizeof(double) * nj6, cudaMemcpyDeviceToHost, b->stream));
+    if (joint_f) CU(cudaMemcpyAsync(joint_f, b->kp.extra_f, sizeof(double) * nj6, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return JB_OK;
 }
 
 int jb_get_status(JbBatch* b, int32_t* status) {

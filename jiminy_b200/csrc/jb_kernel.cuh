@@ -283,14 +283,51 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
         tError = (tEnd - t) - stepSizeCorrected;
         const double supd = KP->stepper_update_period;
         const bool finitePeriod = supd < 1e300;
+        const int failedMax = opt.successive_iter_failed_max;
+        int successiveIterTooLarge = 0, successiveIterFailed = 0;
         bool hasDynamicsChanged = false;
         bool failed = false;
-        // The cached contact forces of the last evaluation are a pure function of the accepted
-        // state: rebuild them (and the IMU captures) once, so that `up_to_date` evaluations and
-        // sensor refreshes see what the reference keeps in RobotData between calls.
         // Shared memory does not persist between launches: the first evaluation of this launch is a
         // full one (it rebuilds the cached contact forces, a pure function of the accepted state).
         bool need_refresh = true;
+
+        // stepper_->tryStep (abstract_stepper.cc:16-62) + the success / failure bookkeeping of
+        // engine.cc:2132-2221.  rc: 0 success, 1 failure (adaptive step rejected), 2 error (NaN).
+        auto try_step = [&](bool isBreakpointReached) {
+            const double t_next = t + dtLargest;
+            int rc = 0;
+            if (opt.ode_solver == JB_SOLVER_EULER_EXPLICIT) { step_euler(c, dtLargest, &status); dtLargest = D_INF; }
+            else if (opt.ode_solver == JB_SOLVER_RUNGE_KUTTA_4) { step_rk4(c, dtLargest, &status); dtLargest = D_INF; }
+            else rc = step_dopri(c, &dtLargest, &status);
+            need_refresh = false;
+            if (rc == 0 && opt.ode_solver != JB_SOLVER_RUNGE_KUTTA_DOPRI) {
+                bool bad = accel_has_nan(c);
+                bad = __any_sync(c.gmask, bad);
+                if (bad) rc = 2;
+            }
+            if (rc == 0) {
+                successiveIterTooLarge = 0; successiveIterFailed = 0;
+                t = t_next;
+                ++iter;
+                if (isBreakpointReached) {
+                    const double thr = dtLargestPrev * opt.dt_restore_threshold_rel;
+                    if (dt < dtLargest && dtLargest < thr) dtLargest = dtLargestPrev;
+                }
+                tPrev = t;
+                dtLargestPrev = dtLargest;
+            } else {
+                if (rc == 2) {
+                    dtLargest *= 0.1;
+                    // a fixed-step stepper that produced NaN has no smaller step to fall back to
+                    if (opt.ode_solver != JB_SOLVER_RUNGE_KUTTA_DOPRI) { status |= JB_ENV_NAN; failed = true; }
+                }
+                if (rc == 1) ++successiveIterTooLarge;
+                ++successiveIterFailed;
+                ++iterFailed;
+            }
+            dt = fmin(dtLargest, opt.dt_max);
+            return rc;
+        };
 
         while (tEnd - t >= STEPPER_MIN_TIMESTEP && !failed) {
             double tNext = t;
@@ -314,7 +351,7 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
                 else dtNextGlobal = dtNextUpdatePeriod;
                 if (tEnd - t - STEPPER_MIN_TIMESTEP < dtNextGlobal) dtNextGlobal = tEnd - t;
                 tNext += dtNextGlobal;
-                while (tNext - t > STEPPER_MIN_TIMESTEP) {
+                while (tNext - t > STEPPER_MIN_TIMESTEP && !failed) {
                     if (hasDynamicsChanged) {
                         // FSAL repair: same state, cached contact forces, new command (engine.cc:2032-2037)
                         stage_from_accepted(c);
@@ -323,69 +360,44 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
                         hasDynamicsChanged = false;
                     }
                     if (dt < STEPPER_MIN_TIMESTEP) break;
-                    // successiveIterTooLarge == 0 always holds for the fixed-step steppers
-                    const double dtResidualThr = fmin(fmax(0.1 * dt, STEPPER_MIN_TIMESTEP), SIMULATION_MIN_TIMESTEP);
-                    if (tNext - t < dt || tNext - t < dt + dtResidualThr) dt = tNext - t;
+                    double dtResidualThr = STEPPER_MIN_TIMESTEP;
+                    if (successiveIterTooLarge == 0) dtResidualThr = fmin(fmax(0.1 * dt, STEPPER_MIN_TIMESTEP), SIMULATION_MIN_TIMESTEP);
+                    if (tNext - t < dt || (successiveIterTooLarge <= 1 && tNext - t < dt + dtResidualThr)) dt = tNext - t;
                     if (dt > SIMULATION_MIN_TIMESTEP) {
                         const double dtResidual = fmod(dt, SIMULATION_MIN_TIMESTEP);
                         if (dtResidual > STEPPER_MIN_TIMESTEP && dtResidual < SIMULATION_MIN_TIMESTEP - STEPPER_MIN_TIMESTEP &&
                             dt - dtResidual > STEPPER_MIN_TIMESTEP)
                             dt -= dtResidual;
                     }
+                    if (successiveIterFailed > failedMax) break;
                     const bool isBreakpointReached = (dtLargest > dt);
                     dtLargest = dt;
-                    // stepper_->tryStep (abstract_stepper.cc:16-62)
-                    const double t_next = t + dtLargest;
-                    if (opt.ode_solver == JB_SOLVER_EULER_EXPLICIT) step_euler(c, dtLargest, &status);
-                    else step_rk4(c, dtLargest, &status);
-                    need_refresh = false;
-                    dtLargest = D_INF;
-                    bool bad = accel_has_nan(c);
-                    bad = __any_sync(c.gmask, bad);
-                    if (bad) { status |= JB_ENV_NAN; failed = true; ++iterFailed; break; }
-                    t = t_next;
-                    ++iter;
-                    if (isBreakpointReached) {
-                        const double thr = dtLargestPrev * opt.dt_restore_threshold_rel;
-                        if (dt < dtLargest && dtLargest < thr) dtLargest = dtLargestPrev;
-                    }
-                    tPrev = t;
-                    dtLargestPrev = dtLargest;
-                    dt = fmin(dtLargest, opt.dt_max);
+                    try_step(isBreakpointReached);
                 }
             } else {
                 dt = fmin(dt, tEnd - t);
                 const bool isBreakpointReached = (dtLargest > dt);
-                dtLargest = dt;
-                const double t_next = t + dtLargest;
-                if (opt.ode_solver == JB_SOLVER_EULER_EXPLICIT) step_euler(c, dtLargest, &status);
-                else step_rk4(c, dtLargest, &status);
-                need_refresh = false;
-                dtLargest = D_INF;
-                bool bad = accel_has_nan(c);
-                bad = __any_sync(c.gmask, bad);
-                if (bad) { status |= JB_ENV_NAN; failed = true; ++iterFailed; break; }
-                t = t_next;
-                ++iter;
-                if (isBreakpointReached) {
-                    const double thr = dtLargestPrev * opt.dt_restore_threshold_rel;
-                    if (dt < dtLargest && dtLargest < thr) dtLargest = dtLargestPrev;
+                bool isStepSuccessful = false;
+                while (!isStepSuccessful && !failed) {
+                    if (successiveIterFailed > failedMax) break;
+                    dtLargest = dt;
+                    isStepSuccessful = (try_step(isBreakpointReached) == 0);
                 }
-                tPrev = t;
-                dtLargestPrev = dtLargest;
-                dt = fmin(dtLargest, opt.dt_max);
             }
+            if (failed) break;
+            if (successiveIterFailed > failedMax) { status |= JB_ENV_ITER_FAILED; failed = true; break; }
             if (dt < STEPPER_MIN_TIMESTEP) { status |= JB_ENV_DT_UNDERFLOW; failed = true; break; }
             // sensors refresh (engine.cc:2386-2410)
             const double sp = opt.sensors_update_period;
             bool mustUpdateSensors = sp < D_EPS;
             if (!mustUpdateSensors) mustUpdateSensors = period_hit(t, sp);
-            if (mustUpdateSensors && !failed) write_sensors(c);
+            if (mustUpdateSensors) write_sensors(c);
         }
         if (!failed) t = tEnd;
     }
 
     // ---------------- store
+    if (KP->extra_energy != nullptr && !(status & (JB_ENV_NAN | JB_ENV_NOT_STARTED))) extra_terms(c);
     store_outputs(c);
     if (KP->pd_gains != nullptr && c.valid) {
         for (int r = 0; r < KP->nrec; ++r) {

@@ -51,6 +51,7 @@ def compare(eng, orc, tol_state, tol_sens):
         np.testing.assert_allclose(s1, s0, rtol=0, atol=tol_sens * max(1.0, np.abs(s0).max()))
     np.testing.assert_array_equal(eng.get_iters()[0], orc.get_iters()[0])
     np.testing.assert_array_equal(eng.get_status(), orc.get_status())
+    compare_extra_terms(eng, orc, max(tol_sens, 1e-11))
 
 
 def run_scenario(name, n_env, n_steps, api=None, tol_state=1e-9, tol_sens=1e-7, **kw):
@@ -65,3 +66,12 @@ def run_scenario(name, n_env, n_steps, api=None, tol_state=1e-9, tol_sens=1e-7, 
         assert not orc.step(sc.step_dt, parallel=True).any()
         compare(eng, orc, tol_state, tol_sens)
     return eng, orc, sc
+
+
+def compare_extra_terms(eng, orc, tol=1e-9):
+    """computeExtraTerms outputs: energies, joint spatial accelerations, joint internal wrenches."""
+    e1, a1, f1 = eng.get_extra_terms()
+    e0, a0, f0 = orc.get_extra_terms()
+    np.testing.assert_allclose(e1, e0, rtol=0, atol=tol * max(1.0, np.abs(e0).max()))
+    np.testing.assert_allclose(a1, a0, rtol=0, atol=tol * max(1.0, np.abs(a0).max()))
+    np.testing.assert_allclose(f1, f0, rtol=0, atol=tol * max(1.0, np.abs(f0).max()))

@@ -96,3 +96,31 @@ def test_full_size_properties():
 def test_graft_smoke():
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_dopri_adaptive_matches_oracle():
+    """Per-env adaptive Dormand-Prince on the device (config 1's solver): accepted and rejected step
+    counts equal the oracle's for every env, states agree to 1e-9."""
+    robot, opt = R.load_robot("double_pendulum")
+    opt = R.baseline_options("double_pendulum", opt)
+    opt["stepper"].update(odeSolver="runge_kutta_dopri", tolAbs=1e-9, tolRel=1e-9, dtMax=0.02,
+                          sensorsUpdatePeriod=1e-3, controllerUpdatePeriod=1e-3)
+    n = 64
+    rng = np.random.default_rng(4)
+    q0, v0 = rng.uniform(-1.0, 1.0, size=(n, 2)), rng.uniform(-2.0, 2.0, size=(n, 2))
+    eng, orc = BatchedEngine(robot, opt, n), OracleBatch(robot, opt, n)
+    eng.start(q0, v0)
+    assert not orc.start(q0, v0).any()
+    for _ in range(25):
+        eng.step(0.02)
+        assert not orc.step(0.02, parallel=True).any()
+    pc.compare(eng, orc, 1e-9, 1e-8)
+    np.testing.assert_array_equal(eng.get_iters()[1], orc.get_iters()[1])
+    # ANYmal with the engine's default adaptive solver
+    sc = scenarios.make("anymal", 16, solver="runge_kutta_dopri", dt_max=0.02)
+    eng, orc = pc.make_pair(sc)
+    for k in range(2):
+        eng.set_command(sc.sample_targets(k)); orc.set_command(sc.sample_targets(k))
+        eng.step(sc.step_dt)
+        assert not orc.step(sc.step_dt, parallel=True).any()
+    pc.compare(eng, orc, 1e-7, 1e-5)

@@ -189,3 +189,45 @@ def test_batched_env_reset_step_autoreset(api):
     assert trunc.all()                              # duration limit reached -> every env is restarted
     np.testing.assert_allclose(env.engine.get_state()[0], 0.0)
     env.close()
+
+
+@pytest.mark.parametrize("period", [0.0, 1e-3])
+def test_dopri_double_pendulum_and_energy(api, period):
+    """Adaptive Dormand-Prince on the device: same accepted / rejected step sequence as the oracle
+    (iteration counters equal), state within 1e-10, continuous and discrete (1 ms) modes."""
+    robot, opt = R.load_robot("double_pendulum")
+    opt = R.baseline_options("double_pendulum", opt)
+    opt["stepper"].update(odeSolver="runge_kutta_dopri", tolAbs=1e-9, tolRel=1e-9, dtMax=0.02,
+                          sensorsUpdatePeriod=period, controllerUpdatePeriod=period)
+    eng, orc = BatchedEngine(robot, opt, 2, api_=api), OracleBatch(robot, opt, 2)
+    q0, v0 = np.array([[0.0, 0.1], [0.3, -0.2]]), np.array([[0.0, 0.0], [0.5, 0.1]])
+    eng.start(q0, v0)
+    assert not orc.start(q0, v0).any()
+    for _ in range(10):
+        eng.step(0.02)
+        assert not orc.step(0.02).any()
+        pc.compare(eng, orc, 1e-10, 1e-9)
+        np.testing.assert_array_equal(eng.get_iters()[1], orc.get_iters()[1])      # same number of rejected steps
+
+
+def test_dopri_free_flyer_contact_and_unbounded_joint(api):
+    """DOPRI with the SE(3) and SO(2) difference operators in the error norm: branched arm (free-flyer,
+    continuous joints, prismatic) dropping on the ground with the engine's default tolerances."""
+    robot = M.build_robot_table(os.path.join(DATA, "branched_arm.urdf"), True)
+    robot.add_contact_points(["b_sole", "a_tool"])
+    opt = M.default_engine_options()
+    opt["contacts"].update(model="spring_damper", stiffness=1e5, damping=5e2)
+    opt["stepper"].update(odeSolver="runge_kutta_dopri", sensorsUpdatePeriod=5e-3, controllerUpdatePeriod=5e-3)
+    rng = np.random.default_rng(9)
+    q, v = pc.random_states(robot, 2, rng, base_height=0.5)
+    for lanes in (0, 1):
+        _lanes(lanes)
+        eng, orc = BatchedEngine(robot, opt, 2, api_=api), OracleBatch(robot, opt, 2)
+        eng.start(q, v)
+        assert not orc.start(q, v).any()
+        for _ in range(6):
+            eng.step(0.01)
+            assert not orc.step(0.01).any()
+        pc.compare(eng, orc, 1e-8, 1e-6)
+        np.testing.assert_array_equal(eng.get_iters()[1], orc.get_iters()[1])
+    _lanes(0)
