@@ -294,3 +294,184 @@ class BatchedEngine:
             if log:
                 snap()
         return np.array(ts), np.array(qs), np.array(vs), np.array(as_)
+
+
+# ------------------------------------------------------------------------------------------------
+# Single-env facade with the reference's names (python/jiminy_pywrap/src/engine.cc:587-787)
+# ------------------------------------------------------------------------------------------------
+class RobotState:
+    """`jiminy.RobotState` (pywrap engine.cc:175-187): stable numpy buffers refreshed in place after
+    every `start` / `step`, as `BaseJiminyEnv` expects (generic.py:688-690)."""
+
+    def __init__(self, nq: int, nv: int, nm: int, nj: int):
+        self.q, self.v, self.a = np.zeros(nq), np.zeros(nv), np.zeros(nv)
+        self.command, self.u, self.u_motor = np.zeros(nm), np.zeros(nv), np.zeros(nm)
+        self.f_external = np.zeros((nj, 6))
+
+
+class StepperState:
+    """`jiminy.StepperState` (pywrap engine.cc:134-143)."""
+
+    def __init__(self, nq: int, nv: int):
+        self.iter, self.iter_failed, self.t, self.dt = 0, 0, 0.0, 0.0
+        self.q, self.v, self.a = np.zeros(nq), np.zeros(nv), np.zeros(nv)
+
+
+class FunctionalController:
+    """`jiminy.FunctionalController(compute_command, internal_dynamics)` (controller_functor.h:27-80).
+    `compute_command(t, q, v, sensor_measurements, command)` is evaluated on the host at every
+    controller breakpoint and held in between (discrete controllers only)."""
+
+    def __init__(self, compute_command=None, internal_dynamics=None):
+        if internal_dynamics is not None:
+            raise NotImplementedError("Python `internal_dynamics` callbacks cannot run inside the device step; "
+                                      "use `Engine.set_joint_springs` for the linear case.")
+        self.compute_command = compute_command
+
+
+class Engine:
+    """One-robot, one-env engine with the surface `jiminy_py.simulator.Simulator` / `BaseJiminyEnv` use:
+    `add_robot`, `get_options / set_options`, `start`, `step`, `stop`, `simulate`, `robot_states`,
+    `stepper_state`, `is_simulation_running`.  The physics runs on the GPU (a batch of one env); a
+    Python controller is called back on the host once per controller period, like the reference
+    does through `FunctionalController` (engine.cc:1920-1940)."""
+
+    def __init__(self, device: int = 0, api_: Optional[Api] = None):
+        self._device, self._api_ = device, api_
+        self._options = M.default_engine_options()
+        self._options["contacts"]["model"] = "spring_damper"
+        self.robots: list = []
+        self.robot_states: list = []
+        self.stepper_state: Optional[StepperState] = None
+        self.is_simulation_running = False
+        self._batch: Optional[BatchedEngine] = None
+        self._controller: Optional[FunctionalController] = None
+        self._springs = None
+
+    # -- configuration
+    def add_robot(self, robot: M.RobotTable, controller: Optional[FunctionalController] = None) -> None:
+        if self.robots:
+            raise NotImplementedError("Multi-robot engines are outside the accelerated path.")
+        self.robots.append(robot)
+        self._controller = controller
+        self.robot_states = [RobotState(robot.nq, robot.nv, robot.nmotors, robot.njoints)]
+        self.stepper_state = StepperState(robot.nq, robot.nv)
+
+    def get_options(self) -> Dict[str, Any]:
+        import copy
+        return copy.deepcopy(self._options)
+
+    def set_options(self, options: Dict[str, Any]) -> None:
+        if self.is_simulation_running:
+            raise BadControlFlow("Please stop the simulation before updating the options.")
+        M.validate_options(options)
+        self._options = options
+        self._batch = None
+
+    def set_joint_springs(self, stiffness, damping) -> None:
+        self._springs = (np.asarray(stiffness, dtype=np.float64), np.asarray(damping, dtype=np.float64))
+
+    # -- life cycle
+    def _refresh(self) -> None:
+        b, rs, ss = self._batch, self.robot_states[0], self.stepper_state
+        t, q, v, a = b.get_state()
+        u, um, cmd, fext = b.get_efforts()
+        for dst, src in ((rs.q, q[0]), (rs.v, v[0]), (rs.a, a[0]), (rs.u, u[0]), (rs.u_motor, um[0]),
+                         (rs.f_external, fext[0]), (ss.q, q[0]), (ss.v, v[0]), (ss.a, a[0])):
+            np.copyto(dst, src)
+        ss.t = float(t[0])
+        it, itf = b.get_iters()
+        ss.iter, ss.iter_failed = int(it[0]), int(itf[0])
+        self._sensors = b.get_sensors()[0].copy()
+
+    def _call_controller(self) -> None:
+        if self._controller is None or self._controller.compute_command is None:
+            return
+        rs = self.robot_states[0]
+        rs.command[:] = 0.0
+        self._controller.compute_command(self.stepper_state.t, rs.q, rs.v, self._sensors, rs.command)
+        self._batch.set_command(rs.command[None, :])
+
+    def start(self, q_init, v_init, a_init=None, is_state_theoretical: bool = False) -> None:
+        if not self.robots:
+            raise BadControlFlow("No robot to simulate. Please add one before starting a simulation.")
+        if self.is_simulation_running:
+            raise BadControlFlow("A simulation is already running. Please stop it before starting a new one.")
+        robot = self.robots[0]
+        if self._controller is not None and self._controller.compute_command is not None and \
+                self._options["stepper"]["controllerUpdatePeriod"] <= 0.0:
+            raise NotImplementedError("A Python controller needs a discrete controllerUpdatePeriod: it cannot be "
+                                      "called from inside the device-side integrator.")
+        if self._batch is None:
+            self._batch = BatchedEngine(robot, self._options, 1, device=self._device, api_=self._api_)
+            if self._springs is not None:
+                self._batch.set_joint_springs(*self._springs)
+        q0 = np.asarray(q_init, dtype=np.float64).reshape(1, robot.nq)
+        v0 = np.asarray(v_init, dtype=np.float64).reshape(1, robot.nv)
+        self._batch.set_command(np.zeros((1, max(robot.nmotors, 1))))
+        self._batch.start(q0, v0)
+        self._refresh()
+        if self._controller is not None and self._controller.compute_command is not None:
+            # the command participates in the initial acceleration (INIT_ITERATIONS loop, engine.cc:1400-1467)
+            self._call_controller()
+            self._batch.start(q0, v0)
+            self._refresh()
+        st = int(self._batch.get_status()[0])
+        if st & JB_ENV_CONTACT_FORCE:
+            raise ValueError("The initial force exceeds 1e5 for at least one contact point, which is forbidden for "
+                             "the sake of numerical stability. Please update the initial state.")
+        self.is_simulation_running = True
+
+    def step(self, step_dt: float = -1.0) -> None:
+        if not self.is_simulation_running:
+            raise BadControlFlow("No simulation running. Please start one before using step method.")
+        st = self._options["stepper"]
+        cp = float(st["controllerUpdatePeriod"])
+        if step_dt < 2.3e-16:
+            step_dt = cp if cp > 0 else (st["sensorsUpdatePeriod"] if st["sensorsUpdatePeriod"] > 0 else st["dtMax"])
+        has_cb = self._controller is not None and self._controller.compute_command is not None
+        t_end = self.stepper_state.t + step_dt
+        while t_end - self.stepper_state.t >= 1e-10:
+            h = t_end - self.stepper_state.t
+            if has_cb:
+                # stop at every controller breakpoint to call the Python controller back
+                t = self.stepper_state.t
+                nxt = (np.floor(t / cp + 1e-9) + 1.0) * cp
+                if abs(t / cp - round(t / cp)) < 1e-9:
+                    self._call_controller()
+                h = min(h, nxt - t)
+            self._batch.step(h)
+            self._refresh()
+            status = int(self._batch.get_status()[0])
+            if status & JB_ENV_NAN:
+                raise RuntimeError("Low-level ode solver failed. Consider increasing stepper accuracy.")
+            if status & JB_ENV_ITER_FAILED:
+                raise RuntimeError("Too many successive iteration failures. Probably something is wrong with the "
+                                   "physics. Aborting integration.")
+            if status & JB_ENV_DT_UNDERFLOW:
+                raise RuntimeError("The internal time step is getting too small. Impossible to integrate physics "
+                                   "further in time. Aborting integration.")
+
+    def stop(self) -> None:
+        self.is_simulation_running = False
+
+    def reset(self, reset_random_generator: bool = False, remove_all_forces: bool = False) -> None:
+        self.stop()
+
+    def simulate(self, t_end: float, q_init, v_init, a_init=None, is_state_theoretical: bool = False,
+                 callback=None) -> None:
+        """`Engine::simulate` (engine.cc:1614-1699)."""
+        self.reset()
+        self.start(q_init, v_init)
+        st = self._options["stepper"]
+        periods = [p for p in (st["sensorsUpdatePeriod"], st["controllerUpdatePeriod"]) if p > 0]
+        h = min(periods) if periods else st["dtMax"]
+        while t_end - self.stepper_state.t >= 1e-6:
+            if callback is not None and not callback():
+                break
+            self.step(min(h, t_end - self.stepper_state.t))
+        self.stop()
+
+    @property
+    def sensor_measurements(self) -> np.ndarray:
+        return self._sensors

@@ -223,6 +223,8 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
                 kp.all_uniform = 0;
         }
         kp.rint_u[r] = a;
+        kp.kind_u[r] = static_cast<uint8_t>(a.kind);
+        for (int s = 1; s < P.L; ++s) if (P.rint[static_cast<size_t>(r) * P.L + s].kind != a.kind) kp.kind_u[r] = 0;
     }
     if (const char* s = std::getenv("JB_FORCE_PER_LANE")) if (std::atoi(s)) kp.all_uniform = 0;
     JbSensorLayout& L = kp.lay;

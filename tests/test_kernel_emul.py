@@ -231,3 +231,44 @@ def test_dopri_free_flyer_contact_and_unbounded_joint(api):
         pc.compare(eng, orc, 1e-8, 1e-6)
         np.testing.assert_array_equal(eng.get_iters()[1], orc.get_iters()[1])
     _lanes(0)
+
+
+def test_engine_facade_python_controller(api):
+    """`Engine` facade: reference method names, in-place RobotState buffers, Python controller called
+    back once per controller period (spring-damper law written as a controller, vs the analytic solution
+    of test_double_spring_mass.py)."""
+    import scipy.linalg
+    from jiminy_b200.core import Engine, FunctionalController, BadControlFlow
+    robot = M.build_robot_table(os.path.join(DATA, "linear_two_masses.urdf"), False)
+    for j in ("FirstJoint", "SecondJoint"):
+        M.attach_motor(robot, j, j, enableVelocityLimit=False, enableEffortLimit=False)
+    k, nu, m = np.array([200.0, 20.0]), np.array([0.1, 0.2]), np.array([1.0, 2.5])
+    calls = []
+
+    def compute_command(t, q, v, sensors, command):
+        calls.append(t)
+        command[:] = -k * q - nu * v
+
+    engine = Engine(api_=api)
+    engine.add_robot(robot, FunctionalController(compute_command))
+    opt = engine.get_options()
+    opt["stepper"].update(odeSolver="runge_kutta_4", dtMax=1e-4, controllerUpdatePeriod=1e-3, sensorsUpdatePeriod=1e-3)
+    engine.set_options(opt)
+    with pytest.raises(BadControlFlow):
+        engine.step(0.01)
+    x0 = np.array([0.1, -0.1, 0.0, 0.0])
+    engine.start(x0[:2], x0[2:])
+    q_view = engine.robot_states[0].q
+    assert engine.is_simulation_running
+    for _ in range(20):
+        engine.step(0.005)
+    assert q_view is engine.robot_states[0].q and engine.stepper_state.t == pytest.approx(0.1)
+    assert len(calls) >= 100
+    # discrete 1 kHz zero-order-held spring law ~ continuous law up to O(period)
+    Iq = 1.0 / m[1] + 1.0 / m[0]
+    A = np.array([[0, 0, 1, 0], [0, 0, 0, 1], [-k[0] / m[0], k[1] / m[0], -nu[0] / m[0], nu[1] / m[0]],
+                  [k[0] / m[0], -k[1] * Iq, nu[0] / m[0], -nu[1] * Iq]])
+    xa = scipy.linalg.expm(A * 0.1) @ x0
+    np.testing.assert_allclose(np.r_[q_view, engine.robot_states[0].v], xa, atol=2e-2)
+    engine.stop()
+    assert not engine.is_simulation_running
