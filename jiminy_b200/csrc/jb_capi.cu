@@ -227,6 +227,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
         for (int s = 1; s < P.L; ++s) if (P.rint[static_cast<size_t>(r) * P.L + s].kind != a.kind) kp.kind_u[r] = 0;
     }
     if (const char* s = std::getenv("JB_FORCE_PER_LANE")) if (std::atoi(s)) kp.all_uniform = 0;
+    kp.sig_id = 0;
     JbSensorLayout& L = kp.lay;
     L.imu_offset = 0;
     L.force_offset = 6 * m->nimu;
@@ -276,6 +277,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
         kp.extra_energy = d_en; kp.extra_a = d_ea; kp.extra_f = d_ef;
     }
 
+    if (SigQuadruped::matches(kp) && !std::getenv("JB_NO_STATIC_PLAN")) kp.sig_id = SigQuadruped::ID;
     b->smem_bytes = static_cast<size_t>(P.nfields) * 32 * sizeof(double);
     if (b->smem_bytes > 227 * 1024) { jb_batch_destroy(b); return fail(JB_ERR_NOT_IMPLEMENTED, "robot too large: per-warp working set exceeds shared memory (" + P.describe() + ")"); }
     e = cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(b->smem_bytes));
