@@ -2,6 +2,7 @@
 #include "jb_plan.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <functional>
 #include <numeric>
@@ -233,6 +234,8 @@ Plan build_plan(const JbModelDesc& m, int lanes, int n_hist) {
             if (j < 0) continue;
             const int p = m.parent[j];
             ri.kind = rec_kind(m.joint_type[j]);
+            if (ri.kind == REC_REV && std::fabs(m.axis[3 * j]) == 1.0 && m.axis[3 * j + 1] == 0.0 && m.axis[3 * j + 2] == 0.0)
+                ri.kind = REC_REVX;
             ri.joint = j;
             ri.parent_rec = p > 0 ? joint_rec[s][p] : -1;
             const bool trunk_j = is_trunk[j];
@@ -247,7 +250,7 @@ Plan build_plan(const JbModelDesc& m, int lanes, int n_hist) {
             ri.idx_q = m.idx_q[j];
             ri.idx_v = m.idx_v[j];
             ri.owner = (!trunk_j || s == 0) ? 1 : 0;
-            ri.has_limit = (ri.kind == REC_REV || ri.kind == REC_PRISM) ? 1 : 0;
+            ri.has_limit = (ri.kind == REC_REV || ri.kind == REC_REVX || ri.kind == REC_PRISM) ? 1 : 0;
             std::memcpy(rd.placement, m.placement + 12 * j, sizeof rd.placement);
             std::memcpy(rd.axis, m.axis + 3 * j, sizeof rd.axis);
             std::memcpy(rd.inertia, m.inertia + 10 * j, sizeof rd.inertia);

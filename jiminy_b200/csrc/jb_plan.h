@@ -22,7 +22,8 @@
 namespace jb {
 
 // Record kinds (what the lane executes for this record)
-enum : int32_t { REC_PAD = 0, REC_REV = 1, REC_REVU = 2, REC_PRISM = 3, REC_FREE = 4 };
+enum : int32_t { REC_PAD = 0, REC_REV = 1, REC_REVU = 2, REC_PRISM = 3, REC_FREE = 4,
+                 REC_REVX = 5 /* bounded revolute about +-x of the joint frame */ };
 
 constexpr int MAX_CONTACTS_PER_REC = 8;
 
