@@ -274,6 +274,7 @@ Plan build_plan(const JbModelDesc& m, int lanes, int n_hist) {
                         const double effLim = rd.motor[1], velLim = rd.motor[2], velocityDelta = effLim * rd.motor[3];
                         const double thr = std::max(velLim - velocityDelta, 0.0);
                         rd.motor[9] = 1.0 / (velLim - thr);
+                        rd.pad = thr;   // |vMotor| <= thr: no taper
                     }
                 }
             for (int e = 0; e < m.nencoder; ++e)

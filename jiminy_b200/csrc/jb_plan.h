@@ -60,7 +60,7 @@ struct RecDbl {
     double q_lo, q_hi;
     double motor[10];      // SimpleMotor params (see jiminy_b200.h)
     double enc_reduction;
-    double pad;
+    double pad;            // velocity taper threshold of the motor (velocityLimit - effortLimit * velocityEffortInvSlope, >= 0)
 };
 constexpr int REC_DBL_STRIDE = sizeof(RecDbl) / sizeof(double);
 
