@@ -275,6 +275,14 @@ def run_gpu(args):
     e2e_value = total_envs * args.steps / (e2e_ms * 1e-3)
     peaks, peak_kind = read_peaks()
     bytes_per_launch = sc.algorithmic_bytes_per_env_step() * n_env
+    traffic, fp64_pct = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            rec = json.load(fh).get(args.workload)
+        if rec and rec["n_env"] == n_env:
+            traffic, fp64_pct = rec["traffic_bytes"], rec["fp64_pipe_active_pct"]
+    except Exception:
+        pass
     achieved_gbs = bytes_per_launch / (step_ms_dev * 1e-3) / 1e9
     ncores, cpu = (None, None)
     if not args.no_cpu_baseline:
@@ -292,7 +300,8 @@ def run_gpu(args):
                 "d2h_bytes_per_step": int(n_env * width * 8 * world), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                     "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
+                     "fp64_pipe_active_pct_ncu": fp64_pct,
                      "kernel": "env_step_kernel", "kernel_ms": step_ms_dev,
                      "algorithmic_bytes_per_launch": bytes_per_launch,
                      "note": "fp64-pipe / latency bound by construction (state stays on chip for the whole "
