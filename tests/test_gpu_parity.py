@@ -124,3 +124,13 @@ def test_dopri_adaptive_matches_oracle():
         eng.step(sc.step_dt)
         assert not orc.step(sc.step_dt, parallel=True).any()
     pc.compare(eng, orc, 1e-7, 1e-5)
+
+
+def test_cuda_path_vs_closed_forms():
+    """The reference's analytical tests run on the CUDA path directly: rotor inertia + spring vs expm,
+    prismatic chain vs expm, contact equilibrium / sensors / friction steady state, energy conservation."""
+    import analytic_device as ad
+    ad.armature_spring()
+    ad.two_masses()
+    ad.contact_equilibrium_and_friction()
+    ad.energy_conservation()

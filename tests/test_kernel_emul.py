@@ -272,3 +272,12 @@ def test_engine_facade_python_controller(api):
     np.testing.assert_allclose(np.r_[q_view, engine.robot_states[0].v], xa, atol=2e-2)
     engine.stop()
     assert not engine.is_simulation_running
+
+
+def test_device_code_vs_closed_forms(api):
+    """The reference's analytical tests on the kernel source itself (no oracle in the loop)."""
+    import analytic_device as ad
+    ad.armature_spring(api)
+    ad.two_masses(api)
+    ad.contact_equilibrium_and_friction(api)
+    ad.energy_conservation(api)
