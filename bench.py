@@ -209,6 +209,7 @@ def run_gpu(args):
     sampler.start()
     launches0 = eng.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    evk = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_begin.record(stream)
     for k in range(args.steps):
@@ -219,28 +220,25 @@ def run_gpu(args):
         eng.set_command_device(acts_dev[args.warmup + k].data_ptr())
         ev[k][0].record(stream)
         eng.step(sc.step_dt)
+        evk[k].record(stream)
+        gather_obs()                       # multi-GPU: the step kernel's stream waits for the all-gather
         ev[k][1].record(stream)
-        gather_obs()
     t_end.record(stream)
     barrier()
     launches = eng.launch_count() - launches0
     clocks = sampler.stop()
-    kernel_ms = [a.elapsed_time(b) for a, b in ev]
+    kernel_ms = [a.elapsed_time(b) for (a, _), b in zip(ev, evk)]      # step kernel alone (roofline)
+    step_ms = [a.elapsed_time(b) for a, b in ev]                        # step + observation all-gather
     step_ms_dev = float(np.mean(kernel_ms))
     wall_ms = t_begin.elapsed_time(t_end)
-    # the L2 flush kernel sits inside [t_begin, t_end]; the per-step cost of the path is the step kernel
-    # (+ gather); report the sum of the step intervals, max over ranks
-    t_path_ms = float(np.sum(kernel_ms))
+    # [t_begin, t_end] also contains the L2 flush kernels; the cost of the path is the sum of the
+    # per-step intervals (kernel + gather), max over ranks
+    t_path_ms = float(np.sum(step_ms))
+    gather_ms = float(np.mean(step_ms) - np.mean(kernel_ms))
     if world > 1:
-        g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
-        g0.record(); dist.all_gather_into_tensor(gather_out, gather_in); g1.record(); torch.cuda.synchronize()
-        gather_ms = g0.elapsed_time(g1)
-        t_path_ms += gather_ms * args.steps
         tt = torch.tensor([t_path_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_path_ms = float(tt.item())
-    else:
-        gather_ms = 0.0
     status = eng.get_status()
     n_bad = int((status != 0).sum())
 
