@@ -200,6 +200,37 @@ int jb_set_command(JbBatch* batch, const double* cmd);
 /* Same, with `cmd_dev` a device pointer (same layout) on the batch's device: no host copy. */
 int jb_set_command_device(JbBatch* batch, const double* cmd_dev);
 
+/* Replaces: Engine::stop (engine.cc:2419-2448): every env goes back to "not started", which is what
+ * registering or removing forces requires (engine.cc:2456-2461). */
+int jb_stop(JbBatch* batch);
+
+/* Replaces: Engine::registerImpulseForce(robot, frame, t, dt, F) (engine.cc:2450-2491;
+ * python/jiminy_pywrap/src/engine.cc:651-657) and its use by Engine::step: the wrench is active for
+ * t_env in [t, t + dt), both ends are integration breakpoints (engine.cc:1843-1890, :2002-2006, :2228),
+ * and it enters the dynamics through computeExternalForces (engine.cc:3463-3480).  The frame is given
+ * by its parent joint index and its translation in that joint's frame (the wrench is expressed in
+ * world-aligned axes at the frame origin, so the frame's rotation is irrelevant;
+ * convertForceGlobalFrameToJoint, utilities/pinocchio.cc:794-809).  One frame for all envs, per-env
+ * application time, duration and wrench: t [n_env], dt [n_env], wrench [n_env][6] (linear, angular).
+ * Times are relative to each env's own start.  index_out receives the impulse index. */
+int jb_register_impulse_force(JbBatch* batch, int32_t joint, const double* frame_translation, const double* t,
+                              const double* dt, const double* wrench, int32_t* index_out);
+/* Rewrites impulse `index` of the envs selected by mask (NULL = all): what removing and re-registering
+ * the forces of one env at an episode reset does (locomotion.py:314-323).  Call it right before the
+ * masked jb_start of those envs. */
+int jb_set_impulse_force(JbBatch* batch, int32_t index, const uint8_t* mask, const double* t, const double* dt,
+                         const double* wrench);
+/* Replaces: Engine::registerProfileForce(robot, frame, func, updatePeriod) (engine.cc:2518-2567) where
+ * `func` returns the per-env wrench last written with jb_set_profile_force.  update_period == 0: the
+ * value is read at every dynamics evaluation (engine.cc:3488-3491); update_period > 0: it is sampled at
+ * the multiples of the period, which become breakpoints (engine.cc:1892-1917, :2551-2562), and is zero
+ * between start and the first step. */
+int jb_register_profile_force(JbBatch* batch, int32_t joint, const double* frame_translation, double update_period,
+                              int32_t* slot_out);
+int jb_set_profile_force(JbBatch* batch, int32_t slot, const double* wrench /* [n_env][6] */);
+/* Replaces: Engine::removeAllForces (engine.cc:568-573, :2569-2638). */
+int jb_remove_all_forces(JbBatch* batch);
+
 /* Replaces: Engine::step(stepSize) (engine.cc:1724-2417), all envs in lockstep, one launch.
  * step_dt < EPS selects the reference's default step size rule (engine.cc:1758-1777). */
 int jb_step(JbBatch* batch, double step_dt);

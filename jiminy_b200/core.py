@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Any, Dict, Optional, Sequence
+from typing import Any, Dict, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -50,7 +50,8 @@ class Api:
                "jb_compute_dynamics", "jb_get_state", "jb_get_efforts", "jb_get_sensors", "jb_sensor_layout",
                "jb_get_extra_terms", "jb_get_status", "jb_get_iters", "jb_device_views", "jb_get_stream",
                "jb_launch_count", "jb_synchronize", "jb_set_joint_springs", "jb_set_pd_controller", "jb_copy_sensors_device", "jb_describe",
-               "jb_plan_describe")
+               "jb_plan_describe", "jb_stop", "jb_register_impulse_force", "jb_set_impulse_force",
+               "jb_register_profile_force", "jb_set_profile_force", "jb_remove_all_forces")
 
     def __init__(self, cdll: C.CDLL):
         self.dll = L = cdll
@@ -87,6 +88,12 @@ class Api:
         L.jb_copy_sensors_device.argtypes = [vp, vp]
         L.jb_describe.argtypes = [vp, C.c_char_p, C.c_int32]
         L.jb_plan_describe.argtypes = [C.POINTER(JbModelDesc), C.c_int32, C.c_char_p, C.c_int32, c_int32_p]
+        L.jb_stop.argtypes = [vp]
+        L.jb_register_impulse_force.argtypes = [vp, C.c_int32] + [c_double_p] * 4 + [c_int32_p]
+        L.jb_set_impulse_force.argtypes = [vp, C.c_int32, c_uint8_p] + [c_double_p] * 3
+        L.jb_register_profile_force.argtypes = [vp, C.c_int32, c_double_p, C.c_double, c_int32_p]
+        L.jb_set_profile_force.argtypes = [vp, C.c_int32, c_double_p]
+        L.jb_remove_all_forces.argtypes = [vp]
 
     def check(self, rc: int) -> None:
         if rc != JB_OK:
@@ -172,6 +179,59 @@ class BatchedEngine:
         d = np.ascontiguousarray(damping, dtype=np.float64)
         assert k.shape == (self.nv,) and d.shape == (self.nv,)
         self._api.check(self._api.dll.jb_set_joint_springs(self._h, dptr(k), dptr(d)))
+
+    # ---- external forces (Engine.register_impulse_force / register_profile_force / remove_all_forces)
+    def stop(self) -> None:
+        """`Engine.stop`: every env goes back to "not started" (needed before (un)registering forces)."""
+        self._api.check(self._api.dll.jb_stop(self._h))
+
+    def _frame(self, frame) -> Tuple[int, np.ndarray]:
+        """A frame name of the robot, or an explicit (parent joint index, translation in the joint frame)."""
+        if isinstance(frame, str):
+            if frame == "universe":
+                raise ValueError("Impossible to apply external forces to the universe itself!")
+            if frame not in self.robot.frames:
+                raise ValueError(f"Frame '{frame}' does not exist.")
+            f = self.robot.frames[frame]
+            return int(f.joint), np.ascontiguousarray(f.placement.p, dtype=np.float64)
+        joint, p = frame
+        return int(joint), np.ascontiguousarray(p, dtype=np.float64)
+
+    def _per_env(self, x, shape) -> np.ndarray:
+        return np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), (self.n_env,) + shape))
+
+    def register_impulse_force(self, frame, t, dt, force) -> int:
+        """`force` (world-aligned axes, at the frame origin) applied during [t, t + dt) of each env's own
+        clock; `t`, `dt` scalars or [n_env], `force` [6] or [n_env, 6].  Returns the impulse index."""
+        joint, p = self._frame(frame)
+        t, dt, force = self._per_env(t, ()), self._per_env(dt, ()), self._per_env(force, (6,))
+        idx = C.c_int32(-1)
+        self._api.check(self._api.dll.jb_register_impulse_force(self._h, joint, dptr(p), dptr(t), dptr(dt), dptr(force),
+                                                               C.byref(idx)))
+        return int(idx.value)
+
+    def set_impulse_force(self, index: int, t, dt, force, mask: Optional[np.ndarray] = None) -> None:
+        t, dt, force = self._per_env(t, ()), self._per_env(dt, ()), self._per_env(force, (6,))
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self._api.check(self._api.dll.jb_set_impulse_force(
+            self._h, int(index), None if m is None else m.ctypes.data_as(c_uint8_p), dptr(t), dptr(dt), dptr(force)))
+
+    def register_profile_force(self, frame, update_period: float = 0.0) -> int:
+        """A force whose per-env value is whatever `set_profile_force` last wrote (the batched stand-in for
+        the reference's Python force function).  Returns the slot index."""
+        joint, p = self._frame(frame)
+        slot = C.c_int32(-1)
+        self._api.check(self._api.dll.jb_register_profile_force(self._h, joint, dptr(p), float(update_period),
+                                                               C.byref(slot)))
+        return int(slot.value)
+
+    def set_profile_force(self, slot: int, force) -> None:
+        force = self._per_env(force, (6,))
+        self._api.check(self._api.dll.jb_set_profile_force(self._h, int(slot), dptr(force)))
+        self._api.check(self._api.dll.jb_synchronize(self._h))
+
+    def remove_all_forces(self) -> None:
+        self._api.check(self._api.dll.jb_remove_all_forces(self._h))
 
     def set_pd_controller(self, kp, kd) -> None:
         """Device-side `PDController` block (position targets, zero target velocity); `set_command` then
@@ -347,6 +407,8 @@ class Engine:
         self._batch: Optional[BatchedEngine] = None
         self._controller: Optional[FunctionalController] = None
         self._springs = None
+        self._impulse_forces: list = []
+        self._forces_dirty = False
 
     # -- configuration
     def add_robot(self, robot: M.RobotTable, controller: Optional[FunctionalController] = None) -> None:
@@ -370,6 +432,35 @@ class Engine:
 
     def set_joint_springs(self, stiffness, damping) -> None:
         self._springs = (np.asarray(stiffness, dtype=np.float64), np.asarray(damping, dtype=np.float64))
+
+    # -- external forces (python/jiminy_pywrap/src/engine.cc:651-657, :761)
+    def register_impulse_force(self, robot_name: str, frame_name: str, t: float, dt: float, force) -> None:
+        if self.is_simulation_running:
+            raise BadControlFlow("Simulation already running. Please stop it before registering new forces.")
+        if dt < 1e-10:
+            raise ValueError("Force duration cannot be smaller than 1e-10s.")
+        if t < 0.0:
+            raise ValueError("Force application time must be positive.")
+        if frame_name == "universe":
+            raise ValueError("Impossible to apply external forces to the universe itself!")
+        if not self.robots or frame_name not in self.robots[0].frames:
+            raise ValueError(f"Frame '{frame_name}' does not exist.")
+        self._impulse_forces.append((frame_name, float(t), float(dt), np.asarray(force, dtype=np.float64).copy()))
+        self._forces_dirty = True
+
+    def register_profile_force(self, robot_name: str, frame_name: str, force_func, update_period: float = 0.0) -> None:
+        raise NotImplementedError("A Python force function cannot be called from inside the device-side integrator; use "
+                                  "BatchedEngine.register_profile_force / set_profile_force (held per-env wrench).")
+
+    def remove_all_forces(self) -> None:
+        if self.is_simulation_running:
+            raise BadControlFlow("Simulation already running. Please stop it before removing forces.")
+        self._impulse_forces.clear()
+        self._forces_dirty = True
+
+    @property
+    def impulse_forces(self) -> list:
+        return list(self._impulse_forces)
 
     # -- life cycle
     def _refresh(self) -> None:
@@ -406,6 +497,13 @@ class Engine:
             self._batch = BatchedEngine(robot, self._options, 1, device=self._device, api_=self._api_)
             if self._springs is not None:
                 self._batch.set_joint_springs(*self._springs)
+            self._forces_dirty = bool(self._impulse_forces)
+        if self._forces_dirty:
+            self._batch.stop()
+            self._batch.remove_all_forces()
+            for frame_name, t, dt, force in self._impulse_forces:
+                self._batch.register_impulse_force(frame_name, t, dt, force)
+            self._forces_dirty = False
         q0 = np.asarray(q_init, dtype=np.float64).reshape(1, robot.nq)
         v0 = np.asarray(v_init, dtype=np.float64).reshape(1, robot.nv)
         self._batch.set_command(np.zeros((1, max(robot.nmotors, 1))))
@@ -457,6 +555,8 @@ class Engine:
 
     def reset(self, reset_random_generator: bool = False, remove_all_forces: bool = False) -> None:
         self.stop()
+        if remove_all_forces:
+            self.remove_all_forces()
 
     def simulate(self, t_end: float, q_init, v_init, a_init=None, is_state_theoretical: bool = False,
                  callback=None) -> None:

@@ -62,7 +62,27 @@ struct JbBatch {
     int64_t launches = 0;
     bool any_started = false;
     size_t smem_bytes = 0;
+    // external forces: frames (slots), impulse table mirror, profile periods
+    struct ExtFrame { int joint; double p[3]; };
+    std::vector<ExtFrame> eframes;
+    std::vector<double> h_imp;      // [MAX_IMPULSE][IMPULSE_ROWS][n_pad]
+    ExtSlot* d_eslots = nullptr;
+    double *d_imp = nullptr, *d_prof_pending = nullptr, *d_prof_latched = nullptr;
 };
+
+// The dynamic shared-memory opt-in is a per-function, per-device attribute: only ever raise it.
+static std::mutex g_smem_mutex;
+static size_t g_smem_attr[64] = {0};
+static int raise_smem_attr(int device, size_t bytes) {
+#ifndef JB_HOST_EMUL
+    std::lock_guard<std::mutex> lock(g_smem_mutex);
+    if (bytes <= g_smem_attr[device]) return JB_OK;
+    cudaError_t e = cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    if (e != cudaSuccess) return fail(JB_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    g_smem_attr[device] = bytes;
+#endif
+    return JB_OK;
+}
 
 template <typename T>
 static int dev_alloc(JbBatch* b, T** p, size_t count) {
@@ -95,6 +115,7 @@ static int launch(JbBatch* b, int mode, double step_dt) {
     KParams kp = b->kp;
     kp.mode = mode;
     kp.step_dt = step_dt;
+    if (kp.n_eslot > 0) kp.sig_id = 0;   // static plan signatures carry no external-force code
     const int epw = 32 / b->plan.L;
     const int nblocks = (b->n_env + epw - 1) / epw;
 #ifdef JB_HOST_EMUL
@@ -159,6 +180,9 @@ static void apply_options(JbBatch* b, const JbOptions* o) {
     double supd = INFINITY;
     if (o->sensors_update_period > 2.3e-16) supd = std::min(supd, o->sensors_update_period);
     if (o->controller_update_period > 2.3e-16) supd = std::min(supd, o->controller_update_period);
+    // profile forces with a finite update period add breakpoints (engine.cc:2551-2562)
+    for (int j = 0; j < b->kp.n_prof; ++j)
+        if (b->kp.prof_period[j] > 2.3e-16) supd = std::min(supd, b->kp.prof_period[j]);
     b->kp.stepper_update_period = std::isfinite(supd) ? supd : 1e308;
 }
 
@@ -280,8 +304,8 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
     if (SigQuadruped::matches(kp) && !std::getenv("JB_NO_STATIC_PLAN")) kp.sig_id = SigQuadruped::ID;
     b->smem_bytes = static_cast<size_t>(P.nfields) * 32 * sizeof(double);
     if (b->smem_bytes > 227 * 1024) { jb_batch_destroy(b); return fail(JB_ERR_NOT_IMPLEMENTED, "robot too large: per-warp working set exceeds shared memory (" + P.describe() + ")"); }
-    e = cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(b->smem_bytes));
-    if (e != cudaSuccess) { jb_batch_destroy(b); return fail(JB_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
+    kp.n_eslot = 0; kp.n_imp = 0; kp.n_prof = 0; kp.ext_off = P.nfields;
+    if (raise_smem_attr(device, b->smem_bytes)) { jb_batch_destroy(b); return JB_ERR_CUDA; }
     e = cudaStreamSynchronize(b->stream);
     if (e != cudaSuccess) { jb_batch_destroy(b); return fail(JB_ERR_CUDA, std::string("upload failed: ") + cudaGetErrorString(e)); }
     *out = b;
@@ -363,6 +387,157 @@ int jb_start(JbBatch* b, const uint8_t* mask, const double* q0, const double* v0
     if (rc) return rc;
     CU(cudaStreamSynchronize(b->stream));
     b->any_started = true;
+    return JB_OK;
+}
+
+// ---- external forces --------------------------------------------------------------------------
+int jb_stop(JbBatch* b) {
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(b->device));
+    std::vector<int32_t> st(b->n_pad, JB_ENV_NOT_STARTED);
+    CU(cudaMemcpyAsync(b->d_status, st.data(), st.size() * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    b->any_started = false;
+    return JB_OK;
+}
+
+static int ext_slot_for(JbBatch* b, int joint, const double* p, int* slot_out) {
+    if (joint <= 0 || joint >= b->njoints) return fail(JB_ERR_INVALID_ARGUMENT, "Impossible to apply external forces to the universe itself (or unknown joint).");
+    for (size_t e = 0; e < b->eframes.size(); ++e) {
+        const auto& f = b->eframes[e];
+        if (f.joint == joint && f.p[0] == p[0] && f.p[1] == p[1] && f.p[2] == p[2]) { *slot_out = static_cast<int>(e); return JB_OK; }
+    }
+    if (b->eframes.size() >= MAX_ESLOT) return fail(JB_ERR_NOT_IMPLEMENTED, "too many distinct frames carrying external forces");
+    const Plan& P = b->plan;
+    const size_t N = b->n_pad;
+    if (!b->d_eslots) {
+        int rc;
+        if ((rc = dev_alloc(b, &b->d_eslots, static_cast<size_t>(MAX_ESLOT) * P.L))) return rc;
+        if ((rc = dev_alloc(b, &b->d_imp, static_cast<size_t>(MAX_IMPULSE) * IMPULSE_ROWS * N))) return rc;
+        if ((rc = dev_alloc(b, &b->d_prof_pending, static_cast<size_t>(MAX_PROFILE) * 6 * N))) return rc;
+        if ((rc = dev_alloc(b, &b->d_prof_latched, static_cast<size_t>(MAX_PROFILE) * 6 * N))) return rc;
+        b->h_imp.assign(static_cast<size_t>(MAX_IMPULSE) * IMPULSE_ROWS * N, 0.0);
+        b->kp.eslots = b->d_eslots; b->kp.imp_data = b->d_imp;
+        b->kp.prof_pending = b->d_prof_pending; b->kp.prof_latched = b->d_prof_latched;
+    }
+    const size_t smem = static_cast<size_t>(P.nfields + ESLOT_SIZE * (b->eframes.size() + 1)) * 32 * sizeof(double);
+    if (smem > 227 * 1024) return fail(JB_ERR_NOT_IMPLEMENTED, "no shared memory left for an external-force slot");
+    int rc = raise_smem_attr(b->device, smem);
+    if (rc) return rc;
+    JbBatch::ExtFrame f{joint, {p[0], p[1], p[2]}};
+    b->eframes.push_back(f);
+    std::vector<ExtSlot> rows(b->eframes.size() * P.L);
+    for (size_t e = 0; e < b->eframes.size(); ++e)
+        for (int s = 0; s < P.L; ++s) {
+            ExtSlot& x = rows[e * P.L + s];
+            x.p[0] = b->eframes[e].p[0]; x.p[1] = b->eframes[e].p[1]; x.p[2] = b->eframes[e].p[2];
+            x.joint = b->eframes[e].joint; x.rec = -1;
+            for (int r = 0; r < P.nrec; ++r) {
+                const RecInt& ri = P.rint[static_cast<size_t>(r) * P.L + s];
+                if (ri.kind != REC_PAD && ri.joint == x.joint) x.rec = r;
+            }
+        }
+    CU(cudaMemcpyAsync(b->d_eslots, rows.data(), rows.size() * sizeof(ExtSlot), cudaMemcpyHostToDevice, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    b->smem_bytes = smem;
+    b->kp.n_eslot = static_cast<int32_t>(b->eframes.size());
+    *slot_out = b->kp.n_eslot - 1;
+    return JB_OK;
+}
+
+static int upload_impulse(JbBatch* b, int k, const uint8_t* mask, const double* t, const double* dt, const double* wrench) {
+    const size_t N = b->n_pad;
+    double* rows = b->h_imp.data() + static_cast<size_t>(k) * IMPULSE_ROWS * N;
+    for (int i = 0; i < b->n_env; ++i) {
+        if (mask && !mask[i]) continue;
+        if (dt[i] < 1e-10) return fail(JB_ERR_INVALID_ARGUMENT, "Force duration cannot be smaller than 1e-10s.");
+        if (t[i] < 0.0) return fail(JB_ERR_INVALID_ARGUMENT, "Force application time must be positive.");
+        rows[i] = t[i]; rows[N + i] = dt[i];
+        for (int c = 0; c < 6; ++c) rows[(2 + c) * N + i] = wrench[static_cast<size_t>(i) * 6 + c];
+    }
+    for (size_t i = b->n_env; i < N; ++i) { rows[i] = rows[b->n_env - 1]; rows[N + i] = rows[N + b->n_env - 1]; }
+    CU(cudaMemcpyAsync(b->d_imp + static_cast<size_t>(k) * IMPULSE_ROWS * N, rows, sizeof(double) * IMPULSE_ROWS * N, cudaMemcpyHostToDevice, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return JB_OK;
+}
+
+int jb_register_impulse_force(JbBatch* b, int32_t joint, const double* frame_translation, const double* t, const double* dt,
+                              const double* wrench, int32_t* index_out) {
+    if (!b || !frame_translation || !t || !dt || !wrench) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (b->any_started) return fail(JB_ERR_BAD_CONTROL_FLOW, "Simulation already running. Please stop it before registering new forces.");
+    if (b->kp.n_imp >= MAX_IMPULSE) return fail(JB_ERR_NOT_IMPLEMENTED, "too many impulse forces");
+    CU(cudaSetDevice(b->device));
+    int slot = 0;
+    int rc = ext_slot_for(b, joint, frame_translation, &slot);
+    if (rc) return rc;
+    const int k = b->kp.n_imp;
+    rc = upload_impulse(b, k, nullptr, t, dt, wrench);
+    if (rc) return rc;
+    b->kp.imp_slot[k] = slot;
+    b->kp.n_imp = k + 1;
+    if (index_out) *index_out = k;
+    return JB_OK;
+}
+
+int jb_set_impulse_force(JbBatch* b, int32_t index, const uint8_t* mask, const double* t, const double* dt, const double* wrench) {
+    if (!b || !t || !dt || !wrench) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (index < 0 || index >= b->kp.n_imp) return fail(JB_ERR_INVALID_ARGUMENT, "unknown impulse force");
+    CU(cudaSetDevice(b->device));
+    return upload_impulse(b, index, mask, t, dt, wrench);
+}
+
+int jb_register_profile_force(JbBatch* b, int32_t joint, const double* frame_translation, double update_period, int32_t* slot_out) {
+    if (!b || !frame_translation) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (b->any_started) return fail(JB_ERR_BAD_CONTROL_FLOW, "Simulation already running. Please stop it before registering new forces.");
+    if (b->kp.n_prof >= MAX_PROFILE) return fail(JB_ERR_NOT_IMPLEMENTED, "too many profile forces");
+    if (update_period > 2.3e-16 && update_period < 1e-6)
+        return fail(JB_ERR_INVALID_ARGUMENT, "Cannot register external force profile with update period smaller than 1e-06s.");
+    if (update_period > 2.3e-16 && b->kp.stepper_update_period < 1e300) {
+        const double lo = std::min(update_period, b->kp.stepper_update_period), hi = std::max(update_period, b->kp.stepper_update_period);
+        const double r = std::fmod(hi, lo);
+        if (std::min(r, lo - r) > 1e-12)
+            return fail(JB_ERR_INVALID_ARGUMENT, "In discrete mode, the update period of force profiles and the stepper update period must be multiple of each other.");
+    }
+    CU(cudaSetDevice(b->device));
+    int slot = 0;
+    int rc = ext_slot_for(b, joint, frame_translation, &slot);
+    if (rc) return rc;
+    const int j = b->kp.n_prof;
+    b->kp.prof_slot[j] = slot;
+    b->kp.prof_period[j] = update_period;
+    b->kp.n_prof = j + 1;
+    const size_t N = b->n_pad;
+    CU(cudaMemsetAsync(b->d_prof_pending + static_cast<size_t>(j) * 6 * N, 0, sizeof(double) * 6 * N, b->stream));
+    CU(cudaMemsetAsync(b->d_prof_latched + static_cast<size_t>(j) * 6 * N, 0, sizeof(double) * 6 * N, b->stream));
+    const JbOptions o = b->kp.opt;
+    apply_options(b, &o);
+    if (slot_out) *slot_out = j;
+    return JB_OK;
+}
+
+int jb_set_profile_force(JbBatch* b, int32_t slot, const double* wrench) {
+    if (!b || !wrench) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (slot < 0 || slot >= b->kp.n_prof) return fail(JB_ERR_INVALID_ARGUMENT, "unknown profile force");
+    CU(cudaSetDevice(b->device));
+    const size_t N = b->n_pad;
+    int rc = ensure_host_stage(b, sizeof(double) * 6 * N);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(b->stream));   // the staging buffer may still be in flight
+    for (int c = 0; c < 6; ++c)
+        for (size_t i = 0; i < N; ++i)
+            b->h_stage[c * N + i] = wrench[std::min<size_t>(i, b->n_env - 1) * 6 + c];
+    CU(cudaMemcpyAsync(b->d_prof_pending + static_cast<size_t>(slot) * 6 * N, b->h_stage, sizeof(double) * 6 * N, cudaMemcpyHostToDevice, b->stream));
+    return JB_OK;
+}
+
+int jb_remove_all_forces(JbBatch* b) {
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (b->any_started) return fail(JB_ERR_BAD_CONTROL_FLOW, "Simulation already running. Please stop it before removing forces.");
+    b->kp.n_imp = 0; b->kp.n_prof = 0; b->kp.n_eslot = 0;
+    b->eframes.clear();
+    b->smem_bytes = static_cast<size_t>(b->plan.nfields) * 32 * sizeof(double);
+    const JbOptions o = b->kp.opt;
+    apply_options(b, &o);
     return JB_OK;
 }
 

@@ -83,12 +83,6 @@ __device__ __noinline__ void update_pd_commands(const Ctx c) {
     }
 }
 
-JB_DI bool period_hit(double t, double period) {
-    // `dtNext < SIMULATION_MIN_TIMESTEP || period - dtNext < STEPPER_MIN_TIMESTEP` (engine.cc:1924-1927, :2388-2395)
-    const double dtNext = period - fmod(t, period);
-    return dtNext < SIMULATION_MIN_TIMESTEP || period - dtNext < STEPPER_MIN_TIMESTEP;
-}
-
 __device__ __noinline__ void store_outputs(const Ctx c) {
     if (!c.valid) return;
     const int L = KP->L;
@@ -140,6 +134,7 @@ __device__ __noinline__ void store_outputs(const Ctx c) {
                 const V3 Fl = mk(CO(0), CO(1), CO(2));
                 fext.l = fext.l + Fl; fext.a = fext.a + cross(ld3(ct->placement + 9), Fl);
             }
+            add_cached_ext_wrench(c, r, L, fext);
             double* o = KP->eff_fext + (col * KP->njoints + ri->joint) * 6;
             o[0] = fext.l.x; o[1] = fext.l.y; o[2] = fext.l.z; o[3] = fext.a.x; o[4] = fext.a.y; o[5] = fext.a.z;
         }
@@ -183,6 +178,7 @@ __device__ __noinline__ void store_dynamics(const Ctx c) {
                 const V3 Fl = mk(CO(0), CO(1), CO(2));
                 fext.l = fext.l + Fl; fext.a = fext.a + cross(ld3(ct->placement + 9), Fl);
             }
+            add_cached_ext_wrench(c, r, L, fext);
             double* o = KP->fext_out + (col * KP->njoints + ri->joint) * 6;
             o[0] = fext.l.x; o[1] = fext.l.y; o[2] = fext.l.z; o[3] = fext.a.x; o[4] = fext.a.y; o[5] = fext.a.z;
         }
@@ -227,6 +223,7 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
     }
     for (int k = 0; k < CSLOT_SIZE * KP->ncslot; ++k) SMF(c, KP->cslot_off + k) = 0.0;
     for (int k = 0; k < IMUSLOT_SIZE * KP->nimuslot; ++k) SMF(c, KP->imu_off + k) = 0.0;
+    for (int k = 0; k < ESLOT_SIZE * KP->n_eslot; ++k) SMF(c, KP->ext_off + k) = 0.0;
 
     if (mode == MODE_DYNAMICS) {
         stage_from_accepted(c);
@@ -247,6 +244,7 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
         dt = SIMULATION_MIN_TIMESTEP; dtLargest = dt; dtLargestPrev = dt;
         iter = 0; iterFailed = 0;
         if (KP->pd_gains != nullptr) update_pd_commands(c);
+        if (KP->n_eslot > 0) { bool ch = false; refresh_external_forces(c, 0.0, true, false, ch); }
         stage_from_accepted(c);
         rhs(c, false, &status);
         // forceMax > 1e5 guard (engine.cc:1310-1346)
@@ -331,6 +329,9 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
 
         while (tEnd - t >= STEPPER_MIN_TIMESTEP && !failed) {
             double tNext = t;
+            // impulse forces: active set + next breakpoint; profile forces: held values (engine.cc:1843-1917)
+            double tImpulseForceNext = D_INF;
+            if (KP->n_eslot > 0) tImpulseForceNext = refresh_external_forces(c, t, false, finitePeriod, hasDynamicsChanged);
             if (finitePeriod && opt.controller_update_period > D_EPS) {
                 if (period_hit(t, opt.controller_update_period)) {
                     // computeCommand (engine.cc:1920-1940): zero-order hold of the action, or the PD block
@@ -347,8 +348,8 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
             if (finitePeriod) {
                 double dtNextGlobal;
                 const double dtNextUpdatePeriod = supd - fmod(t, supd);
-                if (dtNextUpdatePeriod < SIMULATION_MIN_TIMESTEP) dtNextGlobal = dtNextUpdatePeriod + supd;
-                else dtNextGlobal = dtNextUpdatePeriod;
+                if (dtNextUpdatePeriod < SIMULATION_MIN_TIMESTEP) dtNextGlobal = fmin(dtNextUpdatePeriod + supd, tImpulseForceNext - t);
+                else dtNextGlobal = fmin(dtNextUpdatePeriod, tImpulseForceNext - t);
                 if (tEnd - t - STEPPER_MIN_TIMESTEP < dtNextGlobal) dtNextGlobal = tEnd - t;
                 tNext += dtNextGlobal;
                 while (tNext - t > STEPPER_MIN_TIMESTEP && !failed) {
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
                     try_step(isBreakpointReached);
                 }
             } else {
-                dt = fmin(dt, tEnd - t);
+                dt = fmin(fmin(dt, tEnd - t), tImpulseForceNext - t);
                 const bool isBreakpointReached = (dtLargest > dt);
                 bool isStepSuccessful = false;
                 while (!isStepSuccessful && !failed) {

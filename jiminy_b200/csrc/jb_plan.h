@@ -74,6 +74,19 @@ struct ContactSlot {  // per lane contact slot (rows[(c * L + s)])
     double force_p[3];
 };
 
+// External-force slot (Engine::registerImpulseForce / registerProfileForce): one per distinct frame
+// (parent joint, translation in the joint frame); rows[(e * L + s)].  `rec` is the record that applies the
+// slot's wrench on sub-lane s: the joint's record on its owning lane (on every lane for a trunk joint,
+// whose own bias force is replicated, not reduced), -1 elsewhere.
+struct ExtSlot {
+    double p[3];
+    int32_t rec;
+    int32_t joint;
+};
+constexpr int MAX_ESLOT = 4, MAX_IMPULSE = 16, MAX_PROFILE = 4;
+constexpr int ESLOT_SIZE = 12;   // wrench in world-aligned axes at the frame origin (6) | same wrench in the joint frame (6)
+constexpr int IMPULSE_ROWS = 8;  // t, dt, wrench[6]
+
 struct Plan {
     int L = 1;                 // lanes per env (1, 2, 4, 8)
     int nrec = 0;              // records per lane

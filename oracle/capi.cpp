@@ -51,6 +51,50 @@ void orc_set_springs(OrcBatch* b, const double* k, const double* d) {
     for (auto& e : b->envs) { e->spring_k.assign(k, k + b->nv); e->spring_d.assign(d, d + b->nv); }
 }
 
+// ---- external forces (Engine::register_impulse_force / register_profile_force / remove_all_forces / stop)
+void orc_stop(OrcBatch* b) { for (auto& e : b->envs) e->stop(); }
+int orc_register_impulse_force(OrcBatch* b, int joint, const double* p, const double* t, const double* dt, const double* F) {
+    int rc = 0;
+    for (size_t i = 0; i < b->envs.size(); ++i) {
+        const int r = b->envs[i]->registerImpulseForce(joint, p, t[i], dt[i], F + 6 * i);
+        if (r < 0) rc = r;
+    }
+    return rc < 0 ? rc : static_cast<int>(b->envs[0]->impulseForces.size()) - 1;
+}
+// rewrite impulse `k` of the envs selected by `mask` (what re-registering at an episode reset does)
+int orc_set_impulse_force(OrcBatch* b, int k, const uint8_t* mask, const double* t, const double* dt, const double* F) {
+    for (size_t i = 0; i < b->envs.size(); ++i) {
+        if (mask && !mask[i]) continue;
+        Engine& e = *b->envs[i];
+        if (k < 0 || k >= static_cast<int>(e.impulseForces.size())) return JB_ERR_INVALID_ARGUMENT;
+        if (dt[i] < orc::STEPPER_MIN_TIMESTEP || t[i] < 0.0) return JB_ERR_INVALID_ARGUMENT;
+        auto& f = e.impulseForces[k];
+        f.t = t[i]; f.dt = dt[i];
+        f.F = orc::Force{orc::V3(F[6 * i], F[6 * i + 1], F[6 * i + 2]), orc::V3(F[6 * i + 3], F[6 * i + 4], F[6 * i + 5])};
+        e.impulseForceBreakpoints.clear();
+        for (const auto& g : e.impulseForces) { e.impulseForceBreakpoints.push_back(g.t); e.impulseForceBreakpoints.push_back(g.t + g.dt); }
+        std::sort(e.impulseForceBreakpoints.begin(), e.impulseForceBreakpoints.end());
+        e.impulseForceBreakpoints.erase(std::unique(e.impulseForceBreakpoints.begin(), e.impulseForceBreakpoints.end()),
+                                        e.impulseForceBreakpoints.end());
+    }
+    return JB_OK;
+}
+int orc_register_profile_force(OrcBatch* b, int joint, const double* p, double update_period) {
+    int rc = 0;
+    for (auto& e : b->envs) rc = e->registerProfileForce(joint, p, update_period);
+    return rc;
+}
+int orc_set_profile_force(OrcBatch* b, int slot, const double* F) {
+    for (size_t i = 0; i < b->envs.size(); ++i) {
+        Engine& e = *b->envs[i];
+        if (slot < 0 || slot >= static_cast<int>(e.profileForces.size())) return JB_ERR_INVALID_ARGUMENT;
+        e.profileForces[slot].pending =
+            orc::Force{orc::V3(F[6 * i], F[6 * i + 1], F[6 * i + 2]), orc::V3(F[6 * i + 3], F[6 * i + 4], F[6 * i + 5])};
+    }
+    return JB_OK;
+}
+void orc_remove_all_forces(OrcBatch* b) { for (auto& e : b->envs) e->removeAllForces(); }
+
 // returns the number of envs whose start failed; rc[i] receives the per-env return code
 int orc_start(OrcBatch* b, const uint8_t* mask, const double* q0, const double* v0, int* rc) {
     int bad = 0;

@@ -93,9 +93,64 @@ void Engine::set_options(const JbOptions& o) {
     static_cast<JbOptions&>(opt) = o;
     // stepperUpdatePeriod_ = min strictly positive of the two periods (engine.cc:2699-2715, :2794)
     const double sp = o.sensors_update_period, cp = o.controller_update_period;
+    (void)sp; (void)cp;
+    refreshStepperUpdatePeriod();
+}
+
+// isGcdIncluded over the controller / sensor / profile-force periods (engine.cc:2492-2516, :2551-2562):
+// the caller guarantees they are multiples of each other, the breakpoint period is the smallest one.
+void Engine::refreshStepperUpdatePeriod() {
     stepperUpdatePeriod = INF;
-    if (sp > EPS) stepperUpdatePeriod = std::min(stepperUpdatePeriod, sp);
-    if (cp > EPS) stepperUpdatePeriod = std::min(stepperUpdatePeriod, cp);
+    if (opt.sensors_update_period > EPS) stepperUpdatePeriod = std::min(stepperUpdatePeriod, opt.sensors_update_period);
+    if (opt.controller_update_period > EPS) stepperUpdatePeriod = std::min(stepperUpdatePeriod, opt.controller_update_period);
+    for (const ProfileForce& pf : profileForces)
+        if (pf.updatePeriod > EPS) stepperUpdatePeriod = std::min(stepperUpdatePeriod, pf.updatePeriod);
+}
+
+// Engine::registerImpulseForce (engine.cc:2450-2491)
+int Engine::registerImpulseForce(int joint, const double* p, double tf, double dtf, const double* F) {
+    if (running) return JB_ERR_BAD_CONTROL_FLOW;
+    if (dtf < STEPPER_MIN_TIMESTEP || tf < 0.0 || joint <= 0 || joint >= model.njoints) return JB_ERR_INVALID_ARGUMENT;
+    ImpulseForce f{joint, V3(p[0], p[1], p[2]), tf, dtf, Force{V3(F[0], F[1], F[2]), V3(F[3], F[4], F[5])}, false};
+    impulseForces.push_back(f);
+    for (double b : {tf, tf + dtf}) {
+        auto it = std::lower_bound(impulseForceBreakpoints.begin(), impulseForceBreakpoints.end(), b);
+        if (it == impulseForceBreakpoints.end() || *it != b) impulseForceBreakpoints.insert(it, b);
+    }
+    return JB_OK;
+}
+
+// Engine::registerProfileForce (engine.cc:2518-2567); the force function is "return the caller's buffer"
+int Engine::registerProfileForce(int joint, const double* p, double updatePeriod) {
+    if (running) return JB_ERR_BAD_CONTROL_FLOW;
+    if (joint <= 0 || joint >= model.njoints) return JB_ERR_INVALID_ARGUMENT;
+    if (EPS < updatePeriod && updatePeriod < SIMULATION_MIN_TIMESTEP) return JB_ERR_INVALID_ARGUMENT;
+    profileForces.push_back(ProfileForce{joint, V3(p[0], p[1], p[2]), updatePeriod, Force{}, Force{}});
+    refreshStepperUpdatePeriod();
+    return static_cast<int>(profileForces.size()) - 1;
+}
+
+void Engine::removeAllForces() {
+    impulseForces.clear(); impulseForceBreakpoints.clear(); profileForces.clear();
+    refreshStepperUpdatePeriod();
+}
+
+// convertForceGlobalFrameToJoint (core/src/utilities/pinocchio.cc:794-809)
+Force Engine::convertForceGlobalFrameToJoint(int joint, const V3& p, const Force& F) const {
+    Force out;
+    out.lin = tmul(data.oMi[joint].R, F.lin);
+    out.ang = tmul(data.oMi[joint].R, F.ang) + cross(p, out.lin);
+    return out;
+}
+
+// Engine::computeExternalForces (engine.cc:3455-3495)
+void Engine::computeExternalForces(std::vector<Force>& fext) {
+    for (const ImpulseForce& f : impulseForces)
+        if (f.active) fext[f.joint] += convertForceGlobalFrameToJoint(f.joint, f.p, f.F);
+    for (ProfileForce& pf : profileForces) {
+        if (pf.updatePeriod < EPS) pf.force = pf.pending;   // profileForce.func(t, q, v)
+        fext[pf.joint] += convertForceGlobalFrameToJoint(pf.joint, pf.p, pf.force);
+    }
 }
 
 // ============================================================================ joint calc
@@ -246,7 +301,7 @@ void Engine::computeAllTerms(double /*t*/, const double* qv, const double* vv, b
     std::fill(state.uInternal.begin(), state.uInternal.end(), 0.0);
     computeInternalDynamics(qv, vv, state.uInternal);
     computeCollisionForces(state.fExternal, isStateUpToDate);
-    // computeExternalForces: impulse/profile forces are not part of the restated path
+    computeExternalForces(state.fExternal);
 }
 
 // Engine::computeCommand (engine.cc:3240-3251).  Without a functor the command buffer is a
@@ -829,6 +884,11 @@ int Engine::start(const double* q0, const double* v0) {
     std::fill(state.uTransmission.begin(), state.uTransmission.end(), 0.0);
     std::fill(state.uCustom.begin(), state.uCustom.end(), 0.0);
     std::fill(limitViolated.begin(), limitViolated.end(), false);
+    // impulse forces: breakpoint iterator, active set (engine.cc:1214-1238); a profile force with a
+    // finite update period is first evaluated by the first `step` (its value is zero until then)
+    impulseForceBreakpointNext = 0;
+    for (ImpulseForce& f : impulseForces) f.active = f.t < STEPPER_MIN_TIMESTEP;
+    for (ProfileForce& pf : profileForces) pf.force = Force{};
     forwardKinematics(state.q.data(), state.v.data(), state.a.data());
     double forceMax = 0.0;
     for (int c = 0; c < model.ncontacts; ++c) {
@@ -862,7 +922,7 @@ int Engine::start(const double* q0, const double* v0) {
 }
 
 // ============================================================================ step
-// Engine::step (engine.cc:1724-2417).  No impulse / profile forces, telemetry or timeout.
+// Engine::step (engine.cc:1724-2417).  No telemetry or timeout.
 int Engine::step(double stepSize) {
     if (!running) return JB_ERR_BAD_CONTROL_FLOW;
     for (double x : q) if (x != x) { status |= JB_ENV_NAN; return JB_ERR_RUNTIME; }
@@ -909,7 +969,30 @@ int Engine::step(double stepSize) {
 
     while (tEnd - t >= STEPPER_MIN_TIMESTEP) {
         double tNext = t;
-        const double tImpulseForceNext = INF;
+        // active set and next breakpoint of the impulse forces (engine.cc:1843-1890)
+        double tImpulseForceNext = INF;
+        for (ImpulseForce& f : impulseForces) {
+            if (t > f.t - STEPPER_MIN_TIMESTEP) { f.active = true; hasDynamicsChanged = true; }
+            if (t >= f.t + f.dt - STEPPER_MIN_TIMESTEP) { f.active = false; hasDynamicsChanged = true; }
+        }
+        while (impulseForceBreakpointNext < impulseForceBreakpoints.size() &&
+               impulseForceBreakpoints[impulseForceBreakpointNext] - t < STEPPER_MIN_TIMESTEP)
+            ++impulseForceBreakpointNext;
+        if (impulseForceBreakpointNext < impulseForceBreakpoints.size())
+            tImpulseForceNext = std::min(tImpulseForceNext, impulseForceBreakpoints[impulseForceBreakpointNext]);
+        // profile forces with a finite update period (engine.cc:1892-1917)
+        if (finitePeriod) {
+            for (ProfileForce& pf : profileForces) {
+                if (pf.updatePeriod > EPS) {
+                    const double dtNextForceUpdatePeriod = pf.updatePeriod - std::fmod(t, pf.updatePeriod);
+                    if (dtNextForceUpdatePeriod < SIMULATION_MIN_TIMESTEP ||
+                        pf.updatePeriod - dtNextForceUpdatePeriod < STEPPER_MIN_TIMESTEP) {
+                        pf.force = pf.pending;
+                        hasDynamicsChanged = true;
+                    }
+                }
+            }
+        }
         // Controller update (engine.cc:1920-1940)
         if (finitePeriod && opt.controller_update_period > EPS) {
             const double cp = opt.controller_update_period;

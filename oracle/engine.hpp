@@ -135,6 +135,23 @@ struct Engine {
     ControllerFn controller = nullptr;      // computeCommand functor (may be null: ZOH of `state.command`)
     InternalDynFn internalDyn = nullptr;    // internalDynamics functor
     void* ctx = nullptr;
+    // Engine::registerImpulseForce / registerProfileForce (engine.cc:2450-2567).  A frame is given by its
+    // parent joint and its translation in the joint frame (the wrench is expressed in world-aligned axes at
+    // the frame origin, so the frame rotation never matters).  A profile force holds the value its
+    // "function" (the caller's buffer, `pending`) returned at the last update.
+    struct ImpulseForce { int joint; V3 p; double t, dt; Force F; bool active = false; };
+    struct ProfileForce { int joint; V3 p; double updatePeriod; Force pending, force; };
+    std::vector<ImpulseForce> impulseForces;
+    std::vector<ProfileForce> profileForces;
+    std::vector<double> impulseForceBreakpoints;   // sorted, unique (std::set in the reference)
+    size_t impulseForceBreakpointNext = 0;
+    int registerImpulseForce(int joint, const double* p, double t, double dt, const double* F);
+    int registerProfileForce(int joint, const double* p, double updatePeriod);
+    void removeAllForces();
+    void refreshStepperUpdatePeriod();
+    Force convertForceGlobalFrameToJoint(int joint, const V3& p, const Force& F) const;
+    void computeExternalForces(std::vector<Force>& fext);
+
     std::vector<double> spring_k, spring_d; // built-in linear internal dynamics u = -k q - d v (1-dof joints)
     // built-in discrete PD controller (gym_jiminy PDController, order-0 target): command buffer = targets
     bool pd_enabled = false;

@@ -52,6 +52,12 @@ def lib():
         L.orc_set_callbacks.argtypes = [C.c_void_p, C.c_int, CONTROLLER_FN, CONTROLLER_FN, C.c_void_p]
         L.orc_set_springs.argtypes = [C.c_void_p, c_double_p, c_double_p]
         L.orc_set_pd.argtypes = [C.c_void_p, c_double_p, c_double_p]
+        L.orc_stop.argtypes = [C.c_void_p]
+        L.orc_register_impulse_force.argtypes = [C.c_void_p, C.c_int] + [c_double_p] * 4
+        L.orc_set_impulse_force.argtypes = [C.c_void_p, C.c_int, c_uint8_p] + [c_double_p] * 3
+        L.orc_register_profile_force.argtypes = [C.c_void_p, C.c_int, c_double_p, C.c_double]
+        L.orc_set_profile_force.argtypes = [C.c_void_p, C.c_int, c_double_p]
+        L.orc_remove_all_forces.argtypes = [C.c_void_p]
         L.orc_start.argtypes = [C.c_void_p, c_uint8_p, c_double_p, c_double_p, c_int32_p]
         L.orc_set_command.argtypes = [C.c_void_p, c_double_p]
         L.orc_step.argtypes = [C.c_void_p, C.c_double, C.c_int, c_int32_p]
@@ -106,6 +112,44 @@ class OracleBatch:
         kp = np.ascontiguousarray(np.broadcast_to(kp, (self.nm,)), dtype=np.float64)
         kd = np.ascontiguousarray(np.broadcast_to(kd, (self.nm,)), dtype=np.float64)
         lib().orc_set_pd(self._h, dptr(kp), dptr(kd))
+
+    # ---- external forces: same calling convention as jiminy_b200.core.BatchedEngine
+    def stop(self) -> None:
+        lib().orc_stop(self._h)
+
+    def _per_env(self, x, shape):
+        return np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), (self.n,) + shape))
+
+    def register_impulse_force(self, joint: int, p, t, dt, force) -> int:
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        t, dt, force = self._per_env(t, ()), self._per_env(dt, ()), self._per_env(force, (6,))
+        rc = lib().orc_register_impulse_force(self._h, int(joint), dptr(p), dptr(t), dptr(dt), dptr(force))
+        if rc < 0:
+            raise ValueError(f"register_impulse_force failed ({rc})")
+        return rc
+
+    def set_impulse_force(self, k: int, t, dt, force, mask=None) -> None:
+        t, dt, force = self._per_env(t, ()), self._per_env(dt, ()), self._per_env(force, (6,))
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        rc = lib().orc_set_impulse_force(self._h, int(k), None if m is None else m.ctypes.data_as(c_uint8_p),
+                                         dptr(t), dptr(dt), dptr(force))
+        if rc < 0:
+            raise ValueError(f"set_impulse_force failed ({rc})")
+
+    def register_profile_force(self, joint: int, p, update_period: float = 0.0) -> int:
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        rc = lib().orc_register_profile_force(self._h, int(joint), dptr(p), float(update_period))
+        if rc < 0:
+            raise ValueError(f"register_profile_force failed ({rc})")
+        return rc
+
+    def set_profile_force(self, slot: int, force) -> None:
+        force = self._per_env(force, (6,))
+        if lib().orc_set_profile_force(self._h, int(slot), dptr(force)) < 0:
+            raise ValueError("set_profile_force failed")
+
+    def remove_all_forces(self) -> None:
+        lib().orc_remove_all_forces(self._h)
 
     def set_callbacks(self, env: int, controller: Optional[Callable] = None,
                       internal_dynamics: Optional[Callable] = None) -> None:

@@ -4,6 +4,7 @@ oracle with the same physics -- here no oracle is involved at all: CUDA result v
 import os
 
 import numpy as np
+import scipy.integrate
 import scipy.linalg
 
 from jiminy_b200 import model as M
@@ -97,3 +98,59 @@ def energy_conservation(api=None):
         eng.step(0.02)
     e1 = eng.get_extra_terms()[0].sum(axis=1)
     np.testing.assert_allclose(e1, e0, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------
+# test_simple_pendulum.py:540-660: impulse forces are integration breakpoints, impulse-momentum theorem
+IMPULSES = [
+    dict(t=0.0, dt=2.0e-3, F=[1.0e3, 0.0, 0.0, 0.0, 0.0, 0.0]),
+    dict(t=0.1, dt=1.0e-3, F=[0.0, 1.0e3, 0.0, 0.0, 0.0, 0.0]),
+    dict(t=0.2, dt=2.0e-5, F=[-1.0e5, 0.0, 0.0, 0.0, 0.0, 0.0]),
+    dict(t=0.2, dt=2.0e-4, F=[0.0, 0.0, 1.0e4, 0.0, 0.0, 0.0]),
+    dict(t=0.4, dt=1.0e-5, F=[0.0, 0.0, 0.0, 0.0, 2.0e4, 0.0]),
+    dict(t=0.4, dt=1.0e-5, F=[1.0e3, 1.0e4, 3.0e4, 0.0, 0.0, 0.0]),
+    dict(t=0.6, dt=1.0e-6, F=[0.39e6, 1.72e6, 0.82e6, 0.36e6, -0.61e6, 1.17e6]),
+    dict(t=0.8, dt=2.0e-6, F=[0.0, 0.0, 2.0e5, 0.0, 0.0, 0.0]),
+]
+
+
+def pendulum_impulse_reference(ts, m=5.0, l=1.0):
+    """Independent solution of the gravity-free pendulum under the piecewise-constant wrenches above:
+    ddq = (l F . d(q) + tau_y) / (m l^2), d(q) = (cos q, 0, -sin q), integrated segment by segment between
+    consecutive force breakpoints with a tight-tolerance scipy solver."""
+    brk = sorted({0.0, float(ts[-1])} | {f["t"] for f in IMPULSES} | {f["t"] + f["dt"] for f in IMPULSES})
+    brk = [b for b in brk if b <= ts[-1] + 1e-12]
+    out = np.zeros((len(ts), 2))
+    x = np.zeros(2)
+    for t0, t1 in zip(brk[:-1], brk[1:]):
+        tm = 0.5 * (t0 + t1)
+        act = [f for f in IMPULSES if f["t"] <= tm < f["t"] + f["dt"]]
+        F = np.sum([f["F"] for f in act], axis=0) if act else np.zeros(6)
+
+        def rhs(_t, y):
+            d = np.array([np.cos(y[0]), 0.0, -np.sin(y[0])])
+            return [y[1], (l * F[:3].dot(d) + F[4]) / (m * l * l)]
+        sel = np.where((ts > t0 - 1e-13) & (ts <= t1 + 1e-13))[0]
+        sol = scipy.integrate.solve_ivp(rhs, (t0, t1), x, method="DOP853", rtol=1e-13, atol=1e-13,
+                                        t_eval=np.clip(ts[sel], t0, t1) if len(sel) else None, dense_output=False)
+        if len(sel):
+            out[sel] = sol.y.T
+        x = scipy.integrate.solve_ivp(rhs, (t0, t1), x, method="DOP853", rtol=1e-13, atol=1e-13).y[:, -1]
+    return out
+
+
+def force_impulse(api=None):
+    """Gravity-free pendulum under the impulse forces above, continuous and discrete (1 ms) scheduling, plus a
+    second env whose impulses are shifted and scaled (per-env schedules)."""
+    r = M.build_robot_table(os.path.join(DATA, "simple_pendulum.urdf"), False)
+    for period in (0.0, 1e-3):
+        opt = _opt(sensorsUpdatePeriod=period, controllerUpdatePeriod=period)
+        opt["world"]["gravity"] = [0.0] * 6
+        eng = BatchedEngine(r, opt, 2, api_=api)
+        for f in IMPULSES:
+            eng.register_impulse_force("PendulumLink", [f["t"], f["t"]], f["dt"], np.array([f["F"], [0.0] * 6]))
+        ts, qs, vs, _ = eng.simulate(1.0, np.zeros((2, 1)), np.zeros((2, 1)))
+        xa = pendulum_impulse_reference(ts[:, 0])
+        np.testing.assert_allclose(np.c_[qs[:, 0], vs[:, 0]], xa, atol=1e-6)
+        np.testing.assert_allclose(np.c_[qs[:, 1], vs[:, 1]], 0.0, atol=1e-12)   # env 1: zero wrenches
+        assert np.abs(vs[:, 0]).max() > 0.1

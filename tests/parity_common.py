@@ -75,3 +75,69 @@ def compare_extra_terms(eng, orc, tol=1e-9):
     np.testing.assert_allclose(e1, e0, rtol=0, atol=tol * max(1.0, np.abs(e0).max()))
     np.testing.assert_allclose(a1, a0, rtol=0, atol=tol * max(1.0, np.abs(a0).max()))
     np.testing.assert_allclose(f1, f0, rtol=0, atol=tol * max(1.0, np.abs(f0).max()))
+
+
+def _force_pair(sc, api):
+    eng = BatchedEngine(sc.robot, sc.options, sc.n_env, api_=api)
+    orc = OracleBatch(sc.robot, sc.options, sc.n_env)
+    if sc.kp is not None:
+        eng.set_pd_controller(sc.kp, sc.kd)
+        orc.set_pd_controller(sc.kp, sc.kd)
+    return eng, orc
+
+
+def external_forces_scenario(api, n_env=6, n_steps=3, solver="runge_kutta_4", tol=1e-9):
+    """Impulse forces with per-env schedules on the base (trunk joint) and on a shank (private joint, off-origin
+    frame), a sampled profile force (finite update period) and a continuous one: Engine::computeExternalForces
+    + the breakpoint handling of Engine::step, against the oracle."""
+    sc = scenarios.make("anymal", n_env, seed=3, solver=solver)
+    eng, orc = _force_pair(sc, api)
+    rng = np.random.default_rng(5)
+    rob = sc.robot
+    base = rob.frames["base"] if "base" in rob.frames else rob.frames["root_joint"]
+    shank_name = next(n for n in rob.frames if "SHANK" in n.upper())
+    shank = rob.frames[shank_name]
+    imp = [
+        ((base.joint, base.placement.p), rng.uniform(0.0, 0.05, n_env), rng.uniform(2e-3, 2e-2, n_env), rng.normal(size=(n_env, 6)) * 200.0),
+        ((base.joint, base.placement.p), np.zeros(n_env), np.full(n_env, 7e-3), rng.normal(size=(n_env, 6)) * 100.0),
+        ((shank.joint, shank.placement.p + [0.0, 0.0, -0.1]), rng.uniform(0.03, 0.09, n_env), rng.uniform(1e-3, 3e-2, n_env), rng.normal(size=(n_env, 6)) * 50.0),
+    ]
+    for fr, t, dt, F in imp:
+        k1 = eng.register_impulse_force(fr, t, dt, F)
+        k0 = orc.register_impulse_force(fr[0], fr[1], t, dt, F)
+        assert k1 == k0
+    s_eng = [eng.register_profile_force((base.joint, base.placement.p), 0.01), eng.register_profile_force(shank_name, 0.0)]
+    s_orc = [orc.register_profile_force(base.joint, base.placement.p, 0.01), orc.register_profile_force(shank.joint, shank.placement.p, 0.0)]
+    assert s_eng == s_orc
+    for x in (eng, orc):
+        x.set_command(sc.target0)
+    w0, w1 = rng.normal(size=(n_env, 6)) * 30.0, rng.normal(size=(n_env, 6)) * 20.0
+    for x, sl in ((eng, s_eng), (orc, s_orc)):
+        x.set_profile_force(sl[0], w0)
+        x.set_profile_force(sl[1], w1)
+    eng.start(sc.q0, sc.v0)
+    assert not orc.start(sc.q0, sc.v0).any()
+    compare(eng, orc, 1e-13, 1e-12)
+    np.testing.assert_allclose(eng.get_efforts()[3], orc.get_efforts()[3], rtol=0, atol=1e-9)
+    for k in range(n_steps):
+        act = sc.sample_targets(k)
+        w0, w1 = rng.normal(size=(n_env, 6)) * 30.0, rng.normal(size=(n_env, 6)) * 20.0
+        for x, sl in ((eng, s_eng), (orc, s_orc)):
+            x.set_command(act)
+            x.set_profile_force(sl[0], w0)
+            x.set_profile_force(sl[1], w1)
+        eng.step(sc.step_dt)
+        assert not orc.step(sc.step_dt, parallel=True).any()
+        compare(eng, orc, tol, 100 * tol)
+        np.testing.assert_allclose(eng.get_efforts()[3], orc.get_efforts()[3], rtol=0, atol=1e-7)
+    # the forces did something: the same run without them ends elsewhere
+    q_with = eng.get_state()[1]
+    eng.stop()
+    eng.remove_all_forces()
+    eng.set_command(sc.target0)
+    eng.start(sc.q0, sc.v0)
+    for k in range(n_steps):
+        eng.set_command(sc.sample_targets(k))
+        eng.step(sc.step_dt)
+    assert np.abs(eng.get_state()[1] - q_with).max() > 1e-4
+    return eng, orc

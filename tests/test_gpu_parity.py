@@ -134,3 +134,9 @@ def test_cuda_path_vs_closed_forms():
     ad.two_masses()
     ad.contact_equilibrium_and_friction()
     ad.energy_conservation()
+    ad.force_impulse()
+
+
+def test_external_forces_match_oracle():
+    """Impulse + profile forces (Engine::computeExternalForces, impulse breakpoints) on 70 ANYmal envs."""
+    pc.external_forces_scenario(None, n_env=70, n_steps=4)

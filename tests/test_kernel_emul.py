@@ -281,3 +281,67 @@ def test_device_code_vs_closed_forms(api):
     ad.two_masses(api)
     ad.contact_equilibrium_and_friction(api)
     ad.energy_conservation(api)
+    ad.force_impulse(api)
+
+
+def test_external_forces_anymal(api):
+    pc.external_forces_scenario(api)
+
+
+def test_external_forces_control_flow(api):
+    sc = scenarios.make("cartpole", 2)
+    eng = BatchedEngine(sc.robot, sc.options, 2, api_=api)
+    with pytest.raises(ValueError):
+        eng.register_impulse_force("universe", 0.0, 1e-3, np.zeros(6))
+    with pytest.raises(ValueError):
+        eng.register_impulse_force("no_such_frame", 0.0, 1e-3, np.zeros(6))
+    fr = next(n for n, f in sc.robot.frames.items() if f.joint > 0)
+    with pytest.raises(ValueError):
+        eng.register_impulse_force(fr, 0.0, 1e-12, np.zeros(6))       # duration below STEPPER_MIN_TIMESTEP
+    with pytest.raises(ValueError):
+        eng.register_impulse_force(fr, -1.0, 1e-3, np.zeros(6))
+    eng.set_command(sc.target0)
+    eng.start(sc.q0, sc.v0)
+    from jiminy_b200.core import BadControlFlow
+    with pytest.raises(BadControlFlow):
+        eng.register_impulse_force(fr, 0.0, 1e-3, np.zeros(6))
+    with pytest.raises(BadControlFlow):
+        eng.remove_all_forces()
+    eng.stop()
+    assert (eng.get_status() & 16).all()
+    eng.register_impulse_force(fr, 0.0, 1e-3, np.zeros(6))
+    eng.remove_all_forces()
+
+
+def test_engine_facade_impulse_forces(api):
+    """`Engine.register_impulse_force(robot_name, frame_name, t, dt, F)` + `simulate`, read like
+    test_simple_pendulum.py:540-605 (first three forces, 0.25 s)."""
+    import analytic_device as ad
+    from jiminy_b200.core import Engine, BadControlFlow
+    robot = M.build_robot_table(os.path.join(DATA, "simple_pendulum.urdf"), False)
+    engine = Engine(api_=api)
+    engine.add_robot(robot)
+    opt = engine.get_options()
+    opt["world"]["gravity"] = np.zeros(6)
+    opt["stepper"].update(sensorsUpdatePeriod=0.0, controllerUpdatePeriod=0.0)
+    engine.set_options(opt)
+    for f in ad.IMPULSES:
+        engine.register_impulse_force("", "PendulumLink", f["t"], f["dt"], np.array(f["F"]))
+    with pytest.raises(ValueError):
+        engine.register_impulse_force("", "universe", 0.0, 1e-3, np.zeros(6))
+    engine.start(np.zeros(1), np.zeros(1))
+    with pytest.raises(BadControlFlow):
+        engine.register_impulse_force("", "PendulumLink", 0.0, 1e-3, np.zeros(6))
+    ts, xs = [], []
+    while engine.stepper_state.t < 0.25 - 1e-9:
+        engine.step(1e-3)
+        ts.append(engine.stepper_state.t)
+        xs.append([engine.robot_states[0].q[0], engine.robot_states[0].v[0]])
+    xa = ad.pendulum_impulse_reference(np.array(ts))
+    np.testing.assert_allclose(np.array(xs), xa, atol=1e-6)
+    engine.stop()
+    engine.reset(remove_all_forces=True)
+    assert engine.impulse_forces == []
+    engine.start(np.zeros(1), np.zeros(1))
+    engine.step(0.01)
+    assert abs(engine.robot_states[0].v[0]) < 1e-14

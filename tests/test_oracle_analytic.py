@@ -223,3 +223,24 @@ def test_step_scheduler_microsecond_first_step_and_iters():
     o.step(0.04)
     assert o.get_iters()[0][0] == 81
     np.testing.assert_allclose(o.get_state()[0][0], 0.08, atol=1e-15)
+
+
+# ---------------------------------------------------------------------------------------------
+# 8. unit_py/test_simple_pendulum.py:540-660 .......... impulse forces: breakpoints + impulse-momentum
+from analytic_device import IMPULSES, pendulum_impulse_reference  # noqa: E402
+
+
+@pytest.mark.parametrize("period", [0.0, 1e-3])
+def test_pendulum_force_impulse(period):
+    r = _pendulum()
+    opt = _opt(sensorsUpdatePeriod=period, controllerUpdatePeriod=period)
+    opt["world"]["gravity"] = [0.0] * 6
+    o = OracleBatch(r, opt)
+    fr = r.frames["PendulumLink"]
+    for f in IMPULSES:
+        o.register_impulse_force(fr.joint, fr.placement.p, f["t"], f["dt"], f["F"])
+    ts, qs, vs, _ = o.simulate(1.0, [0.0], [0.0])
+    xa = pendulum_impulse_reference(ts)
+    np.testing.assert_allclose(np.c_[qs, vs], xa, atol=1e-6)
+    # without breakpoints at t and t + dt a 1 us, 1e6 N impulse would be mis-integrated by orders of magnitude
+    assert np.abs(vs).max() > 0.1 and abs(qs[-1, 0]) > 0.01
