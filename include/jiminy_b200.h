@@ -38,12 +38,12 @@ extern "C" {
 #define JB_ENV_NAN 1              /* NaN in (q, v, a): "Low-level ode solver failed"                */
 #define JB_ENV_ITER_FAILED 2      /* too many successive failed inner iterations                    */
 #define JB_ENV_DT_UNDERFLOW 4     /* "The internal time step is getting too small"                  */
-#define JB_ENV_JOINT_LIMIT 8      /* a bounded joint left [lo, hi]: the reference would switch this
-                                     env to the JointConstraint/PGS path (engine.cc:3285-3293), which
-                                     this round does not implement; the env keeps integrating with
-                                     ABA and is flagged                                             */
+#define JB_ENV_JOINT_LIMIT 8      /* informational, sticky: a bounded joint left [lo, hi] at some point,
+                                     i.e. its JointConstraint was enabled (engine.cc:3285-3293)     */
 #define JB_ENV_NOT_STARTED 16     /* env has never been started (jb_start not called on it)         */
 #define JB_ENV_CONTACT_FORCE 32   /* jb_start: initial contact force > 1e5 N (engine.cc:1338-1345)  */
+#define JB_ENV_SOLVER_FAILED 64   /* "Too many successive constraint solving failures" (engine.cc:2363-2372) */
+#define JB_ENV_CONSTRAINT_OVERFLOW 128 /* more constraint rows enabled at once than the batch was sized for */
 
 /* ---------------------------------------------------------------- joint model types --- */
 /* Pinocchio 2.7 joint models produced by its URDF parser. */
@@ -118,11 +118,13 @@ typedef struct JbModelDesc {
 /* ---------------------------------------------------------------- engine options ------ */
 /* The subset of `Engine::EngineOptions` (core/include/jiminy/core/engine/engine.h:260-353) the
  * step path reads.  Defaults: jb_default_options(). */
+enum { JB_CONTACT_SPRING_DAMPER = 0, JB_CONTACT_CONSTRAINT = 1 };
+
 typedef struct JbOptions {
     int32_t ode_solver;               /* stepper.odeSolver, JB_SOLVER_*                           */
     int32_t successive_iter_failed_max; /* stepper.successiveIterFailedMax (1000)                 */
     int32_t iter_max;                 /* stepper.iterMax (0 = unlimited), reserved                */
-    int32_t reserved0;
+    int32_t contact_model;            /* contacts.model: JB_CONTACT_SPRING_DAMPER / JB_CONTACT_CONSTRAINT */
     double tol_abs, tol_rel;          /* stepper.tolAbs / tolRel                                  */
     double dt_max;                    /* stepper.dtMax                                            */
     double dt_restore_threshold_rel;  /* stepper.dtRestoreThresholdRel                            */
@@ -134,6 +136,9 @@ typedef struct JbOptions {
     double contact_transition_eps;    /* contacts.transitionEps                                   */
     double contact_transition_velocity; /* contacts.transitionVelocity                            */
     double gravity[6];                /* world.gravity (only the linear part acts)                */
+    double contact_torsion;           /* contacts.torsion (constraint model)                      */
+    double contact_stabilization_freq; /* contacts.stabilizationFreq: Baumgarte frequency [Hz]    */
+    double constraint_regularization; /* constraints.regularization (PGS diagonal damping)        */
 } JbOptions;
 
 typedef struct JbBatch JbBatch;

@@ -39,13 +39,15 @@ class JbModelDesc(C.Structure):
 class JbOptions(C.Structure):
     _fields_ = [
         ("ode_solver", C.c_int32), ("successive_iter_failed_max", C.c_int32),
-        ("iter_max", C.c_int32), ("reserved0", C.c_int32),
+        ("iter_max", C.c_int32), ("contact_model", C.c_int32),
         ("tol_abs", C.c_double), ("tol_rel", C.c_double), ("dt_max", C.c_double),
         ("dt_restore_threshold_rel", C.c_double),
         ("sensors_update_period", C.c_double), ("controller_update_period", C.c_double),
         ("contact_stiffness", C.c_double), ("contact_damping", C.c_double),
         ("contact_friction", C.c_double), ("contact_transition_eps", C.c_double),
         ("contact_transition_velocity", C.c_double), ("gravity", C.c_double * 6),
+        ("contact_torsion", C.c_double), ("contact_stabilization_freq", C.c_double),
+        ("constraint_regularization", C.c_double),
     ]
 
 
@@ -55,6 +57,7 @@ class JbSensorLayout(C.Structure):
 
 
 SOLVERS = {"euler_explicit": 0, "runge_kutta_4": 1, "runge_kutta_dopri": 2}
+CONTACT_MODELS = {"spring_damper": 0, "constraint": 1}
 
 
 def _d(a) -> np.ndarray:
@@ -135,11 +138,15 @@ class ModelDescHolder:
 def make_options(opt: Dict[str, Any]) -> JbOptions:
     """Engine option dict (reference layout, `Engine.get_options()`) -> JbOptions."""
     st, ct, world = opt["stepper"], opt["contacts"], opt["world"]
-    if ct["model"] != "spring_damper":
-        raise NotImplementedError(
-            "Only contacts.model='spring_damper' is on the accelerated path; the 'constraint' (PGS) "
-            "model is a later scope row (SURVEY.md 8f-1).")
+    if ct["model"] not in CONTACT_MODELS:
+        raise ValueError(f"Requested contact model '{ct['model']}' not available.")
+    if opt.get("constraints", {}).get("solver", "PGS") != "PGS":
+        raise ValueError("Requested constraint solver not available.")
     o = JbOptions()
+    o.contact_model = CONTACT_MODELS[ct["model"]]
+    o.contact_torsion = float(ct.get("torsion", 0.0))
+    o.contact_stabilization_freq = float(ct.get("stabilizationFreq", 20.0))
+    o.constraint_regularization = float(opt.get("constraints", {}).get("regularization", 1e-3))
     o.ode_solver = SOLVERS[st["odeSolver"]]
     o.successive_iter_failed_max = int(st["successiveIterFailedMax"])
     o.iter_max = int(st.get("iterMax", 0))

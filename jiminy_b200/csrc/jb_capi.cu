@@ -156,9 +156,15 @@ void jb_default_options(JbOptions* o) {
     o->contact_stiffness = 1e6; o->contact_damping = 2e3; o->contact_friction = 1.0;
     o->contact_transition_eps = 1e-3; o->contact_transition_velocity = 1e-2;
     o->gravity[2] = -9.81;
+    o->contact_model = JB_CONTACT_SPRING_DAMPER;
+    o->contact_torsion = 0.0; o->contact_stabilization_freq = 20.0; o->constraint_regularization = 1e-3;
 }
 
 static int check_options(const JbOptions* o) {
+    if (o->contact_model != JB_CONTACT_SPRING_DAMPER && o->contact_model != JB_CONTACT_CONSTRAINT)
+        return fail(JB_ERR_INVALID_ARGUMENT, "unknown contact model");
+    if (o->contact_model == JB_CONTACT_CONSTRAINT)
+        return fail(JB_ERR_NOT_IMPLEMENTED, "contacts.model = 'constraint' is not on the device path yet");
     if (o->ode_solver < JB_SOLVER_EULER_EXPLICIT || o->ode_solver > JB_SOLVER_RUNGE_KUTTA_DOPRI)
         return fail(JB_ERR_INVALID_ARGUMENT, "unknown ODE solver");
     if (!(o->dt_max >= 1e-6 - 1e-16 && o->dt_max <= 0.02 + 1e-16)) return fail(JB_ERR_INVALID_ARGUMENT, "'dtMax' option is out of range.");

@@ -79,7 +79,7 @@ Engine::Engine(const JbModelDesc& d, const JbOptions& o) : model(make_model(d)) 
     contactForcesPrev.assign(model.ncontacts, Force{});
     fPrev.assign(n, Force{}); aPrev.assign(n, Motion{}); fExtBuffer.assign(n, Force{});
     sensors.assign(model.layout.width, 0.0);
-    limitViolated.assign(n, false);
+    buildConstraints();
     spring_k.assign(nv, 0.0); spring_d.assign(nv, 0.0);
     ki.resize(7);
     for (auto& k : ki) { k.v.assign(nv, 0.0); k.a.assign(nv, 0.0); }
@@ -274,25 +274,19 @@ void Engine::computeContactDynamicsAtFrame(int c, Force& fextLocal) const {
 void Engine::computeCollisionForces(std::vector<Force>& fext, bool isStateUpToDate) {
     for (int c = 0; c < model.ncontacts; ++c) {
         Force& fextLocal = contactFrameForces[c];
-        if (!isStateUpToDate) computeContactDynamicsAtFrame(c, fextLocal);
+        if (!isStateUpToDate) {
+            if (opt.contact_model == JB_CONTACT_CONSTRAINT) updateContactConstraint(c);
+            else computeContactDynamicsAtFrame(c, fextLocal);
+        }
         fext[model.contact_joint[c]] += fextLocal;
         contactForces[c] = act_inv(model.contact_placement[c], fextLocal);
     }
 }
 
-// Engine::computeInternalDynamics (engine.cc:3340-3392): only the bound check; an out-of-bounds
-// joint would enable a JointConstraint and leave the ABA path (engine.cc:3285-3293, :3722).
-// That path is not restated: the env is flagged (JB_ENV_JOINT_LIMIT) and keeps using ABA.
+// Engine::computeInternalDynamics (engine.cc:3340-3392): joint position bounds -> JointConstraint
+// enable / disable (flexibility joints are outside the path)
 void Engine::computeInternalDynamics(const double* qv, const double* /*vv*/, std::vector<double>& /*uInternal*/) {
-    for (int i = 1; i < model.njoints; ++i) {
-        const int t = model.jtype[i];
-        if (t == JB_JOINT_FREEFLYER || Model::is_unbounded(t)) continue;
-        const double qJoint = qv[model.idx_q[i]];
-        const double lo = model.q_lower[model.idx_q[i]], hi = model.q_upper[model.idx_q[i]];
-        const double eps = opt.contact_transition_eps;
-        if (hi < qJoint || qJoint < lo) { limitViolated[i] = true; status |= JB_ENV_JOINT_LIMIT; }
-        else if (lo + eps < qJoint && qJoint < hi - eps) limitViolated[i] = false;
-    }
+    updateJointBoundConstraints(qv);
 }
 
 // Engine::computeAllTerms (engine.cc:3538-3583)
@@ -564,7 +558,7 @@ void Engine::computeRobotsDynamics(double tt, const double* qv, const double* vv
     computeCustom(tt, qv, vv);
     for (int k = 0; k < model.nv; ++k) state.u[k] = state.uInternal[k] + state.uCustom[k];
     for (int m = 0; m < model.nmotors; ++m) state.u[model.idx_v[model.motor_joint[m]]] += state.uTransmission[m];
-    aOutV = aba(qv, vv, state.u, state.fExternal);
+    aOutV = computeAcceleration(qv, vv, state.u, state.fExternal, isStateUpToDate, false);
 }
 
 // computeExtraTerms (engine.cc:800-905): energies, true joint accelerations `data.a`, joint
@@ -883,18 +877,20 @@ int Engine::start(const double* q0, const double* v0) {
     std::fill(state.uMotor.begin(), state.uMotor.end(), 0.0);
     std::fill(state.uTransmission.begin(), state.uTransmission.end(), 0.0);
     std::fill(state.uCustom.begin(), state.uCustom.end(), 0.0);
-    std::fill(limitViolated.begin(), limitViolated.end(), false);
     // impulse forces: breakpoint iterator, active set (engine.cc:1214-1238); a profile force with a
     // finite update period is first evaluated by the first `step` (its value is zero until then)
     impulseForceBreakpointNext = 0;
     for (ImpulseForce& f : impulseForces) f.active = f.t < STEPPER_MIN_TIMESTEP;
     for (ProfileForce& pf : profileForces) pf.force = Force{};
     forwardKinematics(state.q.data(), state.v.data(), state.a.data());
+    resetConstraints(state.q.data());
     double forceMax = 0.0;
     for (int c = 0; c < model.ncontacts; ++c) {
         contactFrameForces[c] = Force{};
-        computeContactDynamicsAtFrame(c, contactFrameForces[c]);
-        forceMax = std::max(forceMax, norm(contactFrameForces[c].lin));
+        if (opt.contact_model == JB_CONTACT_SPRING_DAMPER) {
+            computeContactDynamicsAtFrame(c, contactFrameForces[c]);
+            forceMax = std::max(forceMax, norm(contactFrameForces[c].lin));
+        }
     }
     if (forceMax > 1e5) { status |= JB_ENV_CONTACT_FORCE; return JB_ERR_INVALID_ARGUMENT; }
     running = true;
@@ -904,7 +900,7 @@ int Engine::start(const double* q0, const double* v0) {
     for (int i = 0; i < INIT_ITERATIONS; ++i) {
         state.fExternal = fextNoConst;
         state.uInternal = uInternalConst;
-        state.a = aba(state.q.data(), state.v.data(), state.u, state.fExternal);
+        state.a = computeAcceleration(state.q.data(), state.v.data(), state.u, state.fExternal, i > 0, i == 0);
         for (double x : state.a) if (x != x) { status |= JB_ENV_NAN; return JB_ERR_RUNTIME; }
         computeExtraTerms();
         computeSensorMeasurements(state.q.data(), state.v.data(), state.uMotor);
@@ -960,11 +956,13 @@ int Engine::step(double stepSize) {
         dtLargestPrev = dtLargest;
         statePrev = state;
     };
+    uint32_t successiveSolveFailedBackup = successiveSolveFailed;   // engine.cc:2104-2112, :2245-2252
     auto onFailure = [&]() {
         if (rc == IS_ERROR) dtLargest *= 0.1;
         if (rc == IS_FAILURE) ++successiveIterTooLarge;
         ++successiveIterFailed;
         ++iterFailed;
+        successiveSolveFailed = successiveSolveFailedBackup;       // engine.cc:2211-2217
     };
 
     while (tEnd - t >= STEPPER_MIN_TIMESTEP) {
@@ -1039,6 +1037,7 @@ int Engine::step(double stepSize) {
                         dt -= dtResidual;
                 }
                 if (successiveIterFailed > failedMax) break;
+                successiveSolveFailedBackup = successiveSolveFailed;
                 isBreakpointReached = (dtLargest > dt);
                 dtLargest = dt;
                 rc = tryStep(t, dtLargest);
@@ -1051,6 +1050,7 @@ int Engine::step(double stepSize) {
             bool isStepSuccessful = false;
             while (!isStepSuccessful) {
                 if (successiveIterFailed > failedMax) break;
+                successiveSolveFailedBackup = successiveSolveFailed;
                 dtLargest = dt;
                 rc = tryStep(t, dtLargest);
                 isStepSuccessful = (rc == IS_SUCCESS);
@@ -1059,6 +1059,7 @@ int Engine::step(double stepSize) {
             }
         }
         if (successiveIterFailed > failedMax) { status |= JB_ENV_ITER_FAILED; return JB_ERR_RUNTIME; }
+        if (successiveSolveFailed > failedMax) { status |= JB_ENV_SOLVER_FAILED; return JB_ERR_RUNTIME; }
         if (dt < STEPPER_MIN_TIMESTEP) { status |= JB_ENV_DT_UNDERFLOW; return JB_ERR_RUNTIME; }
         // Sensors update (engine.cc:2386-2410)
         const double sp = opt.sensors_update_period;

@@ -130,7 +130,39 @@ struct Engine {
     std::vector<Motion> aPrev;
     std::vector<Force> fExtBuffer;          // `fPrev_` argument of computeExtraTerms used as fExt buffer
     std::vector<double> sensors;
-    std::vector<bool> limitViolated;        // joint-bound constraint enable flags (detect only)
+    // ---- kinematic constraints (oracle/constraints.cpp)
+    struct Constraint {
+        int kind = 0;          // 0: JointConstraint (bounds), 1: FrameConstraint {x, y, z, rot z} (contact frame)
+        int joint = 0, contact = -1, dim = 1;
+        bool enabled = false;
+        double kp = 0.0, kd = 0.0;                  // Baumgarte gains
+        double lambda[4] = {0, 0, 0, 0};
+        double qRef = 0.0; bool reversed = false;   // JointConstraint
+        SE3 transformRef = SE3::identity(); V3 normal; M3 rotationLocal = M3::identity();   // FrameConstraint
+        std::vector<double> jac;                    // dim x nv
+        double drift[4] = {0, 0, 0, 0};
+        int startIndex = 0;
+    };
+    std::vector<Constraint> constraints;
+    int rowsMax = 0;
+    uint32_t successiveSolveFailed = 0;
+    int64_t pgsIterations = 0;
+    std::vector<double> Mmat, Mchol, Jworld, nle, torqueResidual;
+    std::vector<Motion> aDrift;
+    std::vector<double> solverJ, solverGamma, solverLambda, solverB, solverY, solverYPrev, solverA;
+    void buildConstraints();
+    bool hasConstraints() const;
+    void resetConstraints(const double* q);
+    void updateJointBoundConstraints(const double* q);
+    void updateContactConstraint(int contact);
+    void computeCrba();
+    void computeNle();
+    void computeConstraints(const double* q, const double* v);
+    void pgsIter(int m, const std::vector<double>& A, const double* b, double w, double* x);
+    bool pgsSolve(int m, const std::vector<double>& A, const double* b, double* x);
+    bool solveBoxedForwardDynamics(double dampingInv, bool isStateUpToDate, bool ignoreBounds);
+    const std::vector<double>& computeAcceleration(const double* q, const double* v, std::vector<double>& u,
+                                                   std::vector<Force>& fext, bool isStateUpToDate, bool ignoreBounds);
 
     ControllerFn controller = nullptr;      // computeCommand functor (may be null: ZOH of `state.command`)
     InternalDynFn internalDyn = nullptr;    // internalDynamics functor

@@ -24,7 +24,7 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("engine.cpp", "capi.cpp", "engine.hpp", "spatial.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("engine.cpp", "constraints.cpp", "capi.cpp", "engine.hpp", "spatial.hpp")]
     srcs.append(os.path.join(_HERE, "..", "include", "jiminy_b200.h"))
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)

@@ -244,3 +244,85 @@ def test_pendulum_force_impulse(period):
     np.testing.assert_allclose(np.c_[qs, vs], xa, atol=1e-6)
     # without breakpoints at t and t + dt a 1 us, 1e6 N impulse would be mis-integrated by orders of magnitude
     assert np.abs(vs).max() > 0.1 and abs(qs[-1, 0]) > 0.01
+
+
+# ---------------------------------------------------------------------------------------------
+# contacts.model = "constraint" and joint position bounds: the PGS path (engine.cc:3709-3866).
+# Physical closed forms the boxed LCP must reproduce: normal force = weight at rest, Coulomb cone
+# (stick below mu * weight, slide with a = (F - mu * weight) / m above), a joint stopped at its bound,
+# and the reference's own check that the contact / force sensors equal f_external in the frame
+# (test_simple_mass.py:181-246, which runs with both contact models).
+def _point_mass_constraint(**contacts):
+    r, opt = _point_mass(**contacts)
+    opt["contacts"]["model"] = "constraint"
+    opt["stepper"].update(dtMax=1e-3, controllerUpdatePeriod=1e-3, odeSolver="runge_kutta_4")
+    return r, opt
+
+
+def test_constraint_contact_rest_and_sensors():
+    r, opt = _point_mass_constraint()
+    o = OracleBatch(r, opt)
+    o.set_callbacks(0, internal_dynamics=lambda t, q, v, s, u: u.__setitem__(slice(3, 6), 1.0))   # spinning mass
+    q0 = r.neutral()
+    q0[2] = 0.02
+    assert not o.start(q0, np.zeros(6)).any()
+    lay = r.sensor_layout()
+    P = r.frames["Sensor"].placement
+    for k in range(100):
+        assert not o.step(0.01).any()
+        # sensors == f_external[parent joint] expressed in the sensor frames, at every step (falling, impact, rest)
+        fext = o.get_efforts()[3][0, 1]
+        s = o.get_sensors()[0]
+        cont = s[lay["ContactSensor"][0]:lay["ContactSensor"][0] + 3]
+        F = s[lay["ForceSensor"][0]:lay["ForceSensor"][0] + 6]
+        np.testing.assert_allclose(cont, fext[:3], atol=TOL)
+        np.testing.assert_allclose(P.R @ F[:3], fext[:3], atol=TOL)
+        np.testing.assert_allclose(P.R @ F[3:] + np.cross(P.p, P.R @ F[:3]), fext[3:], atol=TOL)
+    _, q, v, a = o.get_state()
+    # at rest on the ground: z ~ 0 (Baumgarte pulls the frame back to the surface), zero linear motion
+    assert abs(q[0, 2]) < 1e-5 and np.abs(v[0, :3]).max() < 1e-6 and np.abs(a[0, :3]).max() < 1e-4
+    # normal force = weight, expressed in the (spinning) body frame: its norm is the weight
+    np.testing.assert_allclose(np.linalg.norm(o.get_efforts()[3][0, 1, :3]), 9.81, rtol=1e-4)
+    # torsion = 0: the spin about z is not resisted by the contact
+    assert v[0, 5] > 0.5
+
+
+@pytest.mark.parametrize("Fx,slides", [(4.0, False), (15.0, True)])
+def test_constraint_contact_coulomb_cone(Fx, slides):
+    mu = 0.8
+    r, opt = _point_mass_constraint(friction=mu)
+    opt["world"]["gravity"] = [Fx, 0.0, -9.81, 0.0, 0.0, 0.0]   # unit mass: horizontal gravity = constant push
+    o = OracleBatch(r, opt)
+    assert not o.start(r.neutral(), np.zeros(6)).any()
+    for _ in range(30):
+        assert not o.step(0.01).any()
+    _, q, v, a = o.get_state()
+    if slides:
+        np.testing.assert_allclose(a[0, 0], Fx - mu * 9.81, rtol=2e-3)      # regularization 1e-3 softens the cone
+        np.testing.assert_allclose(v[0, 0], (Fx - mu * 9.81) * 0.3, rtol=5e-3)
+    else:
+        assert abs(v[0, 0]) < 1e-3 and abs(a[0, 0]) < 1e-2                    # sticks (up to the solver compliance)
+    assert abs(q[0, 2]) < 1e-4
+
+
+@pytest.mark.parametrize("model", ["spring_damper", "constraint"])
+def test_joint_bound_stops_pendulum(model):
+    """A pendulum falling onto its upper position bound stops there (JointConstraint, lambda >= 0 pushes back
+    inside), whatever the contact model: the bounds dynamics always goes through the constraint solver."""
+    r = _pendulum()
+    r.q_upper[0], r.q_lower[0] = 0.5, -0.5
+    opt = _opt(odeSolver="runge_kutta_4", dtMax=1e-3, controllerUpdatePeriod=1e-3, sensorsUpdatePeriod=1e-3)
+    opt["contacts"]["model"] = model
+    o = OracleBatch(r, opt)
+    assert not o.start([0.3], [0.0]).any()
+    qmax = 0.0
+    for _ in range(300):
+        assert not o.step(0.01).any()
+        qmax = max(qmax, o.get_state()[1][0, 0])
+    _, q, v, a = o.get_state()
+    assert 0.5 - 1e-3 < q[0, 0] < 0.5 + 2e-3 and qmax < 0.52     # rests on the bound, small overshoot at impact
+    assert abs(v[0, 0]) < 1e-4
+    u = o.get_efforts()[0]
+    # the bound holds the gravity torque m g l sin(q): reported in u (engine.cc:3770-3788)
+    np.testing.assert_allclose(abs(u[0, 0]), 5.0 * 9.81 * np.sin(q[0, 0]), rtol=2e-3)
+    assert o.get_status()[0] & 8
