@@ -115,7 +115,8 @@ static int launch(JbBatch* b, int mode, double step_dt) {
     KParams kp = b->kp;
     kp.mode = mode;
     kp.step_dt = step_dt;
-    if (kp.n_eslot > 0) kp.sig_id = 0;   // static plan signatures carry no external-force code
+    // static plan signatures carry no external-force / constraint-contact code
+    if (kp.n_eslot > 0 || kp.opt.contact_model == JB_CONTACT_CONSTRAINT) kp.sig_id = 0;
     const int epw = 32 / b->plan.L;
     const int nblocks = (b->n_env + epw - 1) / epw;
 #ifdef JB_HOST_EMUL
@@ -163,8 +164,8 @@ void jb_default_options(JbOptions* o) {
 static int check_options(const JbOptions* o) {
     if (o->contact_model != JB_CONTACT_SPRING_DAMPER && o->contact_model != JB_CONTACT_CONSTRAINT)
         return fail(JB_ERR_INVALID_ARGUMENT, "unknown contact model");
-    if (o->contact_model == JB_CONTACT_CONSTRAINT)
-        return fail(JB_ERR_NOT_IMPLEMENTED, "contacts.model = 'constraint' is not on the device path yet");
+    if (o->contact_torsion < 0.0 || o->contact_stabilization_freq < 0.0 || o->constraint_regularization < 0.0)
+        return fail(JB_ERR_INVALID_ARGUMENT, "contact / constraint options must be positive");
     if (o->ode_solver < JB_SOLVER_EULER_EXPLICIT || o->ode_solver > JB_SOLVER_RUNGE_KUTTA_DOPRI)
         return fail(JB_ERR_INVALID_ARGUMENT, "unknown ODE solver");
     if (!(o->dt_max >= 1e-6 - 1e-16 && o->dt_max <= 0.02 + 1e-16)) return fail(JB_ERR_INVALID_ARGUMENT, "'dtMax' option is out of range.");
@@ -308,9 +309,56 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
     }
 
     if (SigQuadruped::matches(kp) && !std::getenv("JB_NO_STATIC_PLAN")) kp.sig_id = SigQuadruped::ID;
-    b->smem_bytes = static_cast<size_t>(P.nfields) * 32 * sizeof(double);
+    b->smem_bytes = static_cast<size_t>(P.nfields + 1) * 32 * sizeof(double);
     if (b->smem_bytes > 227 * 1024) { jb_batch_destroy(b); return fail(JB_ERR_NOT_IMPLEMENTED, "robot too large: per-warp working set exceeds shared memory (" + P.describe() + ")"); }
-    kp.n_eslot = 0; kp.n_imp = 0; kp.n_prof = 0; kp.ext_off = P.nfields;
+    // ---- constraint path: lookup tables, persistent state and workspace (jb_constraints.cuh)
+    {
+        std::vector<JointMap> jmap(m->njoints);
+        std::vector<int32_t> jc_joint, jc_of_joint(m->njoints, -1);
+        for (int j = 0; j < m->njoints; ++j) {
+            JointMap& jm = jmap[j];
+            jm = JointMap{-1, 0, j ? m->parent[j] : 0, j ? m->idx_q[j] : 0, j ? m->idx_v[j] : 0, 0, REC_PAD, 0};
+            if (!j) continue;
+            int found = 0;
+            for (int r = 0; r < P.nrec; ++r)
+                for (int s = 0; s < P.L; ++s) {
+                    const RecInt& ri = P.rint[static_cast<size_t>(r) * P.L + s];
+                    if (ri.kind == REC_PAD || ri.joint != j) continue;
+                    if (!found) { jm.rec = r; jm.sub = s; jm.kind = ri.kind; jm.nvj = ri.kind == REC_FREE ? 6 : 1; }
+                    ++found;
+                }
+            jm.trunk = found > 1;
+            if (m->joint_type[j] != JB_JOINT_FREEFLYER) { jc_of_joint[j] = static_cast<int32_t>(jc_joint.size()); jc_joint.push_back(j); }
+        }
+        std::vector<ContactMap> cmap(std::max(m->ncontacts, 1));
+        for (int k = 0; k < m->ncontacts; ++k) {
+            ContactMap& cm = cmap[k];
+            cm.joint = m->contact_joint[k]; cm.sub = 0; cm.cslot = 0; cm.trunk = 0;
+            std::memcpy(cm.placement, m->contact_placement + 12 * k, sizeof cm.placement);
+            int found = 0;
+            for (int cs = 0; cs < P.ncslot; ++cs)
+                for (int s = 0; s < P.L; ++s)
+                    if (P.cslots[static_cast<size_t>(cs) * P.L + s].contact == k) { if (!found) { cm.cslot = cs; cm.sub = s; } ++found; }
+            cm.trunk = found > 1;
+        }
+        kp.n_jc = static_cast<int32_t>(jc_joint.size()); kp.n_cc = m->ncontacts;
+        kp.m_max = kp.n_jc + 4 * kp.n_cc;
+        kp.cons_on = (m->nv <= 64) ? 1 : 0;
+        kp.cons_off = P.nfields;
+        if (kp.cons_on) {
+            JointMap* d_jmap; ContactMap* d_cmap; int32_t *d_jcj, *d_jcof; double *d_cst, *d_cwk;
+            const int cs_fields = CS_JOINT0 + CS_JOINT_SIZE * kp.n_jc + CS_CONTACT_SIZE * kp.n_cc;
+            const CwLayout w = cw_layout(m->njoints, m->nv, kp.m_max);
+            ALLOC(d_jmap, jmap.size()); ALLOC(d_cmap, cmap.size()); ALLOC(d_jcj, std::max<size_t>(jc_joint.size(), 1)); ALLOC(d_jcof, jc_of_joint.size());
+            ALLOC(d_cst, static_cast<size_t>(cs_fields) * N); ALLOC(d_cwk, static_cast<size_t>(w.total) * N);
+            cudaMemcpyAsync(d_jmap, jmap.data(), jmap.size() * sizeof(JointMap), cudaMemcpyHostToDevice, b->stream);
+            cudaMemcpyAsync(d_cmap, cmap.data(), cmap.size() * sizeof(ContactMap), cudaMemcpyHostToDevice, b->stream);
+            if (!jc_joint.empty()) cudaMemcpyAsync(d_jcj, jc_joint.data(), jc_joint.size() * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream);
+            cudaMemcpyAsync(d_jcof, jc_of_joint.data(), jc_of_joint.size() * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream);
+            kp.jmap = d_jmap; kp.cmap = d_cmap; kp.jc_joint = d_jcj; kp.jc_of_joint = d_jcof; kp.cstate = d_cst; kp.cwork = d_cwk;
+        }
+    }
+    kp.n_eslot = 0; kp.n_imp = 0; kp.n_prof = 0; kp.ext_off = P.nfields + 1;
     if (raise_smem_attr(device, b->smem_bytes)) { jb_batch_destroy(b); return JB_ERR_CUDA; }
     e = cudaStreamSynchronize(b->stream);
     if (e != cudaSuccess) { jb_batch_destroy(b); return fail(JB_ERR_CUDA, std::string("upload failed: ") + cudaGetErrorString(e)); }
@@ -426,7 +474,7 @@ static int ext_slot_for(JbBatch* b, int joint, const double* p, int* slot_out) {
         b->kp.eslots = b->d_eslots; b->kp.imp_data = b->d_imp;
         b->kp.prof_pending = b->d_prof_pending; b->kp.prof_latched = b->d_prof_latched;
     }
-    const size_t smem = static_cast<size_t>(P.nfields + ESLOT_SIZE * (b->eframes.size() + 1)) * 32 * sizeof(double);
+    const size_t smem = static_cast<size_t>(P.nfields + 1 + ESLOT_SIZE * (b->eframes.size() + 1)) * 32 * sizeof(double);
     if (smem > 227 * 1024) return fail(JB_ERR_NOT_IMPLEMENTED, "no shared memory left for an external-force slot");
     int rc = raise_smem_attr(b->device, smem);
     if (rc) return rc;
@@ -541,7 +589,7 @@ int jb_remove_all_forces(JbBatch* b) {
     if (b->any_started) return fail(JB_ERR_BAD_CONTROL_FLOW, "Simulation already running. Please stop it before removing forces.");
     b->kp.n_imp = 0; b->kp.n_prof = 0; b->kp.n_eslot = 0;
     b->eframes.clear();
-    b->smem_bytes = static_cast<size_t>(b->plan.nfields) * 32 * sizeof(double);
+    b->smem_bytes = static_cast<size_t>(b->plan.nfields + 1) * 32 * sizeof(double);
     const JbOptions o = b->kp.opt;
     apply_options(b, &o);
     return JB_OK;

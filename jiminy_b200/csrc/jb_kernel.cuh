@@ -120,6 +120,11 @@ __device__ __noinline__ void store_outputs(const Ctx c) {
                     motor_effort(rd, ri->motor_flags, RP(R1_CMD), vv, uM, uT);
                     u += uT;
                 }
+                // an enabled position-bound constraint reports its multiplier in u / uInternal (engine.cc:3770-3788)
+                if (KP->cons_on) {
+                    const int kc = KP->jc_of_joint[ri->joint];
+                    if (kc >= 0 && CST(cs_joint(kc)) != 0.0) u += CST(cs_joint(kc) + 3);
+                }
                 KP->eff_u[col * KP->nv + ri->idx_v] = u;
             }
             if (KP->eff_umotor && ri->motor >= 0) KP->eff_umotor[col * KP->nmotors + ri->motor] = RP(R1_UMOTOR);
@@ -132,7 +137,7 @@ __device__ __noinline__ void store_outputs(const Ctx c) {
                 const int co = KP->cslot_off + CSLOT_SIZE * cs;
                 double* const cp = jb_smem + co * 32 + c.lane;
                 const V3 Fl = mk(CO(0), CO(1), CO(2));
-                fext.l = fext.l + Fl; fext.a = fext.a + cross(ld3(ct->placement + 9), Fl);
+                fext.l = fext.l + Fl; fext.a = fext.a + cross(ld3(ct->placement + 9), Fl) + mk(CO(3), CO(4), CO(5));
             }
             add_cached_ext_wrench(c, r, L, fext);
             double* o = KP->eff_fext + (col * KP->njoints + ri->joint) * 6;
@@ -176,7 +181,7 @@ __device__ __noinline__ void store_dynamics(const Ctx c) {
                 const int co = KP->cslot_off + CSLOT_SIZE * cs;
                 double* const cp = jb_smem + co * 32 + c.lane;
                 const V3 Fl = mk(CO(0), CO(1), CO(2));
-                fext.l = fext.l + Fl; fext.a = fext.a + cross(ld3(ct->placement + 9), Fl);
+                fext.l = fext.l + Fl; fext.a = fext.a + cross(ld3(ct->placement + 9), Fl) + mk(CO(3), CO(4), CO(5));
             }
             add_cached_ext_wrench(c, r, L, fext);
             double* o = KP->fext_out + (col * KP->njoints + ri->joint) * 6;
@@ -194,6 +199,8 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
     const int env_raw = blockIdx.x * epw + c.lane / L;
     c.valid = env_raw < KP->n_env;
     c.env = c.valid ? env_raw : (KP->n_env - 1);
+    c.col = env_raw;   // < n_pad: padding envs keep their own column of the per-env global tables
+    c.zero_u = false; c.ignore_bounds = false;
     c.gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (c.lane - c.sub));
     const size_t N = KP->n_pad, col = c.env;
     const int mode = KP->mode;
@@ -201,7 +208,7 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
 
     const bool masked_out = (mode == MODE_START) && KP->mask != nullptr && KP->mask[c.env] == 0;
     if (masked_out) return;   // whole env (all its lanes) leaves: group masks keep the others safe
-    if (mode == MODE_STEP && (status & (JB_ENV_NOT_STARTED | JB_ENV_NAN | JB_ENV_ITER_FAILED | JB_ENV_DT_UNDERFLOW))) return;
+    if (mode == MODE_STEP && (status & (JB_ENV_NOT_STARTED | JB_ENV_NAN | JB_ENV_ITER_FAILED | JB_ENV_DT_UNDERFLOW | JB_ENV_SOLVER_FAILED))) return;
 
     // ---------------- load state into the lane records
     for (int r = 0; r < KP->nrec; ++r) {
@@ -224,6 +231,10 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
     for (int k = 0; k < CSLOT_SIZE * KP->ncslot; ++k) SMF(c, KP->cslot_off + k) = 0.0;
     for (int k = 0; k < IMUSLOT_SIZE * KP->nimuslot; ++k) SMF(c, KP->imu_off + k) = 0.0;
     for (int k = 0; k < ESLOT_SIZE * KP->n_eslot; ++k) SMF(c, KP->ext_off + k) = 0.0;
+    if (KP->cons_on) {
+        if (mode == MODE_STEP) cons_load_count(c);
+        else SMF(c, KP->cons_off) = 0.0;
+    }
 
     if (mode == MODE_DYNAMICS) {
         stage_from_accepted(c);
@@ -246,7 +257,16 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
         if (KP->pd_gains != nullptr) update_pd_commands(c);
         if (KP->n_eslot > 0) { bool ch = false; refresh_external_forces(c, 0.0, true, false, ch); }
         stage_from_accepted(c);
-        rhs(c, false, &status);
+        if (KP->cons_on) {
+            // resetConstraints, then the INIT_ITERATIONS fixed point of engine.cc:1400-1467: the first evaluation sees
+            // zero joint efforts and solves the enabled constraints as equalities, the next three run the boxed
+            // solver warm-started on an up-to-date state
+            cons_reset(c);
+            Ctx c0 = c; c0.zero_u = true; c0.ignore_bounds = true;
+            rhs(c0, false, &status);
+            const bool constrained = __any_sync(c.gmask, SMF(c, KP->cons_off) != 0.0);
+            for (int it = 1; it < (constrained ? 4 : 2); ++it) rhs(c, true, &status);
+        } else rhs(c, false, &status);
         // forceMax > 1e5 guard (engine.cc:1310-1346)
         double fmax2 = 0.0;
         for (int k = 0; k < KP->ncslot; ++k) {
@@ -294,6 +314,8 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
         auto try_step = [&](bool isBreakpointReached) {
             const double t_next = t + dtLargest;
             int rc = 0;
+            // successive constraint-solver failures are rolled back with a failed step (engine.cc:2104-2112, :2211-2217)
+            const double solveFailedBackup = KP->cons_on ? CST(CS_SOLVE_FAILED) : 0.0;
             if (opt.ode_solver == JB_SOLVER_EULER_EXPLICIT) { step_euler(c, dtLargest, &status); dtLargest = D_INF; }
             else if (opt.ode_solver == JB_SOLVER_RUNGE_KUTTA_4) { step_rk4(c, dtLargest, &status); dtLargest = D_INF; }
             else rc = step_dopri(c, &dtLargest, &status);
@@ -322,6 +344,7 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
                 if (rc == 1) ++successiveIterTooLarge;
                 ++successiveIterFailed;
                 ++iterFailed;
+                if (KP->cons_on && c.sub == 0) CST(CS_SOLVE_FAILED) = solveFailedBackup;
             }
             dt = fmin(dtLargest, opt.dt_max);
             return rc;
@@ -387,6 +410,7 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
             }
             if (failed) break;
             if (successiveIterFailed > failedMax) { status |= JB_ENV_ITER_FAILED; failed = true; break; }
+            if (KP->cons_on && __any_sync(c.gmask, c.sub == 0 && CST(CS_SOLVE_FAILED) > failedMax)) { status |= JB_ENV_SOLVER_FAILED; failed = true; break; }
             if (dt < STEPPER_MIN_TIMESTEP) { status |= JB_ENV_DT_UNDERFLOW; failed = true; break; }
             // sensors refresh (engine.cc:2386-2410)
             const double sp = opt.sensors_update_period;

@@ -83,6 +83,24 @@ struct ExtSlot {
     int32_t rec;
     int32_t joint;
 };
+// Constraint path (joint position bounds, contacts.model == "constraint"): lookup tables for the lane that
+// walks the whole tree in joint order, and the layout of the per-env state / workspace in global memory.
+struct JointMap {      // [njoints], index 0 (universe) unused
+    int32_t rec, sub;  // where the joint's record lives (trunk joints: sub-lane 0, replicated on every lane)
+    int32_t parent;    // parent joint index (0 = universe)
+    int32_t idx_q, idx_v, nvj, kind;
+    int32_t trunk;     // 1: replicated on all L lanes
+};
+struct ContactMap {    // [ncontacts]
+    int32_t joint, sub, cslot, trunk;
+    double placement[12];
+};
+// persistent constraint state, one column per env: [CS_*][n_pad]
+constexpr int CS_SOLVE_FAILED = 0;       // successiveSolveFailed
+constexpr int CS_JOINT0 = 1;             // per joint constraint: enabled, reversed, qRef, lambda
+constexpr int CS_JOINT_SIZE = 4;
+constexpr int CS_CONTACT_SIZE = 17;      // per contact constraint: enabled, lambda[4], reference R[9], p[3]
+
 constexpr int MAX_ESLOT = 4, MAX_IMPULSE = 16, MAX_PROFILE = 4;
 constexpr int ESLOT_SIZE = 12;   // wrench in world-aligned axes at the frame origin (6) | same wrench in the joint frame (6)
 constexpr int IMPULSE_ROWS = 8;  // t, dt, wrench[6]
@@ -134,7 +152,7 @@ constexpr int RF_SV = 50;     // 6
 constexpr int RF_SA = 56;     // 6
 constexpr int RF_KA = 62;     // DOPRI history (7 x 6) starts here
 constexpr int POOL_SIZE = 27; // union { oMi 12 + v 6 | Y 21 + f 6 | a_gf 6 }
-constexpr int CSLOT_SIZE = 3; // cached contact force (linear, joint frame)
+constexpr int CSLOT_SIZE = 6; // cached contact wrench in the joint frame: force at the contact point (3), pure torque (3)
 constexpr int IMUSLOT_SIZE = 12; // v (6) captured in pass 1, a_gf (6) captured in pass 3
 
 // Build the plan.  `lanes` = 0 chooses L automatically.  `n_hist` = number of stage-derivative

@@ -54,5 +54,10 @@ def test_no_cpu_fallback():
 
 def test_unsupported_options_are_rejected():
     robot, opt = R.load_robot("anymal")
-    with pytest.raises(NotImplementedError):          # default contact model of the TOML is 'constraint'
+    opt["contacts"]["model"] = "impulse"
+    with pytest.raises(ValueError):
+        core.BatchedEngine(robot, opt, 1)
+    opt["contacts"]["model"] = "constraint"
+    opt["constraints"]["solver"] = "other"
+    with pytest.raises(ValueError):
         core.BatchedEngine(robot, opt, 1)
