@@ -76,7 +76,7 @@ class ClockSampler(threading.Thread):
         return out
 
 
-def cpu_baseline(sc_name, threads_all=True, budget_s=12.0):
+def cpu_baseline(sc_name, threads_all=True, budget_s=12.0, contact_model=None):
     """The oracle (a C++ restatement of the reference's CPU path) on this box's host cores: a bounded
     sample of the same workload.  Returns env-steps/s single-thread and with all OpenMP threads."""
     from jiminy_b200 import scenarios
@@ -84,7 +84,7 @@ def cpu_baseline(sc_name, threads_all=True, budget_s=12.0):
     ncores = OracleBatch.max_threads()
     out = {}
     for label, n_env, par in (("single_thread", 8, False), ("all_threads", 32 * ncores, True)):
-        sc = scenarios.make(sc_name, n_env)
+        sc = scenarios.make(sc_name, n_env, contact_model=contact_model)
         orc = OracleBatch(sc.robot, sc.options, n_env)
         if sc.kp is not None:
             orc.set_pd_controller(sc.kp, sc.kd)
@@ -113,7 +113,7 @@ def run_reference(args):
     from oracle.oracle import OracleBatch
     ncores = OracleBatch.max_threads()
     n_env = min(args.n_env, 64 * ncores)        # bounded sample of the 4096-env batch
-    sc = scenarios.make(args.workload, n_env)
+    sc = scenarios.make(args.workload, n_env, contact_model=args.contact_model)
     orc = OracleBatch(sc.robot, sc.options, n_env)
     if sc.kp is not None:
         orc.set_pd_controller(sc.kp, sc.kd)
@@ -157,7 +157,7 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_env = args.n_env                                   # per GPU (weak scaling: envs are independent)
-    sc = scenarios.make(args.workload, n_env, seed=rank)
+    sc = scenarios.make(args.workload, n_env, seed=rank, contact_model=args.contact_model)
     eng = core.BatchedEngine(sc.robot, sc.options, n_env, device=local_rank)
     if sc.kp is not None:
         eng.set_pd_controller(sc.kp, sc.kd)
@@ -276,7 +276,7 @@ def run_gpu(args):
     traffic, fp64_pct = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
-            rec = json.load(fh).get(args.workload)
+            rec = json.load(fh).get(args.workload) if args.contact_model in (None, "spring_damper") else None
         if rec and rec["n_env"] == n_env:
             traffic, fp64_pct = rec["traffic_bytes"], rec["fp64_pipe_active_pct"]
     except Exception:
@@ -284,7 +284,7 @@ def run_gpu(args):
     achieved_gbs = bytes_per_launch / (step_ms_dev * 1e-3) / 1e9
     ncores, cpu = (None, None)
     if not args.no_cpu_baseline:
-        ncores, cpu = cpu_baseline(args.workload)
+        ncores, cpu = cpu_baseline(args.workload, contact_model=args.contact_model)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_path_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -322,6 +322,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="jiminy_b200", choices=["jiminy_b200", "reference"])
     ap.add_argument("--workload", default="anymal", choices=["anymal", "atlas", "cartpole", "double_pendulum"])
+    ap.add_argument("--contact-model", default=None, choices=["spring_damper", "constraint"],
+                    help="override contacts.model of the scenario (the BASELINE metric is quoted on spring_damper)")
     ap.add_argument("--n-env", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

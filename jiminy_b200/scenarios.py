@@ -99,19 +99,22 @@ def standing_posture(name: str, robot: RobotTable) -> np.ndarray:
     return q
 
 
-def make(name: str, n_env: int, seed: int = 0, dt_max: Optional[float] = None, solver: Optional[str] = None) -> Scenario:
+def make(name: str, n_env: int, seed: int = 0, dt_max: Optional[float] = None, solver: Optional[str] = None,
+         contact_model: Optional[str] = None) -> Scenario:
     robot, base = R.load_robot(name)
     opt = R.baseline_options(name, copy.deepcopy(base))
     if dt_max is not None:
         opt["stepper"]["dtMax"] = dt_max
     if solver is not None:
         opt["stepper"]["odeSolver"] = solver
+    if contact_model is not None:
+        opt["contacts"]["model"] = contact_model
     rng = np.random.default_rng([seed, 104729])
     nm = max(robot.nmotors, 1)
     if name in ("anymal", "atlas"):
         qs = standing_posture(name, robot)
         # keep the posture 0.25 rad inside the joint bounds (Atlas' neutral arm pose sits exactly on
-        # some of them): a joint leaving its bounds belongs to the constraint path, which is out of scope
+        # some of them): a joint leaving its bounds switches the env to the (slower) constraint path
         qs[7:] = np.clip(qs[7:], robot.q_lower[7:] + 0.25, robot.q_upper[7:] - 0.25)
         q0 = np.tile(qs, (n_env, 1))
         # per-env joint perturbation U(-0.05, 0.05) rad, feet on the ground
@@ -130,8 +133,10 @@ def make(name: str, n_env: int, seed: int = 0, dt_max: Optional[float] = None, s
         target0 = np.tile(qs[mq], (n_env, 1))
         return Scenario(name, robot, opt, n_env, 0.04, q0, v0, kp, kd, target0, 0.02, seed,
                         f"{name}: PD standing (reference gains), targets = posture + U(-0.02, 0.02) rad per env-step, "
-                        f"{opt['stepper']['odeSolver']} dtMax={opt['stepper']['dtMax']}, spring-damper contact "
-                        f"k={opt['contacts']['stiffness']:g} c={opt['contacts']['damping']:g} mu={opt['contacts']['friction']:g}",
+                        f"{opt['stepper']['odeSolver']} dtMax={opt['stepper']['dtMax']}, " +
+                        (f"spring-damper contact k={opt['contacts']['stiffness']:g} c={opt['contacts']['damping']:g} "
+                         if opt["contacts"]["model"] == "spring_damper" else "constraint contact (PGS) ") +
+                        f"mu={opt['contacts']['friction']:g}",
                         _motor_q=mq)
     if name == "cartpole":
         # x, theta, dx, dtheta ~ U(-0.05, 0.05) (cartpole.py:184-199); q = (x, cos, sin)

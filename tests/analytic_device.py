@@ -154,3 +154,43 @@ def force_impulse(api=None):
         np.testing.assert_allclose(np.c_[qs[:, 0], vs[:, 0]], xa, atol=1e-6)
         np.testing.assert_allclose(np.c_[qs[:, 1], vs[:, 1]], 0.0, atol=1e-12)   # env 1: zero wrenches
         assert np.abs(vs[:, 0]).max() > 0.1
+
+
+
+# ---------------------------------------------------------------------------------------------
+# constraint path on the device, against physical closed forms (no oracle): normal force = weight at rest,
+# Coulomb cone (stick below mu * weight, slide with a = F - mu * weight above), a joint stopped on its bound.
+def constraint_closed_forms(api=None):
+    r = M.build_robot_table(os.path.join(DATA, "point_mass.urdf"), True)
+    r.add_contact_points(["MassBody"])
+    mu = 0.8
+    for Fx, slides in ((4.0, False), (15.0, True)):
+        opt = _opt(dtMax=1e-3, controllerUpdatePeriod=1e-3, odeSolver="runge_kutta_4")
+        opt["contacts"].update(model="constraint", friction=mu, transitionEps=1e-6)
+        opt["world"]["gravity"] = [Fx, 0.0, -9.81, 0.0, 0.0, 0.0]
+        eng = BatchedEngine(r, opt, 2, api_=api)
+        q0 = np.tile(r.neutral(), (2, 1))
+        eng.start(q0, np.zeros((2, 6)))
+        for _ in range(30):
+            eng.step(0.01)
+        _, q, v, a = eng.get_state()
+        fext = eng.get_efforts()[3]
+        np.testing.assert_allclose(fext[:, 1, 2], 9.81, rtol=1e-3)                    # normal force = weight
+        if slides:
+            np.testing.assert_allclose(a[:, 0], Fx - mu * 9.81, rtol=2e-3)
+            np.testing.assert_allclose(np.hypot(fext[:, 1, 0], fext[:, 1, 1]), mu * 9.81, rtol=2e-3)
+        else:
+            assert np.abs(v[:, 0]).max() < 1e-3 and np.abs(a[:, 0]).max() < 1e-2
+            np.testing.assert_allclose(fext[:, 1, 0], -Fx, rtol=5e-3)                 # static friction balances the push
+        assert np.abs(q[:, 2]).max() < 1e-4 and not eng.get_status().any()
+    # pendulum resting on its upper position bound
+    rp = M.build_robot_table(os.path.join(DATA, "simple_pendulum.urdf"), False)
+    rp.q_upper[0], rp.q_lower[0] = 0.5, -0.5
+    opt = _opt(odeSolver="runge_kutta_4", dtMax=1e-3, controllerUpdatePeriod=1e-3, sensorsUpdatePeriod=1e-3)
+    eng = BatchedEngine(rp, opt, 2, api_=api)
+    eng.start(np.array([[0.3], [0.45]]), np.zeros((2, 1)))
+    for _ in range(300):
+        eng.step(0.01)
+    _, q, v, _ = eng.get_state()
+    assert np.all(np.abs(q - 0.5) < 2e-3) and np.abs(v).max() < 1e-4
+    np.testing.assert_allclose(np.abs(eng.get_efforts()[0][:, 0]), 5.0 * 9.81 * np.sin(q[:, 0]), rtol=2e-3)

@@ -142,3 +142,87 @@ def external_forces_scenario(api, n_env=6, n_steps=3, solver="runge_kutta_4", to
         eng.step(sc.step_dt)
     assert np.abs(eng.get_state()[1] - q_with).max() > 1e-4
     return eng, orc
+
+
+# ---------------------------------------------------------------------------------------------
+# constraint path (joint position bounds, contacts.model = "constraint") against the oracle
+def _cons_opt(**stepper):
+    from jiminy_b200 import model as M
+    opt = M.default_engine_options()
+    opt["contacts"]["model"] = "spring_damper"
+    opt["stepper"].update(stepper)
+    return opt
+
+
+def bounds_scenario(api, data_dir, model="spring_damper", n_steps=60):
+    """A pendulum thrown against its position bounds: JointConstraint enable / disable hysteresis, PGS with a
+    single boxed multiplier, multiplier reported in u."""
+    import os
+    from jiminy_b200 import model as M
+    r = M.build_robot_table(os.path.join(data_dir, "simple_pendulum.urdf"), False)
+    M.attach_motor(r, "PendulumJoint", "PendulumJoint", enableVelocityLimit=False, enableEffortLimit=False)
+    r.q_upper[0], r.q_lower[0] = 0.5, -0.5
+    opt = _cons_opt(odeSolver="runge_kutta_4", dtMax=1e-3, controllerUpdatePeriod=1e-3, sensorsUpdatePeriod=1e-3)
+    opt["contacts"]["model"] = model
+    eng, orc = BatchedEngine(r, opt, 3, api_=api), OracleBatch(r, opt, 3)
+    q0, v0 = np.array([[0.3], [0.1], [-0.45]]), np.array([[0.0], [1.0], [-2.0]])
+    for x in (eng, orc):
+        x.set_command(np.zeros((3, 1)))
+    eng.start(q0, v0)
+    assert not orc.start(q0, v0).any()
+    compare(eng, orc, 1e-13, 1e-11)
+    for _ in range(n_steps):
+        eng.step(0.01)
+        assert not orc.step(0.01).any()
+        compare(eng, orc, 1e-9, 1e-7)
+        np.testing.assert_allclose(eng.get_efforts()[0], orc.get_efforts()[0], rtol=0, atol=1e-7)
+    q = eng.get_state()[1]
+    assert np.all(np.abs(np.abs(q) - 0.5) < 2e-3) and (eng.get_status() & 8).all()
+    return eng, orc
+
+
+def point_mass_constraint_scenario(api, data_dir, n_steps=40, torsion=0.0):
+    """A free-flying mass on the ground with the constraint contact model: resting, sliding (Coulomb cone) and
+    spinning envs; contact / force sensors and f_external included in the comparison."""
+    import os
+    from jiminy_b200 import model as M
+    r = M.build_robot_table(os.path.join(data_dir, "point_mass.urdf"), True)
+    r.add_contact_points(["MassBody"])
+    M.attach_sensor(r, "ContactSensor", "MassBody", frame_name="MassBody")
+    r.add_frame("Sensor", "MassBody", M.SE3(M.rpy_to_matrix([0.3, -0.2, 0.5]), np.array([0.1, 0.2, -0.05])))
+    M.attach_sensor(r, "ForceSensor", "F", frame_name="Sensor")
+    opt = _cons_opt(dtMax=1e-3, controllerUpdatePeriod=1e-3, odeSolver="runge_kutta_4")
+    opt["contacts"].update(model="constraint", friction=0.8, transitionEps=1e-6, torsion=torsion)
+    opt["world"]["gravity"] = [4.0, 1.0, -9.81, 0, 0, 0]
+    n = 3
+    eng, orc = BatchedEngine(r, opt, n, api_=api), OracleBatch(r, opt, n)
+    q0 = np.tile(r.neutral(), (n, 1))
+    q0[:, 2] = [0.0, 0.02, -1e-4]
+    v0 = np.zeros((n, 6))
+    v0[1, :3] = [0.3, 0.0, 0.0]
+    v0[2, 3:] = [0.5, 0.2, 1.0]
+    eng.start(q0, v0)
+    assert not orc.start(q0, v0).any()
+    compare(eng, orc, 1e-13, 1e-10)
+    for _ in range(n_steps):
+        eng.step(0.01)
+        assert not orc.step(0.01).any()
+        compare(eng, orc, 1e-9, 1e-7)
+        np.testing.assert_allclose(eng.get_efforts()[3], orc.get_efforts()[3], rtol=0, atol=1e-7)
+    return eng, orc
+
+
+def robot_constraint_scenario(name, n_env, n_steps, api=None, tol_state=1e-8, tol_sens=1e-6, **kw):
+    """A BASELINE robot with contacts.model = "constraint" (the default of the reference's option files)."""
+    sc = scenarios.make(name, n_env, **kw)
+    sc.options["contacts"]["model"] = "constraint"
+    eng, orc = make_pair(sc, api)
+    compare(eng, orc, 1e-12, 1e-9)
+    for k in range(n_steps):
+        act = sc.sample_targets(k)
+        eng.set_command(act)
+        orc.set_command(act)
+        eng.step(sc.step_dt)
+        assert not orc.step(sc.step_dt, parallel=True).any()
+        compare(eng, orc, tol_state, tol_sens)
+    return eng, orc, sc

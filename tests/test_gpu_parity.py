@@ -9,6 +9,7 @@ from jiminy_b200 import scenarios
 from jiminy_b200.core import BatchedEngine
 from oracle.oracle import OracleBatch
 
+from conftest import DATA
 import parity_common as pc
 
 pytestmark = pytest.mark.gpu
@@ -135,8 +136,24 @@ def test_cuda_path_vs_closed_forms():
     ad.contact_equilibrium_and_friction()
     ad.energy_conservation()
     ad.force_impulse()
+    ad.constraint_closed_forms()
 
 
 def test_external_forces_match_oracle():
     """Impulse + profile forces (Engine::computeExternalForces, impulse breakpoints) on 70 ANYmal envs."""
     pc.external_forces_scenario(None, n_env=70, n_steps=4)
+
+
+@pytest.mark.parametrize("model", ["spring_damper", "constraint"])
+def test_joint_bounds_constraint_path(model):
+    pc.bounds_scenario(None, DATA, model)
+
+
+def test_constraint_contact_matches_oracle():
+    """contacts.model = "constraint" (boxed PGS): point mass (rest / slide / spin, torsion), 40 ANYmal envs,
+    Atlas (78 constraint rows at most)."""
+    pc.point_mass_constraint_scenario(None, DATA)
+    pc.point_mass_constraint_scenario(None, DATA, n_steps=15, torsion=0.05)
+    eng, orc, sc = pc.robot_constraint_scenario("anymal", 40, 3, seed=2)
+    assert (eng.get_state()[1][:, 2] > 0.4).all()
+    pc.robot_constraint_scenario("atlas", 6, 1, seed=1, tol_state=1e-7, tol_sens=1e-5)

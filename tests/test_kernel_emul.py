@@ -282,6 +282,7 @@ def test_device_code_vs_closed_forms(api):
     ad.contact_equilibrium_and_friction(api)
     ad.energy_conservation(api)
     ad.force_impulse(api)
+    ad.constraint_closed_forms(api)
 
 
 def test_external_forces_anymal(api):
@@ -345,3 +346,29 @@ def test_engine_facade_impulse_forces(api):
     engine.start(np.zeros(1), np.zeros(1))
     engine.step(0.01)
     assert abs(engine.robot_states[0].v[0]) < 1e-14
+
+
+@pytest.mark.parametrize("model", ["spring_damper", "constraint"])
+def test_joint_bounds_constraint_path(api, model):
+    pc.bounds_scenario(api, DATA, model)
+
+
+def test_constraint_contact_point_mass(api):
+    pc.point_mass_constraint_scenario(api, DATA)
+    pc.point_mass_constraint_scenario(api, DATA, n_steps=15, torsion=0.05)
+
+
+def test_constraint_contact_anymal(api):
+    eng, orc, sc = pc.robot_constraint_scenario("anymal", 5, 2, api, seed=2)
+    assert (eng.get_state()[1][:, 2] > 0.4).all()      # still standing
+
+
+def test_constraint_contact_atlas_rhs(api):
+    """Atlas (12 contact points, 30 bounded joints, 78 constraint rows at most): start + a short step."""
+    sc = scenarios.make("atlas", 1, seed=1)
+    sc.options["contacts"]["model"] = "constraint"
+    eng, orc = pc.make_pair(sc, api)
+    pc.compare(eng, orc, 1e-12, 1e-8)
+    eng.step(0.005)
+    assert not orc.step(0.005).any()
+    pc.compare(eng, orc, 1e-9, 1e-6)
