@@ -39,7 +39,8 @@ _LIB_NAME = "libjiminy_b200.so"
 
 
 def library_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+    # JB_LIBRARY: development override (A/B builds of the same C ABI)
+    return os.environ.get("JB_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 
 class Api:

@@ -61,7 +61,9 @@ struct JbBatch {
     size_t h_stage_bytes = 0;
     int64_t launches = 0;
     bool any_started = false;
+    bool no_fast_kernel = false;   // JB_NO_FAST_KERNEL: always the full kernel (development / tests)
     size_t smem_bytes = 0;
+    int32_t* d_needs_full = nullptr;
     // external forces: frames (slots), impulse table mirror, profile periods
     struct ExtFrame { int joint; double p[3]; };
     std::vector<ExtFrame> eframes;
@@ -77,7 +79,8 @@ static int raise_smem_attr(int device, size_t bytes) {
 #ifndef JB_HOST_EMUL
     std::lock_guard<std::mutex> lock(g_smem_mutex);
     if (bytes <= g_smem_attr[device]) return JB_OK;
-    cudaError_t e = cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    cudaError_t e = cudaFuncSetAttribute(env_step_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(env_step_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
     if (e != cudaSuccess) return fail(JB_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     g_smem_attr[device] = bytes;
 #endif
@@ -111,20 +114,16 @@ static int ensure_host_stage(JbBatch* b, size_t bytes) {
     return JB_OK;
 }
 
-static int launch(JbBatch* b, int mode, double step_dt) {
-    KParams kp = b->kp;
-    kp.mode = mode;
-    kp.step_dt = step_dt;
-    // static plan signatures carry no external-force / constraint-contact code
-    if (kp.n_eslot > 0 || kp.opt.contact_model == JB_CONTACT_CONSTRAINT) kp.sig_id = 0;
+// One launch of the step kernel.  `fast`: the hot-path instantiation; `only_flagged`: the full kernel as the fix-up
+// pass behind it (envs the fast kernel left untouched).
+static int launch_one(JbBatch* b, KParams kp, bool fast) {
     const int epw = 32 / b->plan.L;
     const int nblocks = (b->n_env + epw - 1) / epw;
 #ifdef JB_HOST_EMUL
     emul::current_L = b->plan.L;
-#endif
-#ifdef JB_HOST_EMUL
     g_kp_host = kp;
-    JB_LAUNCH(env_step_kernel, nblocks, 32, b->smem_bytes, b->stream);
+    if (fast) JB_LAUNCH(env_step_kernel_t<true>, nblocks, 32, b->smem_bytes, b->stream);
+    else JB_LAUNCH(env_step_kernel_t<false>, nblocks, 32, b->smem_bytes, b->stream);
 #else
     {
         // one constant-memory parameter block per device: order this launch after the previous one
@@ -133,13 +132,30 @@ static int launch(JbBatch* b, int mode, double step_dt) {
         if (!evt) CU(cudaEventCreateWithFlags(&evt, cudaEventDisableTiming));
         else CU(cudaStreamWaitEvent(b->stream, evt, 0));
         CU(cudaMemcpyToSymbolAsync(g_kp, &kp, sizeof kp, 0, cudaMemcpyHostToDevice, b->stream));
-        JB_LAUNCH(env_step_kernel, nblocks, 32, b->smem_bytes, b->stream);
+        if (fast) JB_LAUNCH(env_step_kernel_t<true>, nblocks, 32, b->smem_bytes, b->stream);
+        else JB_LAUNCH(env_step_kernel_t<false>, nblocks, 32, b->smem_bytes, b->stream);
         CU(cudaEventRecord(evt, b->stream));
     }
 #endif
     CU(cudaGetLastError());
     ++b->launches;
     return JB_OK;
+}
+
+static int launch(JbBatch* b, int mode, double step_dt) {
+    KParams kp = b->kp;
+    kp.mode = mode;
+    kp.step_dt = step_dt;
+    kp.only_flagged = 0;
+    // static plan signatures carry no external-force / constraint-contact code
+    if (kp.n_eslot > 0 || kp.opt.contact_model == JB_CONTACT_CONSTRAINT) kp.sig_id = 0;
+    const bool fast_ok = mode == MODE_STEP && kp.n_eslot == 0 && kp.opt.contact_model == JB_CONTACT_SPRING_DAMPER &&
+                         kp.opt.ode_solver != JB_SOLVER_RUNGE_KUTTA_DOPRI && !b->no_fast_kernel;
+    if (!fast_ok) return launch_one(b, kp, false);
+    int rc = launch_one(b, kp, true);
+    if (rc) return rc;
+    kp.only_flagged = 1;
+    return launch_one(b, kp, false);
 }
 
 extern "C" {
@@ -355,10 +371,14 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
             cudaMemcpyAsync(d_cmap, cmap.data(), cmap.size() * sizeof(ContactMap), cudaMemcpyHostToDevice, b->stream);
             if (!jc_joint.empty()) cudaMemcpyAsync(d_jcj, jc_joint.data(), jc_joint.size() * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream);
             cudaMemcpyAsync(d_jcof, jc_of_joint.data(), jc_of_joint.size() * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream);
+            kp.cs_total = cs_fields; kp.cw_total = w.total;
             kp.jmap = d_jmap; kp.cmap = d_cmap; kp.jc_joint = d_jcj; kp.jc_of_joint = d_jcof; kp.cstate = d_cst; kp.cwork = d_cwk;
         }
     }
     kp.n_eslot = 0; kp.n_imp = 0; kp.n_prof = 0; kp.ext_off = P.nfields + 1;
+    ALLOC(b->d_needs_full, N);
+    kp.needs_full = b->d_needs_full; kp.only_flagged = 0;
+    if (const char* s = std::getenv("JB_NO_FAST_KERNEL")) b->no_fast_kernel = std::atoi(s) != 0;
     if (raise_smem_attr(device, b->smem_bytes)) { jb_batch_destroy(b); return JB_ERR_CUDA; }
     e = cudaStreamSynchronize(b->stream);
     if (e != cudaSuccess) { jb_batch_destroy(b); return fail(JB_ERR_CUDA, std::string("upload failed: ") + cudaGetErrorString(e)); }

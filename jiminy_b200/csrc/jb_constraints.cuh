@@ -30,8 +30,10 @@ constexpr int CONS_PGS_MAX_ITER = 100;             // engine.cc:62
 constexpr int CONS_RELAX_MIN_ITER = 20, CONS_RELAX_MAX_ITER = 30;
 
 // ---- addressing -----------------------------------------------------------------------------------
-#define CST(off) (KP->cstate[static_cast<size_t>(off) * KP->n_pad + c.col])
-#define CWK(off) (KP->cwork[static_cast<size_t>(off) * KP->n_pad + c.col])
+// this env's own row of the per-env global tables (padding envs of the last warp get their own rows, < n_pad)
+#define CONS_COL(c) (static_cast<size_t>(blockIdx.x) * (32 / KP->L) + (c).lane / KP->L)
+#define CST(off) (KP->cstate[CONS_COL(c) * KP->cs_total + (off)])
+#define CWK(off) (KP->cwork[CONS_COL(c) * KP->cw_total + (off)])
 JB_DI int cs_joint(int k) { return CS_JOINT0 + CS_JOINT_SIZE * k; }
 JB_DI int cs_contact(int k) { return CS_JOINT0 + CS_JOINT_SIZE * KP->n_jc + CS_CONTACT_SIZE * k; }
 // workspace layout (doubles per env)
@@ -152,23 +154,28 @@ __device__ __noinline__ void cons_load_count(const Ctx c) {
     SMF(c, KP->cons_off) = count;
 }
 
-// computePositionLimitsForcesAlgo (engine.cc:3253-3338) for the bounded joint of record r (owner lane only)
-__device__ __noinline__ void cons_update_bound(const Ctx c, int r, double q, double lo, double hi, int* status) {
-    const RecInt* ri = KP->rint + (r * KP->L + c.sub);
-    if (!ri->owner) return;
-    const int k = KP->jc_of_joint[ri->joint];
-    if (k < 0) return;
-    const int o = cs_joint(k);
-    const bool was = CST(o) != 0.0;
+// computePositionLimitsForcesAlgo (engine.cc:3253-3338) for the bounded joints this lane owns, at the stage state
+__device__ __noinline__ void cons_update_bounds(const Ctx c, int* status) {
+    const int L = KP->L;
     const double eps = KP->opt.contact_transition_eps;
-    if (hi < q || q < lo) {
-        CST(o + 2) = fmin(fmax(q, lo), hi);
-        CST(o + 1) = (hi < q) ? 1.0 : 0.0;
-        CST(o) = 1.0;
-        if (!was) SMF(c, KP->cons_off) += 1.0;
-        *status |= JB_ENV_JOINT_LIMIT;
-    } else if (lo + eps < q && q < hi - eps) {
-        if (was) { CST(o) = 0.0; CST(o + 3) = 0.0; SMF(c, KP->cons_off) -= 1.0; }
+    for (int r = 0; r < KP->nrec; ++r) {
+        const RecInt* ri = KP->rint + (r * L + c.sub);
+        if (ri->kind == REC_PAD || ri->kind == REC_FREE || !ri->owner || !ri->has_limit) continue;
+        const int k = KP->jc_of_joint[ri->joint];
+        if (k < 0) continue;
+        const RecDbl* rd = KP->rdbl + (r * L + c.sub);
+        const double q = SMF(c, KP->rec_off[r] + R1_QS), lo = rd->q_lo, hi = rd->q_hi;
+        const int o = cs_joint(k);
+        const bool was = CST(o) != 0.0;
+        if (hi < q || q < lo) {
+            CST(o + 2) = fmin(fmax(q, lo), hi);
+            CST(o + 1) = (hi < q) ? 1.0 : 0.0;
+            CST(o) = 1.0;
+            if (!was) SMF(c, KP->cons_off) += 1.0;
+            *status |= JB_ENV_JOINT_LIMIT;
+        } else if (lo + eps < q && q < hi - eps) {
+            if (was) { CST(o) = 0.0; CST(o + 3) = 0.0; SMF(c, KP->cons_off) -= 1.0; }
+        }
     }
 }
 
@@ -543,7 +550,7 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
     // ---------------- 4. multipliers, accelerations, contact wrenches (sub-lane 0)
     bool ok = true;
     if (c.sub == 0) {
-        if (c.ignore_bounds) {
+        if (c.flags & CTX_IGNORE_BOUNDS) {
             // solveJMinvJtv (overload.h:539-551): exact equality solve
             for (int r = 0; r < m; ++r) for (int q = 0; q < m; ++q) CWK(w.AL + r * ld + q) = CWK(w.AA + r * ld + q);
             if (cw_llt(c, w.AL, m, ld)) {

@@ -190,7 +190,11 @@ __device__ __noinline__ void store_dynamics(const Ctx c) {
     }
 }
 
-__global__ void __launch_bounds__(32) env_step_kernel() {
+// FAST = true: the product hot path only (MODE_STEP, Euler / RK4, spring-damper contacts, no external forces,
+// no enabled constraint).  An env that needs anything else leaves untouched and is stepped by the full kernel,
+// launched right behind as a fix-up pass (KParams::only_flagged).
+template <bool FAST>
+__global__ void __launch_bounds__(32) env_step_kernel_t() {
     Ctx c;
     c.lane = threadIdx.x & 31;
     const int L = KP->L;
@@ -199,8 +203,7 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
     const int env_raw = blockIdx.x * epw + c.lane / L;
     c.valid = env_raw < KP->n_env;
     c.env = c.valid ? env_raw : (KP->n_env - 1);
-    c.col = env_raw;   // < n_pad: padding envs keep their own column of the per-env global tables
-    c.zero_u = false; c.ignore_bounds = false;
+    c.flags = 0;
     c.gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (c.lane - c.sub));
     const size_t N = KP->n_pad, col = c.env;
     const int mode = KP->mode;
@@ -209,6 +212,9 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
     const bool masked_out = (mode == MODE_START) && KP->mask != nullptr && KP->mask[c.env] == 0;
     if (masked_out) return;   // whole env (all its lanes) leaves: group masks keep the others safe
     if (mode == MODE_STEP && (status & (JB_ENV_NOT_STARTED | JB_ENV_NAN | JB_ENV_ITER_FAILED | JB_ENV_DT_UNDERFLOW | JB_ENV_SOLVER_FAILED))) return;
+    int32_t* const needs_full = KP->needs_full + (blockIdx.x * epw + c.lane / L);   // own row, also for padding envs
+    if constexpr (FAST) { if (*needs_full != 0) return; }
+    else if (mode == MODE_STEP && KP->only_flagged && *needs_full == 0) return;
 
     // ---------------- load state into the lane records
     for (int r = 0; r < KP->nrec; ++r) {
@@ -230,13 +236,15 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
     }
     for (int k = 0; k < CSLOT_SIZE * KP->ncslot; ++k) SMF(c, KP->cslot_off + k) = 0.0;
     for (int k = 0; k < IMUSLOT_SIZE * KP->nimuslot; ++k) SMF(c, KP->imu_off + k) = 0.0;
-    for (int k = 0; k < ESLOT_SIZE * KP->n_eslot; ++k) SMF(c, KP->ext_off + k) = 0.0;
-    if (KP->cons_on) {
-        if (mode == MODE_STEP) cons_load_count(c);
-        else SMF(c, KP->cons_off) = 0.0;
+    if constexpr (!FAST) {
+        for (int k = 0; k < ESLOT_SIZE * KP->n_eslot; ++k) SMF(c, KP->ext_off + k) = 0.0;
+        if (KP->cons_on) {
+            if (mode == MODE_STEP) cons_load_count(c);
+            else SMF(c, KP->cons_off) = 0.0;
+        }
     }
 
-    if (mode == MODE_DYNAMICS) {
+    if (!FAST && mode == MODE_DYNAMICS) {
         stage_from_accepted(c);
         int st = 0;
         rhs(c, false, &st);
@@ -246,7 +254,7 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
 
     double t, dt, dtLargest, dtLargestPrev, tError, tPrev;
     long long iter, iterFailed;
-    if (mode == MODE_START) {
+    if (!FAST && mode == MODE_START) {
         // Engine::start (engine.cc:952-1533): stepperState_.reset(SIMULATION_MIN_TIMESTEP, ...), forward
         // kinematics, initial contact-force guard, then the INIT_ITERATIONS fixed point, which for a
         // zero-order-held command converges to one evaluation of the dynamics.
@@ -262,7 +270,7 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
             // zero joint efforts and solves the enabled constraints as equalities, the next three run the boxed
             // solver warm-started on an up-to-date state
             cons_reset(c);
-            Ctx c0 = c; c0.zero_u = true; c0.ignore_bounds = true;
+            Ctx c0 = c; c0.flags = CTX_ZERO_U | CTX_IGNORE_BOUNDS;
             rhs(c0, false, &status);
             const bool constrained = __any_sync(c.gmask, SMF(c, KP->cons_off) != 0.0);
             for (int it = 1; it < (constrained ? 4 : 2); ++it) rhs(c, true, &status);
@@ -315,10 +323,15 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
             const double t_next = t + dtLargest;
             int rc = 0;
             // successive constraint-solver failures are rolled back with a failed step (engine.cc:2104-2112, :2211-2217)
-            const double solveFailedBackup = KP->cons_on ? CST(CS_SOLVE_FAILED) : 0.0;
-            if (opt.ode_solver == JB_SOLVER_EULER_EXPLICIT) { step_euler(c, dtLargest, &status); dtLargest = D_INF; }
-            else if (opt.ode_solver == JB_SOLVER_RUNGE_KUTTA_4) { step_rk4(c, dtLargest, &status); dtLargest = D_INF; }
-            else rc = step_dopri(c, &dtLargest, &status);
+            double solveFailedBackup = 0.0;
+            if constexpr (!FAST) { if (KP->cons_on) solveFailedBackup = CST(CS_SOLVE_FAILED); }
+            if (opt.ode_solver == JB_SOLVER_EULER_EXPLICIT) { step_euler<FAST>(c, dtLargest, &status); dtLargest = D_INF; }
+            else if (FAST || opt.ode_solver == JB_SOLVER_RUNGE_KUTTA_4) { step_rk4<FAST>(c, dtLargest, &status); dtLargest = D_INF; }
+            else { if constexpr (!FAST) rc = step_dopri(c, &dtLargest, &status); }
+            if constexpr (FAST) {
+                // a joint left its position bounds: this env is re-done by the full kernel
+                if (__any_sync(c.gmask, (status & ENV_RETRY_FULL) != 0)) { status |= ENV_RETRY_FULL; failed = true; }
+            }
             need_refresh = false;
             if (rc == 0 && opt.ode_solver != JB_SOLVER_RUNGE_KUTTA_DOPRI) {
                 bool bad = accel_has_nan(c);
@@ -344,7 +357,7 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
                 if (rc == 1) ++successiveIterTooLarge;
                 ++successiveIterFailed;
                 ++iterFailed;
-                if (KP->cons_on && c.sub == 0) CST(CS_SOLVE_FAILED) = solveFailedBackup;
+                if constexpr (!FAST) { if (KP->cons_on && c.sub == 0) CST(CS_SOLVE_FAILED) = solveFailedBackup; }
             }
             dt = fmin(dtLargest, opt.dt_max);
             return rc;
@@ -354,7 +367,7 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
             double tNext = t;
             // impulse forces: active set + next breakpoint; profile forces: held values (engine.cc:1843-1917)
             double tImpulseForceNext = D_INF;
-            if (KP->n_eslot > 0) tImpulseForceNext = refresh_external_forces(c, t, false, finitePeriod, hasDynamicsChanged);
+            if constexpr (!FAST) { if (KP->n_eslot > 0) tImpulseForceNext = refresh_external_forces(c, t, false, finitePeriod, hasDynamicsChanged); }
             if (finitePeriod && opt.controller_update_period > D_EPS) {
                 if (period_hit(t, opt.controller_update_period)) {
                     // computeCommand (engine.cc:1920-1940): zero-order hold of the action, or the PD block
@@ -364,7 +377,7 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
             }
             if (!finitePeriod && hasDynamicsChanged) {
                 stage_from_accepted(c);
-                rhs(c, !need_refresh, &status);
+                if constexpr (FAST) rhs_fast(c, !need_refresh, &status); else rhs(c, !need_refresh, &status);
                 need_refresh = false;
                 hasDynamicsChanged = false;
             }
@@ -379,7 +392,7 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
                     if (hasDynamicsChanged) {
                         // FSAL repair: same state, cached contact forces, new command (engine.cc:2032-2037)
                         stage_from_accepted(c);
-                        rhs(c, !need_refresh, &status);
+                        if constexpr (FAST) rhs_fast(c, !need_refresh, &status); else rhs(c, !need_refresh, &status);
                         need_refresh = false;
                         hasDynamicsChanged = false;
                     }
@@ -410,7 +423,9 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
             }
             if (failed) break;
             if (successiveIterFailed > failedMax) { status |= JB_ENV_ITER_FAILED; failed = true; break; }
-            if (KP->cons_on && __any_sync(c.gmask, c.sub == 0 && CST(CS_SOLVE_FAILED) > failedMax)) { status |= JB_ENV_SOLVER_FAILED; failed = true; break; }
+            if constexpr (!FAST) {
+                if (KP->cons_on && __any_sync(c.gmask, c.sub == 0 && CST(CS_SOLVE_FAILED) > failedMax)) { status |= JB_ENV_SOLVER_FAILED; failed = true; break; }
+            }
             if (dt < STEPPER_MIN_TIMESTEP) { status |= JB_ENV_DT_UNDERFLOW; failed = true; break; }
             // sensors refresh (engine.cc:2386-2410)
             const double sp = opt.sensors_update_period;
@@ -422,6 +437,16 @@ __global__ void __launch_bounds__(32) env_step_kernel() {
     }
 
     // ---------------- store
+    if constexpr (FAST) {
+        if (__any_sync(c.gmask, (status & ENV_RETRY_FULL) != 0)) {   // nothing of this launch is kept: the full kernel redoes the env
+            if (c.sub == 0) *needs_full = 1;
+            return;
+        }
+    } else if (KP->cons_on) {
+        // envs that still own enabled constraints stay with the full kernel
+        const bool any = __any_sync(c.gmask, SMF(c, KP->cons_off) != 0.0);
+        if (c.sub == 0) *needs_full = any ? 1 : 0;
+    }
     if (KP->extra_energy != nullptr && !(status & (JB_ENV_NAN | JB_ENV_NOT_STARTED))) extra_terms(c);
     store_outputs(c);
     if (KP->pd_gains != nullptr && c.valid) {

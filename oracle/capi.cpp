@@ -172,6 +172,11 @@ void orc_get_iters(OrcBatch* b, int64_t* iter, int64_t* iter_failed) {
         if (iter_failed) iter_failed[i] = b->envs[i]->iterFailed;
     }
 }
+int64_t orc_pgs_iterations(OrcBatch* b) {
+    int64_t n = 0;
+    for (auto& e : b->envs) n += e->pgsIterations;
+    return n;
+}
 int64_t orc_rhs_count(OrcBatch* b) {
     int64_t s = 0;
     for (auto& e : b->envs) s += e->rhs_count;

@@ -149,8 +149,15 @@ def test_status_flags(api):
     orc = OracleBatch(robot, opt, 1)
     eng.start(q, v)
     orc.start(q, v)
-    eng.step(0.01)
-    orc.step(0.01)
+    eng.set_command(np.zeros((1, robot.nmotors)))
+    orc.set_command(np.zeros((1, robot.nmotors)))
+    pc.compare(eng, orc, 1e-13, 1e-11)
+    # the joint hits its bound inside the first step: the fast kernel hands the env over to the full kernel
+    # (constraint path), which keeps it until the bound constraint switches off again
+    for _ in range(6):
+        eng.step(0.01)
+        assert not orc.step(0.01).any()
+        pc.compare(eng, orc, 1e-9, 1e-7)
     assert eng.get_status()[0] & JB_ENV_JOINT_LIMIT and orc.get_status()[0] & JB_ENV_JOINT_LIMIT
     bad = q.copy()
     bad[robot.idx_q[robot.joint_index("LF_HAA")]] = 0.6
