@@ -63,6 +63,7 @@ struct JbBatch {
     bool any_started = false;
     bool no_fast_kernel = false;   // JB_NO_FAST_KERNEL: always the full kernel (development / tests)
     size_t smem_bytes = 0;
+    int base_fields = 0;           // plan fields + constraint bookkeeping, before the external-force slots
     int32_t* d_needs_full = nullptr;
     // external forces: frames (slots), impulse table mirror, profile periods
     struct ExtFrame { int joint; double p[3]; };
@@ -325,8 +326,6 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
     }
 
     if (SigQuadruped::matches(kp) && !std::getenv("JB_NO_STATIC_PLAN")) kp.sig_id = SigQuadruped::ID;
-    b->smem_bytes = static_cast<size_t>(P.nfields + 1) * 32 * sizeof(double);
-    if (b->smem_bytes > 227 * 1024) { jb_batch_destroy(b); return fail(JB_ERR_NOT_IMPLEMENTED, "robot too large: per-warp working set exceeds shared memory (" + P.describe() + ")"); }
     // ---- constraint path: lookup tables, persistent state and workspace (jb_constraints.cuh)
     {
         std::vector<JointMap> jmap(m->njoints);
@@ -361,6 +360,10 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
         kp.m_max = kp.n_jc + 4 * kp.n_cc;
         kp.cons_on = (m->nv <= 64) ? 1 : 0;
         kp.cons_off = P.nfields;
+        kp.cq_off = P.nfields + 1;
+        kp.cq_on = (kp.cons_on && opt->contact_model == JB_CONTACT_CONSTRAINT && cons_quadruped_matches(kp, P, *m) &&
+                    !(std::getenv("JB_NO_STRUCTURED_CONS") && std::atoi(std::getenv("JB_NO_STRUCTURED_CONS")))) ? 1 : 0;
+        b->base_fields = P.nfields + 1 + (kp.cq_on ? CQ_SIZE : 0);
         if (kp.cons_on) {
             JointMap* d_jmap; ContactMap* d_cmap; int32_t *d_jcj, *d_jcof; double *d_cst, *d_cwk;
             const int cs_fields = CS_JOINT0 + CS_JOINT_SIZE * kp.n_jc + CS_CONTACT_SIZE * kp.n_cc;
@@ -375,7 +378,9 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
             kp.jmap = d_jmap; kp.cmap = d_cmap; kp.jc_joint = d_jcj; kp.jc_of_joint = d_jcof; kp.cstate = d_cst; kp.cwork = d_cwk;
         }
     }
-    kp.n_eslot = 0; kp.n_imp = 0; kp.n_prof = 0; kp.ext_off = P.nfields + 1;
+    kp.n_eslot = 0; kp.n_imp = 0; kp.n_prof = 0; kp.ext_off = b->base_fields;
+    b->smem_bytes = static_cast<size_t>(b->base_fields) * 32 * sizeof(double);
+    if (b->smem_bytes > 227 * 1024) { jb_batch_destroy(b); return fail(JB_ERR_NOT_IMPLEMENTED, "robot too large: per-warp working set exceeds shared memory (" + P.describe() + ")"); }
     ALLOC(b->d_needs_full, N);
     kp.needs_full = b->d_needs_full; kp.only_flagged = 0;
     if (const char* s = std::getenv("JB_NO_FAST_KERNEL")) b->no_fast_kernel = std::atoi(s) != 0;
@@ -388,7 +393,8 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
 
 int jb_describe(JbBatch* b, char* buf, int32_t len) {
     if (!b || !buf) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
-    std::snprintf(buf, len, "%s", b->plan.describe().c_str());
+    std::snprintf(buf, len, "%s; constraints: %s", b->plan.describe().c_str(),
+                  !b->kp.cons_on ? "flag only" : (b->kp.cq_on ? "structured quadruped solver + generic" : "generic solver"));
     return JB_OK;
 }
 
@@ -494,7 +500,7 @@ static int ext_slot_for(JbBatch* b, int joint, const double* p, int* slot_out) {
         b->kp.eslots = b->d_eslots; b->kp.imp_data = b->d_imp;
         b->kp.prof_pending = b->d_prof_pending; b->kp.prof_latched = b->d_prof_latched;
     }
-    const size_t smem = static_cast<size_t>(P.nfields + 1 + ESLOT_SIZE * (b->eframes.size() + 1)) * 32 * sizeof(double);
+    const size_t smem = static_cast<size_t>(b->base_fields + ESLOT_SIZE * (b->eframes.size() + 1)) * 32 * sizeof(double);
     if (smem > 227 * 1024) return fail(JB_ERR_NOT_IMPLEMENTED, "no shared memory left for an external-force slot");
     int rc = raise_smem_attr(b->device, smem);
     if (rc) return rc;
@@ -609,7 +615,7 @@ int jb_remove_all_forces(JbBatch* b) {
     if (b->any_started) return fail(JB_ERR_BAD_CONTROL_FLOW, "Simulation already running. Please stop it before removing forces.");
     b->kp.n_imp = 0; b->kp.n_prof = 0; b->kp.n_eslot = 0;
     b->eframes.clear();
-    b->smem_bytes = static_cast<size_t>(b->plan.nfields + 1) * 32 * sizeof(double);
+    b->smem_bytes = static_cast<size_t>(b->base_fields) * 32 * sizeof(double);
     const JbOptions o = b->kp.opt;
     apply_options(b, &o);
     return JB_OK;

@@ -1,0 +1,436 @@
+// jiminy_b200 -- structured constraint solve for quadruped-shaped plans (ANYmal): L = 4, one trunk free-flyer,
+// a chain of three revolute joints per lane with one contact frame on the last one.
+//
+// Same mathematics as jb_constraints.cuh (Engine::computeAcceleration with enabled constraints,
+// core/src/engine/engine.cc:3709-3866; PGSSolver, core/src/solver/constraint_solvers.cc:107-448), but the
+// joint-space inertia is never formed as a dense matrix.  With the dofs ordered (trunk | leg 0 | ... | leg 3)
+//       M = [ M_tt   M_t0 ... M_t3 ]        legs couple only through the trunk (branch-induced sparsity), so
+//           [ M_0t   M_00          ]          M^-1 = blockdiag(0, M_ll^-1) + [1; -W] S^-1 [1, -W^T],
+//           [  ...         ...     ]          W_l = M_ll^-1 M_lt ,  S = M_tt - sum_l M_tl W_l   (6 x 6)
+// and for constraint rows r (owned by lane l(r), Jacobian [J_t | J_l]):
+//       A_rs = [l(r) = l(s)] J_l,r M_ll^-1 J_l,s^T + g_r . S^-1 g_s ,   g_r = J_t,r - J_l,r W_l(r).
+// Every lane builds its own 3 x 3 block, its W, its rows and g, h = S^-1 g in registers / shared memory; the only
+// exchanges between the lanes of an env are one 21-number all-reduce (S) and, inside the Gauss-Seidel sweep,
+// the 6-vector z = sum_r g_r lambda_r (A.col(k) . lambda = local part + h_k . z).  The sweep order is the
+// reference's (contact frames in registry order, normal / torsion / friction blocks breadth-first).
+//
+// Handles the common case -- contact constraints only, boxed solve.  Envs with an enabled joint-bound constraint,
+// and the first start iteration (equality solve), take the generic path of jb_constraints.cuh.
+#pragma once
+
+// per-lane shared-memory fields of the structured solver (after KParams::cq_off)
+constexpr int CQ_G = 0;      // 4 x 6  g_r
+constexpr int CQ_H = 24;     // 4 x 6  h_r = S^-1 g_r
+constexpr int CQ_JL = 48;    // 4 x 3  J_l,r
+constexpr int CQ_AL = 60;    // 4 x 4  J_l M_ll^-1 J_l^T (full, row-major)
+constexpr int CQ_B = 76;     // 4
+constexpr int CQ_LA = 80;    // 4  multipliers
+constexpr int CQ_Y = 84;     // 4  residuals
+constexpr int CQ_YP = 88;    // 4  previous residuals
+constexpr int CQ_AD = 92;    // 4  diagonal of A, regularised
+constexpr int CQ_RG = 96;    // 4  regularisation term of the diagonal
+constexpr int CQ_W = 100;    // 3 x 6
+constexpr int CQ_MI = 118;   // 6  M_ll^-1 (xx,xy,yy,xz,yz,zz)
+constexpr int CQ_R3 = 124;   // 9  world rotation of the last joint of the chain
+constexpr int CQ_SF = 133;   // 21 factor of S: A^-1 (6), T = A^-1 B (9), (D - B^T T)^-1 (6)
+constexpr int CQ_X = 154;    // 21 exchange slot (all-reduce input, then dz of the sweep)
+constexpr int CQ_SIZE = 175;
+#define CQF(off) (jb_smem[(KP->cq_off + (off)) * 32 + c.lane])
+#define CQF_OF(off, s) (jb_smem[(KP->cq_off + (off)) * 32 + (c.lane - c.sub + (s))])
+
+struct Spd6 { double Ai[6], T[9], Si[6]; };
+JB_DI void spd6_factor(const SymY& Y, Spd6& f) {
+    sym3_inverse(Y.A, f.Ai);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const V3 col = symmul(f.Ai, mk(Y.B[j], Y.B[3 + j], Y.B[6 + j]));
+        f.T[j] = col.x; f.T[3 + j] = col.y; f.T[6 + j] = col.z;
+    }
+    double S[6];
+    S[0] = Y.D[0] - (Y.B[0] * f.T[0] + Y.B[3] * f.T[3] + Y.B[6] * f.T[6]);
+    S[1] = Y.D[1] - (Y.B[0] * f.T[1] + Y.B[3] * f.T[4] + Y.B[6] * f.T[7]);
+    S[2] = Y.D[2] - (Y.B[1] * f.T[1] + Y.B[4] * f.T[4] + Y.B[7] * f.T[7]);
+    S[3] = Y.D[3] - (Y.B[0] * f.T[2] + Y.B[3] * f.T[5] + Y.B[6] * f.T[8]);
+    S[4] = Y.D[4] - (Y.B[1] * f.T[2] + Y.B[4] * f.T[5] + Y.B[7] * f.T[8]);
+    S[5] = Y.D[5] - (Y.B[2] * f.T[2] + Y.B[5] * f.T[5] + Y.B[8] * f.T[8]);
+    sym3_inverse(S, f.Si);
+}
+// x = Y^-1 b with Y = [[A, B], [B^T, D]]:  x2 = Si (b2 - T^T b1) ,  x1 = Ai b1 - T x2
+JB_DI Mot spd6_apply(const Spd6& f, Mot b) {
+    const V3 r2 = b.a - rtmul(f.T, b.l);
+    Mot x;
+    x.a = symmul(f.Si, r2);
+    x.l = symmul(f.Ai, b.l) - rmul(f.T, x.a);
+    return x;
+}
+
+// does the plan have the shape this solver assumes?  (host side, at batch creation)
+static bool cons_quadruped_matches(const KParams& kp, const Plan& P, const JbModelDesc& m) {
+    if (kp.L != 4 || kp.nrec != 4 || kp.ntrunk != 1 || kp.ncslot != 1 || m.ncontacts != 4 || kp.n_hist != 0) return false;
+    bool seen[4] = {false, false, false, false};
+    for (int s = 0; s < 4; ++s) {
+        for (int r = 0; r < 4; ++r) {
+            const RecInt& ri = P.rint[static_cast<size_t>(r) * 4 + s];
+            if (r == 0) { if (ri.kind != REC_FREE || ri.parent_rec >= 0) return false; continue; }
+            if ((ri.kind != REC_REV && ri.kind != REC_REVX) || ri.parent_rec != r - 1) return false;
+            if (ri.ncontact != (r == 3 ? 1 : 0)) return false;
+        }
+        const int k = P.cslots[s].contact;
+        if (k < 0 || k >= 4 || seen[k]) return false;
+        seen[k] = true;
+    }
+    return true;
+}
+
+// Called by the four lanes of the env after the ABA sweeps, when only contact constraints are enabled.
+__device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
+    constexpr int L = 4;
+    const JbOptions& opt = KP->opt;
+    const RecDbl* rd0 = KP->rdbl + (0 * L + c.sub);
+    const ContactSlot* ct = KP->cslots + c.sub;       // contact slot 0 of this lane
+    const int kc = ct->contact;                        // contact index == constraint index among the contact frames
+    const int cso = cs_contact(kc);
+    const bool en = CST(cso) != 0.0;
+    __syncwarp(c.gmask);
+    // ---------------- kinematics along the chain, composite inertias, inertia blocks
+    Xf oM; Mot v, aD;
+    {
+        double* const rp = jb_smem + KP->rec_off[0] * 32 + c.lane;
+        sm_load_xf(c, KP->rec_off[0] + RF_LIMI, oM);
+        v = sm_load_mot(c, KP->rec_off[0] + RF_VS);
+        aD = mzero();
+        (void)rp;
+    }
+    const Xf oM0 = oM;
+    V3 wax[3], parm[3];        // world axes and world positions of the three leg joints
+#pragma unroll
+    for (int i = 1; i <= 3; ++i) {
+        const RecDbl* rd = KP->rdbl + (i * L + c.sub);
+        const int base = KP->rec_off[i];
+        Xf li; sm_load_xf(c, base + R1_LIMI, li);
+        Xf o2;
+        mat3mul(oM.R, li.R, o2.R);
+        o2.p = oM.p + rmul(oM.R, li.p);
+        oM = o2;
+        const V3 ax = ld3(rd->axis);
+        Mot vJ = mzero(); vJ.a = SMF(c, base + R1_VS) * ax;
+        v = motion_act_inv(li, v) + vJ;
+        aD = sm_load_mot(c, base + R1_BIAS) + motion_act_inv(li, aD);
+        wax[i - 1] = rmul(oM.R, ax);
+        parm[i - 1] = oM.p;
+    }
+    // composite-rigid-body recursion from the foot to the trunk; F_i = Yc_i S_i carried up to the trunk frame
+    double Mll[6];             // (11, 12, 22, 13, 23, 33)
+    Mot Ft[3];                 // columns of M_tl (force in the trunk joint frame)
+    SymY Yleg;
+    {
+        SymY Yc;
+        Mot F[3];
+#pragma unroll
+        for (int i = 3; i >= 1; --i) {
+            const RecDbl* rd = KP->rdbl + (i * L + c.sub);
+            const V3 ax = ld3(rd->axis);
+            SymY Yi;
+            inertia_to_sym(rd->inertia[0], ld3(rd->inertia + 1), rd->inertia + 4, Yi);
+            if (i < 3) {
+                Xf lic; sm_load_xf(c, KP->rec_off[i + 1] + R1_LIMI, lic);
+                SymY T;
+                sym_transform(lic, Yc, T);
+                sym_add(Yi, T);
+                // forces of the dofs below, one frame up
+#pragma unroll
+                for (int j = i + 1; j <= 3; ++j) F[j - 1] = force_act(lic, F[j - 1]);
+            }
+            Yc = Yi;
+            Mot S = mzero(); S.a = ax;
+            F[i - 1] = sym_mul_motion(Yc, S);
+            // row i of M_ll: S_i . F_j (j >= i), all expressed in frame i
+            Mll[i == 1 ? 0 : (i == 2 ? 2 : 5)] = dot(ax, F[i - 1].a) + rd->armature;
+            if (i == 2) Mll[4] = dot(ax, F[2].a);
+            if (i == 1) { Mll[1] = dot(ax, F[1].a); Mll[3] = dot(ax, F[2].a); }
+        }
+        Xf li1; sm_load_xf(c, KP->rec_off[1] + R1_LIMI, li1);
+        sym_transform(li1, Yc, Yleg);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Ft[j] = force_act(li1, F[j]);
+    }
+    double Mi[6];
+    sym3_inverse(Mll, Mi);
+    // W = M_ll^-1 M_lt (3 x 6), T = Yleg - M_tl W
+    double W[3][6];
+    {
+        const double Mfull[3][3] = {{Mi[0], Mi[1], Mi[3]}, {Mi[1], Mi[2], Mi[4]}, {Mi[3], Mi[4], Mi[5]}};
+        double Fv[3][6];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { Fv[j][0] = Ft[j].l.x; Fv[j][1] = Ft[j].l.y; Fv[j][2] = Ft[j].l.z; Fv[j][3] = Ft[j].a.x; Fv[j][4] = Ft[j].a.y; Fv[j][5] = Ft[j].a.z; }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int d = 0; d < 6; ++d) W[i][d] = Mfull[i][0] * Fv[0][d] + Mfull[i][1] * Fv[1][d] + Mfull[i][2] * Fv[2][d];
+        auto sp = [&](int a, int b) { return Fv[0][a] * W[0][b] + Fv[1][a] * W[1][b] + Fv[2][a] * W[2][b]; };
+        // symmetric 6 x 6 in SymY layout: A (lin-lin), B[3 a + b] (lin a, ang b), D (ang-ang)
+        CQF(CQ_X + 0) = Yleg.A[0] - sp(0, 0); CQF(CQ_X + 1) = Yleg.A[1] - sp(0, 1); CQF(CQ_X + 2) = Yleg.A[2] - sp(1, 1);
+        CQF(CQ_X + 3) = Yleg.A[3] - sp(0, 2); CQF(CQ_X + 4) = Yleg.A[4] - sp(1, 2); CQF(CQ_X + 5) = Yleg.A[5] - sp(2, 2);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) CQF(CQ_X + 6 + 3 * a + b) = Yleg.B[3 * a + b] - sp(a, 3 + b);
+        CQF(CQ_X + 15) = Yleg.D[0] - sp(3, 3); CQF(CQ_X + 16) = Yleg.D[1] - sp(3, 4); CQF(CQ_X + 17) = Yleg.D[2] - sp(4, 4);
+        CQF(CQ_X + 18) = Yleg.D[3] - sp(3, 5); CQF(CQ_X + 19) = Yleg.D[4] - sp(4, 5); CQF(CQ_X + 20) = Yleg.D[5] - sp(5, 5);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int d = 0; d < 6; ++d) CQF(CQ_W + 6 * i + d) = W[i][d];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) CQF(CQ_MI + k) = Mi[k];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) CQF(CQ_R3 + k) = oM.R[k];
+    }
+    __syncwarp(c.gmask);
+    // ---------------- S = I_trunk + sum over the lanes (fixed order: identical on every lane), factored once
+    Spd6 sf;
+    {
+        SymY S;
+        inertia_to_sym(rd0->inertia[0], ld3(rd0->inertia + 1), rd0->inertia + 4, S);
+        for (int s = 0; s < L; ++s) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { S.A[k] += CQF_OF(CQ_X + k, s); S.D[k] += CQF_OF(CQ_X + 15 + k, s); }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) S.B[k] += CQF_OF(CQ_X + 6 + k, s);
+        }
+        spd6_factor(S, sf);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { CQF(CQ_SF + k) = sf.Ai[k]; CQF(CQ_SF + 15 + k) = sf.Si[k]; }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) CQF(CQ_SF + 6 + k) = sf.T[k];
+    }
+    // ---------------- constraint rows of this lane's contact frame (FrameConstraint::computeJacobianAndDrift)
+    Mot zpart = mzero();
+    {
+        Xf P;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) P.R[k] = ct->placement[k];
+        P.p = ld3(ct->placement + 9);
+        double Rf[9];
+        mat3mul(oM.R, P.R, Rf);
+        const V3 pf = oM.p + rmul(oM.R, P.p);
+        // unconstrained accelerations: trunk (6) and this leg (3)
+        const Mot at = sm_load_mot(c, KP->rec_off[0] + RF_A);
+        const double al[3] = {SMF(c, KP->rec_off[1] + R1_A), SMF(c, KP->rec_off[2] + R1_A), SMF(c, KP->rec_off[3] + R1_A)};
+        // drift with Baumgarte stabilisation
+        const Mot vLoc = motion_act_inv(P, v), aLoc = motion_act_inv(P, aD);
+        const V3 vl = rmul(Rf, vLoc.l), va = rmul(Rf, vLoc.a);
+        V3 dl = rmul(Rf, aLoc.l) + cross(va, vl), da = rmul(Rf, aLoc.a);
+        const double omega = 2.0 * 3.14159265358979323846 * opt.contact_stabilization_freq;
+        const double kp = omega * omega, kd = 2.0 * omega;
+        double RrT[9], Rref[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Rref[e] = CST(cso + 5 + e);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b2 = 0; b2 < 3; ++b2) RrT[3 * a + b2] = Rf[3 * a] * Rref[3 * b2] + Rf[3 * a + 1] * Rref[3 * b2 + 1] + Rf[3 * a + 2] * Rref[3 * b2 + 2];
+        dl = dl + kp * (pf - mk(CST(cso + 14), CST(cso + 15), CST(cso + 16))) + kd * vl;
+        da = da + kp * cons_log3(RrT) + kd * va;
+        const double gamma[4] = {dl.x, dl.y, dl.z, da.z};
+        const V3 lever0 = oM0.p - pf;
+        const double Mfull[3][3] = {{Mi[0], Mi[1], Mi[3]}, {Mi[1], Mi[2], Mi[4]}, {Mi[3], Mi[4], Mi[5]}};
+        double Jl[4][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const V3 lin = cross(parm[i] - pf, wax[i]);
+            Jl[0][i] = lin.x; Jl[1][i] = lin.y; Jl[2][i] = lin.z; Jl[3][i] = wax[i].z;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            // J_t row: trunk subspace = identity in the trunk joint frame
+            double Jt[6];
+            if (r < 3) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const V3 col = mk(oM0.R[d], oM0.R[3 + d], oM0.R[6 + d]);   // R_0 e_d
+                    const V3 lin = cross(lever0, col);
+                    Jt[d] = (r == 0 ? col.x : (r == 1 ? col.y : col.z));
+                    Jt[3 + d] = (r == 0 ? lin.x : (r == 1 ? lin.y : lin.z));
+                }
+            } else {
+                Jt[0] = 0.0; Jt[1] = 0.0; Jt[2] = 0.0; Jt[3] = oM0.R[6]; Jt[4] = oM0.R[7]; Jt[5] = oM0.R[8];
+            }
+            double g[6];
+#pragma unroll
+            for (int d = 0; d < 6; ++d) g[d] = Jt[d] - (Jl[r][0] * W[0][d] + Jl[r][1] * W[1][d] + Jl[r][2] * W[2][d]);
+            Mot gm; gm.l = mk(g[0], g[1], g[2]); gm.a = mk(g[3], g[4], g[5]);
+            const Mot h = spd6_apply(sf, gm);
+            const double hv[6] = {h.l.x, h.l.y, h.l.z, h.a.x, h.a.y, h.a.z};
+            const double lam = en ? CST(cso + 1 + r) : 0.0;
+#pragma unroll
+            for (int d = 0; d < 6; ++d) { CQF(CQ_G + 6 * r + d) = en ? g[d] : 0.0; CQF(CQ_H + 6 * r + d) = en ? hv[d] : 0.0; }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) CQF(CQ_JL + 3 * r + i) = en ? Jl[r][i] : 0.0;
+            double mj[3];   // M_ll^-1 J_l,r^T
+#pragma unroll
+            for (int i = 0; i < 3; ++i) mj[i] = Mfull[i][0] * Jl[r][0] + Mfull[i][1] * Jl[r][1] + Mfull[i][2] * Jl[r][2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) CQF(CQ_AL + 4 * r + q) = Jl[q][0] * mj[0] + Jl[q][1] * mj[1] + Jl[q][2] * mj[2];
+            const double a0 = (Jl[r][0] * mj[0] + Jl[r][1] * mj[1] + Jl[r][2] * mj[2]) + (g[0] * hv[0] + g[1] * hv[1] + g[2] * hv[2] + g[3] * hv[3] + g[4] * hv[4] + g[5] * hv[5]);
+            const double reg = fmax(a0 * opt.constraint_regularization, CONS_MIN_REGULARIZER);
+            CQF(CQ_AD + r) = a0 + reg; CQF(CQ_RG + r) = reg;
+            const double jd = Jt[0] * at.l.x + Jt[1] * at.l.y + Jt[2] * at.l.z + Jt[3] * at.a.x + Jt[4] * at.a.y + Jt[5] * at.a.z +
+                              Jl[r][0] * al[0] + Jl[r][1] * al[1] + Jl[r][2] * al[2];
+            CQF(CQ_B + r) = -gamma[r] - jd;
+            CQF(CQ_LA + r) = lam; CQF(CQ_Y + r) = 0.0;
+            if (en) { zpart.l = zpart.l + lam * gm.l; zpart.a = zpart.a + lam * gm.a; }
+        }
+    }
+    // z = sum over all rows of g_r lambda_r (all-reduce in fixed order)
+    __syncwarp(c.gmask);   // everybody has consumed the S exchange
+    CQF(CQ_X + 0) = zpart.l.x; CQF(CQ_X + 1) = zpart.l.y; CQF(CQ_X + 2) = zpart.l.z;
+    CQF(CQ_X + 3) = zpart.a.x; CQF(CQ_X + 4) = zpart.a.y; CQF(CQ_X + 5) = zpart.a.z;
+    __syncwarp(c.gmask);
+    double z[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int s = 0; s < L; ++s)
+#pragma unroll
+        for (int d = 0; d < 6; ++d) z[d] += CQF_OF(CQ_X + d, s);
+    __syncwarp(c.gmask);
+    // ---------------- projected Gauss-Seidel sweep (constraint_solvers.cc:107-318)
+    // Sweep order = contact index order; the lane owning contact k updates its multipliers from the current z and
+    // broadcasts the change of z to the other lanes of the env with shuffles.
+    auto residual = [&](int k) {
+        double s = CQF(CQ_AL + 4 * 0 + k) * CQF(CQ_LA + 0) + CQF(CQ_AL + 4 * 1 + k) * CQF(CQ_LA + 1) +
+                   CQF(CQ_AL + 4 * 2 + k) * CQF(CQ_LA + 2) + CQF(CQ_AL + 4 * 3 + k) * CQF(CQ_LA + 3);
+        const double hz = (CQF(CQ_H + 6 * k + 0) * z[0] + CQF(CQ_H + 6 * k + 1) * z[1]) + (CQF(CQ_H + 6 * k + 2) * z[2] + CQF(CQ_H + 6 * k + 3) * z[3]) +
+                          (CQF(CQ_H + 6 * k + 4) * z[4] + CQF(CQ_H + 6 * k + 5) * z[5]);
+        return CQF(CQ_B + k) - (s + hz) - CQF(CQ_RG + k) * CQF(CQ_LA + k);
+    };
+    const int lane0 = c.lane - c.sub;
+    bool ok = false;
+    for (int iter = 0; iter < CONS_PGS_MAX_ITER && !ok; ++iter) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) CQF(CQ_YP + r) = CQF(CQ_Y + r);
+        const double ratio = (static_cast<double>(CONS_PGS_MAX_ITER - CONS_RELAX_MIN_ITER) - iter) /
+                             (CONS_PGS_MAX_ITER - CONS_RELAX_MIN_ITER - CONS_RELAX_MAX_ITER);
+        double wr = CONS_RELAX_MAX;
+        if (ratio < 1.0) {
+            wr = CONS_RELAX_MIN;
+            if (ratio > 0.0) wr += (CONS_RELAX_MAX - CONS_RELAX_MIN) * (ratio * ratio);
+        }
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+            if (pass == 1 && opt.contact_torsion < D_EPS) {
+                // torsion disabled: the multiplier is forced to zero (it is zero already unless a warm start says
+                // otherwise); no coupling between contacts, so all lanes do it at once
+                const double d3 = -CQF(CQ_LA + 3);
+                CQF(CQ_LA + 3) = 0.0;
+                if (__any_sync(c.gmask, d3 != 0.0)) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int src = lane0 + KP->cmap[k].sub;
+#pragma unroll
+                        for (int d = 0; d < 6; ++d) z[d] += __shfl_sync(c.gmask, CQF(CQ_G + 18 + d) * d3, src);
+                    }
+                }
+                continue;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int own = KP->cmap[k].sub;
+                double dz[6] = {0, 0, 0, 0, 0, 0};
+                if (own == c.sub && en) {
+                    if (pass == 0) {
+                        const double y = residual(2);
+                        CQF(CQ_Y + 2) = y;
+                        const double e = fmax(CQF(CQ_LA + 2) + wr * y / CQF(CQ_AD + 2), 0.0);
+                        const double d2 = e - CQF(CQ_LA + 2);
+                        CQF(CQ_LA + 2) = e;
+#pragma unroll
+                        for (int d = 0; d < 6; ++d) dz[d] = CQF(CQ_G + 12 + d) * d2;
+                    } else if (pass == 1) {
+                        const double y = residual(3);
+                        CQF(CQ_Y + 3) = y;
+                        const double thr = opt.contact_torsion * CQF(CQ_LA + 2);
+                        const double e = fmin(fmax(CQF(CQ_LA + 3) + wr * y / CQF(CQ_AD + 3), -thr), thr);
+                        const double d3 = e - CQF(CQ_LA + 3);
+                        CQF(CQ_LA + 3) = e;
+#pragma unroll
+                        for (int d = 0; d < 6; ++d) dz[d] = CQF(CQ_G + 18 + d) * d3;
+                    } else {
+                        double e0, e1;
+                        if (opt.contact_friction < D_EPS) { e0 = CQF(CQ_LA + 0) * 0.0; e1 = CQF(CQ_LA + 1) * 0.0; }
+                        else {
+                            const double y0 = residual(0), y1 = residual(1);
+                            CQF(CQ_Y + 0) = y0; CQF(CQ_Y + 1) = y1;
+                            const double A_max = fmax(CQF(CQ_AD + 0), CQF(CQ_AD + 1));
+                            e0 = CQF(CQ_LA + 0) + wr * y0 / A_max;
+                            e1 = CQF(CQ_LA + 1) + wr * y1 / A_max;
+                            const double thr = opt.contact_friction * CQF(CQ_LA + 2);
+                            const double sq = e0 * e0 + e1 * e1;
+                            if (sq > thr * thr) { const double scale = thr / sqrt(sq); e0 *= scale; e1 *= scale; }
+                        }
+                        const double d0 = e0 - CQF(CQ_LA + 0), d1 = e1 - CQF(CQ_LA + 1);
+                        CQF(CQ_LA + 0) = e0; CQF(CQ_LA + 1) = e1;
+#pragma unroll
+                        for (int d = 0; d < 6; ++d) dz[d] = CQF(CQ_G + d) * d0 + CQF(CQ_G + 6 + d) * d1;
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < 6; ++d) z[d] += __shfl_sync(c.gmask, dz[d], lane0 + own);
+            }
+        }
+        // stopping criterion on the stagnation of the residuals (constraint_solvers.cc:256-274)
+        double ymax = 0.0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) ymax = fmax(ymax, fabs(CQF(CQ_Y + r)));
+        for (int o = 1; o < L; o <<= 1) ymax = fmax(ymax, __shfl_xor_sync(c.gmask, ymax, o));
+        const double tol = opt.tol_abs + opt.tol_rel * ymax + D_EPS;
+        bool conv = true;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) conv = conv && (fabs(CQF(CQ_Y + r) - CQF(CQ_YP + r)) < tol);
+        ok = __all_sync(c.gmask, conv);
+    }
+    // ---------------- accelerations: ddq_t = ddq_free_t + S^-1 z ; ddq_l = ddq_free_l + M_ll^-1 J_l^T lambda - W ddq_t'
+    {
+        Mot zm; zm.l = mk(z[0], z[1], z[2]); zm.a = mk(z[3], z[4], z[5]);
+        Spd6 sf2;   // reloaded: nothing big stays live across the sweep
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { sf2.Ai[k] = CQF(CQ_SF + k); sf2.Si[k] = CQF(CQ_SF + 15 + k); }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) sf2.T[k] = CQF(CQ_SF + 6 + k);
+        const Mot xt = spd6_apply(sf2, zm);
+        const double xv[6] = {xt.l.x, xt.l.y, xt.l.z, xt.a.x, xt.a.y, xt.a.z};
+        double* const r0 = jb_smem + KP->rec_off[0] * 32 + c.lane;
+#pragma unroll
+        for (int d = 0; d < 6; ++d) r0[(RF_A + d) * 32] += xv[d];
+        double rl[3] = {0, 0, 0};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) rl[i] += CQF(CQ_JL + 3 * r + i) * CQF(CQ_LA + r);
+        const double m0 = CQF(CQ_MI + 0), m1 = CQF(CQ_MI + 1), m2 = CQF(CQ_MI + 2), m3 = CQF(CQ_MI + 3), m4 = CQF(CQ_MI + 4), m5 = CQF(CQ_MI + 5);
+        const double Mfull[3][3] = {{m0, m1, m3}, {m1, m2, m4}, {m3, m4, m5}};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            double x = Mfull[i][0] * rl[0] + Mfull[i][1] * rl[1] + Mfull[i][2] * rl[2];
+#pragma unroll
+            for (int d = 0; d < 6; ++d) x -= CQF(CQ_W + 6 * i + d) * xv[d];
+            SMF(c, KP->rec_off[i + 1] + R1_A) += x;
+        }
+        // multipliers back into the constraint, contact wrench in the parent joint frame (engine.cc:3790-3822)
+        double* const cp = jb_smem + KP->cslot_off * 32 + c.lane;
+        if (en) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) CST(cso + 1 + r) = CQF(CQ_LA + r);
+            double R3[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) R3[k] = CQF(CQ_R3 + k);
+            const V3 Fl = rtmul(R3, mk(CQF(CQ_LA + 0), CQF(CQ_LA + 1), CQF(CQ_LA + 2)));
+            const V3 Tl = rtmul(R3, mk(0.0, 0.0, CQF(CQ_LA + 3)));
+            CO(0) = Fl.x; CO(1) = Fl.y; CO(2) = Fl.z; CO(3) = Tl.x; CO(4) = Tl.y; CO(5) = Tl.z;
+        }
+        if (c.sub == 0) CST(CS_SOLVE_FAILED) = ok ? 0.0 : CST(CS_SOLVE_FAILED) + 1.0;
+    }
+    __syncwarp(c.gmask);
+    cons_refresh_accelerations(c);
+    (void)status;
+    return ok;
+}

@@ -64,6 +64,13 @@ inline int __shfl_xor_sync(unsigned mask, int x, int o) {
     emul::sync_group(mask);
     return r;
 }
+inline double __shfl_sync(unsigned mask, double x, int src) {
+    emul::warp->dslot[emul::lane_id] = x;
+    emul::sync_group(mask);
+    const double r = emul::warp->dslot[src & 31];
+    emul::sync_group(mask);
+    return r;
+}
 inline bool __any_sync(unsigned mask, bool p) {
     emul::warp->islot[emul::lane_id] = p ? 1 : 0;
     emul::sync_group(mask);
@@ -73,6 +80,7 @@ inline bool __any_sync(unsigned mask, bool p) {
     emul::sync_group(mask);
     return r;
 }
+inline bool __all_sync(unsigned mask, bool p) { return !__any_sync(mask, !p); }
 inline double __longlong_as_double(long long x) { double d; std::memcpy(&d, &x, sizeof d); return d; }
 inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
