@@ -181,7 +181,7 @@ def bounds_scenario(api, data_dir, model="spring_damper", n_steps=60):
     return eng, orc
 
 
-def point_mass_constraint_scenario(api, data_dir, n_steps=40, torsion=0.0):
+def point_mass_constraint_scenario(api, data_dir, n_steps=40, torsion=0.0, solver="runge_kutta_4", impulse=False):
     """A free-flying mass on the ground with the constraint contact model: resting, sliding (Coulomb cone) and
     spinning envs; contact / force sensors and f_external included in the comparison."""
     import os
@@ -191,11 +191,18 @@ def point_mass_constraint_scenario(api, data_dir, n_steps=40, torsion=0.0):
     M.attach_sensor(r, "ContactSensor", "MassBody", frame_name="MassBody")
     r.add_frame("Sensor", "MassBody", M.SE3(M.rpy_to_matrix([0.3, -0.2, 0.5]), np.array([0.1, 0.2, -0.05])))
     M.attach_sensor(r, "ForceSensor", "F", frame_name="Sensor")
-    opt = _cons_opt(dtMax=1e-3, controllerUpdatePeriod=1e-3, odeSolver="runge_kutta_4")
+    opt = _cons_opt(dtMax=1e-3, controllerUpdatePeriod=1e-3, odeSolver=solver)
+    if solver == "runge_kutta_dopri":
+        opt["stepper"].update(dtMax=5e-3, tolAbs=1e-7, tolRel=1e-6)
     opt["contacts"].update(model="constraint", friction=0.8, transitionEps=1e-6, torsion=torsion)
     opt["world"]["gravity"] = [4.0, 1.0, -9.81, 0, 0, 0]
     n = 3
     eng, orc = BatchedEngine(r, opt, n, api_=api), OracleBatch(r, opt, n)
+    if impulse:   # a push and a lift while in contact: external forces and constraints in the same evaluation
+        fr = r.frames["MassBody"]
+        for x in (eng, orc):
+            args = ((fr.joint, fr.placement.p),) if x is eng else (fr.joint, fr.placement.p)
+            x.register_impulse_force(*args, [0.05, 0.02, 0.11], [0.05, 0.1, 0.02], [[20.0, 0, 0, 0, 0, 0], [0, 0, 30.0, 0, 0, 0], [0, -15.0, 5.0, 0, 0, 1.0]])
     q0 = np.tile(r.neutral(), (n, 1))
     q0[:, 2] = [0.0, 0.02, -1e-4]
     v0 = np.zeros((n, 6))

@@ -363,6 +363,8 @@ def test_joint_bounds_constraint_path(api, model):
 def test_constraint_contact_point_mass(api):
     pc.point_mass_constraint_scenario(api, DATA)
     pc.point_mass_constraint_scenario(api, DATA, n_steps=15, torsion=0.05)
+    pc.point_mass_constraint_scenario(api, DATA, n_steps=20, solver="runge_kutta_dopri")     # adaptive steps + PGS
+    pc.point_mass_constraint_scenario(api, DATA, n_steps=20, impulse=True)                   # external forces + PGS
 
 
 def test_constraint_contact_anymal(api):

@@ -15,12 +15,17 @@ tail -5 $OUT/bench.err
 for W in atlas cartpole; do
   timeout 300 python bench.py --workload $W --steps 10 --warmup 3 --no-cpu-baseline 2>> $OUT/bench.err | tee -a $OUT/bench_$W.log
 done
+# the other BASELINE configs at their own sizes, and the constraint contact model (the reference's default)
+timeout 300 python bench.py --workload cartpole --n-env 512 --steps 50 --warmup 5 2>> $OUT/bench.err | tee -a $OUT/bench_cartpole512.log
+timeout 300 python bench.py --workload double_pendulum --n-env 1 --steps 50 --warmup 5 2>> $OUT/bench.err | tee -a $OUT/bench_double_pendulum1.log
+timeout 300 python bench.py --workload anymal --contact-model constraint --steps 5 --warmup 3 2>> $OUT/bench.err | tee -a $OUT/bench_anymal_constraint.log
 echo "== reference arm" | tee $OUT/bench_ref.log
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 2>> $OUT/bench.err | tee -a $OUT/bench_ref.log
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 3 --warmup 1 --no-cpu-baseline > $OUT/ncu_launch_run.log 2>&1
 echo "== ncu full capture of env_step_kernel"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:env_step_kernel -s 3 -c 2 -f -o $OUT/prof_step \
+# launches: 0 = start (full kernel), then per step: fast kernel, full kernel as fix-up pass -> odd indices are the hot kernel
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:env_step_kernel -s 5 -c 1 -f -o $OUT/prof_step \
     python bench.py --steps 3 --warmup 1 --no-cpu-baseline > $OUT/ncu_full_run.log 2>&1
 ls -la $OUT
