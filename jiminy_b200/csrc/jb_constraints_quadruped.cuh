@@ -35,8 +35,8 @@ constexpr int CQ_R3 = 124;   // 9  world rotation of the last joint of the chain
 constexpr int CQ_SF = 133;   // 21 factor of S: A^-1 (6), T = A^-1 B (9), (D - B^T T)^-1 (6)
 constexpr int CQ_X = 154;    // 21 exchange slot (all-reduce input, then dz of the sweep)
 constexpr int CQ_SIZE = 175;
-#define CQF(off) (jb_smem[(KP->cq_off + (off)) * 32 + c.lane])
-#define CQF_OF(off, s) (jb_smem[(KP->cq_off + (off)) * 32 + (c.lane - c.sub + (s))])
+#define CQF(off) (cq[(off) * 32])                                   // cq = this lane's column of the region
+#define CQF_OF(off, s) (cq[(off) * 32 + ((s) - c.sub)])                // same field, sub-lane s of the env
 
 struct Spd6 { double Ai[6], T[9], Si[6]; };
 JB_DI void spd6_factor(const SymY& Y, Spd6& f) {
@@ -91,6 +91,7 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
     const int kc = ct->contact;                        // contact index == constraint index among the contact frames
     const int cso = cs_contact(kc);
     const bool en = CST(cso) != 0.0;
+    double* const cq = jb_smem + KP->cq_off * 32 + c.lane;
     __syncwarp(c.gmask);
     // ---------------- kinematics along the chain, composite inertias, inertia blocks
     Xf oM; Mot v, aD;
@@ -295,19 +296,33 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
     __syncwarp(c.gmask);
     // ---------------- projected Gauss-Seidel sweep (constraint_solvers.cc:107-318)
     // Sweep order = contact index order; the lane owning contact k updates its multipliers from the current z and
-    // broadcasts the change of z to the other lanes of the env with shuffles.
+    // broadcasts the change of z to the other lanes of the env with shuffles.  Everything the sweep touches is in
+    // registers (all indices are compile-time after unrolling); divisions by the regularised diagonal are
+    // multiplications by its reciprocal.
+    double G[4][6], H[4][6], AL[4][4], B[4], LA[4], Y[4], YP[4], iAD[4], RG[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int d = 0; d < 6; ++d) { G[r][d] = CQF(CQ_G + 6 * r + d); H[r][d] = CQF(CQ_H + 6 * r + d); }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) AL[r][q] = CQF(CQ_AL + 4 * r + q);
+        B[r] = CQF(CQ_B + r); LA[r] = CQF(CQ_LA + r); Y[r] = 0.0; YP[r] = 0.0;
+        iAD[r] = 1.0 / CQF(CQ_AD + r); RG[r] = CQF(CQ_RG + r);
+    }
+    const double iAmax = 1.0 / fmax(CQF(CQ_AD + 0), CQF(CQ_AD + 1));
     auto residual = [&](int k) {
-        double s = CQF(CQ_AL + 4 * 0 + k) * CQF(CQ_LA + 0) + CQF(CQ_AL + 4 * 1 + k) * CQF(CQ_LA + 1) +
-                   CQF(CQ_AL + 4 * 2 + k) * CQF(CQ_LA + 2) + CQF(CQ_AL + 4 * 3 + k) * CQF(CQ_LA + 3);
-        const double hz = (CQF(CQ_H + 6 * k + 0) * z[0] + CQF(CQ_H + 6 * k + 1) * z[1]) + (CQF(CQ_H + 6 * k + 2) * z[2] + CQF(CQ_H + 6 * k + 3) * z[3]) +
-                          (CQF(CQ_H + 6 * k + 4) * z[4] + CQF(CQ_H + 6 * k + 5) * z[5]);
-        return CQF(CQ_B + k) - (s + hz) - CQF(CQ_RG + k) * CQF(CQ_LA + k);
+        const double s = (AL[0][k] * LA[0] + AL[1][k] * LA[1]) + (AL[2][k] * LA[2] + AL[3][k] * LA[3]);
+        const double hz = (H[k][0] * z[0] + H[k][1] * z[1]) + (H[k][2] * z[2] + H[k][3] * z[3]) + (H[k][4] * z[4] + H[k][5] * z[5]);
+        return B[k] - (s + hz) - RG[k] * LA[k];
     };
     const int lane0 = c.lane - c.sub;
+    int own_of[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) own_of[k] = KP->cmap[k].sub;
     bool ok = false;
     for (int iter = 0; iter < CONS_PGS_MAX_ITER && !ok; ++iter) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) CQF(CQ_YP + r) = CQF(CQ_Y + r);
+        for (int r = 0; r < 4; ++r) YP[r] = Y[r];
         const double ratio = (static_cast<double>(CONS_PGS_MAX_ITER - CONS_RELAX_MIN_ITER) - iter) /
                              (CONS_PGS_MAX_ITER - CONS_RELAX_MIN_ITER - CONS_RELAX_MAX_ITER);
         double wr = CONS_RELAX_MAX;
@@ -320,74 +335,70 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
             if (pass == 1 && opt.contact_torsion < D_EPS) {
                 // torsion disabled: the multiplier is forced to zero (it is zero already unless a warm start says
                 // otherwise); no coupling between contacts, so all lanes do it at once
-                const double d3 = -CQF(CQ_LA + 3);
-                CQF(CQ_LA + 3) = 0.0;
+                const double d3 = -LA[3];
+                LA[3] = 0.0;
                 if (__any_sync(c.gmask, d3 != 0.0)) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int src = lane0 + KP->cmap[k].sub;
+                    for (int k = 0; k < 4; ++k)
 #pragma unroll
-                        for (int d = 0; d < 6; ++d) z[d] += __shfl_sync(c.gmask, CQF(CQ_G + 18 + d) * d3, src);
-                    }
+                        for (int d = 0; d < 6; ++d) z[d] += __shfl_sync(c.gmask, G[3][d] * d3, lane0 + own_of[k]);
                 }
                 continue;
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int own = KP->cmap[k].sub;
                 double dz[6] = {0, 0, 0, 0, 0, 0};
-                if (own == c.sub && en) {
+                if (own_of[k] == c.sub && en) {
                     if (pass == 0) {
                         const double y = residual(2);
-                        CQF(CQ_Y + 2) = y;
-                        const double e = fmax(CQF(CQ_LA + 2) + wr * y / CQF(CQ_AD + 2), 0.0);
-                        const double d2 = e - CQF(CQ_LA + 2);
-                        CQF(CQ_LA + 2) = e;
+                        Y[2] = y;
+                        const double e = fmax(LA[2] + wr * y * iAD[2], 0.0);
+                        const double d2 = e - LA[2];
+                        LA[2] = e;
 #pragma unroll
-                        for (int d = 0; d < 6; ++d) dz[d] = CQF(CQ_G + 12 + d) * d2;
+                        for (int d = 0; d < 6; ++d) dz[d] = G[2][d] * d2;
                     } else if (pass == 1) {
                         const double y = residual(3);
-                        CQF(CQ_Y + 3) = y;
-                        const double thr = opt.contact_torsion * CQF(CQ_LA + 2);
-                        const double e = fmin(fmax(CQF(CQ_LA + 3) + wr * y / CQF(CQ_AD + 3), -thr), thr);
-                        const double d3 = e - CQF(CQ_LA + 3);
-                        CQF(CQ_LA + 3) = e;
+                        Y[3] = y;
+                        const double thr = opt.contact_torsion * LA[2];
+                        const double e = fmin(fmax(LA[3] + wr * y * iAD[3], -thr), thr);
+                        const double d3 = e - LA[3];
+                        LA[3] = e;
 #pragma unroll
-                        for (int d = 0; d < 6; ++d) dz[d] = CQF(CQ_G + 18 + d) * d3;
+                        for (int d = 0; d < 6; ++d) dz[d] = G[3][d] * d3;
                     } else {
                         double e0, e1;
-                        if (opt.contact_friction < D_EPS) { e0 = CQF(CQ_LA + 0) * 0.0; e1 = CQF(CQ_LA + 1) * 0.0; }
+                        if (opt.contact_friction < D_EPS) { e0 = LA[0] * 0.0; e1 = LA[1] * 0.0; }
                         else {
                             const double y0 = residual(0), y1 = residual(1);
-                            CQF(CQ_Y + 0) = y0; CQF(CQ_Y + 1) = y1;
-                            const double A_max = fmax(CQF(CQ_AD + 0), CQF(CQ_AD + 1));
-                            e0 = CQF(CQ_LA + 0) + wr * y0 / A_max;
-                            e1 = CQF(CQ_LA + 1) + wr * y1 / A_max;
-                            const double thr = opt.contact_friction * CQF(CQ_LA + 2);
+                            Y[0] = y0; Y[1] = y1;
+                            e0 = LA[0] + wr * y0 * iAmax;
+                            e1 = LA[1] + wr * y1 * iAmax;
+                            const double thr = opt.contact_friction * LA[2];
                             const double sq = e0 * e0 + e1 * e1;
                             if (sq > thr * thr) { const double scale = thr / sqrt(sq); e0 *= scale; e1 *= scale; }
                         }
-                        const double d0 = e0 - CQF(CQ_LA + 0), d1 = e1 - CQF(CQ_LA + 1);
-                        CQF(CQ_LA + 0) = e0; CQF(CQ_LA + 1) = e1;
+                        const double d0 = e0 - LA[0], d1 = e1 - LA[1];
+                        LA[0] = e0; LA[1] = e1;
 #pragma unroll
-                        for (int d = 0; d < 6; ++d) dz[d] = CQF(CQ_G + d) * d0 + CQF(CQ_G + 6 + d) * d1;
+                        for (int d = 0; d < 6; ++d) dz[d] = G[0][d] * d0 + G[1][d] * d1;
                     }
                 }
 #pragma unroll
-                for (int d = 0; d < 6; ++d) z[d] += __shfl_sync(c.gmask, dz[d], lane0 + own);
+                for (int d = 0; d < 6; ++d) z[d] += __shfl_sync(c.gmask, dz[d], lane0 + own_of[k]);
             }
         }
         // stopping criterion on the stagnation of the residuals (constraint_solvers.cc:256-274)
-        double ymax = 0.0;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) ymax = fmax(ymax, fabs(CQF(CQ_Y + r)));
+        double ymax = fmax(fmax(fabs(Y[0]), fabs(Y[1])), fmax(fabs(Y[2]), fabs(Y[3])));
         for (int o = 1; o < L; o <<= 1) ymax = fmax(ymax, __shfl_xor_sync(c.gmask, ymax, o));
         const double tol = opt.tol_abs + opt.tol_rel * ymax + D_EPS;
         bool conv = true;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) conv = conv && (fabs(CQF(CQ_Y + r) - CQF(CQ_YP + r)) < tol);
+        for (int r = 0; r < 4; ++r) conv = conv && (fabs(Y[r] - YP[r]) < tol);
         ok = __all_sync(c.gmask, conv);
     }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) CQF(CQ_LA + r) = LA[r];
     // ---------------- accelerations: ddq_t = ddq_free_t + S^-1 z ; ddq_l = ddq_free_l + M_ll^-1 J_l^T lambda - W ddq_t'
     {
         Mot zm; zm.l = mk(z[0], z[1], z[2]); zm.a = mk(z[3], z[4], z[5]);
