@@ -36,13 +36,46 @@ def read_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons / power during the timed region (B200_PROFILING.md's clocks line), polled through
+    NVML every 5 ms (nvidia-smi itself needs ~100 ms per sample, longer than a short timed region); falls back to
+    `nvidia-smi -lms` when pynvml is unavailable."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self._stop_evt, self.proc = index, [], threading.Event(), None
 
+    def _run_nvml(self) -> bool:
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            try:   # the CUDA ordinal is not the NVML index when CUDA_VISIBLE_DEVICES reorders / hides devices
+                import torch
+                h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)).encode())
+            except Exception:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while True:
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx),
+                                     str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)] +
+                                    ["Active" if (r & bits[n]) else "Not Active" for n in
+                                     ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+            except Exception:
+                break
+            if self._stop_evt.wait(0.005):
+                break
+        return True
+
     def run(self):
+        if self._run_nvml():
+            return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -61,6 +94,7 @@ class ClockSampler(threading.Thread):
         self._stop_evt.set()
         if self.proc is not None:
             self.proc.terminate()
+        self.join(timeout=1.0)
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(self.samples)}
         try:
             sm = [float(s[0]) for s in self.samples if len(s) >= 7]
