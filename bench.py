@@ -211,9 +211,19 @@ def run_gpu(args):
     sens_ptr, _ = eng.device_views()
     # multi-GPU: the only collective of the path is the end-of-step observation all-gather
     gather_out = gather_in = None
+    use_p2p = world > 1 and not args.nccl_gather
+    obs_gather = "none (1 GPU)"
     if world > 1:
         gather_in = torch.empty((n_env, width), dtype=torch.float64, device=f"cuda:{local_rank}")
         gather_out = torch.empty((world * n_env, width), dtype=torch.float64, device=f"cuda:{local_rank}")
+        obs_gather = "nccl all_gather_into_tensor after the step"
+    if use_p2p:
+        # every env writes its sensor row into every rank's gathered buffer from inside the step kernel (stores over
+        # NVLink / NVSwitch peer memory): the exchange overlaps the physics, no collective is left on the path
+        handles = [None] * world
+        dist.all_gather_object(handles, eng.peer_obs_create(world, rank))
+        eng.peer_obs_connect(handles)
+        obs_gather = "in-kernel stores into peer memory (IPC-mapped gathered buffers), signal + wait kernels"
     flush = torch.empty(160 * 1024 * 1024 // 8, dtype=torch.float64, device=f"cuda:{local_rank}")  # > 126 MB L2
 
     def barrier():
@@ -221,8 +231,17 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    class _DevArray:   # zero-copy torch view of a raw device pointer
+        def __init__(self, ptr, shape):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+    def peer_view():
+        return torch.as_tensor(_DevArray(eng.peer_obs_view(), (world * n_env, width)), device=f"cuda:{local_rank}")
+
     def gather_obs():
-        if world > 1:
+        if use_p2p:
+            eng.peer_obs_wait()      # the rows were published by the step kernel itself
+        elif world > 1:
             eng.copy_sensors_to(gather_in.data_ptr())
             ev = torch.cuda.Event()
             ev.record(stream)
@@ -240,6 +259,17 @@ def run_gpu(args):
         eng.step(sc.step_dt)
         gather_obs()
     barrier()
+    if use_p2p:
+        # the peer-memory exchange against the plain NCCL all-gather of the same step: must be identical
+        eng.copy_sensors_to(gather_in.data_ptr())
+        torch.cuda.synchronize()
+        dist.all_gather_into_tensor(gather_out, gather_in)
+        torch.cuda.synchronize()
+        got = peer_view()
+        if not torch.equal(got, gather_out):
+            raise RuntimeError("peer-memory observation exchange differs from the NCCL all-gather")
+        obs_gather += "; verified bit-equal to nccl all_gather"
+        barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = eng.launch_count()
@@ -326,7 +356,7 @@ def run_gpu(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {n_env} envs per GPU, {world} GPU(s), one Engine::step({sc.step_dt}) per step",
                    "scenario": sc.description, "envs_total": total_envs, "lane_plan": eng.describe(),
-                   "l2": "160 MB buffer rewritten between timed steps (flush)", "obs_all_gather_ms": gather_ms,
+                   "l2": "160 MB buffer rewritten between timed steps (flush)", "obs_all_gather_ms": gather_ms, "obs_exchange": obs_gather,
                    "envs_flagged": n_bad, "timed_region_wall_ms": wall_ms},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_env * nm * 8 * world),
@@ -357,6 +387,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="jiminy_b200", choices=["jiminy_b200", "reference"])
     ap.add_argument("--workload", default="anymal", choices=["anymal", "atlas", "cartpole", "double_pendulum"])
+    ap.add_argument("--nccl-gather", action="store_true",
+                    help="multi-GPU: exchange observations with an NCCL all-gather after the step instead of the in-kernel "
+                         "stores into peer memory")
     ap.add_argument("--contact-model", default=None, choices=["spring_damper", "constraint"],
                     help="override contacts.model of the scenario (the BASELINE metric is quoted on spring_damper)")
     ap.add_argument("--n-env", type=int, default=4096, help="envs per GPU")

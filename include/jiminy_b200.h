@@ -282,6 +282,21 @@ int jb_device_views(JbBatch* batch, double** sensors_dev, double** qv_dev);
  * caller-owned device buffer, e.g. the send buffer of the observation all-gather. */
 int jb_copy_sensors_device(JbBatch* batch, double* dst_dev);
 
+/* ---- multi-GPU observation exchange over peer memory (NVLink / NVSwitch), one process per GPU ----
+ * Replaces the end-of-step observation concat of a sharded rollout -- an ncclAllGather in the
+ * plain layout -- by stores issued from inside the step kernel: every env writes its sensor row straight into
+ * the gathered buffer `[world][n_env][width]` of every rank, so the exchange overlaps the physics of the other
+ * warps and costs no collective.  Protocol: each rank calls jb_peer_obs_create (allocates its buffer, returns
+ * the 64-byte CUDA IPC handle), the handles are exchanged out of band (e.g. torch.distributed
+ * all_gather_object), each rank calls jb_peer_obs_connect with all of them.  From then on jb_step publishes and
+ * signals; jb_peer_obs_wait enqueues (on the batch stream) the wait for every rank's signal of the last step;
+ * jb_peer_obs_view returns the gathered buffer of that step (two buffers alternate, so a fast rank never
+ * overwrites what a slower one is still reading). */
+int jb_peer_obs_create(JbBatch* batch, int32_t world, int32_t rank, uint8_t handle_out[64]);
+int jb_peer_obs_connect(JbBatch* batch, const uint8_t* handles /* [world][64], rank order */);
+int jb_peer_obs_wait(JbBatch* batch);
+int jb_peer_obs_view(JbBatch* batch, double** obs_dev /* [world][n_env][width] */);
+
 /* Stream the batch launches on (a `cudaStream_t` cast to void*), for CUDA-event timing. */
 int jb_get_stream(JbBatch* batch, void** stream);
 /* Number of kernel launches issued by this batch so far (bench.py `gpu_launches`). */

@@ -52,7 +52,8 @@ class Api:
                "jb_get_extra_terms", "jb_get_status", "jb_get_iters", "jb_device_views", "jb_get_stream",
                "jb_launch_count", "jb_synchronize", "jb_set_joint_springs", "jb_set_pd_controller", "jb_copy_sensors_device", "jb_describe",
                "jb_plan_describe", "jb_stop", "jb_register_impulse_force", "jb_set_impulse_force",
-               "jb_register_profile_force", "jb_set_profile_force", "jb_remove_all_forces")
+               "jb_register_profile_force", "jb_set_profile_force", "jb_remove_all_forces",
+               "jb_peer_obs_create", "jb_peer_obs_connect", "jb_peer_obs_wait", "jb_peer_obs_view")
 
     def __init__(self, cdll: C.CDLL):
         self.dll = L = cdll
@@ -95,6 +96,10 @@ class Api:
         L.jb_register_profile_force.argtypes = [vp, C.c_int32, c_double_p, C.c_double, c_int32_p]
         L.jb_set_profile_force.argtypes = [vp, C.c_int32, c_double_p]
         L.jb_remove_all_forces.argtypes = [vp]
+        L.jb_peer_obs_create.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p]
+        L.jb_peer_obs_connect.argtypes = [vp, C.c_char_p]
+        L.jb_peer_obs_wait.argtypes = [vp]
+        L.jb_peer_obs_view.argtypes = [vp, C.POINTER(vp)]
 
     def check(self, rc: int) -> None:
         if rc != JB_OK:
@@ -233,6 +238,28 @@ class BatchedEngine:
 
     def remove_all_forces(self) -> None:
         self._api.check(self._api.dll.jb_remove_all_forces(self._h))
+
+    # ---- multi-GPU observation exchange over peer memory (one process per GPU)
+    def peer_obs_create(self, world: int, rank: int) -> bytes:
+        """Allocates this rank's gathered observation buffer `[world][n_env][width]`; returns its CUDA IPC handle."""
+        buf = C.create_string_buffer(64)
+        self._api.check(self._api.dll.jb_peer_obs_create(self._h, int(world), int(rank), buf))
+        return buf.raw
+
+    def peer_obs_connect(self, handles: Sequence[bytes]) -> None:
+        """`handles[r]` = what rank r's `peer_obs_create` returned (exchange them with e.g. all_gather_object).
+        From now on every `step` publishes this rank's sensor rows into every rank's buffer from inside the kernel."""
+        self._api.check(self._api.dll.jb_peer_obs_connect(self._h, b"".join(bytes(h) for h in handles)))
+
+    def peer_obs_wait(self) -> None:
+        """Enqueues (on the batch stream) the wait for every rank's rows of the last step."""
+        self._api.check(self._api.dll.jb_peer_obs_wait(self._h))
+
+    def peer_obs_view(self) -> int:
+        """Device pointer of the gathered observations `[world][n_env][width]` of the last step."""
+        p = C.c_void_p()
+        self._api.check(self._api.dll.jb_peer_obs_view(self._h, C.byref(p)))
+        return int(p.value)
 
     def set_pd_controller(self, kp, kd) -> None:
         """Device-side `PDController` block (position targets, zero target velocity); `set_command` then

@@ -65,6 +65,14 @@ struct JbBatch {
     size_t smem_bytes = 0;
     int base_fields = 0;           // plan fields + constraint bookkeeping, before the external-force slots
     int32_t* d_needs_full = nullptr;
+    // observation exchange over peer memory
+    int peer_world = 0, peer_rank = 0;
+    char* d_peer_buf = nullptr;                 // [2][world][n_env][width] doubles, then flags [2][world] int64
+    size_t peer_obs_doubles = 0;                // doubles of ONE parity buffer
+    std::vector<void*> peer_opened;             // mapped buffers of the other ranks
+    char* peer_base[8] = {nullptr};
+    int* d_peer_timeout = nullptr;
+    long long step_id = 0;
     // external forces: frames (slots), impulse table mirror, profile periods
     struct ExtFrame { int joint; double p[3]; };
     std::vector<ExtFrame> eframes;
@@ -150,13 +158,33 @@ static int launch(JbBatch* b, int mode, double step_dt) {
     kp.only_flagged = 0;
     // static plan signatures carry no external-force / constraint-contact code
     if (kp.n_eslot > 0 || kp.opt.contact_model == JB_CONTACT_CONSTRAINT) kp.sig_id = 0;
+    if (mode == MODE_STEP && b->peer_world > 1 && !b->peer_opened.empty()) {
+        ++b->step_id;
+        kp.peer_parity = static_cast<int32_t>(b->step_id & 1);
+    } else kp.peer_n = 0;
     const bool fast_ok = mode == MODE_STEP && kp.n_eslot == 0 && kp.opt.contact_model == JB_CONTACT_SPRING_DAMPER &&
                          kp.opt.ode_solver != JB_SOLVER_RUNGE_KUTTA_DOPRI && !b->no_fast_kernel;
-    if (!fast_ok) return launch_one(b, kp, false);
-    int rc = launch_one(b, kp, true);
+    int rc;
+    if (!fast_ok) rc = launch_one(b, kp, false);
+    else {
+        rc = launch_one(b, kp, true);
+        if (rc) return rc;
+        kp.only_flagged = 1;
+        rc = launch_one(b, kp, false);
+    }
     if (rc) return rc;
-    kp.only_flagged = 1;
-    return launch_one(b, kp, false);
+#ifndef JB_HOST_EMUL
+    if (kp.peer_n > 0) {
+        // every env of this rank has published its row: tell the other ranks
+        PeerFlags f{};
+        const size_t flag_off = 2 * b->peer_obs_doubles * sizeof(double);
+        for (int p = 0; p < b->peer_world; ++p) f.p[p] = reinterpret_cast<long long*>(b->peer_base[p] + flag_off);
+        JB_LAUNCH(peer_signal_kernel, 1, 1, 0, b->stream, f, b->peer_world, b->peer_rank, kp.peer_parity, b->step_id);
+        CU(cudaGetLastError());
+        ++b->launches;
+    }
+#endif
+    return JB_OK;
 }
 
 extern "C" {
@@ -214,6 +242,9 @@ int jb_batch_destroy(JbBatch* b) {
     if (!b) return JB_OK;
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
+#ifndef JB_HOST_EMUL
+    for (void* p : b->peer_opened) cudaIpcCloseMemHandle(p);
+#endif
     for (void* p : b->allocs) cudaFree(p);
     if (b->h_stage) cudaFreeHost(b->h_stage);
     if (b->stream) cudaStreamDestroy(b->stream);
@@ -746,6 +777,81 @@ int jb_copy_sensors_device(JbBatch* b, double* dst_dev) {
     if (!b || !dst_dev) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
     CU(cudaSetDevice(b->device));
     if (b->width) CU(cudaMemcpyAsync(dst_dev, b->d_sensors, sizeof(double) * b->n_env * b->width, cudaMemcpyDeviceToDevice, b->stream));
+    return JB_OK;
+}
+
+// ---- observation exchange over peer memory ----------------------------------------------------------------
+int jb_peer_obs_create(JbBatch* b, int32_t world, int32_t rank, uint8_t handle_out[64]) {
+#ifdef JB_HOST_EMUL
+    return fail(JB_ERR_NOT_IMPLEMENTED, "peer memory needs CUDA devices");
+#else
+    if (!b || !handle_out) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (world < 2 || world > 8 || rank < 0 || rank >= world) return fail(JB_ERR_INVALID_ARGUMENT, "world must be 2..8 and 0 <= rank < world");
+    if (b->d_peer_buf) return fail(JB_ERR_BAD_CONTROL_FLOW, "peer buffer already created");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaSetDevice(b->device));
+    b->peer_world = world; b->peer_rank = rank;
+    b->peer_obs_doubles = static_cast<size_t>(world) * b->n_env * std::max(b->width, 1);
+    const size_t bytes = 2 * b->peer_obs_doubles * sizeof(double) + 2 * world * sizeof(long long);
+    void* raw = nullptr;
+    CU(cudaMalloc(&raw, bytes));          // a dedicated allocation: IPC handles map whole allocations
+    CU(cudaMemset(raw, 0, bytes));
+    b->allocs.push_back(raw);
+    b->d_peer_buf = static_cast<char*>(raw);
+    int rc = dev_alloc(b, &b->d_peer_timeout, 1);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, raw));
+    std::memcpy(handle_out, &h, 64);
+    CU(cudaStreamSynchronize(b->stream));
+    return JB_OK;
+#endif
+}
+
+int jb_peer_obs_connect(JbBatch* b, const uint8_t* handles) {
+#ifdef JB_HOST_EMUL
+    return fail(JB_ERR_NOT_IMPLEMENTED, "peer memory needs CUDA devices");
+#else
+    if (!b || !handles) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!b->d_peer_buf) return fail(JB_ERR_BAD_CONTROL_FLOW, "call jb_peer_obs_create first");
+    if (!b->peer_opened.empty()) return fail(JB_ERR_BAD_CONTROL_FLOW, "already connected");
+    CU(cudaSetDevice(b->device));
+    for (int p = 0; p < b->peer_world; ++p) {
+        if (p == b->peer_rank) { b->peer_base[p] = b->d_peer_buf; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + 64 * p, 64);
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(JB_ERR_CUDA, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(p) + "): " + cudaGetErrorString(e));
+        b->peer_opened.push_back(ptr);
+        b->peer_base[p] = static_cast<char*>(ptr);
+    }
+    b->kp.peer_n = b->peer_world; b->kp.peer_rank = b->peer_rank; b->kp.peer_parity = 0;
+    for (int p = 0; p < b->peer_world; ++p) b->kp.peer_obs[p] = reinterpret_cast<double*>(b->peer_base[p]);
+    return JB_OK;
+#endif
+}
+
+int jb_peer_obs_wait(JbBatch* b) {
+#ifdef JB_HOST_EMUL
+    return fail(JB_ERR_NOT_IMPLEMENTED, "peer memory needs CUDA devices");
+#else
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (b->peer_opened.empty() || b->step_id == 0) return fail(JB_ERR_BAD_CONTROL_FLOW, "no published step to wait for");
+    CU(cudaSetDevice(b->device));
+    const int parity = static_cast<int>(b->step_id & 1);
+    volatile long long* mine = reinterpret_cast<volatile long long*>(b->d_peer_buf + 2 * b->peer_obs_doubles * sizeof(double));
+    JB_LAUNCH(peer_wait_kernel, 1, 1, 0, b->stream, mine, b->peer_world, parity, b->step_id, b->d_peer_timeout);
+    CU(cudaGetLastError());
+    ++b->launches;
+    return JB_OK;
+#endif
+}
+
+int jb_peer_obs_view(JbBatch* b, double** obs_dev) {
+    if (!b || !obs_dev) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!b->d_peer_buf) return fail(JB_ERR_BAD_CONTROL_FLOW, "call jb_peer_obs_create first");
+    *obs_dev = reinterpret_cast<double*>(b->d_peer_buf) + static_cast<size_t>(b->step_id & 1) * b->peer_obs_doubles;
     return JB_OK;
 }
 

@@ -449,6 +449,17 @@ __global__ void __launch_bounds__(32) env_step_kernel_t() {
     }
     if (KP->extra_energy != nullptr && !(status & (JB_ENV_NAN | JB_ENV_NOT_STARTED))) extra_terms(c);
     store_outputs(c);
+    // multi-GPU: publish this env's sensor row into every rank's gathered buffer (stores over NVLink / NVSwitch)
+    if (KP->peer_n > 0 && c.valid) {
+        __syncwarp(c.gmask);   // the row was written by the owner lanes of the env
+        const int width = KP->lay.width;
+        const double* row = KP->sensors + col * width;
+        const size_t dst = ((static_cast<size_t>(KP->peer_parity) * KP->peer_n + KP->peer_rank) * KP->n_env + col) * width;
+        for (int p = 0; p < KP->peer_n; ++p) {
+            double* out = KP->peer_obs[p] + dst;
+            for (int k = c.sub; k < width; k += L) out[k] = row[k];
+        }
+    }
     if (KP->pd_gains != nullptr && c.valid) {
         for (int r = 0; r < KP->nrec; ++r) {
             const RecInt* ri = KP->rint + (r * L + c.sub);
@@ -468,3 +479,19 @@ __global__ void __launch_bounds__(32) env_step_kernel_t() {
 }
 
 }  // namespace jb
+
+// ---- observation exchange over peer memory: completion signal and wait (one thread each)
+#ifndef JB_HOST_EMUL
+struct PeerFlags { long long* p[8]; };
+__global__ void peer_signal_kernel(PeerFlags flags, int world, int rank, int parity, long long step) {
+    __threadfence_system();   // the step kernels of this stream have completed: their peer stores are performed
+    for (int p = 0; p < world; ++p) flags.p[p][parity * world + rank] = step;
+}
+__global__ void peer_wait_kernel(volatile long long* mine, int world, int parity, long long step, int* timed_out) {
+    const long long t0 = clock64();
+    for (int p = 0; p < world; ++p)
+        while (mine[parity * world + p] < step)
+            if (clock64() - t0 > 20000000000LL) { *timed_out = 1; return; }   // ~10 s: a rank died
+    __threadfence_system();
+}
+#endif
