@@ -161,30 +161,18 @@ static int launch(JbBatch* b, int mode, double step_dt) {
     if (mode == MODE_STEP && b->peer_world > 1 && !b->peer_opened.empty()) {
         ++b->step_id;
         kp.peer_parity = static_cast<int32_t>(b->step_id & 1);
+        kp.peer_step = b->step_id;
     } else kp.peer_n = 0;
+    kp.peer_signal = 0;
     const bool fast_ok = mode == MODE_STEP && kp.n_eslot == 0 && kp.opt.contact_model == JB_CONTACT_SPRING_DAMPER &&
                          kp.opt.ode_solver != JB_SOLVER_RUNGE_KUTTA_DOPRI && !b->no_fast_kernel;
-    int rc;
-    if (!fast_ok) rc = launch_one(b, kp, false);
-    else {
-        rc = launch_one(b, kp, true);
-        if (rc) return rc;
-        kp.only_flagged = 1;
-        rc = launch_one(b, kp, false);
-    }
+    // the full kernel is always the last launch of a step: its last block signals the other ranks
+    if (!fast_ok) { kp.peer_signal = kp.peer_n > 0; return launch_one(b, kp, false); }
+    int rc = launch_one(b, kp, true);
     if (rc) return rc;
-#ifndef JB_HOST_EMUL
-    if (kp.peer_n > 0) {
-        // every env of this rank has published its row: tell the other ranks
-        PeerFlags f{};
-        const size_t flag_off = 2 * b->peer_obs_doubles * sizeof(double);
-        for (int p = 0; p < b->peer_world; ++p) f.p[p] = reinterpret_cast<long long*>(b->peer_base[p] + flag_off);
-        JB_LAUNCH(peer_signal_kernel, 1, 1, 0, b->stream, f, b->peer_world, b->peer_rank, kp.peer_parity, b->step_id);
-        CU(cudaGetLastError());
-        ++b->launches;
-    }
-#endif
-    return JB_OK;
+    kp.only_flagged = 1;
+    kp.peer_signal = kp.peer_n > 0;
+    return launch_one(b, kp, false);
 }
 
 extern "C" {
@@ -827,7 +815,16 @@ int jb_peer_obs_connect(JbBatch* b, const uint8_t* handles) {
         b->peer_base[p] = static_cast<char*>(ptr);
     }
     b->kp.peer_n = b->peer_world; b->kp.peer_rank = b->peer_rank; b->kp.peer_parity = 0;
-    for (int p = 0; p < b->peer_world; ++p) b->kp.peer_obs[p] = reinterpret_cast<double*>(b->peer_base[p]);
+    const size_t flag_off = 2 * b->peer_obs_doubles * sizeof(double);
+    for (int p = 0; p < b->peer_world; ++p) {
+        b->kp.peer_obs[p] = reinterpret_cast<double*>(b->peer_base[p]);
+        b->kp.peer_flags[p] = reinterpret_cast<long long*>(b->peer_base[p] + flag_off);
+    }
+    unsigned int* d_counter = nullptr;
+    int rc2 = dev_alloc(b, &d_counter, 1);
+    if (rc2) return rc2;
+    CU(cudaStreamSynchronize(b->stream));
+    b->kp.peer_counter = d_counter;
     return JB_OK;
 #endif
 }

@@ -194,7 +194,7 @@ __device__ __noinline__ void store_dynamics(const Ctx c) {
 // no enabled constraint).  An env that needs anything else leaves untouched and is stepped by the full kernel,
 // launched right behind as a fix-up pass (KParams::only_flagged).
 template <bool FAST>
-__global__ void __launch_bounds__(32) env_step_kernel_t() {
+__device__ __forceinline__ void env_step_body() {
     Ctx c;
     c.lane = threadIdx.x & 31;
     const int L = KP->L;
@@ -478,7 +478,26 @@ __global__ void __launch_bounds__(32) env_step_kernel_t() {
     if (c.valid && c.sub == 0) KP->status[c.env] = status;
 }
 
-}  // namespace jb
+template <bool FAST>
+__global__ void __launch_bounds__(32) env_step_kernel_t() {
+    env_step_body<FAST>();
+#ifndef JB_HOST_EMUL
+    // observation exchange over peer memory: the last block of the last launch of a step tells the other ranks
+    // that every row of this rank has been published (release: fence, then the flags)
+    if (!FAST && KP->peer_signal) {
+        __syncwarp();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            const unsigned int done = atomicAdd(KP->peer_counter, 1u);
+            if (done == gridDim.x - 1) {
+                *KP->peer_counter = 0u;
+                __threadfence_system();
+                for (int p = 0; p < KP->peer_n; ++p) KP->peer_flags[p][KP->peer_parity * KP->peer_n + KP->peer_rank] = KP->peer_step;
+            }
+        }
+    }
+#endif
+}
 
 // ---- observation exchange over peer memory: completion signal and wait (one thread each)
 #ifndef JB_HOST_EMUL
@@ -495,3 +514,5 @@ __global__ void peer_wait_kernel(volatile long long* mine, int world, int parity
     __threadfence_system();
 }
 #endif
+
+}  // namespace jb
