@@ -449,15 +449,34 @@ __device__ __forceinline__ void env_step_body() {
     }
     if (KP->extra_energy != nullptr && !(status & (JB_ENV_NAN | JB_ENV_NOT_STARTED))) extra_terms(c);
     store_outputs(c);
-    // multi-GPU: publish this env's sensor row into every rank's gathered buffer (stores over NVLink / NVSwitch)
-    if (KP->peer_n > 0 && c.valid) {
-        __syncwarp(c.gmask);   // the row was written by the owner lanes of the env
+    // multi-GPU: publish the sensor rows into every rank's gathered buffer (stores over NVLink / NVSwitch).  The rows
+    // of a warp's envs are contiguous: when the whole warp is here it copies them with coalesced 16-byte stores,
+    // otherwise (some env of the warp failed or was handed to the full kernel) every env copies its own row.
+    if (KP->peer_n > 0) {
         const int width = KP->lay.width;
-        const double* row = KP->sensors + col * width;
-        const size_t dst = ((static_cast<size_t>(KP->peer_parity) * KP->peer_n + KP->peer_rank) * KP->n_env + col) * width;
-        for (int p = 0; p < KP->peer_n; ++p) {
-            double* out = KP->peer_obs[p] + dst;
-            for (int k = c.sub; k < width; k += L) out[k] = row[k];
+        const size_t slot = (static_cast<size_t>(KP->peer_parity) * KP->peer_n + KP->peer_rank) * KP->n_env;
+#ifndef JB_HOST_EMUL
+        const unsigned act = __activemask();
+#else
+        const unsigned act = 0u;
+#endif
+        if (act == 0xffffffffu && (width & 1) == 0) {
+            __syncwarp();
+            const int env0 = blockIdx.x * epw;
+            const int nrow = min(epw, KP->n_env - env0);
+            const int n2 = nrow * width / 2;
+            const double2* src = reinterpret_cast<const double2*>(KP->sensors + static_cast<size_t>(env0) * width);
+            for (int p = 0; p < KP->peer_n; ++p) {
+                double2* out = reinterpret_cast<double2*>(KP->peer_obs[p] + (slot + env0) * width);
+                for (int i = c.lane; i < n2; i += 32) out[i] = src[i];
+            }
+        } else if (c.valid) {
+            __syncwarp(c.gmask);   // the row was written by the owner lanes of the env
+            const double* row = KP->sensors + col * width;
+            for (int p = 0; p < KP->peer_n; ++p) {
+                double* out = KP->peer_obs[p] + (slot + col) * width;
+                for (int k = c.sub; k < width; k += L) out[k] = row[k];
+            }
         }
     }
     if (KP->pd_gains != nullptr && c.valid) {
