@@ -18,25 +18,20 @@
 // and the first start iteration (equality solve), take the generic path of jb_constraints.cuh.
 #pragma once
 
-// per-lane shared-memory fields of the structured solver (after KParams::cq_off)
-constexpr int CQ_G = 0;      // 4 x 6  g_r
-constexpr int CQ_H = 24;     // 4 x 6  h_r = S^-1 g_r
-constexpr int CQ_JL = 48;    // 4 x 3  J_l,r
-constexpr int CQ_AL = 60;    // 4 x 4  J_l M_ll^-1 J_l^T (full, row-major)
-constexpr int CQ_B = 76;     // 4
-constexpr int CQ_LA = 80;    // 4  multipliers
-constexpr int CQ_Y = 84;     // 4  residuals
-constexpr int CQ_YP = 88;    // 4  previous residuals
-constexpr int CQ_AD = 92;    // 4  diagonal of A, regularised
-constexpr int CQ_RG = 96;    // 4  regularisation term of the diagonal
-constexpr int CQ_W = 100;    // 3 x 6
-constexpr int CQ_MI = 118;   // 6  M_ll^-1 (xx,xy,yy,xz,yz,zz)
-constexpr int CQ_R3 = 124;   // 9  world rotation of the last joint of the chain
-constexpr int CQ_SF = 133;   // 21 factor of S: A^-1 (6), T = A^-1 B (9), (D - B^T T)^-1 (6)
-constexpr int CQ_X = 154;    // 21 exchange slot (all-reduce input, then dz of the sweep)
-constexpr int CQ_SIZE = 175;
-#define CQF(off) (cq[(off) * 32])                                   // cq = this lane's column of the region
-#define CQF_OF(off, s) (cq[(off) * 32 + ((s) - c.sub)])                // same field, sub-lane s of the env
+// The solver needs no shared memory of its own (the occupancy of the step kernel is unchanged): the sweep runs on
+// registers, the lanes exchange through shuffles, and the few values that must survive the sweep are parked in
+// record fields that are dead between the third ABA sweep and the refresh of the accelerations:
+//   W (3 x 6) and M_ll^-1 (6) in the U / Dinv / u fields of the three leg records, the world rotation of the foot
+//   joint (9) and J_l (4 x 3) in the trunk's pool entry.
+constexpr int CQ_SIZE = 0;
+JB_DI double cq_bcast_sum4(const Ctx& c, double x) {   // sum over the 4 lanes of the env, same order on every lane
+    const int l0 = c.lane - c.sub;
+    double s = __shfl_sync(c.gmask, x, l0);
+    s += __shfl_sync(c.gmask, x, l0 + 1);
+    s += __shfl_sync(c.gmask, x, l0 + 2);
+    s += __shfl_sync(c.gmask, x, l0 + 3);
+    return s;
+}
 
 struct Spd6 { double Ai[6], T[9], Si[6]; };
 JB_DI void spd6_factor(const SymY& Y, Spd6& f) {
@@ -91,7 +86,6 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
     const int kc = ct->contact;                        // contact index == constraint index among the contact frames
     const int cso = cs_contact(kc);
     const bool en = CST(cso) != 0.0;
-    double* const cq = jb_smem + KP->cq_off * 32 + c.lane;
     __syncwarp(c.gmask);
     // ---------------- kinematics along the chain, composite inertias, inertia blocks
     Xf oM; Mot v, aD;
@@ -159,6 +153,7 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
     sym3_inverse(Mll, Mi);
     // W = M_ll^-1 M_lt (3 x 6), T = Yleg - M_tl W
     double W[3][6];
+    SymY Tl;
     {
         const double Mfull[3][3] = {{Mi[0], Mi[1], Mi[3]}, {Mi[1], Mi[2], Mi[4]}, {Mi[3], Mi[4], Mi[5]}};
         double Fv[3][6];
@@ -169,43 +164,39 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
 #pragma unroll
             for (int d = 0; d < 6; ++d) W[i][d] = Mfull[i][0] * Fv[0][d] + Mfull[i][1] * Fv[1][d] + Mfull[i][2] * Fv[2][d];
         auto sp = [&](int a, int b) { return Fv[0][a] * W[0][b] + Fv[1][a] * W[1][b] + Fv[2][a] * W[2][b]; };
-        // symmetric 6 x 6 in SymY layout: A (lin-lin), B[3 a + b] (lin a, ang b), D (ang-ang)
-        CQF(CQ_X + 0) = Yleg.A[0] - sp(0, 0); CQF(CQ_X + 1) = Yleg.A[1] - sp(0, 1); CQF(CQ_X + 2) = Yleg.A[2] - sp(1, 1);
-        CQF(CQ_X + 3) = Yleg.A[3] - sp(0, 2); CQF(CQ_X + 4) = Yleg.A[4] - sp(1, 2); CQF(CQ_X + 5) = Yleg.A[5] - sp(2, 2);
+        // T = Yleg - M_tl W, symmetric 6 x 6 in SymY layout: A (lin-lin), B[3 a + b] (lin a, ang b), D (ang-ang)
+        Tl.A[0] = Yleg.A[0] - sp(0, 0); Tl.A[1] = Yleg.A[1] - sp(0, 1); Tl.A[2] = Yleg.A[2] - sp(1, 1);
+        Tl.A[3] = Yleg.A[3] - sp(0, 2); Tl.A[4] = Yleg.A[4] - sp(1, 2); Tl.A[5] = Yleg.A[5] - sp(2, 2);
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int b = 0; b < 3; ++b) CQF(CQ_X + 6 + 3 * a + b) = Yleg.B[3 * a + b] - sp(a, 3 + b);
-        CQF(CQ_X + 15) = Yleg.D[0] - sp(3, 3); CQF(CQ_X + 16) = Yleg.D[1] - sp(3, 4); CQF(CQ_X + 17) = Yleg.D[2] - sp(4, 4);
-        CQF(CQ_X + 18) = Yleg.D[3] - sp(3, 5); CQF(CQ_X + 19) = Yleg.D[4] - sp(4, 5); CQF(CQ_X + 20) = Yleg.D[5] - sp(5, 5);
+            for (int b = 0; b < 3; ++b) Tl.B[3 * a + b] = Yleg.B[3 * a + b] - sp(a, 3 + b);
+        Tl.D[0] = Yleg.D[0] - sp(3, 3); Tl.D[1] = Yleg.D[1] - sp(3, 4); Tl.D[2] = Yleg.D[2] - sp(4, 4);
+        Tl.D[3] = Yleg.D[3] - sp(3, 5); Tl.D[4] = Yleg.D[4] - sp(4, 5); Tl.D[5] = Yleg.D[5] - sp(5, 5);
+        // park W and M_ll^-1 in the dead U / Dinv / u fields of the leg records, the foot rotation in the pool entry
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 3; ++i) {
+            double* const rq = jb_smem + KP->rec_off[i + 1] * 32 + c.lane;
 #pragma unroll
-            for (int d = 0; d < 6; ++d) CQF(CQ_W + 6 * i + d) = W[i][d];
+            for (int d = 0; d < 6; ++d) rq[(R1_FU + d) * 32] = W[i][d];
+            rq[R1_DINV * 32] = Mi[2 * i]; rq[R1_U * 32] = Mi[2 * i + 1];
+        }
 #pragma unroll
-        for (int k = 0; k < 6; ++k) CQF(CQ_MI + k) = Mi[k];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) CQF(CQ_R3 + k) = oM.R[k];
+        for (int k = 0; k < 9; ++k) SMF(c, KP->pool_off + k) = oM.R[k];
     }
-    __syncwarp(c.gmask);
     // ---------------- S = I_trunk + sum over the lanes (fixed order: identical on every lane), factored once
     Spd6 sf;
     {
         SymY S;
         inertia_to_sym(rd0->inertia[0], ld3(rd0->inertia + 1), rd0->inertia + 4, S);
-        for (int s = 0; s < L; ++s) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) { S.A[k] += CQF_OF(CQ_X + k, s); S.D[k] += CQF_OF(CQ_X + 15 + k, s); }
+        for (int k = 0; k < 6; ++k) { S.A[k] += cq_bcast_sum4(c, Tl.A[k]); S.D[k] += cq_bcast_sum4(c, Tl.D[k]); }
 #pragma unroll
-            for (int k = 0; k < 9; ++k) S.B[k] += CQF_OF(CQ_X + 6 + k, s);
-        }
+        for (int k = 0; k < 9; ++k) S.B[k] += cq_bcast_sum4(c, Tl.B[k]);
         spd6_factor(S, sf);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) { CQF(CQ_SF + k) = sf.Ai[k]; CQF(CQ_SF + 15 + k) = sf.Si[k]; }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) CQF(CQ_SF + 6 + k) = sf.T[k];
     }
     // ---------------- constraint rows of this lane's contact frame (FrameConstraint::computeJacobianAndDrift)
+    double G[4][6], H[4][6], AL[4][4], B[4], LA[4], Y[4], YP[4], iAD[4], RG[4], AD01[2];
     Mot zpart = mzero();
     {
         Xf P;
@@ -265,51 +256,35 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
             const double hv[6] = {h.l.x, h.l.y, h.l.z, h.a.x, h.a.y, h.a.z};
             const double lam = en ? CST(cso + 1 + r) : 0.0;
 #pragma unroll
-            for (int d = 0; d < 6; ++d) { CQF(CQ_G + 6 * r + d) = en ? g[d] : 0.0; CQF(CQ_H + 6 * r + d) = en ? hv[d] : 0.0; }
+            for (int d = 0; d < 6; ++d) { G[r][d] = en ? g[d] : 0.0; H[r][d] = en ? hv[d] : 0.0; }
 #pragma unroll
-            for (int i = 0; i < 3; ++i) CQF(CQ_JL + 3 * r + i) = en ? Jl[r][i] : 0.0;
+            for (int i = 0; i < 3; ++i) SMF(c, KP->pool_off + 9 + 3 * r + i) = en ? Jl[r][i] : 0.0;   // parked in the pool entry
             double mj[3];   // M_ll^-1 J_l,r^T
 #pragma unroll
             for (int i = 0; i < 3; ++i) mj[i] = Mfull[i][0] * Jl[r][0] + Mfull[i][1] * Jl[r][1] + Mfull[i][2] * Jl[r][2];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) CQF(CQ_AL + 4 * r + q) = Jl[q][0] * mj[0] + Jl[q][1] * mj[1] + Jl[q][2] * mj[2];
+            for (int q = 0; q < 4; ++q) AL[r][q] = Jl[q][0] * mj[0] + Jl[q][1] * mj[1] + Jl[q][2] * mj[2];
             const double a0 = (Jl[r][0] * mj[0] + Jl[r][1] * mj[1] + Jl[r][2] * mj[2]) + (g[0] * hv[0] + g[1] * hv[1] + g[2] * hv[2] + g[3] * hv[3] + g[4] * hv[4] + g[5] * hv[5]);
             const double reg = fmax(a0 * opt.constraint_regularization, CONS_MIN_REGULARIZER);
-            CQF(CQ_AD + r) = a0 + reg; CQF(CQ_RG + r) = reg;
+            iAD[r] = 1.0 / (a0 + reg); RG[r] = reg;
+            if (r < 2) AD01[r] = a0 + reg;
             const double jd = Jt[0] * at.l.x + Jt[1] * at.l.y + Jt[2] * at.l.z + Jt[3] * at.a.x + Jt[4] * at.a.y + Jt[5] * at.a.z +
                               Jl[r][0] * al[0] + Jl[r][1] * al[1] + Jl[r][2] * al[2];
-            CQF(CQ_B + r) = -gamma[r] - jd;
-            CQF(CQ_LA + r) = lam; CQF(CQ_Y + r) = 0.0;
+            B[r] = -gamma[r] - jd;
+            LA[r] = lam; Y[r] = 0.0; YP[r] = 0.0;
             if (en) { zpart.l = zpart.l + lam * gm.l; zpart.a = zpart.a + lam * gm.a; }
         }
     }
     // z = sum over all rows of g_r lambda_r (all-reduce in fixed order)
-    __syncwarp(c.gmask);   // everybody has consumed the S exchange
-    CQF(CQ_X + 0) = zpart.l.x; CQF(CQ_X + 1) = zpart.l.y; CQF(CQ_X + 2) = zpart.l.z;
-    CQF(CQ_X + 3) = zpart.a.x; CQF(CQ_X + 4) = zpart.a.y; CQF(CQ_X + 5) = zpart.a.z;
-    __syncwarp(c.gmask);
-    double z[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int s = 0; s < L; ++s)
-#pragma unroll
-        for (int d = 0; d < 6; ++d) z[d] += CQF_OF(CQ_X + d, s);
-    __syncwarp(c.gmask);
+    double z[6];
+    z[0] = cq_bcast_sum4(c, zpart.l.x); z[1] = cq_bcast_sum4(c, zpart.l.y); z[2] = cq_bcast_sum4(c, zpart.l.z);
+    z[3] = cq_bcast_sum4(c, zpart.a.x); z[4] = cq_bcast_sum4(c, zpart.a.y); z[5] = cq_bcast_sum4(c, zpart.a.z);
     // ---------------- projected Gauss-Seidel sweep (constraint_solvers.cc:107-318)
     // Sweep order = contact index order; the lane owning contact k updates its multipliers from the current z and
     // broadcasts the change of z to the other lanes of the env with shuffles.  Everything the sweep touches is in
     // registers (all indices are compile-time after unrolling); divisions by the regularised diagonal are
     // multiplications by its reciprocal.
-    double G[4][6], H[4][6], AL[4][4], B[4], LA[4], Y[4], YP[4], iAD[4], RG[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-#pragma unroll
-        for (int d = 0; d < 6; ++d) { G[r][d] = CQF(CQ_G + 6 * r + d); H[r][d] = CQF(CQ_H + 6 * r + d); }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) AL[r][q] = CQF(CQ_AL + 4 * r + q);
-        B[r] = CQF(CQ_B + r); LA[r] = CQF(CQ_LA + r); Y[r] = 0.0; YP[r] = 0.0;
-        iAD[r] = 1.0 / CQF(CQ_AD + r); RG[r] = CQF(CQ_RG + r);
-    }
-    const double iAmax = 1.0 / fmax(CQF(CQ_AD + 0), CQF(CQ_AD + 1));
+    const double iAmax = 1.0 / fmax(AD01[0], AD01[1]);
     auto residual = [&](int k) {
         const double s = (AL[0][k] * LA[0] + AL[1][k] * LA[1]) + (AL[2][k] * LA[2] + AL[3][k] * LA[3]);
         const double hz = (H[k][0] * z[0] + H[k][1] * z[1]) + (H[k][2] * z[2] + H[k][3] * z[3]) + (H[k][4] * z[4] + H[k][5] * z[5]);
@@ -397,18 +372,17 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
         for (int r = 0; r < 4; ++r) conv = conv && (fabs(Y[r] - YP[r]) < tol);
         ok = __all_sync(c.gmask, conv);
     }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) CQF(CQ_LA + r) = LA[r];
-    // ---------------- accelerations: ddq_t = ddq_free_t + S^-1 z ; ddq_l = ddq_free_l + M_ll^-1 J_l^T lambda - W ddq_t'
+    // ---------------- accelerations: ddq_t = ddq_free_t + S^-1 z = ddq_free_t + sum_r h_r lambda_r ;
+    //                  ddq_l = ddq_free_l + M_ll^-1 J_l^T lambda - W (ddq_t - ddq_free_t)
     {
-        Mot zm; zm.l = mk(z[0], z[1], z[2]); zm.a = mk(z[3], z[4], z[5]);
-        Spd6 sf2;   // reloaded: nothing big stays live across the sweep
+        double xp[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { sf2.Ai[k] = CQF(CQ_SF + k); sf2.Si[k] = CQF(CQ_SF + 15 + k); }
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int k = 0; k < 9; ++k) sf2.T[k] = CQF(CQ_SF + 6 + k);
-        const Mot xt = spd6_apply(sf2, zm);
-        const double xv[6] = {xt.l.x, xt.l.y, xt.l.z, xt.a.x, xt.a.y, xt.a.z};
+            for (int d = 0; d < 6; ++d) xp[d] += H[r][d] * LA[r];
+        double xv[6];
+#pragma unroll
+        for (int d = 0; d < 6; ++d) xv[d] = cq_bcast_sum4(c, xp[d]);
         double* const r0 = jb_smem + KP->rec_off[0] * 32 + c.lane;
 #pragma unroll
         for (int d = 0; d < 6; ++d) r0[(RF_A + d) * 32] += xv[d];
@@ -416,27 +390,29 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int i = 0; i < 3; ++i) rl[i] += CQF(CQ_JL + 3 * r + i) * CQF(CQ_LA + r);
-        const double m0 = CQF(CQ_MI + 0), m1 = CQF(CQ_MI + 1), m2 = CQF(CQ_MI + 2), m3 = CQF(CQ_MI + 3), m4 = CQF(CQ_MI + 4), m5 = CQF(CQ_MI + 5);
-        const double Mfull[3][3] = {{m0, m1, m3}, {m1, m2, m4}, {m3, m4, m5}};
+            for (int i = 0; i < 3; ++i) rl[i] += SMF(c, KP->pool_off + 9 + 3 * r + i) * LA[r];
+        double mi[6];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { mi[2 * i] = SMF(c, KP->rec_off[i + 1] + R1_DINV); mi[2 * i + 1] = SMF(c, KP->rec_off[i + 1] + R1_U); }
+        const double Mfull[3][3] = {{mi[0], mi[1], mi[3]}, {mi[1], mi[2], mi[4]}, {mi[3], mi[4], mi[5]}};
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             double x = Mfull[i][0] * rl[0] + Mfull[i][1] * rl[1] + Mfull[i][2] * rl[2];
 #pragma unroll
-            for (int d = 0; d < 6; ++d) x -= CQF(CQ_W + 6 * i + d) * xv[d];
+            for (int d = 0; d < 6; ++d) x -= SMF(c, KP->rec_off[i + 1] + R1_FU + d) * xv[d];
             SMF(c, KP->rec_off[i + 1] + R1_A) += x;
         }
         // multipliers back into the constraint, contact wrench in the parent joint frame (engine.cc:3790-3822)
         double* const cp = jb_smem + KP->cslot_off * 32 + c.lane;
         if (en) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) CST(cso + 1 + r) = CQF(CQ_LA + r);
+            for (int r = 0; r < 4; ++r) CST(cso + 1 + r) = LA[r];
             double R3[9];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) R3[k] = CQF(CQ_R3 + k);
-            const V3 Fl = rtmul(R3, mk(CQF(CQ_LA + 0), CQF(CQ_LA + 1), CQF(CQ_LA + 2)));
-            const V3 Tl = rtmul(R3, mk(0.0, 0.0, CQF(CQ_LA + 3)));
-            CO(0) = Fl.x; CO(1) = Fl.y; CO(2) = Fl.z; CO(3) = Tl.x; CO(4) = Tl.y; CO(5) = Tl.z;
+            for (int k = 0; k < 9; ++k) R3[k] = SMF(c, KP->pool_off + k);
+            const V3 Fl = rtmul(R3, mk(LA[0], LA[1], LA[2]));
+            const V3 Tq = rtmul(R3, mk(0.0, 0.0, LA[3]));
+            CO(0) = Fl.x; CO(1) = Fl.y; CO(2) = Fl.z; CO(3) = Tq.x; CO(4) = Tq.y; CO(5) = Tq.z;
         }
         if (c.sub == 0) CST(CS_SOLVE_FAILED) = ok ? 0.0 : CST(CS_SOLVE_FAILED) + 1.0;
     }

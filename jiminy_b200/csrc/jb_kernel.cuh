@@ -449,17 +449,14 @@ __device__ __forceinline__ void env_step_body() {
     }
     if (KP->extra_energy != nullptr && !(status & (JB_ENV_NAN | JB_ENV_NOT_STARTED))) extra_terms(c);
     store_outputs(c);
+#ifndef JB_HOST_EMUL
     // multi-GPU: publish the sensor rows into every rank's gathered buffer (stores over NVLink / NVSwitch).  The rows
     // of a warp's envs are contiguous: when the whole warp is here it copies them with coalesced 16-byte stores,
     // otherwise (some env of the warp failed or was handed to the full kernel) every env copies its own row.
     if (KP->peer_n > 0) {
         const int width = KP->lay.width;
         const size_t slot = (static_cast<size_t>(KP->peer_parity) * KP->peer_n + KP->peer_rank) * KP->n_env;
-#ifndef JB_HOST_EMUL
         const unsigned act = __activemask();
-#else
-        const unsigned act = 0u;
-#endif
         if (act == 0xffffffffu && (width & 1) == 0) {
             __syncwarp();
             const int env0 = blockIdx.x * epw;
@@ -479,6 +476,7 @@ __device__ __forceinline__ void env_step_body() {
             }
         }
     }
+#endif
     if (KP->pd_gains != nullptr && c.valid) {
         for (int r = 0; r < KP->nrec; ++r) {
             const RecInt* ri = KP->rint + (r * L + c.sub);
