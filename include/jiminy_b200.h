@@ -205,6 +205,16 @@ int jb_set_command(JbBatch* batch, const double* cmd);
 /* Same, with `cmd_dev` a device pointer (same layout) on the batch's device: no host copy. */
 int jb_set_command_device(JbBatch* batch, const double* cmd_dev);
 
+/* gym_jiminy's `PDController` block on the device (blocks/proportional_derivative_controller.py:301-535), with
+ * the optional `MotorSafetyLimit` on top (blocks/motor_safety_limit.py:21-86).  jb_set_command then uploads target
+ * motor ACCELERATIONS; at every controller update the (position, velocity, acceleration) targets of each motor are
+ * integrated by `integrate_zoh` (:24-98) within [state_lower, state_upper] ([3][nmotors]: position, velocity,
+ * acceleration bounds) and the torque is clip(kp ((q_des - q) + kd (v_des - v)), +-effort_limit) (:104-165);
+ * jb_start restarts the targets from the clipped measurement.  `safety` = NULL, or [4][nmotors]: kp, kd, soft lower
+ * and soft upper position of `apply_safety_limits`.  kp = NULL disables the block. */
+int jb_set_pd_controller_full(JbBatch* batch, const double* kp, const double* kd, const double* state_lower,
+                              const double* state_upper, const double* safety);
+
 /* Replaces: Engine::stop (engine.cc:2419-2448): every env goes back to "not started", which is what
  * registering or removing forces requires (engine.cc:2456-2461). */
 int jb_stop(JbBatch* batch);

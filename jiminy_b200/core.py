@@ -53,7 +53,8 @@ class Api:
                "jb_launch_count", "jb_synchronize", "jb_set_joint_springs", "jb_set_pd_controller", "jb_copy_sensors_device", "jb_describe",
                "jb_plan_describe", "jb_stop", "jb_register_impulse_force", "jb_set_impulse_force",
                "jb_register_profile_force", "jb_set_profile_force", "jb_remove_all_forces",
-               "jb_peer_obs_create", "jb_peer_obs_connect", "jb_peer_obs_wait", "jb_peer_obs_view")
+               "jb_peer_obs_create", "jb_peer_obs_connect", "jb_peer_obs_wait", "jb_peer_obs_view",
+               "jb_set_pd_controller_full")
 
     def __init__(self, cdll: C.CDLL):
         self.dll = L = cdll
@@ -96,6 +97,7 @@ class Api:
         L.jb_register_profile_force.argtypes = [vp, C.c_int32, c_double_p, C.c_double, c_int32_p]
         L.jb_set_profile_force.argtypes = [vp, C.c_int32, c_double_p]
         L.jb_remove_all_forces.argtypes = [vp]
+        L.jb_set_pd_controller_full.argtypes = [vp] + [c_double_p] * 5
         L.jb_peer_obs_create.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p]
         L.jb_peer_obs_connect.argtypes = [vp, C.c_char_p]
         L.jb_peer_obs_wait.argtypes = [vp]
@@ -238,6 +240,22 @@ class BatchedEngine:
 
     def remove_all_forces(self) -> None:
         self._api.check(self._api.dll.jb_remove_all_forces(self._h))
+
+    def set_pd_controller_full(self, kp, kd, state_lower, state_upper, safety=None) -> None:
+        """gym_jiminy's `PDController` block on the device (+ `MotorSafetyLimit` when `safety` = [kp, kd, soft_lower,
+        soft_upper], each [nmotors]): `set_command` then uploads target motor accelerations.  `state_lower/upper`:
+        [3, nmotors] position / velocity / acceleration bounds of the targets.  `kp=None` disables it."""
+        if kp is None:
+            self._api.check(self._api.dll.jb_set_pd_controller_full(self._h, None, None, None, None, None))
+            return
+        nm = self.nm
+        kp = np.ascontiguousarray(np.broadcast_to(kp, (nm,)), dtype=np.float64)
+        kd = np.ascontiguousarray(np.broadcast_to(kd, (nm,)), dtype=np.float64)
+        lo = np.ascontiguousarray(state_lower, dtype=np.float64).reshape(3, nm)
+        hi = np.ascontiguousarray(state_upper, dtype=np.float64).reshape(3, nm)
+        sf = None if safety is None else np.ascontiguousarray(safety, dtype=np.float64).reshape(4, nm)
+        self._api.check(self._api.dll.jb_set_pd_controller_full(self._h, dptr(kp), dptr(kd), dptr(lo), dptr(hi),
+                                                                None if sf is None else dptr(sf)))
 
     # ---- multi-GPU observation exchange over peer memory (one process per GPU)
     def peer_obs_create(self, world: int, rank: int) -> bytes:

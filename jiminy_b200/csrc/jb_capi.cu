@@ -53,7 +53,7 @@ struct JbBatch {
     double *d_cmd = nullptr, *d_sensors = nullptr, *d_qv = nullptr;
     double *d_qin = nullptr, *d_vin = nullptr, *d_aout = nullptr, *d_fext = nullptr, *d_u = nullptr, *d_umotor = nullptr;
     double* d_springs = nullptr;
-    double *d_pd = nullptr, *d_cmd_torque = nullptr;
+    double *d_pd = nullptr, *d_cmd_torque = nullptr, *d_pdf = nullptr, *d_pdf_state = nullptr;
     uint8_t* d_mask = nullptr;
     double* d_stage = nullptr;  // staging for SoA -> AoS getters
     // pinned host staging
@@ -331,7 +331,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
     std::vector<int32_t> st(N, JB_ENV_NOT_STARTED);
     cudaMemcpyAsync(b->d_status, st.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream);
     kp.rint = d_rint; kp.rdbl = d_rdbl; kp.cslots = d_cs; kp.imu_placement = d_imu; kp.springs = nullptr;
-    kp.pd_gains = nullptr; kp.cmd_torque = b->d_cmd_torque;
+    kp.pd_gains = nullptr; kp.cmd_torque = b->d_cmd_torque; kp.pdf = nullptr; kp.pdf_state = nullptr; kp.pdf_safety = 0;
     kp.q = b->d_q; kp.v = b->d_v; kp.a = b->d_a; kp.sched = b->d_sched; kp.iters = b->d_iters; kp.status = b->d_status;
     kp.command = b->d_cmd; kp.sensors = b->d_sensors; kp.qv_out = b->d_qv;
     kp.q_in = b->d_qin; kp.v_in = b->d_vin; kp.mask = nullptr;
@@ -455,6 +455,38 @@ int jb_set_pd_controller(JbBatch* b, const double* kp, const double* kd) {
     CU(cudaMemcpyAsync(b->d_pd + b->nmotors, kd, sizeof(double) * b->nmotors, cudaMemcpyHostToDevice, b->stream));
     CU(cudaStreamSynchronize(b->stream));
     b->kp.pd_gains = b->d_pd;
+    return JB_OK;
+}
+
+int jb_set_pd_controller_full(JbBatch* b, const double* kp, const double* kd, const double* lower, const double* upper, const double* safety) {
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(b->device));
+    if (!kp) { b->kp.pdf = nullptr; return JB_OK; }
+    if (!kd || !lower || !upper) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!b->nmotors) return fail(JB_ERR_INVALID_ARGUMENT, "the robot has no motor");
+    const JbOptions& o = b->kp.opt;
+    if (!(o.controller_update_period > 2.3e-16))
+        return fail(JB_ERR_NOT_IMPLEMENTED, "the device PD controller needs a discrete controllerUpdatePeriod");
+    if (o.sensors_update_period > 2.3e-16 && std::fabs(o.sensors_update_period - o.controller_update_period) > 1e-12)
+        return fail(JB_ERR_NOT_IMPLEMENTED, "the device PD controller needs sensorsUpdatePeriod == controllerUpdatePeriod (or 0)");
+    const size_t nm = b->nmotors;
+    for (size_t k = 0; k < 3 * nm; ++k) if (!(lower[k] <= upper[k])) return fail(JB_ERR_INVALID_ARGUMENT, "state_lower must not exceed state_upper");
+    if (!b->d_pdf) {
+        int rc = dev_alloc(b, &b->d_pdf, 12 * nm);
+        if (rc) return rc;
+        rc = dev_alloc(b, &b->d_pdf_state, static_cast<size_t>(b->n_env) * 3 * nm);
+        if (rc) return rc;
+    }
+    std::vector<double> h(12 * nm, 0.0);
+    std::memcpy(h.data(), kp, sizeof(double) * nm);
+    std::memcpy(h.data() + nm, kd, sizeof(double) * nm);
+    std::memcpy(h.data() + 2 * nm, lower, sizeof(double) * 3 * nm);
+    std::memcpy(h.data() + 5 * nm, upper, sizeof(double) * 3 * nm);
+    if (safety) std::memcpy(h.data() + 8 * nm, safety, sizeof(double) * 4 * nm);
+    CU(cudaMemcpyAsync(b->d_pdf, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    b->kp.pdf = b->d_pdf; b->kp.pdf_state = b->d_pdf_state; b->kp.pdf_safety = safety ? 1 : 0;
+    b->kp.pd_gains = nullptr;
     return JB_OK;
 }
 

@@ -66,8 +66,37 @@ JB_DI void normalize_record(const Ctx& c, const RecInt* ri, int base) {
 //     tau = clip(kp * ((q_des - q_enc) + kd * (0 - v_enc)), +-effort_limit),
 // evaluated on the motor-side encoder data of the accepted state at every controller breakpoint.
 // The action buffer (`command`) holds the targets; the torque goes to the CMD field of the record.
-__device__ __noinline__ void update_pd_commands(const Ctx c) {
-    const int L = KP->L;
+// gym_jiminy `integrate_zoh` (blocks/proportional_derivative_controller.py:24-98) for one motor
+JB_DI void integrate_zoh_1(double& position, double& velocity, double& acceleration, double position_min, double position_max,
+                           double velocity_min, double velocity_max, double acceleration_min, double acceleration_max, double dt) {
+    if (fabs(dt) < 1e-9) return;
+    acceleration = fmin(fmax(acceleration, acceleration_min), acceleration_max);
+    const double velocity_prev = velocity;
+    velocity += acceleration * dt;
+    velocity = fmin(fmax(velocity, velocity_min), velocity_max);
+    const double horizon = fmax(static_cast<double>(static_cast<long long>(fabs(velocity_prev) / acceleration_max / dt)) * dt, dt);
+    double position_min_delta = position_min - position, position_max_delta = position_max - position;
+    if (horizon > dt) {
+        const double drift = 0.5 * (horizon * (horizon - dt)) * acceleration_max;
+        position_min_delta -= drift;
+        position_max_delta += drift;
+    }
+    velocity = fmin(fmax(velocity, position_min_delta / horizon), position_max_delta / horizon);
+    if (fabs(velocity) > dt * acceleration_max) {
+        const double vmin = -fmax(position_min_delta / velocity, dt) * acceleration_max;
+        const double vmax = fmax(position_max_delta / velocity, dt) * acceleration_max;
+        velocity = fmin(fmax(velocity, vmin), vmax);
+    }
+    acceleration = (velocity - velocity_prev) / dt;
+    position += dt * velocity;
+}
+
+// Controller update.  Two device-side blocks: the plain PD law on a held position target (jb_set_pd_controller), or
+// gym_jiminy's PDController block -- integrate_zoh + pd_controller, optionally followed by MotorSafetyLimit's
+// apply_safety_limits (jb_set_pd_controller_full).  `running` = false inside Engine::start (control_dt = 0 and the
+// targets restart from the clipped measurement, proportional_derivative_controller.py:510-535).
+__device__ __noinline__ void update_pd_commands(const Ctx c, bool running) {
+    const int L = KP->L, nm = KP->nmotors;
     for (int r = 0; r < KP->nrec; ++r) {
         const RecInt* ri = KP->rint + (r * L + c.sub);
         if (ri->kind == REC_PAD || ri->kind == REC_FREE || ri->motor < 0) continue;
@@ -77,9 +106,47 @@ __device__ __noinline__ void update_pd_commands(const Ctx c) {
         const double red = rd->motor[0], lim = rd->motor[1];
         const double pos = (ri->kind == REC_REVU) ? atan2(RP(R1_Q + 1), RP(R1_Q)) : RP(R1_Q);
         const double q_enc = pos * red, v_enc = RP(R1_V) * red;
-        const double target = KP->command[static_cast<size_t>(c.env) * KP->nmotors + ri->motor];
-        const double tau = KP->pd_gains[ri->motor] * ((target - q_enc) + KP->pd_gains[KP->nmotors + ri->motor] * (0.0 - v_enc));
+        const int m = ri->motor;
+        const double action = KP->command[static_cast<size_t>(c.env) * nm + m];
+        if (KP->pdf != nullptr) {
+            const double* P = KP->pdf;
+            double* st = KP->pdf_state + static_cast<size_t>(c.env) * 3 * nm;
+            double p = st[m], v = st[nm + m], a = action;
+            if (!running) {
+                p = fmin(fmax(q_enc, P[2 * nm + m]), P[5 * nm + m]);
+                v = fmin(fmax(v_enc, P[3 * nm + m]), P[6 * nm + m]);
+            }
+            integrate_zoh_1(p, v, a, P[2 * nm + m], P[5 * nm + m], P[3 * nm + m], P[6 * nm + m], P[4 * nm + m], P[7 * nm + m],
+                            running ? KP->opt.controller_update_period : 0.0);
+            // parked in fields that are free between integrator steps; written back once every lane has read its inputs
+            // (trunk motors are evaluated by all the lanes of the env)
+            RP(R1_SV) = p; RP(R1_SA) = v; RP(R1_U) = a;
+            double tau = P[m] * ((p - q_enc) + P[nm + m] * (v - v_enc));
+            tau = fmin(fmax(tau, -lim), lim);
+            if (KP->pdf_safety) {
+                const double* S = P + 8 * nm;
+                const double vlim = rd->motor[2];
+                const double sv_lo = vlim * fmin(fmax(-S[m] * (q_enc - S[2 * nm + m]), -1.0), 1.0);
+                const double sv_hi = vlim * fmin(fmax(-S[m] * (q_enc - S[3 * nm + m]), -1.0), 1.0);
+                const double se_lo = lim * fmin(fmax(-S[nm + m] * (v_enc - sv_lo), -1.0), 1.0);
+                const double se_hi = lim * fmin(fmax(-S[nm + m] * (v_enc - sv_hi), -1.0), 1.0);
+                tau = fmin(fmax(tau, se_lo), se_hi);
+            }
+            RP(R1_CMD) = tau;
+            continue;
+        }
+        const double tau = KP->pd_gains[m] * ((action - q_enc) + KP->pd_gains[nm + m] * (0.0 - v_enc));
         RP(R1_CMD) = fmin(fmax(tau, -lim), lim);
+    }
+    if (KP->pdf != nullptr) {
+        __syncwarp(c.gmask);
+        double* st = KP->pdf_state + static_cast<size_t>(c.env) * 3 * nm;
+        for (int r = 0; r < KP->nrec; ++r) {
+            const RecInt* ri = KP->rint + (r * L + c.sub);
+            if (ri->kind == REC_PAD || ri->kind == REC_FREE || ri->motor < 0 || !ri->owner || !c.valid) continue;
+            const double* rp = jb_smem + KP->rec_off[r] * 32 + c.lane;
+            st[ri->motor] = RP(R1_SV); st[nm + ri->motor] = RP(R1_SA); st[2 * nm + ri->motor] = RP(R1_U);
+        }
     }
 }
 
@@ -229,7 +296,7 @@ __device__ __forceinline__ void env_step_body() {
         }
         if (ri->kind != REC_FREE) {
             // torque command: the action itself, or (PD mode) the torque held since the last breakpoint
-            const double* cmd_src = (KP->pd_gains != nullptr && mode == MODE_STEP) ? KP->cmd_torque : KP->command;
+            const double* cmd_src = ((KP->pd_gains != nullptr || KP->pdf != nullptr) && mode == MODE_STEP) ? KP->cmd_torque : KP->command;
             RP(R1_CMD) = (ri->motor >= 0) ? cmd_src[col * KP->nmotors + ri->motor] : 0.0;
             RP(R1_UMOTOR) = 0.0;
         }
@@ -262,7 +329,7 @@ __device__ __forceinline__ void env_step_body() {
         t = 0.0; tPrev = 0.0; tError = 0.0;
         dt = SIMULATION_MIN_TIMESTEP; dtLargest = dt; dtLargestPrev = dt;
         iter = 0; iterFailed = 0;
-        if (KP->pd_gains != nullptr) update_pd_commands(c);
+        if (KP->pd_gains != nullptr || KP->pdf != nullptr) update_pd_commands(c, false);
         if (KP->n_eslot > 0) { bool ch = false; refresh_external_forces(c, 0.0, true, false, ch); }
         stage_from_accepted(c);
         if (KP->cons_on) {
@@ -371,7 +438,7 @@ __device__ __forceinline__ void env_step_body() {
             if (finitePeriod && opt.controller_update_period > D_EPS) {
                 if (period_hit(t, opt.controller_update_period)) {
                     // computeCommand (engine.cc:1920-1940): zero-order hold of the action, or the PD block
-                    if (KP->pd_gains != nullptr) update_pd_commands(c);
+                    if (KP->pd_gains != nullptr || KP->pdf != nullptr) update_pd_commands(c, true);
                     hasDynamicsChanged = true;
                 }
             }
@@ -477,7 +544,7 @@ __device__ __forceinline__ void env_step_body() {
         }
     }
 #endif
-    if (KP->pd_gains != nullptr && c.valid) {
+    if ((KP->pd_gains != nullptr || KP->pdf != nullptr) && c.valid) {
         for (int r = 0; r < KP->nrec; ++r) {
             const RecInt* ri = KP->rint + (r * L + c.sub);
             if (ri->kind == REC_PAD || ri->kind == REC_FREE || ri->motor < 0 || !ri->owner) continue;

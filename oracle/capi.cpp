@@ -109,7 +109,8 @@ int orc_start(OrcBatch* b, const uint8_t* mask, const double* q0, const double* 
 void orc_set_command(OrcBatch* b, const double* cmd) {
     for (size_t i = 0; i < b->envs.size(); ++i) {
         Engine& e = *b->envs[i];
-        if (e.pd_enabled) e.pd_target.assign(cmd + i * b->nmotors, cmd + (i + 1) * b->nmotors);
+        if (e.pdf_enabled) e.pdf_action.assign(cmd + i * b->nmotors, cmd + (i + 1) * b->nmotors);
+        else if (e.pd_enabled) e.pd_target.assign(cmd + i * b->nmotors, cmd + (i + 1) * b->nmotors);
         else std::memcpy(e.state.command.data(), cmd + i * b->nmotors, sizeof(double) * b->nmotors);
     }
 }
@@ -117,6 +118,23 @@ void orc_set_pd(OrcBatch* b, const double* kp, const double* kd) {
     for (auto& e : b->envs) {
         e->pd_enabled = kp != nullptr;
         if (kp) { e->pd_kp.assign(kp, kp + b->nmotors); e->pd_kd.assign(kd, kd + b->nmotors); e->pd_target.assign(b->nmotors, 0.0); }
+    }
+}
+// PDController block with optional MotorSafetyLimit: lower / upper [3][nmotors], safety [4][nmotors] or null
+void orc_set_pd_full(OrcBatch* b, const double* kp, const double* kd, const double* lower, const double* upper, const double* safety) {
+    const int nm = b->nmotors;
+    for (auto& e : b->envs) {
+        e->pdf_enabled = kp != nullptr;
+        if (!kp) continue;
+        e->pd_enabled = false;
+        e->pdf_kp.assign(kp, kp + nm); e->pdf_kd.assign(kd, kd + nm);
+        e->pdf_lower.assign(lower, lower + 3 * nm); e->pdf_upper.assign(upper, upper + 3 * nm);
+        e->pdf_state.assign(3 * nm, 0.0); e->pdf_action.assign(nm, 0.0);
+        e->pdf_safety = safety != nullptr;
+        if (safety) {
+            e->pdf_skp.assign(safety, safety + nm); e->pdf_skd.assign(safety + nm, safety + 2 * nm);
+            e->pdf_slo.assign(safety + 2 * nm, safety + 3 * nm); e->pdf_shi.assign(safety + 3 * nm, safety + 4 * nm);
+        }
     }
 }
 int orc_step(OrcBatch* b, double step_dt, int parallel, int* rc) {

@@ -301,6 +301,29 @@ void Engine::computeAllTerms(double /*t*/, const double* qv, const double* vv, b
 // Engine::computeCommand (engine.cc:3240-3251).  Without a functor the command buffer is a
 // zero-order hold of what the caller wrote (the batched boundary).
 void Engine::computeCommand(double tt, const double* qv, const double* vv, std::vector<double>& command) {
+    if (pdf_enabled) {
+        // PDController.compute_command (proportional_derivative_controller.py:492-535): encoder data = motor-side
+        // position / velocity; the command state restarts from the (clipped) measurement while no simulation is
+        // running, and is integrated over one controller period otherwise
+        const int nm = model.nmotors;
+        std::vector<double> enc(2 * nm), elim(nm), vlim(nm);
+        for (int m = 0; m < nm; ++m) {
+            const int j = model.motor_joint[m];
+            const double red = model.motor_params[10 * m];
+            const double pos = Model::is_unbounded(model.jtype[j]) ? std::atan2(qv[model.idx_q[j] + 1], qv[model.idx_q[j]]) : qv[model.idx_q[j]];
+            enc[m] = pos * red; enc[nm + m] = vv[model.idx_v[j]] * red;
+            elim[m] = model.motor_params[10 * m + 1]; vlim[m] = model.motor_params[10 * m + 2];
+        }
+        if (!simStarted)
+            for (int k = 0; k < 2 * nm; ++k) pdf_state[k] = std::min(std::max(enc[k], pdf_lower[k]), pdf_upper[k]);
+        for (int m = 0; m < nm; ++m) pdf_state[2 * nm + m] = pdf_action[m];
+        pd_controller(enc.data(), pdf_state.data(), pdf_lower.data(), pdf_upper.data(), pdf_kp.data(), pdf_kd.data(), elim.data(),
+                      nm, simStarted ? opt.controller_update_period : 0.0, command.data());
+        if (pdf_safety)
+            apply_safety_limits(command.data(), enc.data(), enc.data() + nm, pdf_skp.data(), pdf_skd.data(), pdf_slo.data(),
+                                pdf_shi.data(), vlim.data(), elim.data(), nm, command.data());
+        return;
+    }
     if (pd_enabled) {
         // gym_jiminy.common.blocks.pd_controller (python/gym_jiminy/common/gym_jiminy/common/blocks/
         // proportional_derivative_controller.py:101-165) with a zero-order-held position target and zero
@@ -864,6 +887,7 @@ int Engine::start(const double* q0, const double* v0) {
         if (EPS < qn[k] - model.q_upper[k] || EPS < model.q_lower[k] - qn[k]) return JB_ERR_INVALID_ARGUMENT;
     }
     normalize(qn.data());
+    simStarted = false;   // is_simulation_running becomes true at the very end of Engine::start (engine.cc:1532)
     q = qn; v.assign(v0, v0 + nv); a.assign(nv, 0.0);
     iter = 0; iterFailed = 0; t = 0.0; tPrev = 0.0; tError = 0.0;
     dt = SIMULATION_MIN_TIMESTEP; dtLargest = dt; dtLargestPrev = dt;
@@ -914,6 +938,7 @@ int Engine::start(const double* q0, const double* v0) {
     syncAccelerationsAndForces();
     q = state.q; v = state.v; a = state.a;  // syncStepperStateWithRobots
     statePrev = state;
+    simStarted = true;
     return JB_OK;
 }
 

@@ -187,6 +187,10 @@ struct Engine {
     std::vector<double> spring_k, spring_d; // built-in linear internal dynamics u = -k q - d v (1-dof joints)
     // built-in discrete PD controller (gym_jiminy PDController, order-0 target): command buffer = targets
     bool pd_enabled = false;
+    // gym_jiminy PDController block (+ optional MotorSafetyLimit), oracle/controllers.cpp: the command buffer holds
+    // target motor accelerations; (position, velocity, acceleration) targets are integrated at controller updates
+    bool pdf_enabled = false, pdf_safety = false, simStarted = false;
+    std::vector<double> pdf_kp, pdf_kd, pdf_lower, pdf_upper, pdf_state, pdf_action, pdf_skp, pdf_skd, pdf_slo, pdf_shi;
     std::vector<double> pd_kp, pd_kd, pd_target;
     int64_t rhs_count = 0;
 
@@ -236,5 +240,13 @@ struct Engine {
     double computeErrorDopri(double dt);
     void f(double t, const std::vector<double>& q, const std::vector<double>& v, Deriv& out);
 };
+
+// gym_jiminy controller blocks (oracle/controllers.cpp)
+void integrate_zoh(double* state, const double* state_min, const double* state_max, int n, double dt);
+void pd_controller(const double* encoder_data, double* command_state, const double* lower, const double* upper,
+                   const double* kp, const double* kd, const double* effort_limit, int n, double control_dt, double* out);
+void apply_safety_limits(const double* command, const double* q, const double* v, const double* kp, const double* kd,
+                         const double* soft_lower, const double* soft_upper, const double* velocity_limit,
+                         const double* effort_limit, int n, double* out);
 
 }  // namespace orc

@@ -24,7 +24,7 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("engine.cpp", "constraints.cpp", "capi.cpp", "engine.hpp", "spatial.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("engine.cpp", "constraints.cpp", "controllers.cpp", "capi.cpp", "engine.hpp", "spatial.hpp")]
     srcs.append(os.path.join(_HERE, "..", "include", "jiminy_b200.h"))
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
@@ -52,6 +52,10 @@ def lib():
         L.orc_set_callbacks.argtypes = [C.c_void_p, C.c_int, CONTROLLER_FN, CONTROLLER_FN, C.c_void_p]
         L.orc_set_springs.argtypes = [C.c_void_p, c_double_p, c_double_p]
         L.orc_set_pd.argtypes = [C.c_void_p, c_double_p, c_double_p]
+        L.orc_integrate_zoh.argtypes = [c_double_p] * 3 + [C.c_int, C.c_double]
+        L.orc_pd_controller.argtypes = [c_double_p] * 7 + [C.c_int, C.c_double, c_double_p]
+        L.orc_apply_safety_limits.argtypes = [c_double_p] * 9 + [C.c_int, c_double_p]
+        L.orc_set_pd_full.argtypes = [C.c_void_p] + [c_double_p] * 5
         L.orc_stop.argtypes = [C.c_void_p]
         L.orc_register_impulse_force.argtypes = [C.c_void_p, C.c_int] + [c_double_p] * 4
         L.orc_set_impulse_force.argtypes = [C.c_void_p, C.c_int, c_uint8_p] + [c_double_p] * 3
@@ -150,6 +154,16 @@ class OracleBatch:
 
     def remove_all_forces(self) -> None:
         lib().orc_remove_all_forces(self._h)
+
+    def set_pd_controller_full(self, kp, kd, lower, upper, safety=None) -> None:
+        """gym_jiminy `PDController` block (+ `MotorSafetyLimit` when `safety` = [kp, kd, soft_lower, soft_upper])."""
+        nm = self.nm
+        kp = np.ascontiguousarray(np.broadcast_to(kp, (nm,)), dtype=np.float64)
+        kd = np.ascontiguousarray(np.broadcast_to(kd, (nm,)), dtype=np.float64)
+        lower = np.ascontiguousarray(lower, dtype=np.float64).reshape(3, nm)
+        upper = np.ascontiguousarray(upper, dtype=np.float64).reshape(3, nm)
+        sf = None if safety is None else np.ascontiguousarray(safety, dtype=np.float64).reshape(4, nm)
+        lib().orc_set_pd_full(self._h, dptr(kp), dptr(kd), dptr(lower), dptr(upper), None if sf is None else dptr(sf))
 
     def set_callbacks(self, env: int, controller: Optional[Callable] = None,
                       internal_dynamics: Optional[Callable] = None) -> None:

@@ -233,3 +233,35 @@ def robot_constraint_scenario(name, n_env, n_steps, api=None, tol_state=1e-8, to
         assert not orc.step(sc.step_dt, parallel=True).any()
         compare(eng, orc, tol_state, tol_sens)
     return eng, orc, sc
+
+
+def pd_block_scenario(api, name="anymal", n_env=4, n_steps=3, safety=False):
+    """gym_jiminy's PDController block (integrate_zoh + pd_controller, optional MotorSafetyLimit) on the device
+    against the oracle's restatement, which is itself pinned by golden vectors of the reference's own functions
+    (tests/test_golden_controller_blocks.py).  Actions = target motor accelerations."""
+    sc = scenarios.make(name, n_env, seed=6)
+    rob = sc.robot
+    nm = rob.nmotors
+    iq = np.array([rob.idx_q[m.joint] for m in rob.motors])
+    vlim = np.array([m.velocity_limit for m in rob.motors])
+    lower = np.stack([rob.q_lower[iq] + 0.05, -0.8 * vlim, np.full(nm, -60.0)])
+    upper = np.stack([rob.q_upper[iq] - 0.05, 0.8 * vlim, np.full(nm, 60.0)])
+    sf = np.stack([np.full(nm, 20.0), np.full(nm, 0.5), rob.q_lower[iq] + 0.02, rob.q_upper[iq] - 0.02]) if safety else None
+    eng, orc = BatchedEngine(rob, sc.options, n_env, api_=api), OracleBatch(rob, sc.options, n_env)
+    rng = np.random.default_rng(11)
+    act = rng.uniform(-40.0, 40.0, size=(n_env, nm))
+    for x in (eng, orc):
+        x.set_pd_controller_full(sc.kp, sc.kd, lower, upper, sf)
+        x.set_command(act)
+    eng.start(sc.q0, sc.v0)
+    assert not orc.start(sc.q0, sc.v0).any()
+    compare(eng, orc, 1e-13, 1e-11)
+    for k in range(n_steps):
+        act = rng.uniform(-80.0, 80.0, size=(n_env, nm))     # beyond the acceleration bound: exercises the clipping
+        eng.set_command(act)
+        orc.set_command(act)
+        eng.step(sc.step_dt)
+        assert not orc.step(sc.step_dt, parallel=True).any()
+        compare(eng, orc, 1e-9, 1e-7)
+        np.testing.assert_allclose(eng.get_efforts()[1], orc.get_efforts()[1], rtol=0, atol=1e-7)   # motor efforts
+    return eng, orc

@@ -187,3 +187,10 @@ def test_constraint_solvers_agree_at_scale():
     np.testing.assert_allclose(runs[0][0], runs[2][0], rtol=0, atol=1e-8)
     np.testing.assert_allclose(runs[0][1], runs[2][1], rtol=0, atol=1e-6)
     assert (runs[0][0][:, 2] > 0.4).all()
+
+
+@pytest.mark.parametrize("safety", [False, True])
+def test_pd_controller_block(safety):
+    """Device-side PDController (+ MotorSafetyLimit) block vs the oracle restatement (pinned by golden vectors of the
+    reference's own functions), 64 ANYmal envs."""
+    pc.pd_block_scenario(None, n_env=64, n_steps=4, safety=safety)

@@ -381,3 +381,8 @@ def test_constraint_contact_atlas_rhs(api):
     eng.step(0.005)
     assert not orc.step(0.005).any()
     pc.compare(eng, orc, 1e-9, 1e-6)
+
+
+@pytest.mark.parametrize("safety", [False, True])
+def test_pd_controller_block(api, safety):
+    pc.pd_block_scenario(api, safety=safety)
