@@ -244,12 +244,13 @@ def pd_block_scenario(api, name="anymal", n_env=4, n_steps=3, safety=False):
     nm = rob.nmotors
     iq = np.array([rob.idx_q[m.joint] for m in rob.motors])
     vlim = np.array([m.velocity_limit for m in rob.motors])
-    lower = np.stack([rob.q_lower[iq] + 0.05, -0.8 * vlim, np.full(nm, -60.0)])
-    upper = np.stack([rob.q_upper[iq] - 0.05, 0.8 * vlim, np.full(nm, 60.0)])
+    # gentle target motion (the stiff spring-damper ground does not survive flailing legs at RK4 1 ms)
+    lower = np.stack([rob.q_lower[iq] + 0.05, np.full(nm, -0.6), np.full(nm, -15.0)])
+    upper = np.stack([rob.q_upper[iq] - 0.05, np.full(nm, 0.6), np.full(nm, 15.0)])
     sf = np.stack([np.full(nm, 20.0), np.full(nm, 0.5), rob.q_lower[iq] + 0.02, rob.q_upper[iq] - 0.02]) if safety else None
     eng, orc = BatchedEngine(rob, sc.options, n_env, api_=api), OracleBatch(rob, sc.options, n_env)
     rng = np.random.default_rng(11)
-    act = rng.uniform(-40.0, 40.0, size=(n_env, nm))
+    act = rng.uniform(-10.0, 10.0, size=(n_env, nm))
     for x in (eng, orc):
         x.set_pd_controller_full(sc.kp, sc.kd, lower, upper, sf)
         x.set_command(act)
@@ -257,7 +258,7 @@ def pd_block_scenario(api, name="anymal", n_env=4, n_steps=3, safety=False):
     assert not orc.start(sc.q0, sc.v0).any()
     compare(eng, orc, 1e-13, 1e-11)
     for k in range(n_steps):
-        act = rng.uniform(-80.0, 80.0, size=(n_env, nm))     # beyond the acceleration bound: exercises the clipping
+        act = rng.uniform(-25.0, 25.0, size=(n_env, nm))     # beyond the acceleration bound: exercises the clipping
         eng.set_command(act)
         orc.set_command(act)
         eng.step(sc.step_dt)
