@@ -219,11 +219,40 @@ def run_gpu(args):
         obs_gather = "nccl all_gather_into_tensor after the step"
     if use_p2p:
         # every env writes its sensor row into every rank's gathered buffer from inside the step kernel (stores over
-        # NVLink / NVSwitch peer memory): the exchange overlaps the physics, no collective is left on the path
+        # NVLink / NVSwitch peer memory): the exchange overlaps the physics, no collective is left on the path.
+        # If the IPC mapping is not available on this box, every rank falls back to the NCCL all-gather together.
+        ok = 1
+        try:
+            handle = eng.peer_obs_create(world, rank)
+        except Exception as e:   # noqa: BLE001
+            print(f"[bench] rank {rank}: peer_obs_create failed: {e}", file=sys.stderr)
+            handle, ok = b"", 0
         handles = [None] * world
-        dist.all_gather_object(handles, eng.peer_obs_create(world, rank))
-        eng.peer_obs_connect(handles)
-        obs_gather = "in-kernel stores into peer memory (IPC-mapped gathered buffers), signal + wait kernels"
+        dist.all_gather_object(handles, handle)
+        if ok and all(len(h) == 64 for h in handles):
+            try:
+                eng.peer_obs_connect(handles)
+            except Exception as e:   # noqa: BLE001
+                print(f"[bench] rank {rank}: peer_obs_connect failed: {e}", file=sys.stderr)
+                ok = 0
+        else:
+            ok = 0
+        flag = torch.tensor([ok], device=f"cuda:{local_rank}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            obs_gather = "in-kernel stores into peer memory (IPC-mapped gathered buffers), signal + wait kernels"
+        else:
+            use_p2p = False
+            obs_gather += " (peer-memory exchange unavailable on this box)"
+            if ok:   # this rank did connect: rebuild the engine without the peer buffers so that all ranks run alike
+                eng.close()
+                eng = core.BatchedEngine(sc.robot, sc.options, n_env, device=local_rank)
+                if sc.kp is not None:
+                    eng.set_pd_controller(sc.kp, sc.kd)
+                eng.set_command(sc.target0)
+                eng.start(sc.q0, sc.v0)
+                stream = torch.cuda.ExternalStream(eng.stream(), device=local_rank)
+                sens_ptr, _ = eng.device_views()
     flush = torch.empty(160 * 1024 * 1024 // 8, dtype=torch.float64, device=f"cuda:{local_rank}")  # > 126 MB L2
 
     def barrier():
@@ -266,8 +295,10 @@ def run_gpu(args):
         dist.all_gather_into_tensor(gather_out, gather_in)
         torch.cuda.synchronize()
         got = peer_view()
-        if not torch.equal(got, gather_out):
-            raise RuntimeError("peer-memory observation exchange differs from the NCCL all-gather")
+        same = torch.tensor([1 if torch.equal(got, gather_out) else 0], device=f"cuda:{local_rank}")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        if int(same.item()) != 1:
+            raise RuntimeError("peer-memory observation exchange differs from the NCCL all-gather (rerun with --nccl-gather)")
         obs_gather += "; verified bit-equal to nccl all_gather"
         barrier()
     sampler = ClockSampler(local_rank)

@@ -395,12 +395,16 @@ __device__ __forceinline__ void env_step_body() {
             if (opt.ode_solver == JB_SOLVER_EULER_EXPLICIT) { step_euler<FAST>(c, dtLargest, &status); dtLargest = D_INF; }
             else if (FAST || opt.ode_solver == JB_SOLVER_RUNGE_KUTTA_4) { step_rk4<FAST>(c, dtLargest, &status); dtLargest = D_INF; }
             else { if constexpr (!FAST) rc = step_dopri(c, &dtLargest, &status); }
-            if constexpr (FAST) {
-                // a joint left its position bounds: this env is re-done by the full kernel
-                if (__any_sync(c.gmask, (status & ENV_RETRY_FULL) != 0)) { status |= ENV_RETRY_FULL; failed = true; }
-            }
             need_refresh = false;
-            if (rc == 0 && opt.ode_solver != JB_SOLVER_RUNGE_KUTTA_DOPRI) {
+            if constexpr (FAST) {
+                // one vote for the two rare events of a step: NaN in the new acceleration, or a joint that left its
+                // position bounds (this env is then re-done by the full kernel)
+                const bool bad = accel_has_nan(c), retry = (status & ENV_RETRY_FULL) != 0;
+                if (__any_sync(c.gmask, bad || retry)) {
+                    if (__any_sync(c.gmask, retry)) { status |= ENV_RETRY_FULL; failed = true; }
+                    if (__any_sync(c.gmask, bad)) rc = 2;
+                }
+            } else if (rc == 0 && opt.ode_solver != JB_SOLVER_RUNGE_KUTTA_DOPRI) {
                 bool bad = accel_has_nan(c);
                 bad = __any_sync(c.gmask, bad);
                 if (bad) rc = 2;
