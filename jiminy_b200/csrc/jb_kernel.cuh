@@ -587,13 +587,8 @@ __global__ void __launch_bounds__(32) env_step_kernel_t() {
 #endif
 }
 
-// ---- observation exchange over peer memory: completion signal and wait (one thread each)
+// ---- observation exchange over peer memory: the consumer's wait (one thread)
 #ifndef JB_HOST_EMUL
-struct PeerFlags { long long* p[8]; };
-__global__ void peer_signal_kernel(PeerFlags flags, int world, int rank, int parity, long long step) {
-    __threadfence_system();   // the step kernels of this stream have completed: their peer stores are performed
-    for (int p = 0; p < world; ++p) flags.p[p][parity * world + rank] = step;
-}
 __global__ void peer_wait_kernel(volatile long long* mine, int world, int parity, long long step, int* timed_out) {
     const long long t0 = clock64();
     for (int p = 0; p < world; ++p)

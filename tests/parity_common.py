@@ -266,3 +266,30 @@ def pd_block_scenario(api, name="anymal", n_env=4, n_steps=3, safety=False):
         compare(eng, orc, 1e-9, 1e-7)
         np.testing.assert_allclose(eng.get_efforts()[1], orc.get_efforts()[1], rtol=0, atol=1e-7)   # motor efforts
     return eng, orc
+
+
+def bounds_handoff_scenario(api, n_env=9, n_steps=3, tol_state=1e-8):
+    """ANYmal envs of which every third is driven into its hip position bounds (PD targets beyond the limits): inside
+    one warp some envs stay on the fast kernel while others abort and are redone by the full kernel with their
+    joint-bound constraints -- all of them must match the oracle."""
+    sc = scenarios.make("anymal", n_env, seed=8)
+    rob = sc.robot
+    eng, orc = make_pair(sc, api)
+    compare(eng, orc, 1e-13, 1e-12)
+    iq = np.array([rob.idx_q[m.joint] for m in rob.motors])
+    haa = [k for k, m in enumerate(rob.motors) if "HAA" in m.name]
+    hit_any = False
+    for k in range(n_steps):
+        act = sc.sample_targets(k)
+        for j in haa:
+            act[::3, j] = rob.q_upper[iq[j]] + 0.3      # beyond the upper bound
+        eng.set_command(act)
+        orc.set_command(act)
+        eng.step(sc.step_dt)
+        assert not orc.step(sc.step_dt, parallel=True).any()
+        compare(eng, orc, tol_state, 1e-6)
+        np.testing.assert_allclose(eng.get_efforts()[0], orc.get_efforts()[0], rtol=0, atol=1e-5 * max(1.0, np.abs(orc.get_efforts()[0]).max()))
+        hit_any = hit_any or bool((eng.get_status() & 8).any())
+    st = eng.get_status()
+    assert hit_any and (st[::3] & 8).all() and not (st[1::3] & 8).any()     # only the driven envs touched their bounds
+    return eng, orc

@@ -194,3 +194,8 @@ def test_pd_controller_block(safety):
     """Device-side PDController (+ MotorSafetyLimit) block vs the oracle restatement (pinned by golden vectors of the
     reference's own functions), 64 ANYmal envs."""
     pc.pd_block_scenario(None, n_env=64, n_steps=4, safety=safety)
+
+
+def test_bounds_handoff_between_kernels_at_scale():
+    """600 ANYmal envs, every third pushed into its joint bounds: fast kernel / full kernel hand-off inside warps."""
+    pc.bounds_handoff_scenario(None, n_env=600, n_steps=5)

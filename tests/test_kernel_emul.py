@@ -386,3 +386,7 @@ def test_constraint_contact_atlas_rhs(api):
 @pytest.mark.parametrize("safety", [False, True])
 def test_pd_controller_block(api, safety):
     pc.pd_block_scenario(api, safety=safety)
+
+
+def test_bounds_handoff_between_kernels(api):
+    pc.bounds_handoff_scenario(api, n_env=9, n_steps=4)
