@@ -215,6 +215,14 @@ int jb_set_command_device(JbBatch* batch, const double* cmd_dev);
 int jb_set_pd_controller_full(JbBatch* batch, const double* kp, const double* kd, const double* state_lower,
                               const double* state_upper, const double* safety);
 
+/* gym_jiminy's `MahonyFilter` observer on the device (blocks/mahony_filter.py:28-101, :337-393 with the default
+ * exact_init = True, ignore_twist = False): the attitude estimate of every IMU starts from the true orientation of
+ * its frame at jb_start (`matrices_to_quat`, utils/math.py:307-350) and receives one `mahony_filter` iteration with
+ * dt = sensorsUpdatePeriod at every sensor refresh of jb_step.  kp < 0 disables it.  jb_get_mahony_filter returns
+ * [n_env][nimu][10]: quaternion (x, y, z, w), gyro-bias estimate (3), unbiased angular velocity (3). */
+int jb_set_mahony_filter(JbBatch* batch, double kp, double ki);
+int jb_get_mahony_filter(JbBatch* batch, double* out);
+
 /* Replaces: Engine::stop (engine.cc:2419-2448): every env goes back to "not started", which is what
  * registering or removing forces requires (engine.cc:2456-2461). */
 int jb_stop(JbBatch* batch);

@@ -53,7 +53,8 @@ struct JbBatch {
     double *d_cmd = nullptr, *d_sensors = nullptr, *d_qv = nullptr;
     double *d_qin = nullptr, *d_vin = nullptr, *d_aout = nullptr, *d_fext = nullptr, *d_u = nullptr, *d_umotor = nullptr;
     double* d_springs = nullptr;
-    double *d_pd = nullptr, *d_cmd_torque = nullptr, *d_pdf = nullptr, *d_pdf_state = nullptr;
+    double *d_pd = nullptr, *d_cmd_torque = nullptr, *d_pdf = nullptr, *d_pdf_state = nullptr, *d_mahony = nullptr;
+    int nimu = 0;
     uint8_t* d_mask = nullptr;
     double* d_stage = nullptr;  // staging for SoA -> AoS getters
     // pinned host staging
@@ -265,7 +266,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
     }
     const Plan& P = b->plan;
     if (P.nrec > MAX_REC) { delete b; return fail(JB_ERR_NOT_IMPLEMENTED, "too many records per lane"); }
-    b->nq = m->nq; b->nv = m->nv; b->nmotors = m->nmotors; b->njoints = m->njoints;
+    b->nq = m->nq; b->nv = m->nv; b->nmotors = m->nmotors; b->njoints = m->njoints; b->nimu = m->nimu;
     b->q_lower.assign(m->q_lower, m->q_lower + m->nq);
     b->q_upper.assign(m->q_upper, m->q_upper + m->nq);
     if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) { delete b; return fail(JB_ERR_CUDA, "stream creation failed"); }
@@ -331,7 +332,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
     std::vector<int32_t> st(N, JB_ENV_NOT_STARTED);
     cudaMemcpyAsync(b->d_status, st.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream);
     kp.rint = d_rint; kp.rdbl = d_rdbl; kp.cslots = d_cs; kp.imu_placement = d_imu; kp.springs = nullptr;
-    kp.pd_gains = nullptr; kp.cmd_torque = b->d_cmd_torque; kp.pdf = nullptr; kp.pdf_state = nullptr; kp.pdf_safety = 0;
+    kp.pd_gains = nullptr; kp.cmd_torque = b->d_cmd_torque; kp.pdf = nullptr; kp.pdf_state = nullptr; kp.pdf_safety = 0; kp.mahony = nullptr; kp.mahony_kp = 1.0; kp.mahony_ki = 0.1;
     kp.q = b->d_q; kp.v = b->d_v; kp.a = b->d_a; kp.sched = b->d_sched; kp.iters = b->d_iters; kp.status = b->d_status;
     kp.command = b->d_cmd; kp.sensors = b->d_sensors; kp.qv_out = b->d_qv;
     kp.q_in = b->d_qin; kp.v_in = b->d_vin; kp.mask = nullptr;
@@ -487,6 +488,32 @@ int jb_set_pd_controller_full(JbBatch* b, const double* kp, const double* kd, co
     CU(cudaStreamSynchronize(b->stream));
     b->kp.pdf = b->d_pdf; b->kp.pdf_state = b->d_pdf_state; b->kp.pdf_safety = safety ? 1 : 0;
     b->kp.pd_gains = nullptr;
+    return JB_OK;
+}
+
+int jb_set_mahony_filter(JbBatch* b, double kp, double ki) {
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(b->device));
+    if (kp < 0.0) { b->kp.mahony = nullptr; return JB_OK; }
+    if (!b->nimu) return fail(JB_ERR_INVALID_ARGUMENT, "the robot has no IMU sensor");
+    if (b->nimu > 1) return fail(JB_ERR_NOT_IMPLEMENTED, "the device Mahony filter handles one IMU per robot");
+    if (!(b->kp.opt.sensors_update_period > 2.3e-16)) return fail(JB_ERR_NOT_IMPLEMENTED, "the Mahony filter needs a discrete sensorsUpdatePeriod");
+    if (ki < 0.0) return fail(JB_ERR_INVALID_ARGUMENT, "ki must be positive");
+    if (!b->d_mahony) {
+        int rc = dev_alloc(b, &b->d_mahony, static_cast<size_t>(b->n_env) * b->nimu * 10);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(b->stream));
+    }
+    b->kp.mahony = b->d_mahony; b->kp.mahony_kp = kp; b->kp.mahony_ki = ki;
+    return JB_OK;
+}
+
+int jb_get_mahony_filter(JbBatch* b, double* out) {
+    if (!b || !out) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!b->kp.mahony) return fail(JB_ERR_BAD_CONTROL_FLOW, "the Mahony filter is not enabled");
+    CU(cudaSetDevice(b->device));
+    CU(cudaMemcpyAsync(out, b->d_mahony, sizeof(double) * b->n_env * b->nimu * 10, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
     return JB_OK;
 }
 

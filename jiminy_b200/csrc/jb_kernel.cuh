@@ -355,7 +355,7 @@ __device__ __forceinline__ void env_step_body() {
         bool bad = accel_has_nan(c);
         bad = __any_sync(c.gmask, bad);
         if (bad) status |= JB_ENV_NAN;
-        write_sensors(c);
+        write_sensors(c, true);
     } else {
         t = KP->sched[SCH_T * N + col]; dt = KP->sched[SCH_DT * N + col];
         dtLargest = KP->sched[SCH_DTLARGEST * N + col]; dtLargestPrev = KP->sched[SCH_DTLARGESTPREV * N + col];
@@ -502,7 +502,7 @@ __device__ __forceinline__ void env_step_body() {
             const double sp = opt.sensors_update_period;
             bool mustUpdateSensors = sp < D_EPS;
             if (!mustUpdateSensors) mustUpdateSensors = period_hit(t, sp);
-            if (mustUpdateSensors) write_sensors(c);
+            if (mustUpdateSensors) write_sensors(c, false);
         }
         if (!failed) t = tEnd;
     }

@@ -137,6 +137,21 @@ void orc_set_pd_full(OrcBatch* b, const double* kp, const double* kd, const doub
         }
     }
 }
+void orc_set_mahony(OrcBatch* b, double kp, double ki) {
+    for (auto& e : b->envs) { e->mahony_enabled = kp >= 0.0; e->mahony_kp = kp; e->mahony_ki = ki; }
+}
+// out: [n_env][nimu][10] = quaternion (x, y, z, w), gyro bias estimate (3), unbiased angular velocity (3)
+void orc_get_mahony(OrcBatch* b, double* out) {
+    for (size_t i = 0; i < b->envs.size(); ++i) {
+        const Engine& e = *b->envs[i];
+        const int M = e.model.nimu;
+        for (int k = 0; k < M; ++k) {
+            double* o = out + (i * M + k) * 10;
+            for (int c = 0; c < 4; ++c) o[c] = e.mahony_q.empty() ? 0.0 : e.mahony_q[c * M + k];
+            for (int c = 0; c < 3; ++c) { o[4 + c] = e.mahony_bias.empty() ? 0.0 : e.mahony_bias[c * M + k]; o[7 + c] = e.mahony_omega.empty() ? 0.0 : e.mahony_omega[c * M + k]; }
+        }
+    }
+}
 int orc_step(OrcBatch* b, double step_dt, int parallel, int* rc) {
     const int n = static_cast<int>(b->envs.size());
     int bad = 0;

@@ -877,6 +877,25 @@ Engine::RC Engine::tryStep(double& tt, double& dtt) {
     return IS_SUCCESS;
 }
 
+// MahonyFilter.refresh_observation (blocks/mahony_filter.py:337-393) with exact_init = True, ignore_twist = False:
+// at start the estimate is the true orientation of the IMU frame, afterwards one filter iteration per sensor refresh
+void Engine::mahonyInit() {
+    const int M = model.nimu;
+    mahony_q.assign(4 * M, 0.0); mahony_bias.assign(3 * M, 0.0); mahony_omega.assign(3 * M, 0.0);
+    for (int k = 0; k < M; ++k) {
+        const M3 R = (data.oMi[model.imu_joint[k]] * model.imu_placement[k]).R;
+        double quat[4];
+        matrix_to_quat_ref(R.m, quat);
+        for (int e = 0; e < 4; ++e) mahony_q[e * M + k] = quat[e];
+    }
+}
+void Engine::mahonyUpdate() {
+    const int M = model.nimu;
+    if (!M) return;
+    const double* s = sensors.data() + model.layout.imu_offset;   // [6][nimu]: gyro (3), accel (3)
+    mahony_filter(mahony_q.data(), mahony_omega.data(), s, s + 3 * M, mahony_bias.data(), M, mahony_kp, mahony_ki, opt.sensors_update_period);
+}
+
 // ============================================================================ start
 // Engine::start (engine.cc:952-1533), single robot, spring-damper contact model
 int Engine::start(const double* q0, const double* v0) {
@@ -935,6 +954,7 @@ int Engine::start(const double* q0, const double* v0) {
         for (int m = 0; m < model.nmotors; ++m) state.u[model.idx_v[model.motor_joint[m]]] += state.uTransmission[m];
     }
     computeSensorMeasurements(state.q.data(), state.v.data(), state.uMotor);
+    if (mahony_enabled) mahonyInit();
     syncAccelerationsAndForces();
     q = state.q; v = state.v; a = state.a;  // syncStepperStateWithRobots
     statePrev = state;
@@ -1093,7 +1113,10 @@ int Engine::step(double stepSize) {
         if (!mustUpdateSensors)
             mustUpdateSensors = dtNextSensorsUpdatePeriod < SIMULATION_MIN_TIMESTEP ||
                                 sp - dtNextSensorsUpdatePeriod < STEPPER_MIN_TIMESTEP;
-        if (mustUpdateSensors) computeSensorMeasurements(state.q.data(), state.v.data(), state.uMotor);
+        if (mustUpdateSensors) {
+            computeSensorMeasurements(state.q.data(), state.v.data(), state.uMotor);
+            if (mahony_enabled) mahonyUpdate();
+        }
     }
     t = tEnd;
     return JB_OK;

@@ -190,6 +190,12 @@ struct Engine {
     // gym_jiminy PDController block (+ optional MotorSafetyLimit), oracle/controllers.cpp: the command buffer holds
     // target motor accelerations; (position, velocity, acceleration) targets are integrated at controller updates
     bool pdf_enabled = false, pdf_safety = false, simStarted = false;
+    // gym_jiminy MahonyFilter observer (oracle/controllers.cpp): attitude estimate of every IMU, refreshed with the sensors
+    bool mahony_enabled = false;
+    double mahony_kp = 1.0, mahony_ki = 0.1;
+    std::vector<double> mahony_q, mahony_bias, mahony_omega;   // [4][nimu], [3][nimu], [3][nimu]
+    void mahonyInit();
+    void mahonyUpdate();
     std::vector<double> pdf_kp, pdf_kd, pdf_lower, pdf_upper, pdf_state, pdf_action, pdf_skp, pdf_skd, pdf_slo, pdf_shi;
     std::vector<double> pd_kp, pd_kd, pd_target;
     int64_t rhs_count = 0;
@@ -245,6 +251,8 @@ struct Engine {
 void integrate_zoh(double* state, const double* state_min, const double* state_max, int n, double dt);
 void pd_controller(const double* encoder_data, double* command_state, const double* lower, const double* upper,
                    const double* kp, const double* kd, const double* effort_limit, int n, double control_dt, double* out);
+void mahony_filter(double* q, double* omega, const double* gyro, const double* acc, double* bias_hat, int M, double kp, double ki, double dt);
+void matrix_to_quat_ref(const double* R, double* out);
 void apply_safety_limits(const double* command, const double* q, const double* v, const double* kp, const double* kd,
                          const double* soft_lower, const double* soft_upper, const double* velocity_limit,
                          const double* effort_limit, int n, double* out);

@@ -56,6 +56,10 @@ def lib():
         L.orc_pd_controller.argtypes = [c_double_p] * 7 + [C.c_int, C.c_double, c_double_p]
         L.orc_apply_safety_limits.argtypes = [c_double_p] * 9 + [C.c_int, c_double_p]
         L.orc_set_pd_full.argtypes = [C.c_void_p] + [c_double_p] * 5
+        L.orc_mahony_filter.argtypes = [c_double_p] * 5 + [C.c_int, C.c_double, C.c_double, C.c_double]
+        L.orc_matrix_to_quat.argtypes = [c_double_p, c_double_p]
+        L.orc_set_mahony.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.orc_get_mahony.argtypes = [C.c_void_p, c_double_p]
         L.orc_stop.argtypes = [C.c_void_p]
         L.orc_register_impulse_force.argtypes = [C.c_void_p, C.c_int] + [c_double_p] * 4
         L.orc_set_impulse_force.argtypes = [C.c_void_p, C.c_int, c_uint8_p] + [c_double_p] * 3
@@ -164,6 +168,16 @@ class OracleBatch:
         upper = np.ascontiguousarray(upper, dtype=np.float64).reshape(3, nm)
         sf = None if safety is None else np.ascontiguousarray(safety, dtype=np.float64).reshape(4, nm)
         lib().orc_set_pd_full(self._h, dptr(kp), dptr(kd), dptr(lower), dptr(upper), None if sf is None else dptr(sf))
+
+    def set_mahony_filter(self, kp: Optional[float] = 1.0, ki: float = 0.1) -> None:
+        lib().orc_set_mahony(self._h, -1.0 if kp is None else float(kp), float(ki))
+
+    def get_mahony_filter(self) -> np.ndarray:
+        """[n_env, nimu, 10]: quaternion estimate (x, y, z, w), gyro bias estimate, unbiased angular velocity."""
+        out = np.zeros((self.n, max(self.robot.sensor_layout()["ImuSensor"][2], 0), 10))
+        if out.size:
+            lib().orc_get_mahony(self._h, dptr(out))
+        return out
 
     def set_callbacks(self, env: int, controller: Optional[Callable] = None,
                       internal_dynamics: Optional[Callable] = None) -> None:

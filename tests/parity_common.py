@@ -293,3 +293,30 @@ def bounds_handoff_scenario(api, n_env=9, n_steps=3, tol_state=1e-8):
     st = eng.get_status()
     assert hit_any and (st[::3] & 8).all() and not (st[1::3] & 8).any()     # only the driven envs touched their bounds
     return eng, orc
+
+
+def mahony_scenario(api, name="anymal", n_env=3, n_steps=3):
+    """Device-side MahonyFilter observer against the oracle's (pinned by golden vectors of the reference's own
+    `mahony_filter` / `matrices_to_quat`): exact initialisation at start, one iteration per sensor refresh."""
+    sc = scenarios.make(name, n_env, seed=5)
+    eng, orc = BatchedEngine(sc.robot, sc.options, n_env, api_=api), OracleBatch(sc.robot, sc.options, n_env)
+    for x in (eng, orc):
+        x.set_pd_controller(sc.kp, sc.kd)
+        x.set_mahony_filter(1.0, 0.1)
+        x.set_command(sc.target0)
+    v0 = sc.v0.copy()
+    v0[:, 3:6] = [0.3, -0.2, 0.5]          # spinning base: the filter has something to track
+    eng.start(sc.q0, v0)
+    assert not orc.start(sc.q0, v0).any()
+    np.testing.assert_allclose(eng.get_mahony_filter(), orc.get_mahony_filter(), rtol=0, atol=1e-14)
+    for k in range(n_steps):
+        act = sc.sample_targets(k)
+        eng.set_command(act)
+        orc.set_command(act)
+        eng.step(sc.step_dt)
+        assert not orc.step(sc.step_dt, parallel=True).any()
+        compare(eng, orc, 1e-9, 1e-7)
+        np.testing.assert_allclose(eng.get_mahony_filter(), orc.get_mahony_filter(), rtol=0, atol=1e-8)
+    m = eng.get_mahony_filter()
+    assert np.all(np.abs(np.linalg.norm(m[:, :, :4], axis=2) - 1.0) < 1e-6) and np.abs(m[:, :, 7:]).max() > 1e-3
+    return eng, orc

@@ -199,3 +199,8 @@ def test_pd_controller_block(safety):
 def test_bounds_handoff_between_kernels_at_scale():
     """600 ANYmal envs, every third pushed into its joint bounds: fast kernel / full kernel hand-off inside warps."""
     pc.bounds_handoff_scenario(None, n_env=600, n_steps=5)
+
+
+def test_mahony_filter_observer():
+    pc.mahony_scenario(None, "anymal", n_env=70, n_steps=4)
+    pc.mahony_scenario(None, "atlas", n_env=5, n_steps=1)

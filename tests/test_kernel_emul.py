@@ -390,3 +390,8 @@ def test_pd_controller_block(api, safety):
 
 def test_bounds_handoff_between_kernels(api):
     pc.bounds_handoff_scenario(api, n_env=9, n_steps=4)
+
+
+def test_mahony_filter_observer(api):
+    pc.mahony_scenario(api, "anymal")
+    pc.mahony_scenario(api, "atlas", n_env=1, n_steps=1)

@@ -20,13 +20,18 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 
 
 def extract(path, names):
+    """Source text of the named top-level functions (the jitted definition, not the typing @overload stubs)."""
     src = open(path).read()
     tree = ast.parse(src)
     chunks = []
     for node in tree.body:
         if isinstance(node, ast.FunctionDef) and node.name in names:
+            decos = [ast.get_source_segment(src, d) or "" for d in node.decorator_list]
+            if any(d.startswith("overload") for d in decos):
+                continue
             start = min([d.lineno for d in node.decorator_list] + [node.lineno])
-            chunks.append("\n".join(src.splitlines()[start - 1:node.end_lineno]))
+            text = "\n".join(src.splitlines()[start - 1:node.end_lineno])
+            chunks.append(text.replace("@no_type_check\n", ""))
     return "\n\n".join(chunks)
 
 
@@ -41,6 +46,10 @@ def main():
         fh.write(extract(os.path.join(REF, "proportional_derivative_controller.py"), {"integrate_zoh", "pd_controller"}))
         fh.write("\n\n")
         fh.write(extract(os.path.join(REF, "motor_safety_limit.py"), {"apply_safety_limits"}))
+        fh.write("\n\nfrom typing import Tuple\nEARTH_SURFACE_GRAVITY = 9.81   # blocks/mahony_filter.py:23\n\n")
+        fh.write(extract(os.path.join(REF, "..", "utils", "math.py"), {"compute_tilt_from_quat", "matrices_to_quat"}))
+        fh.write("\n\n")
+        fh.write(extract(os.path.join(REF, "mahony_filter.py"), {"mahony_filter"}))
         fh.write("\n")
     spec = importlib.util.spec_from_file_location("ref_controller_blocks", mod_path)
     mod = importlib.util.module_from_spec(spec)
@@ -74,6 +83,33 @@ def main():
         for k, x in zip(("s_command", "s_q", "s_v", "s_kp", "s_kd", "s_lo", "s_hi", "s_vlim", "s_elim", "s_out"),
                         (cmd, q, v, skp, skd, lower[0], upper[0], vmax, elim, so)):
             rec[k].append(x.copy())
+    # Mahony filter (blocks/mahony_filter.py:28-101) and matrices_to_quat (utils/math.py:293-350)
+    for k in ("m_q", "m_gyro", "m_acc", "m_bias", "m_kp", "m_ki", "m_dt", "m_q_out", "m_omega", "m_bias_out", "r_mat", "r_quat"):
+        rec[k] = []
+    for case in range(n_cases):
+        M = 2
+        q = rng.normal(size=(4, M)); q /= np.linalg.norm(q, axis=0)
+        gyro = rng.normal(size=(3, M)) * (0.0 if case % 17 == 0 else 1.5)
+        acc = rng.normal(size=(3, M)) * 2.0 + np.array([[0.0], [0.0], [9.81]])
+        if case % 17 == 0:   # exercises the early return: no IMU motion, acceleration aligned with the estimated gravity
+            v = np.stack(mod.compute_tilt_from_quat(q))
+            acc = 9.81 * v
+        bias = rng.normal(size=(3, M)) * (0.0 if case % 17 == 0 else 0.05)
+        kp, ki, dt = float(rng.uniform(0.0, 2.0)), float(rng.uniform(0.0, 0.5)), float(rng.choice([1e-3, 5e-3, 1e-2]))
+        qo, om, cf, bo = q.copy(), np.zeros((3, M)), np.zeros((3, M)), bias.copy()
+        mod.mahony_filter(qo, om, cf, gyro, acc, bo, kp, ki, dt)
+        for k, x in zip(("m_q", "m_gyro", "m_acc", "m_bias", "m_kp", "m_ki", "m_dt", "m_q_out", "m_omega", "m_bias_out"),
+                        (q, gyro, acc, bias, kp, ki, dt, qo, om, bo)):
+            rec[k].append(np.array(x))
+        # random rotation matrices (all four branches of the conversion are hit over the cases)
+        quat = rng.normal(size=4); quat /= np.linalg.norm(quat)
+        x, y, z, w = quat
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        out = np.zeros((4, 1))
+        mod.matrices_to_quat((R,), out)
+        rec["r_mat"].append(R); rec["r_quat"].append(out[:, 0].copy())
     np.savez_compressed(OUT, **{k: np.array(v) for k, v in rec.items()})
     print("wrote", OUT, {k: np.array(v).shape for k, v in rec.items()})
 
