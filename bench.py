@@ -110,7 +110,7 @@ class ClockSampler(threading.Thread):
         return out
 
 
-def cpu_baseline(sc_name, threads_all=True, budget_s=12.0, contact_model=None):
+def cpu_baseline(sc_name, threads_all=True, budget_s=12.0, contact_model=None, solver=None, dt_max=None):
     """The oracle (a C++ restatement of the reference's CPU path) on this box's host cores: a bounded
     sample of the same workload.  Returns env-steps/s single-thread and with all OpenMP threads."""
     from jiminy_b200 import scenarios
@@ -118,7 +118,7 @@ def cpu_baseline(sc_name, threads_all=True, budget_s=12.0, contact_model=None):
     ncores = OracleBatch.max_threads()
     out = {}
     for label, n_env, par in (("single_thread", 8, False), ("all_threads", 32 * ncores, True)):
-        sc = scenarios.make(sc_name, n_env, contact_model=contact_model)
+        sc = scenarios.make(sc_name, n_env, contact_model=contact_model, solver=solver, dt_max=dt_max)
         orc = OracleBatch(sc.robot, sc.options, n_env)
         if sc.kp is not None:
             orc.set_pd_controller(sc.kp, sc.kd)
@@ -148,7 +148,7 @@ def run_reference(args):
     from oracle.oracle import OracleBatch
     ncores = OracleBatch.max_threads()
     n_env = min(args.n_env, 64 * ncores)        # bounded sample of the 4096-env batch
-    sc = scenarios.make(args.workload, n_env, contact_model=args.contact_model)
+    sc = scenarios.make(args.workload, n_env, contact_model=args.contact_model, solver=args.ode_solver, dt_max=args.dt_max)
     orc = OracleBatch(sc.robot, sc.options, n_env)
     if sc.kp is not None:
         orc.set_pd_controller(sc.kp, sc.kd)
@@ -192,7 +192,7 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_env = args.n_env                                   # per GPU (weak scaling: envs are independent)
-    sc = scenarios.make(args.workload, n_env, seed=rank, contact_model=args.contact_model)
+    sc = scenarios.make(args.workload, n_env, seed=rank, contact_model=args.contact_model, solver=args.ode_solver, dt_max=args.dt_max)
     eng = core.BatchedEngine(sc.robot, sc.options, n_env, device=local_rank)
     if sc.kp is not None:
         eng.set_pd_controller(sc.kp, sc.kd)
@@ -372,7 +372,7 @@ def run_gpu(args):
     traffic, fp64_pct = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
-            rec = json.load(fh).get(args.workload) if args.contact_model in (None, "spring_damper") else None
+            rec = json.load(fh).get(args.workload) if (args.contact_model in (None, "spring_damper") and args.ode_solver is None and args.dt_max is None) else None
         if rec and rec["n_env"] == n_env:
             traffic, fp64_pct = rec["traffic_bytes"], rec["fp64_pipe_active_pct"]
     except Exception:
@@ -380,7 +380,7 @@ def run_gpu(args):
     achieved_gbs = bytes_per_launch / (step_ms_dev * 1e-3) / 1e9
     ncores, cpu = (None, None)
     if not args.no_cpu_baseline:
-        ncores, cpu = cpu_baseline(args.workload, contact_model=args.contact_model)
+        ncores, cpu = cpu_baseline(args.workload, contact_model=args.contact_model, solver=args.ode_solver, dt_max=args.dt_max)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_path_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -418,6 +418,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="jiminy_b200", choices=["jiminy_b200", "reference"])
     ap.add_argument("--workload", default="anymal", choices=["anymal", "atlas", "cartpole", "double_pendulum"])
+    ap.add_argument("--ode-solver", default=None, choices=["euler_explicit", "runge_kutta_4", "runge_kutta_dopri"],
+                    help="override stepper.odeSolver of the scenario")
+    ap.add_argument("--dt-max", type=float, default=None, help="override stepper.dtMax of the scenario")
     ap.add_argument("--nccl-gather", action="store_true",
                     help="multi-GPU: exchange observations with an NCCL all-gather after the step instead of the in-kernel "
                          "stores into peer memory")

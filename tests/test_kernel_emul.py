@@ -381,6 +381,8 @@ def test_constraint_contact_atlas_rhs(api):
     eng.step(0.005)
     assert not orc.step(0.005).any()
     pc.compare(eng, orc, 1e-9, 1e-6)
+    # the reference's own Atlas settings (atlas_options.toml, pipeline_benchmark.py): explicit Euler at 5 ms
+    pc.robot_constraint_scenario("atlas", 1, 1, api, seed=2, solver="euler_explicit", dt_max=0.005)
 
 
 @pytest.mark.parametrize("safety", [False, True])
