@@ -115,7 +115,7 @@ def cpu_baseline(sc_name, threads_all=True, budget_s=12.0, contact_model=None, s
     sample of the same workload.  Returns env-steps/s single-thread and with all OpenMP threads."""
     from jiminy_b200 import scenarios
     from oracle.oracle import OracleBatch
-    ncores = OracleBatch.max_threads()
+    ncores = OracleBatch.use_all_cores()
     out = {}
     for label, n_env, par in (("single_thread", 8, False), ("all_threads", 32 * ncores, True)):
         sc = scenarios.make(sc_name, n_env, contact_model=contact_model, solver=solver, dt_max=dt_max)
@@ -146,7 +146,7 @@ def run_reference(args):
         return
     from jiminy_b200 import scenarios
     from oracle.oracle import OracleBatch
-    ncores = OracleBatch.max_threads()
+    ncores = OracleBatch.use_all_cores()
     n_env = min(args.n_env, 64 * ncores)        # bounded sample of the 4096-env batch
     sc = scenarios.make(args.workload, n_env, contact_model=args.contact_model, solver=args.ode_solver, dt_max=args.dt_max)
     orc = OracleBatch(sc.robot, sc.options, n_env)

@@ -22,6 +22,7 @@ struct OrcBatch {
 
 extern "C" {
 
+void orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 int orc_max_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

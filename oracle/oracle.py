@@ -60,6 +60,7 @@ def lib():
         L.orc_matrix_to_quat.argtypes = [c_double_p, c_double_p]
         L.orc_set_mahony.argtypes = [C.c_void_p, C.c_double, C.c_double]
         L.orc_get_mahony.argtypes = [C.c_void_p, c_double_p]
+        L.orc_set_threads.argtypes = [C.c_int]
         L.orc_stop.argtypes = [C.c_void_p]
         L.orc_register_impulse_force.argtypes = [C.c_void_p, C.c_int] + [c_double_p] * 4
         L.orc_set_impulse_force.argtypes = [C.c_void_p, C.c_int, c_uint8_p] + [c_double_p] * 3
@@ -103,6 +104,15 @@ class OracleBatch:
 
     @staticmethod
     def max_threads() -> int:
+        return lib().orc_max_threads()
+
+    @staticmethod
+    def use_all_cores() -> int:
+        """OpenMP thread count = the cores this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it
+        to 1 for its workers)."""
+        import os
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        lib().orc_set_threads(int(n))
         return lib().orc_max_threads()
 
     def set_options(self, options: dict) -> None:
