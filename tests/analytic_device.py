@@ -37,7 +37,7 @@ def armature_spring(api=None):
         np.testing.assert_allclose(np.c_[qs[:, e], vs[:, e]], xa, rtol=1e-5, atol=1e-7)
 
 
-def two_masses(api=None, period=1e-3):
+def two_masses(api=None, period=1e-3, t_end=1.0):
     """test_double_spring_mass.py:85-130 (prismatic chain, discrete periods, adaptive DOPRI)."""
     r = M.build_robot_table(os.path.join(DATA, "linear_two_masses.urdf"), False)
     eng = BatchedEngine(r, _opt(odeSolver="runge_kutta_dopri", tolAbs=1e-8, tolRel=1e-8, sensorsUpdatePeriod=period,
@@ -48,7 +48,7 @@ def two_masses(api=None, period=1e-3):
     A = np.array([[0, 0, 1, 0], [0, 0, 0, 1], [-k[0] / m[0], k[1] / m[0], -nu[0] / m[0], nu[1] / m[0]],
                   [k[0] / m[0], -k[1] * Iq, nu[0] / m[0], -nu[1] * Iq]])
     x0 = np.array([0.1, -0.1, 0.0, 0.0])
-    ts, qs, vs, _ = eng.simulate(1.0, np.tile(x0[:2], (2, 1)), np.tile(x0[2:], (2, 1)))
+    ts, qs, vs, _ = eng.simulate(t_end, np.tile(x0[:2], (2, 1)), np.tile(x0[2:], (2, 1)))
     idx = np.linspace(0, len(ts) - 1, 25).astype(int)
     xa = np.stack([scipy.linalg.expm(A * t) @ x0 for t in ts[idx, 0]])
     np.testing.assert_allclose(np.c_[qs[idx, 1], vs[idx, 1]], xa, rtol=1e-5, atol=1e-7)
@@ -139,7 +139,7 @@ def pendulum_impulse_reference(ts, m=5.0, l=1.0):
     return out
 
 
-def force_impulse(api=None):
+def force_impulse(api=None, t_end=1.0):
     """Gravity-free pendulum under the impulse forces above, continuous and discrete (1 ms) scheduling, plus a
     second env whose impulses are shifted and scaled (per-env schedules)."""
     r = M.build_robot_table(os.path.join(DATA, "simple_pendulum.urdf"), False)
@@ -149,7 +149,7 @@ def force_impulse(api=None):
         eng = BatchedEngine(r, opt, 2, api_=api)
         for f in IMPULSES:
             eng.register_impulse_force("PendulumLink", [f["t"], f["t"]], f["dt"], np.array([f["F"], [0.0] * 6]))
-        ts, qs, vs, _ = eng.simulate(1.0, np.zeros((2, 1)), np.zeros((2, 1)))
+        ts, qs, vs, _ = eng.simulate(t_end, np.zeros((2, 1)), np.zeros((2, 1)))
         xa = pendulum_impulse_reference(ts[:, 0])
         np.testing.assert_allclose(np.c_[qs[:, 0], vs[:, 0]], xa, atol=1e-6)
         np.testing.assert_allclose(np.c_[qs[:, 1], vs[:, 1]], 0.0, atol=1e-12)   # env 1: zero wrenches
