@@ -33,11 +33,12 @@ constexpr int CONS_RELAX_MIN_ITER = 20, CONS_RELAX_MAX_ITER = 30;
 // this env's own row of the per-env global tables (padding envs of the last warp get their own rows, < n_pad)
 #define CONS_COL(c) (static_cast<size_t>(blockIdx.x) * (32 / KP->L) + (c).lane / KP->L)
 #define CST(off) (KP->cstate[CONS_COL(c) * KP->cs_total + (off)])
+// inside the solver the row base is hoisted once (cw / cs): the index arithmetic above costs more than the load
 #define CWK(off) (KP->cwork[CONS_COL(c) * KP->cw_total + (off)])
 JB_DI int cs_joint(int k) { return CS_JOINT0 + CS_JOINT_SIZE * k; }
 JB_DI int cs_contact(int k) { return CS_JOINT0 + CS_JOINT_SIZE * KP->n_jc + CS_CONTACT_SIZE * k; }
 // workspace layout (doubles per env)
-struct CwLayout { int OM, VV, AD, YC, MM, JJ, YY, AA, AL, GA, BB, LA, YV, YP, DD, TT, total; };
+struct CwLayout { int OM, VV, AD, YC, MM, JJ, YY, AA, AL, GA, BB, LA, YV, YP, AC, DD, TT, total; };
 JB_HD CwLayout cw_layout(int njoints, int nv, int m_max) {
     CwLayout w; int o = 0;
     w.OM = o; o += 12 * njoints;
@@ -49,7 +50,7 @@ JB_HD CwLayout cw_layout(int njoints, int nv, int m_max) {
     w.YY = o; o += m_max * nv;
     w.AA = o; o += m_max * m_max;
     w.AL = o; o += m_max * m_max;
-    w.GA = o; o += m_max; w.BB = o; o += m_max; w.LA = o; o += m_max; w.YV = o; o += m_max; w.YP = o; o += m_max;
+    w.GA = o; o += m_max; w.BB = o; o += m_max; w.LA = o; o += m_max; w.YV = o; o += m_max; w.YP = o; o += m_max; w.AC = o; o += m_max;
     w.DD = o; o += nv; w.TT = o; o += nv;
     w.total = o;
     return w;
@@ -205,8 +206,11 @@ __device__ __noinline__ void cons_update_contact(const Ctx c, int contact, const
 }
 
 // ---- dense helpers on the workspace ------------------------------------------------------------------
+// from here on `cw` is the hoisted base of this env's workspace row
+#undef CWK
+#define CWK(off) (cw[(off)])
 // in-place lower Cholesky of the n x n matrix at `off` (row stride ld); false if not positive definite
-JB_DI bool cw_llt(const Ctx& c, int off, int n, int ld) {
+JB_DI bool cw_llt(double* const cw, int off, int n, int ld) {
     for (int j = 0; j < n; ++j) {
         double s = CWK(off + j * ld + j);
         for (int k = 0; k < j; ++k) { const double l = CWK(off + j * ld + k); s -= l * l; }
@@ -221,14 +225,14 @@ JB_DI bool cw_llt(const Ctx& c, int off, int n, int ld) {
     }
     return true;
 }
-JB_DI void cw_forward(const Ctx& c, int Loff, int n, int ld, int x) {   // L y = x, in place
+JB_DI void cw_forward(double* const cw, int Loff, int n, int ld, int x) {   // L y = x, in place
     for (int i = 0; i < n; ++i) {
         double s = CWK(x + i);
         for (int k = 0; k < i; ++k) s -= CWK(Loff + i * ld + k) * CWK(x + k);
         CWK(x + i) = s / CWK(Loff + i * ld + i);
     }
 }
-JB_DI void cw_backward(const Ctx& c, int Loff, int n, int ld, int x) {  // L^T y = x, in place
+JB_DI void cw_backward(double* const cw, int Loff, int n, int ld, int x) {  // L^T y = x, in place
     for (int i = n - 1; i >= 0; --i) {
         double s = CWK(x + i);
         for (int k = i + 1; k < n; ++k) s -= CWK(Loff + k * ld + i) * CWK(x + k);
@@ -238,13 +242,13 @@ JB_DI void cw_backward(const Ctx& c, int Loff, int n, int ld, int x) {  // L^T y
 
 // PGSSolver::ProjectedGaussSeidelIter + Solver (constraint_solvers.cc:107-318).  Constraint order: joint
 // bounds, then contact frames (ConstraintTree::foreach, model.h:43-46).
-JB_DI bool cons_pgs(const Ctx& c, const CwLayout& w, int m) {
+JB_DI bool cons_pgs(const Ctx& c, double* const cw, const CwLayout& w, int m, int n_active) {
     const int ld = KP->m_max;
     const JbOptions& opt = KP->opt;
     for (int k = 0; k < m; ++k) CWK(w.YV + k) = 0.0;
     auto residual = [&](int k) {
         double s = 0.0;
-        for (int r = 0; r < m; ++r) s += CWK(w.AA + r * ld + k) * CWK(w.LA + r);   // A.col(k).dot(x)
+        for (int r = 0; r < m; ++r) s += CWK(w.AA + k * ld + r) * CWK(w.LA + r);   // A.col(k).dot(x) == row k (A is symmetric)
         return CWK(w.BB + k) - s;
     };
     for (int iter = 0; iter < CONS_PGS_MAX_ITER; ++iter) {
@@ -257,13 +261,11 @@ JB_DI bool cons_pgs(const Ctx& c, const CwLayout& w, int m) {
             if (ratio > 0.0) wr += (CONS_RELAX_MAX - CONS_RELAX_MIN) * (ratio * ratio);
         }
         for (int pass = 0; pass < 3; ++pass) {
-            int row = 0;
-            for (int k = 0; k < KP->n_jc + KP->n_cc; ++k) {
-                const bool is_joint = k < KP->n_jc;
-                const int o = is_joint ? cs_joint(k) : cs_contact(k - KP->n_jc);
-                if (CST(o) == 0.0) continue;
-                const int start = row;
-                row += is_joint ? 1 : 4;
+            for (int a = 0; a < n_active; ++a) {
+                // active list entry: first row * 2 + kind (written by constrained_solve)
+                const int code = static_cast<int>(CWK(w.AC + a));
+                const bool is_joint = (code & 1) == 0;
+                const int start = code >> 1;
                 if (is_joint) {
                     if (pass != 0) continue;
                     const double y = residual(start);
@@ -351,6 +353,7 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
     const int L = KP->L, nv = KP->nv, nj = KP->njoints, ld = KP->m_max;
     const CwLayout w = cw_layout(nj, nv, ld);
     const JbOptions& opt = KP->opt;
+    double* const cw = KP->cwork + CONS_COL(c) * KP->cw_total;
     __syncwarp(c.gmask);
     // ---------------- 1. tree quantities, joint-space inertia and its Cholesky factor (sub-lane 0)
     if (c.sub == 0) {
@@ -436,11 +439,11 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
                 for (int k = 0; k < 9; ++k) CWK(w.YC + 21 * p + 6 + k) += T.B[k];
             }
         }
-        if (!cw_llt(c, w.MM, nv, nv)) *status |= JB_ENV_NAN;
+        if (!cw_llt(cw, w.MM, nv, nv)) *status |= JB_ENV_NAN;
     }
     __syncwarp(c.gmask);
     // ---------------- 2. rows of J, drift, rows of L^-1 J^T: constraints dealt round-robin to the lanes
-    int m = 0;
+    int m = 0, n_active = 0;
     {
         int count = 0;
         for (int k = 0; k < KP->n_jc + KP->n_cc; ++k) {
@@ -449,6 +452,8 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
             if (CST(o) == 0.0) continue;
             const int start = m, dim = is_joint ? 1 : 4;
             m += dim;
+            if (c.sub == 0) CWK(w.AC + n_active) = static_cast<double>(2 * start + (is_joint ? 0 : 1));   // list for the sweep
+            ++n_active;
             const bool mine = (count++ % L) == c.sub;
             if (!mine) continue;
             for (int r = 0; r < dim; ++r) for (int e = 0; e < nv; ++e) CWK(w.JJ + (start + r) * nv + e) = 0.0;
@@ -517,7 +522,7 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
             }
             for (int r = start; r < start + dim; ++r) {
                 for (int e = 0; e < nv; ++e) CWK(w.YY + r * nv + e) = CWK(w.JJ + r * nv + e);
-                cw_forward(c, w.MM, nv, nv, w.YY + r * nv);
+                cw_forward(cw, w.MM, nv, nv, w.YY + r * nv);
             }
         }
     }
@@ -533,13 +538,14 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
             row += dim;
             if ((count++ % L) != c.sub) continue;
             for (int r = start; r < start + dim; ++r) {
-                for (int q = 0; q < m; ++q) {
+                // lower triangle only, mirrored (the owner of row r also writes column r of the rows above it)
+                for (int q = 0; q <= r; ++q) {
                     double s = 0.0;
                     for (int e = 0; e < nv; ++e) s += CWK(w.YY + r * nv + e) * CWK(w.YY + q * nv + e);
+                    if (q == r) s += fmax(s * opt.constraint_regularization, CONS_MIN_REGULARIZER);
                     CWK(w.AA + r * ld + q) = s;
+                    CWK(w.AA + q * ld + r) = s;
                 }
-                const double diag = CWK(w.AA + r * ld + r);
-                CWK(w.AA + r * ld + r) = diag + fmax(diag * opt.constraint_regularization, CONS_MIN_REGULARIZER);
                 double s = 0.0;
                 for (int e = 0; e < nv; ++e) s += CWK(w.JJ + r * nv + e) * CWK(w.DD + e);
                 CWK(w.BB + r) = -CWK(w.GA + r) - s;
@@ -553,20 +559,20 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
         if (c.flags & CTX_IGNORE_BOUNDS) {
             // solveJMinvJtv (overload.h:539-551): exact equality solve
             for (int r = 0; r < m; ++r) for (int q = 0; q < m; ++q) CWK(w.AL + r * ld + q) = CWK(w.AA + r * ld + q);
-            if (cw_llt(c, w.AL, m, ld)) {
+            if (cw_llt(cw, w.AL, m, ld)) {
                 for (int r = 0; r < m; ++r) CWK(w.LA + r) = CWK(w.BB + r);
-                cw_forward(c, w.AL, m, ld, w.LA);
-                cw_backward(c, w.AL, m, ld, w.LA);
+                cw_forward(cw, w.AL, m, ld, w.LA);
+                cw_backward(cw, w.AL, m, ld, w.LA);
             }
-        } else ok = cons_pgs(c, w, m);
+        } else ok = cons_pgs(c, cw, w, m, n_active);
         // ddq = ddq_free + M^-1 J^T lambda
         for (int e = 0; e < nv; ++e) {
             double s = 0.0;
             for (int r = 0; r < m; ++r) s += CWK(w.JJ + r * nv + e) * CWK(w.LA + r);
             CWK(w.TT + e) = s;
         }
-        cw_forward(c, w.MM, nv, nv, w.TT);
-        cw_backward(c, w.MM, nv, nv, w.TT);
+        cw_forward(cw, w.MM, nv, nv, w.TT);
+        cw_backward(cw, w.MM, nv, nv, w.TT);
         for (int j = 1; j < nj; ++j) {
             const JointMap jm = KP->jmap[j];
             for (int s = (jm.trunk ? 0 : jm.sub); s < (jm.trunk ? L : jm.sub + 1); ++s) {
