@@ -389,7 +389,22 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
             const int cs_fields = CS_JOINT0 + CS_JOINT_SIZE * kp.n_jc + CS_CONTACT_SIZE * kp.n_cc;
             const CwLayout w = cw_layout(m->njoints, m->nv, kp.m_max);
             ALLOC(d_jmap, jmap.size()); ALLOC(d_cmap, cmap.size()); ALLOC(d_jcj, std::max<size_t>(jc_joint.size(), 1)); ALLOC(d_jcof, jc_of_joint.size());
-            ALLOC(d_cst, static_cast<size_t>(cs_fields) * N); ALLOC(d_cwk, static_cast<size_t>(w.total) * N);
+            // the workspace is scratch of one dynamics evaluation: sized for the blocks that can be resident at once
+            int n_sm = 1, blocks_per_sm = 1;
+#ifndef JB_HOST_EMUL
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+            const size_t smem_guess = static_cast<size_t>(b->base_fields) * 32 * sizeof(double);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, env_step_kernel_t<false>, 32, smem_guess) != cudaSuccess || blocks_per_sm < 1) {
+                cudaGetLastError();
+                blocks_per_sm = 32;
+            }
+            blocks_per_sm = std::min(blocks_per_sm, 32);
+#endif
+            const size_t cw_rows = std::min<size_t>(N, static_cast<size_t>(n_sm) * blocks_per_sm * (32 / P.L));
+            unsigned int* d_slots;
+            ALLOC(d_slots, n_sm);
+            kp.cw_slots = d_slots; kp.cw_blocks_per_sm = blocks_per_sm;
+            ALLOC(d_cst, static_cast<size_t>(cs_fields) * N); ALLOC(d_cwk, static_cast<size_t>(w.total) * std::max<size_t>(cw_rows, static_cast<size_t>(n_sm) * blocks_per_sm * (32 / P.L)));
             cudaMemcpyAsync(d_jmap, jmap.data(), jmap.size() * sizeof(JointMap), cudaMemcpyHostToDevice, b->stream);
             cudaMemcpyAsync(d_cmap, cmap.data(), cmap.size() * sizeof(ContactMap), cudaMemcpyHostToDevice, b->stream);
             if (!jc_joint.empty()) cudaMemcpyAsync(d_jcj, jc_joint.data(), jc_joint.size() * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream);

@@ -34,7 +34,8 @@ constexpr int CONS_RELAX_MIN_ITER = 20, CONS_RELAX_MAX_ITER = 30;
 #define CONS_COL(c) (static_cast<size_t>(blockIdx.x) * (32 / KP->L) + (c).lane / KP->L)
 #define CST(off) (KP->cstate[CONS_COL(c) * KP->cs_total + (off)])
 // inside the solver the row base is hoisted once (cw / cs): the index arithmetic above costs more than the load
-#define CWK(off) (KP->cwork[CONS_COL(c) * KP->cw_total + (off)])
+#define CW_ROW(c) (static_cast<size_t>(jb_cw_slot) * (32 / KP->L) + (c).lane / KP->L)
+#define CWK(off) (KP->cwork[CW_ROW(c) * KP->cw_total + (off)])
 JB_DI int cs_joint(int k) { return CS_JOINT0 + CS_JOINT_SIZE * k; }
 JB_DI int cs_contact(int k) { return CS_JOINT0 + CS_JOINT_SIZE * KP->n_jc + CS_CONTACT_SIZE * k; }
 // workspace layout (doubles per env)
@@ -353,7 +354,7 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
     const int L = KP->L, nv = KP->nv, nj = KP->njoints, ld = KP->m_max;
     const CwLayout w = cw_layout(nj, nv, ld);
     const JbOptions& opt = KP->opt;
-    double* const cw = KP->cwork + CONS_COL(c) * KP->cw_total;
+    double* const cw = KP->cwork + CW_ROW(c) * KP->cw_total;
     __syncwarp(c.gmask);
     // ---------------- 1. tree quantities, joint-space inertia and its Cholesky factor (sub-lane 0)
     if (c.sub == 0) {

@@ -566,9 +566,43 @@ __device__ __forceinline__ void env_step_body() {
     if (c.valid && c.sub == 0) KP->status[c.env] = status;
 }
 
+JB_DI unsigned int jb_smid() {
+#ifdef JB_HOST_EMUL
+    return 0u;
+#else
+    unsigned int id;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(id));
+    return id;
+#endif
+}
+
 template <bool FAST>
 __global__ void __launch_bounds__(32) env_step_kernel_t() {
+    // constraint workspace: one slot per resident block of this SM, taken for the lifetime of the block
+    int my_bit = -1;
+    unsigned int my_sm = 0;
+    if (!FAST && KP->only_flagged && KP->mode == MODE_STEP) {
+        // fix-up pass behind the fast kernel: nothing to do unless an env of this warp was handed over
+        const int flag = KP->needs_full[blockIdx.x * (32 / KP->L) + (threadIdx.x & 31) / KP->L];
+        if (!__any_sync(0xffffffffu, flag != 0)) return;
+    }
+    if (!FAST && KP->cons_on) {
+        if (threadIdx.x == 0) {
+            my_sm = jb_smid();
+            for (int tries = 0; my_bit < 0; ++tries) {
+                const int bit = tries % KP->cw_blocks_per_sm;
+                const unsigned int old = atomicOr(KP->cw_slots + my_sm, 1u << bit);
+                if (!(old & (1u << bit))) my_bit = bit;
+            }
+            jb_cw_slot = static_cast<int>(my_sm) * KP->cw_blocks_per_sm + my_bit;
+        }
+        __syncwarp();
+    }
     env_step_body<FAST>();
+    if (!FAST && KP->cons_on) {
+        __syncwarp();
+        if (threadIdx.x == 0) atomicAnd(KP->cw_slots + my_sm, ~(1u << my_bit));
+    }
 #ifndef JB_HOST_EMUL
     // observation exchange over peer memory: the last block of the last launch of a step tells the other ranks
     // that every row of this rank has been published (release: fence, then the flags)

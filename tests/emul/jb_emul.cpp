@@ -18,6 +18,7 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, int L, const std::
         for (auto& w : warps) {
             w.L = L;
             for (int g = 0; g < 32 / L; ++g) w.bars.emplace_back(new std::barrier<>(L));
+            w.full.reset(new std::barrier<>(32));
         }
         std::vector<std::thread> threads;
         threads.reserve(block);

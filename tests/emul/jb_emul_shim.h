@@ -41,12 +41,16 @@ struct Warp {
     double dslot[32];
     int islot[32];
     std::vector<std::unique_ptr<std::barrier<>>> bars;   // indexed by group id for the current L
+    std::unique_ptr<std::barrier<>> full;                 // whole-warp barrier (mask 0xffffffff)
     int L = 1;
 };
 extern thread_local Warp* warp;
 extern thread_local int lane_id;
 inline int group_of(unsigned mask) { return __builtin_ctz(mask) / warp->L; }
-inline void sync_group(unsigned mask) { warp->bars[group_of(mask)]->arrive_and_wait(); }
+inline void sync_group(unsigned mask) {
+    if (mask == 0xffffffffu && warp->L < 32) warp->full->arrive_and_wait();
+    else warp->bars[group_of(mask)]->arrive_and_wait();
+}
 }  // namespace emul
 
 inline void __syncwarp(unsigned mask = 0xffffffffu) { emul::sync_group(mask); }
@@ -81,6 +85,9 @@ inline bool __any_sync(unsigned mask, bool p) {
     return r;
 }
 inline bool __all_sync(unsigned mask, bool p) { return !__any_sync(mask, !p); }
+// blocks run one after the other in the emulator: plain read-modify-write is enough
+inline unsigned int atomicOr(unsigned int* p, unsigned int v) { const unsigned int o = *p; *p = o | v; return o; }
+inline unsigned int atomicAnd(unsigned int* p, unsigned int v) { const unsigned int o = *p; *p = o & v; return o; }
 inline double __longlong_as_double(long long x) { double d; std::memcpy(&d, &x, sizeof d); return d; }
 inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }

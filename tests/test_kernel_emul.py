@@ -368,7 +368,9 @@ def test_constraint_contact_point_mass(api):
 
 
 def test_constraint_contact_anymal(api):
-    eng, orc, sc = pc.robot_constraint_scenario("anymal", 5, 2, api, seed=2)
+    # (the structured solver exchanges through shuffles, which the thread emulator pays dearly: small case here,
+    # 40 envs x 3 steps in the GPU suite)
+    eng, orc, sc = pc.robot_constraint_scenario("anymal", 3, 1, api, seed=2)
     assert (eng.get_state()[1][:, 2] > 0.4).all()      # still standing
 
 
