@@ -410,6 +410,36 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
             if (!jc_joint.empty()) cudaMemcpyAsync(d_jcj, jc_joint.data(), jc_joint.size() * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream);
             cudaMemcpyAsync(d_jcof, jc_of_joint.data(), jc_of_joint.size() * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream);
             kp.cs_total = cs_fields; kp.cw_total = w.total;
+            // lane-block solver: dof numbering inside the trunk block and each lane's private block, row budget per lane
+            kp.lb_on = 0;
+            if (P.L > 1) {
+                std::vector<int32_t> dof0(static_cast<size_t>(P.nrec) * P.L, 0);
+                int nt = 0, nl = 0, ml = 0;
+                for (int s = 0; s < P.L; ++s) {
+                    int t = 0, l = 0, rows = 0;
+                    for (int r = 0; r < P.nrec; ++r) {
+                        const RecInt& ri = P.rint[static_cast<size_t>(r) * P.L + s];
+                        if (ri.kind == REC_PAD) continue;
+                        const int nd = ri.kind == REC_FREE ? 6 : 1;
+                        int& n = r < P.ntrunk ? t : l;
+                        dof0[static_cast<size_t>(r) * P.L + s] = n;
+                        n += nd;
+                    }
+                    for (size_t k = 0; k < jc_joint.size(); ++k) { const JointMap& jm = jmap[jc_joint[k]]; if ((jm.trunk ? 0 : jm.sub) == s) rows += 1; }
+                    for (int k = 0; k < m->ncontacts; ++k) if ((cmap[k].trunk ? 0 : cmap[k].sub) == s) rows += 4;
+                    nt = t; nl = std::max(nl, l); ml = std::max(ml, rows);
+                    kp.lb_nl_of[s] = l;
+                }
+                const char* off = std::getenv("JB_NO_BLOCK_CONS");
+                if (nt <= LB_MAX_NT && P.L <= 8 && !(off && std::atoi(off))) {
+                    const LbLayout lw = lb_layout(P.nrec, P.ntrunk, nl, nt, ml, kp.n_jc + kp.n_cc);
+                    int32_t* d_dof0; double* d_lwk;
+                    ALLOC(d_dof0, dof0.size());
+                    ALLOC(d_lwk, static_cast<size_t>(lw.total) * 32 * std::max<size_t>(1, static_cast<size_t>(n_sm) * blocks_per_sm));
+                    cudaMemcpyAsync(d_dof0, dof0.data(), dof0.size() * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream);
+                    kp.lb_on = 1; kp.lb_nt = nt; kp.lb_nl = nl; kp.lb_ml = ml; kp.lw_total = lw.total; kp.lb_dof0 = d_dof0; kp.lwork = d_lwk;
+                }
+            }
             kp.jmap = d_jmap; kp.cmap = d_cmap; kp.jc_joint = d_jcj; kp.jc_of_joint = d_jcof; kp.cstate = d_cst; kp.cwork = d_cwk;
         }
     }
@@ -429,7 +459,8 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
 int jb_describe(JbBatch* b, char* buf, int32_t len) {
     if (!b || !buf) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
     std::snprintf(buf, len, "%s; constraints: %s", b->plan.describe().c_str(),
-                  !b->kp.cons_on ? "flag only" : (b->kp.cq_on ? "structured quadruped solver + generic" : "generic solver"));
+                  !b->kp.cons_on ? "flag only" : (b->kp.cq_on ? (b->kp.lb_on ? "structured quadruped solver + lane-block solver" : "structured quadruped solver + generic")
+                                                 : (b->kp.lb_on ? "lane-block solver" : "generic solver")));
     return JB_OK;
 }
 
