@@ -431,13 +431,43 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
                     kp.lb_nl_of[s] = l;
                 }
                 const char* off = std::getenv("JB_NO_BLOCK_CONS");
+                kp.bd_on = 0;
                 if (nt <= LB_MAX_NT && P.L <= 8 && !(off && std::atoi(off))) {
                     const LbLayout lw = lb_layout(P.nrec, P.ntrunk, nl, nt, ml, kp.n_jc + kp.n_cc);
+                    int lw_total = lw.total;
+                    // body-space contact solver: the distinct parent joints of the contact frames
+                    std::vector<int32_t> body_of(std::max(m->ncontacts, 1), 0), body_joint;
+                    for (int k = 0; k < m->ncontacts; ++k) {
+                        size_t bi = 0;
+                        while (bi < body_joint.size() && body_joint[bi] != cmap[k].joint) ++bi;
+                        if (bi == body_joint.size()) body_joint.push_back(cmap[k].joint);
+                        body_of[k] = static_cast<int32_t>(bi);
+                    }
+                    const char* offb = std::getenv("JB_NO_BODY_CONS");
+                    if (m->ncontacts > 0 && body_joint.size() <= BD_MAX_BODIES && opt->contact_model == JB_CONTACT_CONSTRAINT && !(offb && std::atoi(offb))) {
+                        int per_lane[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ncar = 0;
+                        kp.bd_n = static_cast<int32_t>(body_joint.size());
+                        for (int bi = 0; bi < kp.bd_n; ++bi) {
+                            const JointMap& jm = jmap[body_joint[bi]];
+                            kp.bd_rec[bi] = jm.rec; kp.bd_owner[bi] = jm.trunk ? 0 : jm.sub;
+                            kp.bd_slot[bi] = per_lane[kp.bd_owner[bi]]++;
+                            ncar = std::max(ncar, per_lane[kp.bd_owner[bi]]);
+                        }
+                        kp.bd_ncar = ncar;
+                        const BdLane bl = bd_lane_layout(lw.total, ncar, nl, nt, m->ncontacts, kp.bd_n);
+                        const BdLayout bs = bd_layout(kp.bd_n, nt, m->ncontacts);
+                        if (bs.total <= kp.cw_total) {   // the env's row of the generic workspace doubles as the shared area
+                            int32_t* d_bof;
+                            ALLOC(d_bof, body_of.size());
+                            cudaMemcpyAsync(d_bof, body_of.data(), body_of.size() * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream);
+                            kp.bd_of_contact = d_bof; kp.bd_on = 1; lw_total = bl.total;
+                        }
+                    }
                     int32_t* d_dof0; double* d_lwk;
                     ALLOC(d_dof0, dof0.size());
-                    ALLOC(d_lwk, static_cast<size_t>(lw.total) * 32 * std::max<size_t>(1, static_cast<size_t>(n_sm) * blocks_per_sm));
+                    ALLOC(d_lwk, static_cast<size_t>(lw_total) * 32 * std::max<size_t>(1, static_cast<size_t>(n_sm) * blocks_per_sm));
                     cudaMemcpyAsync(d_dof0, dof0.data(), dof0.size() * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream);
-                    kp.lb_on = 1; kp.lb_nt = nt; kp.lb_nl = nl; kp.lb_ml = ml; kp.lw_total = lw.total; kp.lb_dof0 = d_dof0; kp.lwork = d_lwk;
+                    kp.lb_on = 1; kp.lb_nt = nt; kp.lb_nl = nl; kp.lb_ml = ml; kp.lw_total = lw_total; kp.lb_dof0 = d_dof0; kp.lwork = d_lwk;
                 }
             }
             kp.jmap = d_jmap; kp.cmap = d_cmap; kp.jc_joint = d_jcj; kp.jc_of_joint = d_jcof; kp.cstate = d_cst; kp.cwork = d_cwk;
@@ -460,7 +490,7 @@ int jb_describe(JbBatch* b, char* buf, int32_t len) {
     if (!b || !buf) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
     std::snprintf(buf, len, "%s; constraints: %s", b->plan.describe().c_str(),
                   !b->kp.cons_on ? "flag only" : (b->kp.cq_on ? (b->kp.lb_on ? "structured quadruped solver + lane-block solver" : "structured quadruped solver + generic")
-                                                 : (b->kp.lb_on ? "lane-block solver" : "generic solver")));
+                                                 : (b->kp.bd_on ? "body-space contact solver + lane-block solver" : (b->kp.lb_on ? "lane-block solver" : "generic solver"))));
     return JB_OK;
 }
 

@@ -28,6 +28,9 @@ constexpr double CONS_MIN_REGULARIZER = 1.0e-11;   // constraint_solvers.cc:15
 constexpr double CONS_RELAX_MIN = 0.01, CONS_RELAX_MAX = 1.0;
 constexpr int CONS_PGS_MAX_ITER = 100;             // engine.cc:62
 constexpr int CONS_RELAX_MIN_ITER = 20, CONS_RELAX_MAX_ITER = 30;
+// the per-lane count of enabled constraints (shared-memory field cons_off) weighs a joint bound CONS_BOUND_UNIT and a
+// contact frame 1, so that "contacts only" is one comparison
+constexpr double CONS_BOUND_UNIT = 1024.0;
 
 // ---- addressing -----------------------------------------------------------------------------------
 // this env's own row of the per-env global tables (padding envs of the last warp get their own rows, < n_pad)
@@ -121,7 +124,7 @@ __device__ __noinline__ void cons_reset(const Ctx c) {
                 if (cm) CST(cs_joint(k) + 1) = 0.0;   // setRotationDir(false)
                 CST(cs_joint(k) + 2) = RP(R1_Q);
                 CST(cs_joint(k) + 3) = 0.0;
-                if (on) count += 1.0;
+                if (on) count += CONS_BOUND_UNIT;
             }
         }
         for (int q = 0; q < ri->ncontact; ++q) {
@@ -146,7 +149,7 @@ __device__ __noinline__ void cons_load_count(const Ctx c) {
         if (ri->kind == REC_PAD || !ri->owner) continue;
         if (ri->kind != REC_FREE) {
             const int k = KP->jc_of_joint[ri->joint];
-            if (k >= 0 && CST(cs_joint(k)) != 0.0) count += 1.0;
+            if (k >= 0 && CST(cs_joint(k)) != 0.0) count += CONS_BOUND_UNIT;
         }
         for (int q = 0; q < ri->ncontact; ++q) {
             const ContactSlot* ct = KP->cslots + ((ri->contact0 + q) * L + c.sub);
@@ -173,10 +176,10 @@ __device__ __noinline__ void cons_update_bounds(const Ctx c, int* status) {
             CST(o + 2) = fmin(fmax(q, lo), hi);
             CST(o + 1) = (hi < q) ? 1.0 : 0.0;
             CST(o) = 1.0;
-            if (!was) SMF(c, KP->cons_off) += 1.0;
+            if (!was) SMF(c, KP->cons_off) += CONS_BOUND_UNIT;
             *status |= JB_ENV_JOINT_LIMIT;
         } else if (lo + eps < q && q < hi - eps) {
-            if (was) { CST(o) = 0.0; CST(o + 3) = 0.0; SMF(c, KP->cons_off) -= 1.0; }
+            if (was) { CST(o) = 0.0; CST(o + 3) = 0.0; SMF(c, KP->cons_off) -= CONS_BOUND_UNIT; }
         }
     }
 }

@@ -52,32 +52,70 @@ JB_DI double lb_sum_lanes(const Ctx& c, double x) {   // sum over the lanes of t
     for (int k = 1; k < KP->L; ++k) s += __shfl_sync(c.gmask, x, l0 + k);
     return s;
 }
-JB_DI bool lb_llt(double* const lw, int off, int n, int ld) {
+// Small dense factorisations and solves run on a copy in local memory: it is cached write-back in L1, whereas a
+// value just stored to the global workspace is re-read from L2 (stores do not allocate in L1), which would put an
+// L2 round trip on every link of these dependent chains.
+constexpr int LB_LOCAL_N = 12;
+__device__ __noinline__ bool lb_llt(double* const lw, int off, int n, int ld) {
+    if (n > LB_LOCAL_N) {
+        for (int j = 0; j < n; ++j) {
+            double s = LBW(off + j * ld + j);
+            for (int k = 0; k < j; ++k) { const double l = LBW(off + j * ld + k); s -= l * l; }
+            if (!(s > 0.0)) return false;
+            const double d = sqrt(s);
+            LBW(off + j * ld + j) = d;
+            for (int i = j + 1; i < n; ++i) {
+                double t = LBW(off + i * ld + j);
+                for (int k = 0; k < j; ++k) t -= LBW(off + i * ld + k) * LBW(off + j * ld + k);
+                LBW(off + i * ld + j) = t / d;
+            }
+        }
+        return true;
+    }
+    double A[LB_LOCAL_N * LB_LOCAL_N];
+    for (int i = 0; i < n; ++i) for (int k = 0; k <= i; ++k) A[i * LB_LOCAL_N + k] = LBW(off + i * ld + k);
     for (int j = 0; j < n; ++j) {
-        double s = LBW(off + j * ld + j);
-        for (int k = 0; k < j; ++k) { const double l = LBW(off + j * ld + k); s -= l * l; }
+        double s = A[j * LB_LOCAL_N + j];
+        for (int k = 0; k < j; ++k) { const double l = A[j * LB_LOCAL_N + k]; s -= l * l; }
         if (!(s > 0.0)) return false;
         const double d = sqrt(s);
-        LBW(off + j * ld + j) = d;
+        A[j * LB_LOCAL_N + j] = d;
         for (int i = j + 1; i < n; ++i) {
-            double t = LBW(off + i * ld + j);
-            for (int k = 0; k < j; ++k) t -= LBW(off + i * ld + k) * LBW(off + j * ld + k);
-            LBW(off + i * ld + j) = t / d;
+            double t = A[i * LB_LOCAL_N + j];
+            for (int k = 0; k < j; ++k) t -= A[i * LB_LOCAL_N + k] * A[j * LB_LOCAL_N + k];
+            A[i * LB_LOCAL_N + j] = t / d;
         }
     }
+    for (int i = 0; i < n; ++i) for (int k = 0; k <= i; ++k) LBW(off + i * ld + k) = A[i * LB_LOCAL_N + k];
     return true;
 }
-JB_DI void lb_solve(double* const lw, int Loff, int n, int ld, int x) {   // (L L^T) y = x, in place
+__device__ __noinline__ void lb_solve(double* const lw, int Loff, int n, int ld, int x) {   // (L L^T) y = x, in place
+    if (n > 2 * LB_LOCAL_N) {
+        for (int i = 0; i < n; ++i) {
+            double s = LBW(x + i);
+            for (int k = 0; k < i; ++k) s -= LBW(Loff + i * ld + k) * LBW(x + k);
+            LBW(x + i) = s / LBW(Loff + i * ld + i);
+        }
+        for (int i = n - 1; i >= 0; --i) {
+            double s = LBW(x + i);
+            for (int k = i + 1; k < n; ++k) s -= LBW(Loff + k * ld + i) * LBW(x + k);
+            LBW(x + i) = s / LBW(Loff + i * ld + i);
+        }
+        return;
+    }
+    double y[2 * LB_LOCAL_N];
+    for (int i = 0; i < n; ++i) y[i] = LBW(x + i);
     for (int i = 0; i < n; ++i) {
-        double s = LBW(x + i);
-        for (int k = 0; k < i; ++k) s -= LBW(Loff + i * ld + k) * LBW(x + k);
-        LBW(x + i) = s / LBW(Loff + i * ld + i);
+        double s = y[i];
+        for (int k = 0; k < i; ++k) s -= LBW(Loff + i * ld + k) * y[k];
+        y[i] = s / LBW(Loff + i * ld + i);
     }
     for (int i = n - 1; i >= 0; --i) {
-        double s = LBW(x + i);
-        for (int k = i + 1; k < n; ++k) s -= LBW(Loff + k * ld + i) * LBW(x + k);
-        LBW(x + i) = s / LBW(Loff + i * ld + i);
+        double s = y[i];
+        for (int k = i + 1; k < n; ++k) s -= LBW(Loff + k * ld + i) * y[k];
+        y[i] = s / LBW(Loff + i * ld + i);
     }
+    for (int i = 0; i < n; ++i) LBW(x + i) = y[i];
 }
 JB_DI Xf lb_load_xf(const double* p) {
     Xf M;
@@ -100,23 +138,19 @@ JB_DI void lb_add_sym(double* p, const SymY& Y) {
     for (int k = 0; k < 9; ++k) p[6 + k] += Y.B[k];
 }
 
-// Called by all lanes of the env after the ABA sweeps.  Returns false when the sweep did not converge.
-__device__ __noinline__ bool cons_solve_blocks(const Ctx c, int* status) {
-    const int L = KP->L, nrec = KP->nrec, ntrunk = KP->ntrunk, nt = KP->lb_nt, nl = KP->lb_nl, ml = KP->lb_ml;
-    const int n_cons = KP->n_jc + KP->n_cc;
-    const JbOptions& opt = KP->opt;
-    const LbLayout w = lb_layout(nrec, ntrunk, nl, nt, ml, n_cons);
-    double* const lw = KP->lwork + (CW_ROW(c) * L + c.sub) * static_cast<size_t>(KP->lw_total);
+JB_DI int lb_ndof(const RecInt* rint, int r, int L) { const int k = rint[r * L].kind; return k == REC_PAD ? 0 : (k == REC_FREE ? 6 : 1); }
+JB_DI Xf lb_limi(const Ctx& c, int r) { Xf li; sm_load_xf(c, KP->rec_off[r], li); return li; }
+
+// Steps 1-4, shared with jb_constraints_bodies.cuh: kinematics of this lane's records, composite inertias, the
+// inertia blocks and their factors.  `rint`, `rdbl`, `dof0` are this lane's columns of the tables.
+__device__ __noinline__ void lb_prepare(const Ctx c, const LbLayout w, double* const lw, int* status) {
+    const int L = KP->L, nrec = KP->nrec, ntrunk = KP->ntrunk, nt = KP->lb_nt, nl = KP->lb_nl;
     const RecInt* const rint = KP->rint + c.sub;
     const RecDbl* const rdbl = KP->rdbl + c.sub;
     const int32_t* const dof0 = KP->lb_dof0 + c.sub;
     const int my_nl = KP->lb_nl_of[c.sub];
-    const int lane0 = c.lane - c.sub;
-    const double omega = 2.0 * 3.14159265358979323846 * opt.contact_stabilization_freq;
-    const double kp = omega * omega, kd = 2.0 * omega;
-    __syncwarp(c.gmask);
-    auto ndof = [&](int r) { const int k = rint[r * L].kind; return k == REC_PAD ? 0 : (k == REC_FREE ? 6 : 1); };
-    auto li_of = [&](int r) { Xf li; sm_load_xf(c, KP->rec_off[r], li); return li; };
+    auto ndof = [&](int r) { return lb_ndof(rint, r, L); };
+    auto li_of = [&](int r) { return lb_limi(c, r); };
     // ---------------- 1. world placements, velocities, drift accelerations, own inertias (every record of this lane)
     for (int r = 0; r < nrec; ++r) {
         const RecInt* ri = rint + r * L;
@@ -226,6 +260,26 @@ __device__ __noinline__ bool cons_solve_blocks(const Ctx c, int* status) {
             LBW(w.SS + t1 * nt + t2) = val; LBW(w.SS + t2 * nt + t1) = val;
         }
     if (!lb_llt(lw, w.SS, nt, nt)) *status |= JB_ENV_NAN;
+}
+
+// Called by all lanes of the env after the ABA sweeps.  Returns false when the sweep did not converge.
+__device__ __noinline__ bool cons_solve_blocks(const Ctx c, int* status) {
+    const int L = KP->L, nrec = KP->nrec, ntrunk = KP->ntrunk, nt = KP->lb_nt, nl = KP->lb_nl, ml = KP->lb_ml;
+    const int n_cons = KP->n_jc + KP->n_cc;
+    const JbOptions& opt = KP->opt;
+    const LbLayout w = lb_layout(nrec, ntrunk, nl, nt, ml, n_cons);
+    double* const lw = KP->lwork + (CW_ROW(c) * L + c.sub) * static_cast<size_t>(KP->lw_total);
+    const RecInt* const rint = KP->rint + c.sub;
+    const RecDbl* const rdbl = KP->rdbl + c.sub;
+    const int32_t* const dof0 = KP->lb_dof0 + c.sub;
+    const int my_nl = KP->lb_nl_of[c.sub];
+    const int lane0 = c.lane - c.sub;
+    const double omega = 2.0 * 3.14159265358979323846 * opt.contact_stabilization_freq;
+    const double kp = omega * omega, kd = 2.0 * omega;
+    __syncwarp(c.gmask);
+    auto ndof = [&](int r) { const int k = rint[r * L].kind; return k == REC_PAD ? 0 : (k == REC_FREE ? 6 : 1); };
+    auto li_of = [&](int r) { Xf li; sm_load_xf(c, KP->rec_off[r], li); return li; };
+    lb_prepare(c, w, lw, status);
     // ---------------- 5. sweep list (replicated on every lane) and the rows this lane owns
     int n_act = 0, my_rows = 0;
     {

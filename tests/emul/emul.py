@@ -14,7 +14,7 @@ from jiminy_b200.core import Api  # noqa: E402
 _LIB = os.path.join(_HERE, "libjiminy_b200_emul.so")
 _SRCS = [os.path.join(_HERE, f) for f in ("jb_emul.cpp", "jb_emul_shim.h")] + \
         [os.path.join(_ROOT, "jiminy_b200", "csrc", f) for f in
-         ("jb_capi.cu", "jb_kernel.cuh", "jb_device.cuh", "jb_constraints.cuh", "jb_constraints_quadruped.cuh", "jb_constraints_blocks.cuh", "jb_plan.cpp", "jb_plan.h")] + \
+         ("jb_capi.cu", "jb_kernel.cuh", "jb_device.cuh", "jb_constraints.cuh", "jb_constraints_quadruped.cuh", "jb_constraints_blocks.cuh", "jb_constraints_bodies.cuh", "jb_plan.cpp", "jb_plan.h")] + \
         [os.path.join(_ROOT, "include", "jiminy_b200.h")]
 
 

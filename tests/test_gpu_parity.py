@@ -159,6 +159,17 @@ def test_constraint_contact_matches_oracle():
     pc.robot_constraint_scenario("atlas", 6, 1, seed=1, tol_state=1e-7, tol_sens=1e-5)
 
 
+@pytest.mark.parametrize("robot,toggle", [("atlas", None), ("atlas", "JB_NO_BODY_CONS"), ("atlas", "JB_NO_BLOCK_CONS"),
+                                          ("anymal", "JB_NO_STRUCTURED_CONS")])
+def test_constraint_solver_variants(monkeypatch, robot, toggle):
+    """Every device formulation of the constraint solve against the oracle (see tests/test_kernel_emul.py), 24 envs."""
+    if toggle:
+        monkeypatch.setenv(toggle, "1")
+    eng, orc, sc = pc.robot_constraint_scenario(robot, 24, 2, seed=3, solver="euler_explicit", dt_max=0.005, tol_state=1e-7, tol_sens=1e-5)
+    want = {None: "body-space", "JB_NO_BODY_CONS": "lane-block", "JB_NO_BLOCK_CONS": "generic", "JB_NO_STRUCTURED_CONS": "body-space"}[toggle]
+    assert want in eng.describe()
+
+
 def test_constraint_solvers_agree_at_scale():
     """1024 ANYmal envs with the constraint contact model: the structured quadruped solver and the generic dense
     solver (two independent formulations of the same boxed LCP) give the same trajectories; bit-identical when

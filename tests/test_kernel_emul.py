@@ -387,6 +387,18 @@ def test_constraint_contact_atlas_rhs(api):
     pc.robot_constraint_scenario("atlas", 1, 1, api, seed=2, solver="euler_explicit", dt_max=0.005)
 
 
+@pytest.mark.parametrize("robot,toggle", [("atlas", None), ("atlas", "JB_NO_BODY_CONS"), ("atlas", "JB_NO_BLOCK_CONS"),
+                                          ("anymal", "JB_NO_STRUCTURED_CONS")])
+def test_constraint_solver_variants(api, monkeypatch, robot, toggle):
+    """Every device formulation of the constraint solve against the oracle: body-space contact solver (default for
+    Atlas; for ANYmal once the register-resident quadruped solver is switched off), lane-block solver, dense generic."""
+    if toggle:
+        monkeypatch.setenv(toggle, "1")
+    eng, orc, sc = pc.robot_constraint_scenario(robot, 2, 1, api, seed=3, solver="euler_explicit", dt_max=0.005)
+    want = {None: "body-space", "JB_NO_BODY_CONS": "lane-block", "JB_NO_BLOCK_CONS": "generic", "JB_NO_STRUCTURED_CONS": "body-space"}[toggle]
+    assert want in eng.describe() and (toggle != "JB_NO_BODY_CONS" or "body-space" not in eng.describe())
+
+
 @pytest.mark.parametrize("safety", [False, True])
 def test_pd_controller_block(api, safety):
     pc.pd_block_scenario(api, safety=safety)
