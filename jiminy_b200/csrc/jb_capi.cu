@@ -384,6 +384,21 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
         kp.cq_on = (kp.cons_on && opt->contact_model == JB_CONTACT_CONSTRAINT && cons_quadruped_matches(kp, P, *m) &&
                     !(std::getenv("JB_NO_STRUCTURED_CONS") && std::atoi(std::getenv("JB_NO_STRUCTURED_CONS")))) ? 1 : 0;
         b->base_fields = P.nfields + 1 + (kp.cq_on ? CQ_SIZE : 0);
+        // body-space contact solver (jb_constraints_bodies.cuh): the distinct parent joints of the contact frames;
+        // its sweep keeps a = Omega F in shared memory (not reserved when the quadruped solver covers the case)
+        std::vector<int32_t> body_of(std::max(m->ncontacts, 1), 0), body_joint;
+        for (int k = 0; k < m->ncontacts; ++k) {
+            size_t bi = 0;
+            while (bi < body_joint.size() && body_joint[bi] != cmap[k].joint) ++bi;
+            if (bi == body_joint.size()) body_joint.push_back(cmap[k].joint);
+            body_of[k] = static_cast<int32_t>(bi);
+        }
+        const char* offb = std::getenv("JB_NO_BODY_CONS");
+        const bool bd_candidate = kp.cons_on && !kp.cq_on && P.L > 1 && P.L <= 8 && m->ncontacts > 0 && m->ncontacts <= BD_MAX_CONTACTS &&
+                                  body_joint.size() <= BD_MAX_BODIES && opt->contact_model == JB_CONTACT_CONSTRAINT && !(offb && std::atoi(offb));
+        kp.bd_off = b->base_fields; kp.bd_lsh = 0;
+        while ((1 << kp.bd_lsh) < P.L) ++kp.bd_lsh;
+        if (bd_candidate) b->base_fields += 2 * ((6 * static_cast<int>(body_joint.size()) + P.L - 1) / P.L);
         if (kp.cons_on) {
             JointMap* d_jmap; ContactMap* d_cmap; int32_t *d_jcj, *d_jcof; double *d_cst, *d_cwk;
             const int cs_fields = CS_JOINT0 + CS_JOINT_SIZE * kp.n_jc + CS_CONTACT_SIZE * kp.n_cc;
@@ -435,16 +450,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
                 if (nt <= LB_MAX_NT && P.L <= 8 && !(off && std::atoi(off))) {
                     const LbLayout lw = lb_layout(P.nrec, P.ntrunk, nl, nt, ml, kp.n_jc + kp.n_cc);
                     int lw_total = lw.total;
-                    // body-space contact solver: the distinct parent joints of the contact frames
-                    std::vector<int32_t> body_of(std::max(m->ncontacts, 1), 0), body_joint;
-                    for (int k = 0; k < m->ncontacts; ++k) {
-                        size_t bi = 0;
-                        while (bi < body_joint.size() && body_joint[bi] != cmap[k].joint) ++bi;
-                        if (bi == body_joint.size()) body_joint.push_back(cmap[k].joint);
-                        body_of[k] = static_cast<int32_t>(bi);
-                    }
-                    const char* offb = std::getenv("JB_NO_BODY_CONS");
-                    if (m->ncontacts > 0 && body_joint.size() <= BD_MAX_BODIES && opt->contact_model == JB_CONTACT_CONSTRAINT && !(offb && std::atoi(offb))) {
+                    if (bd_candidate) {
                         int per_lane[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ncar = 0;
                         kp.bd_n = static_cast<int32_t>(body_joint.size());
                         for (int bi = 0; bi < kp.bd_n; ++bi) {

@@ -13,17 +13,22 @@
 // acceleration of each contact body due to the multipliers): the residual of a row is b_i - E_i a_b - reg lambda_i,
 // and a change of lambda_i updates a with one 6-column product.  All lanes of the env run the sweep redundantly on
 // private copies of lambda (bit-identical), and share the update of a: each lane owns every L-th row, a is
-// double-buffered in the env's workspace row and one __syncwarp per update orders the exchange.  No shuffles.
+// double-buffered and one __syncwarp per update orders the exchange.  No shuffles.
+// Where the sweep's state lives matters more than its flop count: with one or a few warps per SM every dependent
+// access to the global workspace is an exposed L2 round trip (a value just stored is not in L1).  So the mutable
+// state of the sweep sits on chip -- lambda, y, y_prev and F in local memory (write-back in L1), a in a small
+// shared-memory region spread over the env's lanes -- and only write-once data (Omega, levers, right-hand sides)
+// is read from the workspace.
 #pragma once
 
-constexpr int BD_MAX_BODIES = 4;
+constexpr int BD_MAX_BODIES = 4, BD_MAX_CONTACTS = 16;
 struct BdLayout { int OM, AV, GS, HS, PB, total; };
 constexpr int BD_PB = 16;   // per contact, shared: r (3), b (4), diagonal of A with regularisation (4), regularisation (4)
 JB_HD BdLayout bd_layout(int nb, int nt, int ncc) {
     BdLayout s; int o = 0;
     const int D = 6 * nb, nt1 = nt + 1;
     s.OM = o; o += D * D;
-    s.AV = o; o += 2 * D;
+    s.AV = o; o += 0;
     s.GS = o; o += D * nt1;
     s.HS = o; o += D * nt1;
     s.PB = o; o += BD_PB * (ncc + 1);
@@ -31,15 +36,14 @@ JB_HD BdLayout bd_layout(int nb, int nt, int ncc) {
     return s;
 }
 // per-lane additions, appended to the lane-block layout: per owned body J_l (6 x nl), J_t (6 x nt), X = rows of
-// M_ll^-1 J_l^T (6 x nl), c = J ddq_free (6); private sweep vectors: per contact lambda, y, y_prev (12); F (6 n_b)
+// M_ll^-1 J_l^T (6 x nl), c = J ddq_free (6)
 struct BdLane { int CB, cb_stride, JBL, JBT, XB, CF, PL, FV, total; };
 JB_HD BdLane bd_lane_layout(int base, int ncar, int nl, int nt, int ncc, int nb) {
     BdLane w; int o = base;
     const int nl1 = nl + 1, nt1 = nt + 1;
     w.JBL = 0; w.JBT = 6 * nl1; w.XB = w.JBT + 6 * nt1; w.CF = w.XB + 6 * nl1; w.cb_stride = w.CF + 6;
     w.CB = o; o += w.cb_stride * (ncar + 1);
-    w.PL = o; o += 12 * (ncc + 1);
-    w.FV = o; o += 6 * nb + 6;
+    w.PL = o; w.FV = o;
     w.total = o;
     return w;
 }
@@ -61,6 +65,17 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
     const int my_nl = KP->lb_nl_of[c.sub];
     const double omega = 2.0 * 3.14159265358979323846 * opt.contact_stabilization_freq;
     const double kp = omega * omega, kd = 2.0 * omega;
+    // element e of the env's double-buffered a = Omega F, spread over the env's lanes of the shared-memory region
+    // (row i of buffer p sits in field p * nrow + i / L of lane i % L: every lane updates rows in its own column)
+    double* const a_base = jb_smem + KP->bd_off * 32 + (c.lane - c.sub);
+    const int lsh = KP->bd_lsh, lmask = L - 1, nrow = (D + L - 1) >> lsh;
+#define AVS(p, i) (a_base[((p) * nrow + ((i) >> lsh)) * 32 + ((i) & lmask)])
+    unsigned body_bits = 0;   // contact body of each contact frame, 2 bits each
+    for (int k = 0; k < n_cc; ++k) body_bits |= static_cast<unsigned>(KP->bd_of_contact[k]) << (2 * k);
+    double pl_all[12 * BD_MAX_CONTACTS];   // per contact: lambda (4), y (4), y_prev (4)
+    double Fv[6 * BD_MAX_BODIES];
+    unsigned enabled = 0;
+    for (int k = 0; k < n_cc; ++k) if (CST(cs_contact(k)) != 0.0) enabled |= 1u << k;
     __syncwarp(c.gmask);
     lb_prepare(c, w, lw, status);
     // ---------------- B. the contact bodies this lane owns: Jacobian at the body origin, X, G, H, c
@@ -188,24 +203,27 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
         }
     }
     // ---------------- D. warm start: private lambda, F, then a = Omega F (rows shared out)
-    for (int e = 0; e < D; ++e) LBW(wl.FV + e) = 0.0;
+    for (int e = 0; e < D; ++e) Fv[e] = 0.0;
     __syncwarp(c.gmask);
     for (int k = 0; k < n_cc; ++k) {
         const int o = cs_contact(k);
-        if (CST(o) == 0.0) continue;
+        if (!(enabled >> k & 1u)) continue;
         const double* const pb = sh + ws.PB + BD_PB * k;
-        double* const pl = lw + wl.PL + 12 * k;
+        double* const pl = pl_all + 12 * k;
         for (int e = 0; e < 4; ++e) { pl[e] = CST(o + 1 + e); pl[4 + e] = 0.0; pl[8 + e] = 0.0; }
         const V3 f = mk(pl[0], pl[1], pl[2]), r = ld3(pb);
         const V3 tq = cross(r, f);
-        double* const F = lw + wl.FV + 6 * KP->bd_of_contact[k];
+        double* const F = Fv + 6 * KP->bd_of_contact[k];
         F[0] += f.x; F[1] += f.y; F[2] += f.z; F[3] += tq.x; F[4] += tq.y; F[5] += tq.z + pl[3];
     }
+    // torsion switched off and no torsional multiplier to clear: the second block of the sweep is a no-op
+    bool skip_torsion = opt.contact_torsion < D_EPS;
+    for (int k = 0; k < n_cc; ++k) if ((enabled >> k & 1u) && pl_all[12 * k + 3] != 0.0) skip_torsion = false;
     int cur = 0;
     for (int i = c.sub; i < D; i += L) {
         double s = 0.0;
-        for (int j = 0; j < D; ++j) s += SHW(ws.OM + i * D + j) * LBW(wl.FV + j);
-        SHW(ws.AV + i) = s;
+        for (int j = 0; j < D; ++j) s += SHW(ws.OM + i * D + j) * Fv[j];
+        AVS(0, i) = s;
     }
     __syncwarp(c.gmask);
     // ---------------- E. projected Gauss-Seidel sweep (constraint_solvers.cc:107-318), redundantly on every lane
@@ -219,13 +237,13 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
             if (ratio > 0.0) wr += (CONS_RELAX_MAX - CONS_RELAX_MIN) * (ratio * ratio);
         }
         for (int pass = 0; pass < 3; ++pass) {
+            if (pass == 1 && skip_torsion) continue;
             for (int k = 0; k < n_cc; ++k) {
-                if (CST(cs_contact(k)) == 0.0) continue;
+                if (!(enabled >> k & 1u)) continue;
                 const double* const pb = sh + ws.PB + BD_PB * k;
-                double* const pl = lw + wl.PL + 12 * k;
-                const int b = KP->bd_of_contact[k];
-                const double* const av = sh + ws.AV + cur * D + 6 * b;
-                const V3 r = ld3(pb), al = ld3(av), aa = ld3(av + 3);
+                double* const pl = pl_all + 12 * k;
+                const int b = (body_bits >> (2 * k)) & 3, ae = 6 * b;
+                const V3 r = ld3(pb), al = mk(AVS(cur, ae), AVS(cur, ae + 1), AVS(cur, ae + 2)), aa = mk(AVS(cur, ae + 3), AVS(cur, ae + 4), AVS(cur, ae + 5));
                 if (pass == 0) { pl[8] = pl[4]; pl[9] = pl[5]; pl[10] = pl[6]; pl[11] = pl[7]; }   // y_prev = y
                 const V3 ea = al + cross(aa, r);   // E a, linear rows
                 V3 df = mk(0.0, 0.0, 0.0);
@@ -267,14 +285,25 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
                 // dF = E^T dlambda, a += Omega[:, body b] dF : this lane's rows into the other buffer
                 const V3 tq = cross(r, df);
                 const double dF[6] = {df.x, df.y, df.z, tq.x, tq.y, tq.z + d3};
-                double* const F = lw + wl.FV + 6 * b;
+                double* const F = Fv + 6 * b;
 #pragma unroll
                 for (int e = 0; e < 6; ++e) F[e] += dF[e];
-                const double* const a0 = sh + ws.AV + cur * D;
-                double* const a1 = sh + ws.AV + (1 - cur) * D;
-                for (int i = c.sub; i < D; i += L) {
-                    const double* const Oi = sh + ws.OM + i * D + 6 * b;
-                    a1[i] = a0[i] + (Oi[0] * dF[0] + Oi[1] * dF[1] + Oi[2] * dF[2] + Oi[3] * dF[3] + Oi[4] * dF[4] + Oi[5] * dF[5]);
+                {
+                    const double* const a0 = a_base + cur * nrow * 32 + c.sub;
+                    double* const a1 = a_base + (1 - cur) * nrow * 32 + c.sub;
+                    const double* const Ob = sh + ws.OM + c.sub * D + 6 * b;
+                    const int ostep = L * D;
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {      // independent rows: unrolled so that their chains overlap
+                        if (c.sub + q * L < D) {
+                            const double* const Oi = Ob + q * ostep;
+                            a1[q * 32] = a0[q * 32] + (Oi[0] * dF[0] + Oi[1] * dF[1] + Oi[2] * dF[2] + Oi[3] * dF[3] + Oi[4] * dF[4] + Oi[5] * dF[5]);
+                        }
+                    }
+                    for (int q = 6; c.sub + q * L < D; ++q) {
+                        const double* const Oi = Ob + q * ostep;
+                        a1[q * 32] = a0[q * 32] + (Oi[0] * dF[0] + Oi[1] * dF[1] + Oi[2] * dF[2] + Oi[3] * dF[3] + Oi[4] * dF[4] + Oi[5] * dF[5]);
+                    }
                 }
                 cur = 1 - cur;
                 __syncwarp(c.gmask);
@@ -282,22 +311,22 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
         }
         double ymax = 0.0;
         for (int k = 0; k < n_cc; ++k) {
-            if (CST(cs_contact(k)) == 0.0) continue;
-            const double* const pl = lw + wl.PL + 12 * k;
+            if (!(enabled >> k & 1u)) continue;
+            const double* const pl = pl_all + 12 * k;
             for (int e = 4; e < 8; ++e) ymax = fmax(ymax, fabs(pl[e]));
         }
         const double tol = opt.tol_abs + opt.tol_rel * ymax + D_EPS;
         ok = true;
         for (int k = 0; k < n_cc && ok; ++k) {
-            if (CST(cs_contact(k)) == 0.0) continue;
-            const double* const pl = lw + wl.PL + 12 * k;
+            if (!(enabled >> k & 1u)) continue;
+            const double* const pl = pl_all + 12 * k;
             for (int e = 0; e < 4; ++e) ok = ok && (fabs(pl[4 + e] - pl[8 + e]) < tol);
         }
     }
     // ---------------- F. accelerations: z = sum_b G_b^T F_b ; ddq_t += S^-1 z ; ddq_l += sum_b X_b F_b - W S^-1 z
     for (int t = 0; t < nt; ++t) {
         double s = 0.0;
-        for (int i = 0; i < D; ++i) s += SHW(ws.GS + i * nt + t) * LBW(wl.FV + i);
+        for (int i = 0; i < D; ++i) s += SHW(ws.GS + i * nt + t) * Fv[i];
         LBW(w.TT + t) = s;
     }
     lb_solve(lw, w.SS, nt, nt, w.TT);
@@ -315,7 +344,7 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
                 for (int b = 0; b < nb; ++b) {
                     if (KP->bd_owner[b] != c.sub) continue;
                     const double* const cb = lw + wl.CB + wl.cb_stride * KP->bd_slot[b];
-                    for (int k = 0; k < 6; ++k) x += cb[wl.XB + k * nl + id] * LBW(wl.FV + 6 * b + k);
+                    for (int k = 0; k < 6; ++k) x += cb[wl.XB + k * nl + id] * Fv[6 * b + k];
                 }
                 for (int t = 0; t < nt; ++t) x -= LBW(w.WW + id * nt + t) * LBW(w.TT + t);
             }
@@ -328,7 +357,7 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
         if (CST(o) == 0.0) continue;
         const ContactMap cm = KP->cmap[k];
         const bool mine = (cm.trunk ? 0 : cm.sub) == c.sub;
-        const double* const pl = lw + wl.PL + 12 * k;
+        const double* const pl = pl_all + 12 * k;
         if (mine) for (int e = 0; e < 4; ++e) CST(o + 1 + e) = pl[e];
         if (mine || cm.trunk) {
             const Xf oM = lb_load_xf(lw + w.KI + 24 * KP->jmap[cm.joint].rec);
@@ -345,3 +374,4 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
 }
 #undef LBW
 #undef SHW
+#undef AVS

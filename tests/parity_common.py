@@ -219,10 +219,12 @@ def point_mass_constraint_scenario(api, data_dir, n_steps=40, torsion=0.0, solve
     return eng, orc
 
 
-def robot_constraint_scenario(name, n_env, n_steps, api=None, tol_state=1e-8, tol_sens=1e-6, **kw):
+def robot_constraint_scenario(name, n_env, n_steps, api=None, tol_state=1e-8, tol_sens=1e-6, torsion=None, **kw):
     """A BASELINE robot with contacts.model = "constraint" (the default of the reference's option files)."""
     sc = scenarios.make(name, n_env, **kw)
     sc.options["contacts"]["model"] = "constraint"
+    if torsion is not None:
+        sc.options["contacts"]["torsion"] = torsion
     eng, orc = make_pair(sc, api)
     compare(eng, orc, 1e-12, 1e-9)
     for k in range(n_steps):

@@ -160,13 +160,14 @@ def test_constraint_contact_matches_oracle():
 
 
 @pytest.mark.parametrize("robot,toggle", [("atlas", None), ("atlas", "JB_NO_BODY_CONS"), ("atlas", "JB_NO_BLOCK_CONS"),
-                                          ("anymal", "JB_NO_STRUCTURED_CONS")])
+                                          ("anymal", "JB_NO_STRUCTURED_CONS"), ("atlas", "torsion")])
 def test_constraint_solver_variants(monkeypatch, robot, toggle):
     """Every device formulation of the constraint solve against the oracle (see tests/test_kernel_emul.py), 24 envs."""
-    if toggle:
+    torsion = 0.05 if toggle == "torsion" else None      # torsional friction block of the sweep
+    if toggle and torsion is None:
         monkeypatch.setenv(toggle, "1")
-    eng, orc, sc = pc.robot_constraint_scenario(robot, 24, 2, seed=3, solver="euler_explicit", dt_max=0.005, tol_state=1e-7, tol_sens=1e-5)
-    want = {None: "body-space", "JB_NO_BODY_CONS": "lane-block", "JB_NO_BLOCK_CONS": "generic", "JB_NO_STRUCTURED_CONS": "body-space"}[toggle]
+    eng, orc, sc = pc.robot_constraint_scenario(robot, 24, 2, seed=3, torsion=torsion, solver="euler_explicit", dt_max=0.005, tol_state=1e-7, tol_sens=1e-5)
+    want = {None: "body-space", "JB_NO_BODY_CONS": "lane-block", "JB_NO_BLOCK_CONS": "generic", "JB_NO_STRUCTURED_CONS": "body-space", "torsion": "body-space"}[toggle]
     assert want in eng.describe()
 
 

@@ -388,14 +388,15 @@ def test_constraint_contact_atlas_rhs(api):
 
 
 @pytest.mark.parametrize("robot,toggle", [("atlas", None), ("atlas", "JB_NO_BODY_CONS"), ("atlas", "JB_NO_BLOCK_CONS"),
-                                          ("anymal", "JB_NO_STRUCTURED_CONS")])
+                                          ("anymal", "JB_NO_STRUCTURED_CONS"), ("atlas", "torsion")])
 def test_constraint_solver_variants(api, monkeypatch, robot, toggle):
     """Every device formulation of the constraint solve against the oracle: body-space contact solver (default for
     Atlas; for ANYmal once the register-resident quadruped solver is switched off), lane-block solver, dense generic."""
-    if toggle:
+    torsion = 0.05 if toggle == "torsion" else None      # torsional friction block of the sweep
+    if toggle and torsion is None:
         monkeypatch.setenv(toggle, "1")
-    eng, orc, sc = pc.robot_constraint_scenario(robot, 2, 1, api, seed=3, solver="euler_explicit", dt_max=0.005)
-    want = {None: "body-space", "JB_NO_BODY_CONS": "lane-block", "JB_NO_BLOCK_CONS": "generic", "JB_NO_STRUCTURED_CONS": "body-space"}[toggle]
+    eng, orc, sc = pc.robot_constraint_scenario(robot, 2, 1, api, seed=3, torsion=torsion, solver="euler_explicit", dt_max=0.005)
+    want = {None: "body-space", "JB_NO_BODY_CONS": "lane-block", "JB_NO_BLOCK_CONS": "generic", "JB_NO_STRUCTURED_CONS": "body-space", "torsion": "body-space"}[toggle]
     assert want in eng.describe() and (toggle != "JB_NO_BODY_CONS" or "body-space" not in eng.describe())
 
 
