@@ -468,6 +468,7 @@ class Engine:
         self._springs = None
         self._impulse_forces: list = []
         self._forces_dirty = False
+        self._recorder = None
 
     # -- configuration
     def add_robot(self, robot: M.RobotTable, controller: Optional[FunctionalController] = None) -> None:
@@ -578,6 +579,32 @@ class Engine:
             raise ValueError("The initial force exceeds 1e5 for at least one contact point, which is forbidden for "
                              "the sake of numerical stability. Please update the initial state.")
         self.is_simulation_running = True
+        # telemetry (Engine::start registers the variables and logs the initial state, engine.cc:1495-1527, :1550)
+        from .telemetry import TelemetryRecorder
+        self._recorder = TelemetryRecorder(robot, self._options)
+        self._log_snapshot()
+
+    def _log_snapshot(self) -> None:
+        rs, rec = self.robot_states[0], self._recorder
+        keys = {k for k, _ in rec._groups}
+        energy = float(self._batch.get_extra_terms()[0][0].sum()) if "energy" in keys else None
+        rec.append(self.stepper_state.t, rs.q, rs.v, rs.a, sensors=self._sensors if "sensors" in keys else None,
+                   u=rs.u, command=rs.command, energy=energy)
+
+    @property
+    def log_data(self) -> dict:
+        """`Engine.log_data` (pywrap engine.cc:776): constants and variables of the current / last simulation."""
+        if self._recorder is None:
+            raise BadControlFlow("No simulation has been started: there is no log to read.")
+        return self._recorder.log_data
+
+    def write_log(self, fullpath: str, format: str = "binary") -> None:
+        """`Engine.write_log` (engine.cc:3975-4060), binary format (`TelemetryRecorder::writeLog`)."""
+        if format != "binary":
+            raise NotImplementedError("Only the 'binary' log format is written (the hdf5 one needs h5py).")
+        if self._recorder is None or not self._recorder._times:
+            raise BadControlFlow("No data available. Please start a simulation before writing log.")
+        self._recorder.write_log(fullpath)
 
     def step(self, step_dt: float = -1.0) -> None:
         if not self.is_simulation_running:
@@ -608,6 +635,7 @@ class Engine:
             if status & JB_ENV_DT_UNDERFLOW:
                 raise RuntimeError("The internal time step is getting too small. Impossible to integrate physics "
                                    "further in time. Aborting integration.")
+            self._log_snapshot()      # one line per engine step (telemetry.logInternalStepperSteps = false)
 
     def stop(self) -> None:
         self.is_simulation_running = False

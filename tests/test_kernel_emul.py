@@ -355,6 +355,36 @@ def test_engine_facade_impulse_forces(api):
     assert abs(engine.robot_states[0].v[0]) < 1e-14
 
 
+def test_engine_facade_telemetry_log(api, tmp_path):
+    """`Engine.log_data` / `Engine.write_log` (binary format of the reference): one line at start and per step."""
+    from jiminy_b200.core import Engine, BadControlFlow
+    from jiminy_b200 import telemetry as T
+    robot = M.build_robot_table(os.path.join(DATA, "simple_pendulum.urdf"), False)
+    engine = Engine(api_=api)
+    engine.add_robot(robot)
+    with pytest.raises(BadControlFlow):
+        engine.write_log(str(tmp_path / "none.data"))
+    opt = engine.get_options()
+    opt["stepper"].update(sensorsUpdatePeriod=0.0, controllerUpdatePeriod=0.0)
+    opt["telemetry"]["enableEnergy"] = True
+    engine.set_options(opt)
+    engine.start(np.array([0.3]), np.zeros(1))
+    qs = [engine.robot_states[0].q[0]]
+    for _ in range(5):
+        engine.step(1e-3)
+        qs.append(engine.robot_states[0].q[0])
+    path = str(tmp_path / "pendulum.data")
+    engine.write_log(path)
+    log = T.read_log(path)
+    np.testing.assert_allclose(log["variables"]["Global.Time"], 1e-3 * np.arange(6), atol=1e-12)
+    np.testing.assert_array_equal(log["variables"]["currentPositionPendulum"], np.array(qs))
+    e = log["variables"]["energy"]
+    assert np.abs(e - e[0]).max() < 1e-8                      # RK4 at 1 ms conserves the pendulum's energy
+    assert engine.log_data["variables"].keys() == log["variables"].keys()
+    with pytest.raises(NotImplementedError):
+        engine.write_log(path, format="hdf5")
+
+
 @pytest.mark.parametrize("model", ["spring_damper", "constraint"])
 def test_joint_bounds_constraint_path(api, model):
     pc.bounds_scenario(api, DATA, model)
