@@ -214,6 +214,12 @@ int jb_set_command_device(JbBatch* batch, const double* cmd_dev);
  * and soft upper position of `apply_safety_limits`.  kp = NULL disables the block. */
 int jb_set_pd_controller_full(JbBatch* batch, const double* kp, const double* kd, const double* state_lower,
                               const double* state_upper, const double* safety);
+/* The block's `_command_state` (proportional_derivative_controller.py:390-394, exposed to the pipeline as the
+ * controller's state, :451-456): target motor position / velocity / acceleration, [n_env][3][nmotors].  The
+ * `PDAdapter` block reads it -- and in its instantaneous mode writes it -- once per env-step
+ * (:167-262, :620-640), which is what the getter and the setter are for.  Both need the block enabled. */
+int jb_get_pd_controller_state(JbBatch* batch, double* state);
+int jb_set_pd_controller_state(JbBatch* batch, const double* state);
 
 /* gym_jiminy's `MahonyFilter` observer on the device (blocks/mahony_filter.py:28-101, :337-393 with the default
  * exact_init = True, ignore_twist = False): the attitude estimate of every IMU starts from the true orientation of

@@ -54,7 +54,8 @@ class Api:
                "jb_plan_describe", "jb_stop", "jb_register_impulse_force", "jb_set_impulse_force",
                "jb_register_profile_force", "jb_set_profile_force", "jb_remove_all_forces",
                "jb_peer_obs_create", "jb_peer_obs_connect", "jb_peer_obs_wait", "jb_peer_obs_view",
-               "jb_set_pd_controller_full", "jb_set_mahony_filter", "jb_get_mahony_filter")
+               "jb_set_pd_controller_full", "jb_set_mahony_filter", "jb_get_mahony_filter",
+               "jb_get_pd_controller_state", "jb_set_pd_controller_state")
 
     def __init__(self, cdll: C.CDLL):
         self.dll = L = cdll
@@ -98,6 +99,8 @@ class Api:
         L.jb_set_profile_force.argtypes = [vp, C.c_int32, c_double_p]
         L.jb_remove_all_forces.argtypes = [vp]
         L.jb_set_pd_controller_full.argtypes = [vp] + [c_double_p] * 5
+        L.jb_get_pd_controller_state.argtypes = [vp, c_double_p]
+        L.jb_set_pd_controller_state.argtypes = [vp, c_double_p]
         L.jb_set_mahony_filter.argtypes = [vp, C.c_double, C.c_double]
         L.jb_get_mahony_filter.argtypes = [vp, c_double_p]
         L.jb_peer_obs_create.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p]
@@ -258,6 +261,16 @@ class BatchedEngine:
         sf = None if safety is None else np.ascontiguousarray(safety, dtype=np.float64).reshape(4, nm)
         self._api.check(self._api.dll.jb_set_pd_controller_full(self._h, dptr(kp), dptr(kd), dptr(lo), dptr(hi),
                                                                 None if sf is None else dptr(sf)))
+
+    def get_pd_controller_state(self) -> np.ndarray:
+        """Target motor position / velocity / acceleration of the `PDController` block, [n_env, 3, nmotors]."""
+        out = np.zeros((self.n_env, 3, self.nm))
+        self._api.check(self._api.dll.jb_get_pd_controller_state(self._h, dptr(out)))
+        return out
+
+    def set_pd_controller_state(self, state) -> None:
+        state = np.ascontiguousarray(state, dtype=np.float64).reshape(self.n_env, 3, self.nm)
+        self._api.check(self._api.dll.jb_set_pd_controller_state(self._h, dptr(state)))
 
     def set_mahony_filter(self, kp: Optional[float] = 1.0, ki: float = 0.1) -> None:
         """gym_jiminy's `MahonyFilter` observer on the device (exact_init, no twist removal); `kp=None` disables it."""

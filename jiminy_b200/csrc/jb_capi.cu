@@ -573,6 +573,24 @@ int jb_set_pd_controller_full(JbBatch* b, const double* kp, const double* kd, co
     return JB_OK;
 }
 
+int jb_get_pd_controller_state(JbBatch* b, double* state) {
+    if (!b || !state) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!b->kp.pdf) return fail(JB_ERR_BAD_CONTROL_FLOW, "the PDController block is not enabled (jb_set_pd_controller_full)");
+    CU(cudaSetDevice(b->device));
+    CU(cudaMemcpyAsync(state, b->d_pdf_state, sizeof(double) * b->n_env * 3 * b->nmotors, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return JB_OK;
+}
+
+int jb_set_pd_controller_state(JbBatch* b, const double* state) {
+    if (!b || !state) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!b->kp.pdf) return fail(JB_ERR_BAD_CONTROL_FLOW, "the PDController block is not enabled (jb_set_pd_controller_full)");
+    CU(cudaSetDevice(b->device));
+    CU(cudaMemcpyAsync(b->d_pdf_state, state, sizeof(double) * b->n_env * 3 * b->nmotors, cudaMemcpyHostToDevice, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return JB_OK;
+}
+
 int jb_set_mahony_filter(JbBatch* b, double kp, double ki) {
     if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
     CU(cudaSetDevice(b->device));

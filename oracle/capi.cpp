@@ -138,6 +138,15 @@ void orc_set_pd_full(OrcBatch* b, const double* kp, const double* kd, const doub
         }
     }
 }
+// the block's command state, [n_env][3][nmotors] (what the PDAdapter block reads / writes)
+void orc_get_pd_state(OrcBatch* b, double* out) {
+    const size_t n = 3 * static_cast<size_t>(b->nmotors);
+    for (size_t i = 0; i < b->envs.size(); ++i) std::copy(b->envs[i]->pdf_state.begin(), b->envs[i]->pdf_state.begin() + n, out + i * n);
+}
+void orc_set_pd_state(OrcBatch* b, const double* in) {
+    const size_t n = 3 * static_cast<size_t>(b->nmotors);
+    for (size_t i = 0; i < b->envs.size(); ++i) b->envs[i]->pdf_state.assign(in + i * n, in + (i + 1) * n);
+}
 void orc_set_mahony(OrcBatch* b, double kp, double ki) {
     for (auto& e : b->envs) { e->mahony_enabled = kp >= 0.0; e->mahony_kp = kp; e->mahony_ki = ki; }
 }

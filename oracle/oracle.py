@@ -179,6 +179,17 @@ class OracleBatch:
         sf = None if safety is None else np.ascontiguousarray(safety, dtype=np.float64).reshape(4, nm)
         lib().orc_set_pd_full(self._h, dptr(kp), dptr(kd), dptr(lower), dptr(upper), None if sf is None else dptr(sf))
 
+    def get_pd_controller_state(self) -> np.ndarray:
+        out = np.zeros((self.n, 3, self.nm))
+        lib().orc_get_pd_state.argtypes = [C.c_void_p, c_double_p]
+        lib().orc_get_pd_state(self._h, dptr(out))
+        return out
+
+    def set_pd_controller_state(self, state) -> None:
+        state = np.ascontiguousarray(state, dtype=np.float64).reshape(self.n, 3, self.nm)
+        lib().orc_set_pd_state.argtypes = [C.c_void_p, c_double_p]
+        lib().orc_set_pd_state(self._h, dptr(state))
+
     def set_mahony_filter(self, kp: Optional[float] = 1.0, ki: float = 0.1) -> None:
         lib().orc_set_mahony(self._h, -1.0 if kp is None else float(kp), float(ki))
 

@@ -270,6 +270,45 @@ def pd_block_scenario(api, name="anymal", n_env=4, n_steps=3, safety=False):
     return eng, orc
 
 
+def pd_adapter_scenario(api, name="anymal", n_env=3, n_steps=3, order=0, instantaneous=False):
+    """`PDAdapter` -> `PDController` pipeline (the `*-pid` envs of gym_jiminy): the host-side adapter of
+    jiminy_b200/blocks.py drives the device block through the command-state getter / setter; the same adapter function
+    drives the oracle's block.  Actions = target motor positions (order 0) or velocities (order 1)."""
+    from jiminy_b200.blocks import PDAdapter, pd_adapter
+    sc = scenarios.make(name, n_env, seed=9)
+    rob = sc.robot
+    nm = rob.nmotors
+    iq = np.array([rob.idx_q[m.joint] for m in rob.motors])
+    lower = np.stack([rob.q_lower[iq] + 0.05, np.full(nm, -0.8), np.full(nm, -20.0)])
+    upper = np.stack([rob.q_upper[iq] - 0.05, np.full(nm, 0.8), np.full(nm, 20.0)])
+    eng, orc = BatchedEngine(rob, sc.options, n_env, api_=api), OracleBatch(rob, sc.options, n_env)
+    for x in (eng, orc):
+        x.set_pd_controller_full(sc.kp, sc.kd, lower, upper, None)
+        x.set_command(np.zeros((n_env, nm)))
+    eng.start(sc.q0, sc.v0)
+    assert not orc.start(sc.q0, sc.v0).any()
+    np.testing.assert_allclose(eng.get_pd_controller_state(), orc.get_pd_controller_state(), rtol=0, atol=1e-13)
+    deadband = np.full(nm, 0.02)
+    adapter = PDAdapter(eng, lower, upper, order=order, is_instantaneous=instantaneous, velocity_deadband=deadband, step_dt=sc.step_dt)
+    rng = np.random.default_rng(13)
+    for k in range(n_steps):
+        if order == 0:
+            act = sc.target0 + rng.uniform(-0.03, 0.03, size=(n_env, nm))
+        else:
+            act = rng.uniform(-0.3, 0.3, size=(n_env, nm))
+        adapter.apply(act)
+        st, out = orc.get_pd_controller_state(), np.zeros((n_env, nm))
+        pd_adapter(act.copy(), order, st, lower, upper, instantaneous, deadband, sc.step_dt, out)
+        if instantaneous:
+            orc.set_pd_controller_state(st)
+        orc.set_command(out)
+        eng.step(sc.step_dt)
+        assert not orc.step(sc.step_dt, parallel=True).any()
+        compare(eng, orc, 1e-9, 1e-7)
+        np.testing.assert_allclose(eng.get_pd_controller_state(), orc.get_pd_controller_state(), rtol=0, atol=1e-10)
+    return eng, orc
+
+
 def bounds_handoff_scenario(api, n_env=9, n_steps=3, tol_state=1e-8):
     """ANYmal envs of which every third is driven into its hip position bounds (PD targets beyond the limits): inside
     one warp some envs stay on the fast kernel while others abort and are redone by the full kernel with their

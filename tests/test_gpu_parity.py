@@ -208,6 +208,11 @@ def test_pd_controller_block(safety):
     pc.pd_block_scenario(None, n_env=64, n_steps=4, safety=safety)
 
 
+@pytest.mark.parametrize("order,instantaneous", [(0, False), (1, True)])
+def test_pd_adapter_pipeline(order, instantaneous):
+    pc.pd_adapter_scenario(None, n_env=40, n_steps=4, order=order, instantaneous=instantaneous)
+
+
 def test_bounds_handoff_between_kernels_at_scale():
     """600 ANYmal envs, every third pushed into its joint bounds: fast kernel / full kernel hand-off inside warps."""
     pc.bounds_handoff_scenario(None, n_env=600, n_steps=5)

@@ -435,6 +435,11 @@ def test_pd_controller_block(api, safety):
     pc.pd_block_scenario(api, safety=safety)
 
 
+@pytest.mark.parametrize("order,instantaneous", [(0, False), (1, True)])
+def test_pd_adapter_pipeline(api, order, instantaneous):
+    pc.pd_adapter_scenario(api, order=order, instantaneous=instantaneous)
+
+
 def test_bounds_handoff_between_kernels(api):
     pc.bounds_handoff_scenario(api, n_env=9, n_steps=4)
 

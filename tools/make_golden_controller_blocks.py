@@ -43,7 +43,7 @@ def main():
     mod_path = os.path.join(tmp, "ref_controller_blocks.py")
     with open(mod_path, "w") as fh:
         fh.write("from typing import Optional\nimport numpy as np\nimport numba as nb\n\n")
-        fh.write(extract(os.path.join(REF, "proportional_derivative_controller.py"), {"integrate_zoh", "pd_controller"}))
+        fh.write(extract(os.path.join(REF, "proportional_derivative_controller.py"), {"integrate_zoh", "pd_controller", "pd_adapter"}))
         fh.write("\n\n")
         fh.write(extract(os.path.join(REF, "motor_safety_limit.py"), {"apply_safety_limits"}))
         fh.write("\n\nfrom typing import Tuple\nEARTH_SURFACE_GRAVITY = 9.81   # blocks/mahony_filter.py:23\n\n")
@@ -112,6 +112,29 @@ def main():
         rec["r_mat"].append(R); rec["r_quat"].append(out[:, 0].copy())
     np.savez_compressed(OUT, **{k: np.array(v) for k, v in rec.items()})
     print("wrote", OUT, {k: np.array(v).shape for k, v in rec.items()})
+
+    # pd_adapter (blocks/proportional_derivative_controller.py:166-262): its own file and random stream, so that the
+    # vectors above never change
+    rng = np.random.default_rng(20240925)
+    ad = {k: [] for k in ("action", "order", "state_in", "lower", "upper", "instantaneous", "has_deadband", "deadband",
+                          "step_dt", "out", "state_out")}
+    for case in range(240):
+        pmax, vmax, amax = rng.uniform(0.5, 3.0, nm), rng.uniform(1.0, 10.0, nm), rng.uniform(5.0, 200.0, nm)
+        lower, upper = np.stack([-pmax, -vmax, -amax]), np.stack([pmax, vmax, amax])
+        state = np.stack([rng.uniform(-1.0, 1.0, nm) * pmax, rng.uniform(-1.0, 1.0, nm) * vmax, rng.uniform(-1.0, 1.0, nm) * amax])
+        order, inst, has_db = case % 2, (case // 2) % 2 == 1, (case // 4) % 2 == 1
+        step_dt = float([0.04, 1e-3, 0.0, 0.02][(case // 8) % 4])
+        action = rng.uniform(-1.5, 1.5, nm) * (pmax if order == 0 else vmax)
+        if has_db:
+            action[rng.integers(nm)] *= 1e-3      # something inside the dead band
+        deadband = rng.uniform(0.0, 0.2, nm)
+        out, st = np.full(nm, 7.0), state.copy()
+        mod.pd_adapter(action.copy(), order, st, lower, upper, inst, deadband if has_db else None, step_dt, out)
+        for k, x in zip(ad, (action, order, state, lower, upper, inst, has_db, deadband, step_dt, out, st)):
+            ad[k].append(np.array(x))
+    out_path = os.path.join(os.path.dirname(OUT), "pd_adapter.npz")
+    np.savez_compressed(out_path, **{k: np.array(v) for k, v in ad.items()})
+    print("wrote", out_path, {k: np.array(v).shape for k, v in ad.items()})
 
 
 if __name__ == "__main__":
