@@ -74,9 +74,9 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
     for (int k = 0; k < n_cc; ++k) body_bits |= static_cast<unsigned>(KP->bd_of_contact[k]) << (2 * k);
     double pl_all[12 * BD_MAX_CONTACTS];   // per contact: lambda (4), y (4), y_prev (4)
     double Fv[6 * BD_MAX_BODIES];
+    __syncwarp(c.gmask);      // the enabled flags below were written by the lanes owning the contact frames
     unsigned enabled = 0;
     for (int k = 0; k < n_cc; ++k) if (CST(cs_contact(k)) != 0.0) enabled |= 1u << k;
-    __syncwarp(c.gmask);
     lb_prepare(c, w, lw, status);
     // ---------------- B. the contact bodies this lane owns: Jacobian at the body origin, X, G, H, c
     for (int e = c.sub; e < D * D; e += L) SHW(ws.OM + e) = 0.0;
