@@ -210,8 +210,10 @@ int jb_set_command_device(JbBatch* batch, const double* cmd_dev);
  * motor ACCELERATIONS; at every controller update the (position, velocity, acceleration) targets of each motor are
  * integrated by `integrate_zoh` (:24-98) within [state_lower, state_upper] ([3][nmotors]: position, velocity,
  * acceleration bounds) and the torque is clip(kp ((q_des - q) + kd (v_des - v)), +-effort_limit) (:104-165);
- * jb_start restarts the targets from the clipped measurement.  `safety` = NULL, or [4][nmotors]: kp, kd, soft lower
- * and soft upper position of `apply_safety_limits`.  kp = NULL disables the block. */
+ * jb_start restarts the targets from the clipped measurement.  `safety` = NULL, or [5][nmotors]: kp, kd, soft lower
+ * and soft upper position and the velocity limit of `apply_safety_limits` -- what `MotorSafetyLimit.__init__` derives
+ * from its arguments (:161-175: position limits +- reduction * soft_position_margin,
+ * min(motor velocity limit, reduction * soft_velocity_max)).  kp = NULL disables the block. */
 int jb_set_pd_controller_full(JbBatch* batch, const double* kp, const double* kd, const double* state_lower,
                               const double* state_upper, const double* safety);
 /* The block's `_command_state` (proportional_derivative_controller.py:390-394, exposed to the pipeline as the

@@ -162,3 +162,16 @@ def make_options(opt: Dict[str, Any]) -> JbOptions:
     for k in range(6):
         o.gravity[k] = float(world["gravity"][k])
     return o
+
+
+def safety_table(safety, robot) -> "np.ndarray | None":
+    """`MotorSafetyLimit` parameters as the [5, nmotors] table of jb_set_pd_controller_full: kp, kd, soft lower /
+    upper motor position, velocity limit.  Four rows are accepted for the common case soft_velocity_max = inf: the
+    fifth is then the motors' own velocity limit (motor_safety_limit.py:172-175)."""
+    if safety is None:
+        return None
+    nm = robot.nmotors
+    sf = np.asarray(safety, dtype=np.float64)
+    if sf.shape == (4, nm):
+        sf = np.concatenate([sf, np.array([[m.velocity_limit for m in robot.motors]], dtype=np.float64)], axis=0)
+    return np.ascontiguousarray(sf.reshape(5, nm))

@@ -16,7 +16,7 @@ import numpy as np
 
 from . import model as M
 from ._ctypes_abi import (JbModelDesc, JbOptions, JbSensorLayout, ModelDescHolder, c_double_p, c_int32_p,
-                          c_int64_p, c_uint8_p, dptr, make_options)
+                          c_int64_p, c_uint8_p, dptr, make_options, safety_table)
 
 JB_OK = 0
 JB_ERR_INVALID_ARGUMENT, JB_ERR_BAD_CONTROL_FLOW, JB_ERR_RUNTIME, JB_ERR_NOT_IMPLEMENTED, JB_ERR_CUDA = -1, -2, -3, -4, -5
@@ -248,7 +248,8 @@ class BatchedEngine:
 
     def set_pd_controller_full(self, kp, kd, state_lower, state_upper, safety=None) -> None:
         """gym_jiminy's `PDController` block on the device (+ `MotorSafetyLimit` when `safety` = [kp, kd, soft_lower,
-        soft_upper], each [nmotors]): `set_command` then uploads target motor accelerations.  `state_lower/upper`:
+        soft_upper(, velocity_limit)], each [nmotors]; the velocity limit defaults to the motors' own): `set_command`
+        then uploads target motor accelerations.  `state_lower/upper`:
         [3, nmotors] position / velocity / acceleration bounds of the targets.  `kp=None` disables it."""
         if kp is None:
             self._api.check(self._api.dll.jb_set_pd_controller_full(self._h, None, None, None, None, None))
@@ -258,7 +259,7 @@ class BatchedEngine:
         kd = np.ascontiguousarray(np.broadcast_to(kd, (nm,)), dtype=np.float64)
         lo = np.ascontiguousarray(state_lower, dtype=np.float64).reshape(3, nm)
         hi = np.ascontiguousarray(state_upper, dtype=np.float64).reshape(3, nm)
-        sf = None if safety is None else np.ascontiguousarray(safety, dtype=np.float64).reshape(4, nm)
+        sf = safety_table(safety, self.robot)
         self._api.check(self._api.dll.jb_set_pd_controller_full(self._h, dptr(kp), dptr(kd), dptr(lo), dptr(hi),
                                                                 None if sf is None else dptr(sf)))
 

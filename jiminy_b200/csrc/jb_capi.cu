@@ -555,17 +555,20 @@ int jb_set_pd_controller_full(JbBatch* b, const double* kp, const double* kd, co
     const size_t nm = b->nmotors;
     for (size_t k = 0; k < 3 * nm; ++k) if (!(lower[k] <= upper[k])) return fail(JB_ERR_INVALID_ARGUMENT, "state_lower must not exceed state_upper");
     if (!b->d_pdf) {
-        int rc = dev_alloc(b, &b->d_pdf, 12 * nm);
+        int rc = dev_alloc(b, &b->d_pdf, 13 * nm);
         if (rc) return rc;
         rc = dev_alloc(b, &b->d_pdf_state, static_cast<size_t>(b->n_env) * 3 * nm);
         if (rc) return rc;
     }
-    std::vector<double> h(12 * nm, 0.0);
+    std::vector<double> h(13 * nm, 0.0);
     std::memcpy(h.data(), kp, sizeof(double) * nm);
     std::memcpy(h.data() + nm, kd, sizeof(double) * nm);
     std::memcpy(h.data() + 2 * nm, lower, sizeof(double) * 3 * nm);
     std::memcpy(h.data() + 5 * nm, upper, sizeof(double) * 3 * nm);
-    if (safety) std::memcpy(h.data() + 8 * nm, safety, sizeof(double) * 4 * nm);
+    if (safety) {
+        std::memcpy(h.data() + 8 * nm, safety, sizeof(double) * 5 * nm);
+        for (size_t k = 0; k < nm; ++k) if (!(safety[4 * nm + k] >= 0.0)) return fail(JB_ERR_INVALID_ARGUMENT, "the soft velocity limit must be positive");
+    }
     CU(cudaMemcpyAsync(b->d_pdf, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, b->stream));
     CU(cudaStreamSynchronize(b->stream));
     b->kp.pdf = b->d_pdf; b->kp.pdf_state = b->d_pdf_state; b->kp.pdf_safety = safety ? 1 : 0;

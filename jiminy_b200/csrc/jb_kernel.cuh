@@ -125,7 +125,7 @@ __device__ __noinline__ void update_pd_commands(const Ctx c, bool running) {
             tau = fmin(fmax(tau, -lim), lim);
             if (KP->pdf_safety) {
                 const double* S = P + 8 * nm;
-                const double vlim = rd->motor[2];
+                const double vlim = S[4 * nm + m];     // min(motor velocity limit, reduction * soft_velocity_max)
                 const double sv_lo = vlim * fmin(fmax(-S[m] * (q_enc - S[2 * nm + m]), -1.0), 1.0);
                 const double sv_hi = vlim * fmin(fmax(-S[m] * (q_enc - S[3 * nm + m]), -1.0), 1.0);
                 const double se_lo = lim * fmin(fmax(-S[nm + m] * (v_enc - sv_lo), -1.0), 1.0);

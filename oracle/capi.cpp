@@ -121,7 +121,7 @@ void orc_set_pd(OrcBatch* b, const double* kp, const double* kd) {
         if (kp) { e->pd_kp.assign(kp, kp + b->nmotors); e->pd_kd.assign(kd, kd + b->nmotors); e->pd_target.assign(b->nmotors, 0.0); }
     }
 }
-// PDController block with optional MotorSafetyLimit: lower / upper [3][nmotors], safety [4][nmotors] or null
+// PDController block with optional MotorSafetyLimit: lower / upper [3][nmotors], safety [5][nmotors] or null
 void orc_set_pd_full(OrcBatch* b, const double* kp, const double* kd, const double* lower, const double* upper, const double* safety) {
     const int nm = b->nmotors;
     for (auto& e : b->envs) {
@@ -135,6 +135,7 @@ void orc_set_pd_full(OrcBatch* b, const double* kp, const double* kd, const doub
         if (safety) {
             e->pdf_skp.assign(safety, safety + nm); e->pdf_skd.assign(safety + nm, safety + 2 * nm);
             e->pdf_slo.assign(safety + 2 * nm, safety + 3 * nm); e->pdf_shi.assign(safety + 3 * nm, safety + 4 * nm);
+            e->pdf_svlim.assign(safety + 4 * nm, safety + 5 * nm);
         }
     }
 }

@@ -321,7 +321,7 @@ void Engine::computeCommand(double tt, const double* qv, const double* vv, std::
                       nm, simStarted ? opt.controller_update_period : 0.0, command.data());
         if (pdf_safety)
             apply_safety_limits(command.data(), enc.data(), enc.data() + nm, pdf_skp.data(), pdf_skd.data(), pdf_slo.data(),
-                                pdf_shi.data(), vlim.data(), elim.data(), nm, command.data());
+                                pdf_shi.data(), pdf_svlim.data(), elim.data(), nm, command.data());
         return;
     }
     if (pd_enabled) {

@@ -196,7 +196,7 @@ struct Engine {
     std::vector<double> mahony_q, mahony_bias, mahony_omega;   // [4][nimu], [3][nimu], [3][nimu]
     void mahonyInit();
     void mahonyUpdate();
-    std::vector<double> pdf_kp, pdf_kd, pdf_lower, pdf_upper, pdf_state, pdf_action, pdf_skp, pdf_skd, pdf_slo, pdf_shi;
+    std::vector<double> pdf_kp, pdf_kd, pdf_lower, pdf_upper, pdf_state, pdf_action, pdf_skp, pdf_skd, pdf_slo, pdf_shi, pdf_svlim;
     std::vector<double> pd_kp, pd_kd, pd_target;
     int64_t rhs_count = 0;
 

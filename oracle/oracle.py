@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(_HERE))
 
 from jiminy_b200._ctypes_abi import (JbModelDesc, JbOptions, JbSensorLayout, ModelDescHolder,  # noqa: E402
-                                     c_double_p, c_int32_p, c_int64_p, c_uint8_p, dptr, make_options)
+                                     c_double_p, c_int32_p, c_int64_p, c_uint8_p, dptr, make_options, safety_table)
 from jiminy_b200.model import RobotTable  # noqa: E402
 
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
@@ -176,7 +176,7 @@ class OracleBatch:
         kd = np.ascontiguousarray(np.broadcast_to(kd, (nm,)), dtype=np.float64)
         lower = np.ascontiguousarray(lower, dtype=np.float64).reshape(3, nm)
         upper = np.ascontiguousarray(upper, dtype=np.float64).reshape(3, nm)
-        sf = None if safety is None else np.ascontiguousarray(safety, dtype=np.float64).reshape(4, nm)
+        sf = safety_table(safety, self.robot)
         lib().orc_set_pd_full(self._h, dptr(kp), dptr(kd), dptr(lower), dptr(upper), None if sf is None else dptr(sf))
 
     def get_pd_controller_state(self) -> np.ndarray:

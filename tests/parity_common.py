@@ -249,7 +249,9 @@ def pd_block_scenario(api, name="anymal", n_env=4, n_steps=3, safety=False):
     # gentle target motion (the stiff spring-damper ground does not survive flailing legs at RK4 1 ms)
     lower = np.stack([rob.q_lower[iq] + 0.05, np.full(nm, -0.6), np.full(nm, -15.0)])
     upper = np.stack([rob.q_upper[iq] - 0.05, np.full(nm, 0.6), np.full(nm, 15.0)])
-    sf = np.stack([np.full(nm, 20.0), np.full(nm, 0.5), rob.q_lower[iq] + 0.02, rob.q_upper[iq] - 0.02]) if safety else None
+    # MotorSafetyLimit: kp, kd, soft position bounds, and a soft velocity limit below the motors' own (soft_velocity_max)
+    sf = np.stack([np.full(nm, 20.0), np.full(nm, 0.5), rob.q_lower[iq] + 0.02, rob.q_upper[iq] - 0.02,
+                   np.minimum(vlim, 4.0)]) if safety else None
     eng, orc = BatchedEngine(rob, sc.options, n_env, api_=api), OracleBatch(rob, sc.options, n_env)
     rng = np.random.default_rng(11)
     act = rng.uniform(-10.0, 10.0, size=(n_env, nm))
