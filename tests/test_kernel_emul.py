@@ -440,6 +440,61 @@ def test_pd_adapter_pipeline(api, order, instantaneous):
     pc.pd_adapter_scenario(api, order=order, instantaneous=instantaneous)
 
 
+def test_pd_control_pipeline_env(api):
+    """`PDControlBatchedEnv` = MotorSafetyLimit + PDController + PDAdapter(order 1) + MahonyFilter with the arguments of
+    `AtlasPDControlJiminyEnv` (atlas.py:239-295), on ANYmal: derived bounds, observation layout, and the trajectories
+    against the oracle driven by the same adapter function."""
+    from jiminy_b200.envs import PDControlBatchedEnv, flatten_observation
+    from jiminy_b200.blocks import pd_adapter
+    from jiminy_b200._ctypes_abi import safety_table
+    sc = scenarios.make("anymal", 3, seed=12)
+    env = PDControlBatchedEnv(sc, joint_velocity_limit=4.0, joint_acceleration_limit=30.0, order=1, mahony=(0.75, 0.057),
+                              safety=dict(kp=50.0, kd=0.15, soft_position_margin=0.0, soft_velocity_max=4.0), api_=api)
+    rob, nm = sc.robot, sc.robot.nmotors
+    v_hw = np.array([m.velocity_limit for m in rob.motors])
+    np.testing.assert_array_equal(env.command_state_upper[1], np.minimum(v_hw, 4.0))
+    np.testing.assert_array_equal(env.command_state_upper[2], np.full(nm, 30.0))
+    np.testing.assert_array_equal(env.action_high, env.command_state_upper[1])
+    iq = np.array([rob.idx_q[m.joint] for m in rob.motors])
+    np.testing.assert_array_equal(env.command_state_lower[0], rob.q_lower[iq])
+    # inferred acceleration bound (joint_acceleration_limit=None): bang-bang on velocity or effort, whichever binds
+    env2 = PDControlBatchedEnv(sc, api_=api)
+    eff = np.array([m.effort_limit for m in rob.motors])
+    expect = np.minimum(2.0 * v_hw / sc.step_dt, eff / (sc.kp * sc.step_dt * np.maximum(sc.step_dt, sc.kd)))
+    np.testing.assert_allclose(env2.command_state_upper[2], expect, rtol=1e-15)
+    env2.close()
+    # the oracle with the same blocks
+    orc = OracleBatch(rob, sc.options, sc.n_env)
+    table = np.stack([np.full(nm, 50.0), np.full(nm, 0.15), rob.q_lower[iq], rob.q_upper[iq], np.minimum(v_hw, 4.0)])
+    orc.set_pd_controller_full(sc.kp, sc.kd, env.command_state_lower, env.command_state_upper, table)
+    orc.set_mahony_filter(0.75, 0.057)
+    orc.set_command(np.zeros((sc.n_env, nm)))
+    obs, _ = env.reset()
+    assert not orc.start(sc.q0, sc.v0).any()
+    assert set(obs) == {"t", "states", "measurements", "features"} and obs["states"]["pd_controller"].shape == (3, 2, nm)
+    assert obs["features"]["mahony_filter"].shape == (3, 4, 1)
+    rng = np.random.default_rng(5)
+    for k in range(2):
+        act = rng.uniform(-0.3, 0.3, size=(sc.n_env, nm))
+        obs, reward, terminated, truncated, info = env.step(act)
+        st, out = orc.get_pd_controller_state(), np.zeros((sc.n_env, nm))
+        pd_adapter(act.copy(), 1, st, env.command_state_lower, env.command_state_upper, False, None, sc.step_dt, out)
+        orc.set_command(out)
+        assert not orc.step(sc.step_dt, parallel=True).any()
+        pc.compare(env.engine, orc, 1e-9, 1e-7)
+        np.testing.assert_allclose(obs["states"]["pd_controller"], orc.get_pd_controller_state()[:, :2], atol=1e-10)
+        np.testing.assert_allclose(obs["features"]["mahony_filter"][:, :, 0], orc.get_mahony_filter()[:, 0, :4], atol=1e-10)
+        assert not terminated.any() and not truncated.any() and (reward == 1.0).all()
+    keys = [("states", "pd_controller"), ("measurements", "EncoderSensor"), ("features", "mahony_filter")]
+    low = {keys[0]: env.command_state_lower[:2]}
+    high = {keys[0]: env.command_state_upper[:2]}
+    flat = flatten_observation(obs, keys, low, high)
+    assert flat.shape == (3, 2 * nm + 2 * nm + 4)
+    assert np.abs(flat[:, :2 * nm]).max() <= 1.0 + 1e-12            # normalised by the command-state bounds
+    np.testing.assert_array_equal(flat[:, 2 * nm:4 * nm], obs["measurements"]["EncoderSensor"].reshape(3, -1))   # unbounded: untouched
+    env.close()
+
+
 def test_bounds_handoff_between_kernels(api):
     pc.bounds_handoff_scenario(api, n_env=9, n_steps=4)
 
