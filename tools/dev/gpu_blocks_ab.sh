@@ -1,6 +1,6 @@
 # A/B of the constraint solvers on Atlas with the reference's own settings (Euler 5 ms, constraint contacts)
 OUT=gpurun_out/${1:-r01x}; mkdir -p $OUT
-./jiminy_b200/l1_probe.bin > $OUT/l1_probe.txt 2>&1; cat $OUT/l1_probe.txt
+# (the store->load probe of tools/micro/store_load_latency.cu ran here once: profiles/r01_micro_store_load_latency_b200.txt)
 timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee $OUT/pytest_gpu.log
 A="--workload atlas --contact-model constraint --ode-solver euler_explicit --dt-max 0.005 --steps 5 --warmup 3 --no-cpu-baseline"
 timeout 200 python bench.py $A > $OUT/atlas_ref_bodies.json 2> $OUT/err1.log
