@@ -430,6 +430,31 @@ def test_constraint_solver_variants(api, monkeypatch, robot, toggle):
     assert want in eng.describe() and (toggle != "JB_NO_BODY_CONS" or "body-space" not in eng.describe())
 
 
+@pytest.mark.parametrize("drop_a_foot,solver", [(False, "lane-block"), (True, "body-space")])
+def test_constraint_contact_on_trunk_body(api, drop_a_foot, solver):
+    """A contact frame on the floating base -- a trunk joint, replicated on every lane -- next to the feet: five contact
+    bodies go to the lane-block solver, four (one foot removed) to the body-space solver."""
+    sc = scenarios.make("anymal", 2, seed=4, solver="euler_explicit", dt_max=0.005)
+    sc.options["contacts"]["model"] = "constraint"
+    rob = sc.robot
+    base = [n for n, f in rob.frames.items() if f.joint == 1 and f.kind == "body"][0]
+    z0 = float(sc.q0[:, 2].min())
+    rob.add_frame("belly_contact", base, M.SE3(np.eye(3), np.array([0.05, 0.02, -(z0 + 0.002)])))     # 2 mm into the ground
+    if drop_a_foot:
+        rob.remove_contact_points([rob.contact_frame_names[0]])
+    rob.add_contact_points(["belly_contact"])
+    eng, orc = pc.make_pair(sc, api)
+    assert solver in eng.describe() and "quadruped" not in eng.describe()
+    pc.compare(eng, orc, 1e-12, 1e-9)
+    for k in range(2):
+        act = sc.sample_targets(k)
+        eng.set_command(act)
+        orc.set_command(act)
+        eng.step(sc.step_dt)
+        assert not orc.step(sc.step_dt).any()
+        pc.compare(eng, orc, 1e-9, 1e-7)
+
+
 @pytest.mark.parametrize("safety", [False, True])
 def test_pd_controller_block(api, safety):
     pc.pd_block_scenario(api, safety=safety)
