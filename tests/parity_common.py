@@ -272,6 +272,30 @@ def pd_block_scenario(api, name="anymal", n_env=4, n_steps=3, safety=False):
     return eng, orc
 
 
+def atlas_bounds_and_contacts_scenario(api, n_env=2, n_steps=6):
+    """Atlas on `constraint` contacts whose elbows are driven past their position bounds: contact frames and joint
+    bounds are enabled together (lane-block solver, rows of both kinds on a robot with a four-joint trunk) and the
+    solve switches between the body-space and the lane-block formulation as the bounds come and go."""
+    sc = scenarios.make("atlas", n_env, seed=5, solver="euler_explicit", dt_max=0.005)
+    sc.options["contacts"]["model"] = "constraint"
+    rob = sc.robot
+    eng, orc = make_pair(sc, api)
+    iq = np.array([rob.idx_q[m.joint] for m in rob.motors])
+    sel = [k for k, m in enumerate(rob.motors) if "elx" in m.name or "ely" in m.name]
+    hit = False
+    for k in range(n_steps):
+        act = sc.sample_targets(k)
+        act[:, sel] = rob.q_upper[iq][sel] + 0.4
+        eng.set_command(act)
+        orc.set_command(act)
+        eng.step(sc.step_dt)
+        assert not orc.step(sc.step_dt, parallel=True).any()
+        compare(eng, orc, 1e-8, 1e-6)
+        hit = hit or bool((eng.get_status() & 8).any())
+    assert hit and not (eng.get_status() & ~8).any()
+    return eng, orc
+
+
 def pd_adapter_scenario(api, name="anymal", n_env=3, n_steps=3, order=0, instantaneous=False):
     """`PDAdapter` -> `PDController` pipeline (the `*-pid` envs of gym_jiminy): the host-side adapter of
     jiminy_b200/blocks.py drives the device block through the command-state getter / setter; the same adapter function

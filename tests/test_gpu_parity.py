@@ -171,6 +171,10 @@ def test_constraint_solver_variants(monkeypatch, robot, toggle):
     assert want in eng.describe()
 
 
+def test_atlas_bounds_and_contacts_together():
+    pc.atlas_bounds_and_contacts_scenario(None, n_env=16, n_steps=8)
+
+
 def test_constraint_solvers_agree_at_scale():
     """1024 ANYmal envs with the constraint contact model: the structured quadruped solver and the generic dense
     solver (two independent formulations of the same boxed LCP) give the same trajectories; bit-identical when

@@ -430,6 +430,10 @@ def test_constraint_solver_variants(api, monkeypatch, robot, toggle):
     assert want in eng.describe() and (toggle != "JB_NO_BODY_CONS" or "body-space" not in eng.describe())
 
 
+def test_atlas_bounds_and_contacts_together(api):
+    pc.atlas_bounds_and_contacts_scenario(api)
+
+
 @pytest.mark.parametrize("drop_a_foot,solver", [(False, "lane-block"), (True, "body-space")])
 def test_constraint_contact_on_trunk_body(api, drop_a_foot, solver):
     """A contact frame on the floating base -- a trunk joint, replicated on every lane -- next to the feet: five contact
