@@ -86,11 +86,11 @@ def _force_pair(sc, api):
     return eng, orc
 
 
-def external_forces_scenario(api, n_env=6, n_steps=3, solver="runge_kutta_4", tol=1e-9):
+def external_forces_scenario(api, n_env=6, n_steps=3, solver="runge_kutta_4", tol=1e-9, contact_model=None, dt_max=None):
     """Impulse forces with per-env schedules on the base (trunk joint) and on a shank (private joint, off-origin
     frame), a sampled profile force (finite update period) and a continuous one: Engine::computeExternalForces
     + the breakpoint handling of Engine::step, against the oracle."""
-    sc = scenarios.make("anymal", n_env, seed=3, solver=solver)
+    sc = scenarios.make("anymal", n_env, seed=3, solver=solver, contact_model=contact_model, dt_max=dt_max)
     eng, orc = _force_pair(sc, api)
     rng = np.random.default_rng(5)
     rob = sc.robot

@@ -296,6 +296,15 @@ def test_external_forces_anymal(api):
     pc.external_forces_scenario(api)
 
 
+@pytest.mark.parametrize("toggle", [None, "JB_NO_STRUCTURED_CONS"])
+def test_external_forces_with_constraint_contacts(api, monkeypatch, toggle):
+    """Impulse / profile forces while the contact constraints are solved: register-resident quadruped solver, and
+    the body-space solver when it is switched off."""
+    if toggle:
+        monkeypatch.setenv(toggle, "1")
+    pc.external_forces_scenario(api, n_env=2, n_steps=2, solver="euler_explicit", dt_max=0.005, contact_model="constraint", tol=1e-8)
+
+
 def test_external_forces_control_flow(api):
     sc = scenarios.make("cartpole", 2)
     eng = BatchedEngine(sc.robot, sc.options, 2, api_=api)
