@@ -439,6 +439,15 @@ def test_constraint_solver_variants(api, monkeypatch, robot, toggle):
     assert want in eng.describe() and (toggle != "JB_NO_BODY_CONS" or "body-space" not in eng.describe())
 
 
+@pytest.mark.parametrize("robot", ["atlas", "anymal"])
+def test_dopri_with_constraint_contacts(api, robot):
+    """Adaptive Dormand-Prince steps (error control, rejected steps) over the body-space contact solver."""
+    eng, orc, sc = pc.robot_constraint_scenario(robot, 1, 1, api, seed=2, solver="runge_kutta_dopri")
+    assert "body-space" in eng.describe()
+    it, it_failed = eng.get_iters()
+    assert it[0] > 20
+
+
 def test_atlas_bounds_and_contacts_together(api):
     pc.atlas_bounds_and_contacts_scenario(api)
 
