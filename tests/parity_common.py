@@ -272,6 +272,34 @@ def pd_block_scenario(api, name="anymal", n_env=4, n_steps=3, safety=False):
     return eng, orc
 
 
+def masked_restart_constraint_scenario(api, name, n_env=5):
+    """Masked `start` (a vectorised env restarting some of its envs) while contact constraints are enabled: the
+    restarted envs get fresh constraint state (enabled set, multipliers, reference placements), the others keep theirs."""
+    kw = dict(solver="euler_explicit", dt_max=0.005, contact_model="constraint")
+    sc, sc2 = scenarios.make(name, n_env, seed=7, **kw), scenarios.make(name, n_env, seed=8, **kw)
+    eng, orc = make_pair(sc, api)
+    for k in range(2):
+        act = sc.sample_targets(k)
+        eng.set_command(act)
+        orc.set_command(act)
+        eng.step(sc.step_dt)
+        assert not orc.step(sc.step_dt, parallel=True).any()
+    mask = (np.arange(n_env) % 2 == 0).astype(np.uint8)
+    eng.start(sc2.q0, sc2.v0, mask=mask)
+    assert not orc.start(sc2.q0, sc2.v0, mask=mask).any()
+    compare(eng, orc, 1e-9, 1e-7)
+    for k in range(2):
+        act = sc.sample_targets(2 + k)
+        eng.set_command(act)
+        orc.set_command(act)
+        eng.step(sc.step_dt)
+        assert not orc.step(sc.step_dt, parallel=True).any()
+        compare(eng, orc, 1e-9, 1e-7)
+    t = eng.get_state()[0]
+    np.testing.assert_allclose(t, np.where(mask, 2, 4) * sc.step_dt, atol=1e-12)
+    return eng, orc
+
+
 def atlas_bounds_and_contacts_scenario(api, n_env=2, n_steps=6):
     """Atlas on `constraint` contacts whose elbows are driven past their position bounds: contact frames and joint
     bounds are enabled together (lane-block solver, rows of both kinds on a robot with a four-joint trunk) and the

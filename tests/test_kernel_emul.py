@@ -448,6 +448,11 @@ def test_dopri_with_constraint_contacts(api, robot):
     assert it[0] > 20
 
 
+@pytest.mark.parametrize("robot", ["atlas", "anymal"])
+def test_masked_restart_with_constraint_contacts(api, robot):
+    pc.masked_restart_constraint_scenario(api, robot)
+
+
 def test_atlas_bounds_and_contacts_together(api):
     pc.atlas_bounds_and_contacts_scenario(api)
 
