@@ -439,6 +439,48 @@ def test_constraint_solver_variants(api, monkeypatch, robot, toggle):
     assert want in eng.describe() and (toggle != "JB_NO_BODY_CONS" or "body-space" not in eng.describe())
 
 
+@pytest.mark.parametrize("lanes,toggle,solver", [(0, None, "body-space"), (0, "JB_NO_BODY_CONS", "lane-block"), (1, None, "generic")])
+def test_constraint_contacts_all_joint_models(api, monkeypatch, lanes, toggle, solver):
+    """The branched arm (free-flyer, revolute about arbitrary axes, unbounded revolute, prismatic incl. a skewed axis)
+    lying on two contact frames with `contacts.model = "constraint"`, torsion on: Jacobians of every joint model
+    through each formulation of the constraint solve."""
+    if toggle:
+        monkeypatch.setenv(toggle, "1")
+    robot = M.build_robot_table(os.path.join(DATA, "branched_arm.urdf"), True)
+    robot.add_contact_points(["b_sole", "a_tool"])
+    for jn in ("a_shoulder", "a_elbow", "a_spin", "b_hip", "b_slide", "b_skew_slide", "b_ankle_z", "c_spin_skew"):
+        M.attach_motor(robot, jn, jn, enableArmature=True, armature=0.01)
+        M.attach_sensor(robot, "EncoderSensor", jn, motor_name=jn)
+    M.attach_sensor(robot, "ForceSensor", "sole", frame_name="b_toe")
+    M.attach_sensor(robot, "ContactSensor", "sole_c", frame_name="b_sole")
+    opt = M.default_engine_options()
+    opt["contacts"].update(model="constraint", friction=0.7, torsion=0.02)
+    opt["stepper"].update(odeSolver="runge_kutta_4", dtMax=1e-3, sensorsUpdatePeriod=2e-3, controllerUpdatePeriod=4e-3)
+    rng = np.random.default_rng(5)
+    n = 3
+    q, v = pc.random_states(robot, n, rng, base_height=0.12)
+    cmd = rng.uniform(-3, 3, size=(n, robot.nmotors))
+    _lanes(lanes)
+    try:
+        eng, orc = BatchedEngine(robot, opt, n, api_=api), OracleBatch(robot, opt, n)
+        assert solver in eng.describe()
+        for e in (eng, orc):
+            e.set_command(cmd)
+        eng.start(q, 0.3 * v)
+        assert not orc.start(q, 0.3 * v).any()
+        f_max = 0.0
+        for _ in range(25):
+            eng.step(0.004)
+            assert not orc.step(0.004).any()
+            pc.compare(eng, orc, 1e-9, 1e-7)
+            f_ref = orc.get_efforts()[3]
+            np.testing.assert_allclose(eng.get_efforts()[3], f_ref, rtol=0, atol=1e-8 * max(1.0, np.abs(f_ref).max()))
+            f_max = max(f_max, np.abs(f_ref).max())
+        assert f_max > 50.0          # the contact constraints did carry the robot
+    finally:
+        _lanes(0)
+
+
 @pytest.mark.parametrize("robot", ["atlas", "anymal"])
 def test_dopri_with_constraint_contacts(api, robot):
     """Adaptive Dormand-Prince steps (error control, rejected steps) over the body-space contact solver."""
