@@ -22,6 +22,8 @@ timeout 300 python bench.py --workload anymal --contact-model constraint --steps
 timeout 300 python bench.py --workload atlas --contact-model constraint --n-env 512 --steps 3 --warmup 3 --no-cpu-baseline 2>> $OUT/bench.err | tee -a $OUT/bench_atlas_constraint512.log
 # the reference's own Atlas settings (atlas_options.toml; the config of its only published timing): Euler 5 ms, constraint contacts
 timeout 300 python bench.py --workload atlas --contact-model constraint --ode-solver euler_explicit --dt-max 0.005 --steps 5 --warmup 3 2>> $OUT/bench.err | tee -a $OUT/bench_atlas_reference_settings.log
+# the published benchmark restated: AtlasPDControlJiminyEnv pipeline + observation wrappers, wall clock around env.step
+timeout 300 python tools/bench_pipeline.py --n-env 4096 --steps 10 --warmup 3 2>> $OUT/bench.err | tee -a $OUT/bench_atlas_pd_pipeline.log
 echo "== reference arm" | tee $OUT/bench_ref.log
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 2>> $OUT/bench.err | tee -a $OUT/bench_ref.log
 echo "== ncu launch list"
