@@ -272,7 +272,7 @@ def pd_block_scenario(api, name="anymal", n_env=4, n_steps=3, safety=False):
     return eng, orc
 
 
-def masked_restart_constraint_scenario(api, name, n_env=5):
+def masked_restart_constraint_scenario(api, name, n_env=5, tol_state=1e-9, tol_sens=1e-7):
     """Masked `start` (a vectorised env restarting some of its envs) while contact constraints are enabled: the
     restarted envs get fresh constraint state (enabled set, multipliers, reference placements), the others keep theirs."""
     kw = dict(solver="euler_explicit", dt_max=0.005, contact_model="constraint")
@@ -287,20 +287,20 @@ def masked_restart_constraint_scenario(api, name, n_env=5):
     mask = (np.arange(n_env) % 2 == 0).astype(np.uint8)
     eng.start(sc2.q0, sc2.v0, mask=mask)
     assert not orc.start(sc2.q0, sc2.v0, mask=mask).any()
-    compare(eng, orc, 1e-9, 1e-7)
+    compare(eng, orc, tol_state, tol_sens)
     for k in range(2):
         act = sc.sample_targets(2 + k)
         eng.set_command(act)
         orc.set_command(act)
         eng.step(sc.step_dt)
         assert not orc.step(sc.step_dt, parallel=True).any()
-        compare(eng, orc, 1e-9, 1e-7)
+        compare(eng, orc, tol_state, tol_sens)
     t = eng.get_state()[0]
     np.testing.assert_allclose(t, np.where(mask, 2, 4) * sc.step_dt, atol=1e-12)
     return eng, orc
 
 
-def atlas_bounds_and_contacts_scenario(api, n_env=2, n_steps=6):
+def atlas_bounds_and_contacts_scenario(api, n_env=2, n_steps=6, tol_state=1e-8, tol_sens=1e-6):
     """Atlas on `constraint` contacts whose elbows are driven past their position bounds: contact frames and joint
     bounds are enabled together (lane-block solver, rows of both kinds on a robot with a four-joint trunk) and the
     solve switches between the body-space and the lane-block formulation as the bounds come and go."""
@@ -318,7 +318,7 @@ def atlas_bounds_and_contacts_scenario(api, n_env=2, n_steps=6):
         orc.set_command(act)
         eng.step(sc.step_dt)
         assert not orc.step(sc.step_dt, parallel=True).any()
-        compare(eng, orc, 1e-8, 1e-6)
+        compare(eng, orc, tol_state, tol_sens)
         hit = hit or bool((eng.get_status() & 8).any())
     assert hit and not (eng.get_status() & ~8).any()
     return eng, orc

@@ -173,11 +173,11 @@ def test_constraint_solver_variants(monkeypatch, robot, toggle):
 
 @pytest.mark.parametrize("robot", ["atlas", "anymal"])
 def test_masked_restart_with_constraint_contacts(robot):
-    pc.masked_restart_constraint_scenario(None, robot, n_env=21)
+    pc.masked_restart_constraint_scenario(None, robot, n_env=21, tol_state=1e-7, tol_sens=1e-5)
 
 
 def test_atlas_bounds_and_contacts_together():
-    pc.atlas_bounds_and_contacts_scenario(None, n_env=16, n_steps=8)
+    pc.atlas_bounds_and_contacts_scenario(None, n_env=16, n_steps=8, tol_state=1e-7, tol_sens=1e-5)
 
 
 def test_constraint_solvers_agree_at_scale():
