@@ -18,20 +18,30 @@ _SRCS = [os.path.join(_HERE, f) for f in ("jb_emul.cpp", "jb_emul_shim.h")] + \
         [os.path.join(_ROOT, "include", "jiminy_b200.h")]
 
 
-def build(force=False):
-    stale = not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in _SRCS)
+def build(force=False, fma=False):
+    """`fma=True`: multiply-adds contracted like nvcc does for the device (needs an x86 host with FMA): the rounding
+    of the GPU build, to check that the parity tolerances of the `-m gpu` suite hold before GPU time is spent."""
+    lib = _LIB.replace(".so", "_fma.so") if fma else _LIB
+    stale = not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in _SRCS)
     if force or stale:
-        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-pthread", "-DJB_HOST_EMUL=1",
-                        "-ffp-contract=off", "-I", _HERE, "-x", "c++", os.path.join(_HERE, "jb_emul.cpp"),
-                        os.path.join(_ROOT, "jiminy_b200", "csrc", "jb_plan.cpp"), "-o", _LIB], check=True)
-    return _LIB
+        fp = ["-mfma", "-ffp-contract=fast"] if fma else ["-ffp-contract=off"]
+        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-pthread", "-DJB_HOST_EMUL=1"] + fp +
+                       ["-I", _HERE, "-x", "c++", os.path.join(_HERE, "jb_emul.cpp"),
+                        os.path.join(_ROOT, "jiminy_b200", "csrc", "jb_plan.cpp"), "-o", lib], check=True)
+    return lib
 
 
-_api = None
+_api = {}
 
 
-def emul_api() -> Api:
-    global _api
-    if _api is None:
-        _api = Api(C.CDLL(build()))
-    return _api
+def host_has_fma() -> bool:
+    try:
+        return " fma " in open("/proc/cpuinfo").read()
+    except OSError:
+        return False
+
+
+def emul_api(fma: bool = False) -> Api:
+    if fma not in _api:
+        _api[fma] = Api(C.CDLL(build(fma=fma)))
+    return _api[fma]

@@ -495,6 +495,19 @@ def test_masked_restart_with_constraint_contacts(api, robot):
     pc.masked_restart_constraint_scenario(api, robot)
 
 
+def test_gpu_like_rounding_stays_within_the_gpu_tolerances():
+    """The kernel source built with contracted multiply-adds (what nvcc does for the device): the deviation from the
+    oracle, which is built without contraction, must stay far inside the tolerances of the `-m gpu` suite -- in
+    particular no Gauss-Seidel stopping decision may be so close to its threshold that rounding flips it visibly."""
+    from emul import host_has_fma
+    if not host_has_fma():
+        pytest.skip("host CPU without FMA")
+    api_fma = emul_api(fma=True)
+    pc.atlas_bounds_and_contacts_scenario(api_fma, n_env=4, n_steps=6, tol_state=1e-10, tol_sens=1e-8)
+    pc.robot_constraint_scenario("anymal", 8, 2, api_fma, seed=2, tol_state=1e-10, tol_sens=1e-8)
+    pc.pd_adapter_scenario(api_fma, n_env=8, n_steps=3, order=0)
+
+
 def test_atlas_bounds_and_contacts_together(api):
     pc.atlas_bounds_and_contacts_scenario(api)
 
