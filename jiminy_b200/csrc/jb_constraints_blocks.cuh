@@ -277,8 +277,7 @@ __device__ __noinline__ bool cons_solve_blocks(const Ctx c, int* status) {
     const double omega = 2.0 * 3.14159265358979323846 * opt.contact_stabilization_freq;
     const double kp = omega * omega, kd = 2.0 * omega;
     __syncwarp(c.gmask);
-    auto ndof = [&](int r) { const int k = rint[r * L].kind; return k == REC_PAD ? 0 : (k == REC_FREE ? 6 : 1); };
-    auto li_of = [&](int r) { Xf li; sm_load_xf(c, KP->rec_off[r], li); return li; };
+    auto ndof = [&](int r) { return lb_ndof(rint, r, L); };
     lb_prepare(c, w, lw, status);
     // ---------------- 5. sweep list (replicated on every lane) and the rows this lane owns
     int n_act = 0, my_rows = 0;
