@@ -26,7 +26,7 @@ from __future__ import annotations
 
 import json
 import struct
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 

@@ -6,7 +6,6 @@ Inputs (read-only, only available in the build container): `/root/reference/data
 `*_hardware.toml`, `*_options.toml`.  Output: `RobotTable` + engine options per robot.  Run again
 whenever `jiminy_b200/model.py` changes:   python tools/compile_reference_robots.py
 """
-import copy
 import os
 import sys
 
