@@ -481,6 +481,7 @@ class Engine:
         self._controller: Optional[FunctionalController] = None
         self._springs = None
         self._impulse_forces: list = []
+        self._profile_forces: list = []       # [frame, function, update period, device slot]
         self._forces_dirty = False
         self._recorder = None
 
@@ -523,13 +524,27 @@ class Engine:
         self._forces_dirty = True
 
     def register_profile_force(self, robot_name: str, frame_name: str, force_func, update_period: float = 0.0) -> None:
-        raise NotImplementedError("A Python force function cannot be called from inside the device-side integrator; use "
-                                  "BatchedEngine.register_profile_force / set_profile_force (held per-env wrench).")
+        """`Engine.register_profile_force` (pywrap engine.cc:655; Engine::registerProfileForce, engine.cc:2518-2567) for a
+        force function sampled at a finite `update_period`: `force_func(t, q, v, out)` is called on the host at every
+        multiple of the period -- which is an integration breakpoint, as in the reference -- and its value held in
+        between.  A time-continuous function (`update_period = 0`) would have to run inside the device integrator."""
+        if self.is_simulation_running:
+            raise BadControlFlow("Simulation already running. Please stop it before registering new forces.")
+        if not (update_period > 1e-10):
+            raise NotImplementedError("A time-continuous Python force function cannot be called from inside the device-side "
+                                      "integrator: give it an update period, or use BatchedEngine.set_profile_force.")
+        if frame_name == "universe":
+            raise ValueError("Impossible to apply external forces to the universe itself!")
+        if not self.robots or frame_name not in self.robots[0].frames:
+            raise ValueError(f"Frame '{frame_name}' does not exist.")
+        self._profile_forces.append([frame_name, force_func, float(update_period), -1])
+        self._forces_dirty = True
 
     def remove_all_forces(self) -> None:
         if self.is_simulation_running:
             raise BadControlFlow("Simulation already running. Please stop it before removing forces.")
         self._impulse_forces.clear()
+        self._profile_forces.clear()
         self._forces_dirty = True
 
     @property
@@ -571,16 +586,22 @@ class Engine:
             self._batch = BatchedEngine(robot, self._options, 1, device=self._device, api_=self._api_)
             if self._springs is not None:
                 self._batch.set_joint_springs(*self._springs)
-            self._forces_dirty = bool(self._impulse_forces)
+            self._forces_dirty = bool(self._impulse_forces or self._profile_forces)
         if self._forces_dirty:
             self._batch.stop()
             self._batch.remove_all_forces()
             for frame_name, t, dt, force in self._impulse_forces:
                 self._batch.register_impulse_force(frame_name, t, dt, force)
+            for pf in self._profile_forces:
+                pf[3] = self._batch.register_profile_force(pf[0], pf[2])
             self._forces_dirty = False
         q0 = np.asarray(q_init, dtype=np.float64).reshape(1, robot.nq)
         v0 = np.asarray(v_init, dtype=np.float64).reshape(1, robot.nv)
         self._batch.set_command(np.zeros((1, max(robot.nmotors, 1))))
+        for pf in self._profile_forces:      # the forces at t = 0 take part in the initial acceleration
+            out = np.zeros(6)
+            pf[1](0.0, q0[0], v0[0], out)
+            self._batch.set_profile_force(pf[3], out[None, :])
         self._batch.start(q0, v0)
         self._refresh()
         if self._controller is not None and self._controller.compute_command is not None:
@@ -631,13 +652,20 @@ class Engine:
         t_end = self.stepper_state.t + step_dt
         while t_end - self.stepper_state.t >= 1e-10:
             h = t_end - self.stepper_state.t
+            t = self.stepper_state.t
             if has_cb:
                 # stop at every controller breakpoint to call the Python controller back
-                t = self.stepper_state.t
                 nxt = (np.floor(t / cp + 1e-9) + 1.0) * cp
                 if abs(t / cp - round(t / cp)) < 1e-9:
                     self._call_controller()
                 h = min(h, nxt - t)
+            for frame_name, func, period, slot in self._profile_forces:
+                # ... and at every update of a sampled force function
+                if abs(t / period - round(t / period)) < 1e-9:
+                    out = np.zeros(6)
+                    func(t, self.robot_states[0].q, self.robot_states[0].v, out)
+                    self._batch.set_profile_force(slot, out[None, :])
+                h = min(h, (np.floor(t / period + 1e-9) + 1.0) * period - t)
             self._batch.step(h)
             self._refresh()
             status = int(self._batch.get_status()[0])

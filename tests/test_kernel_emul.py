@@ -364,6 +364,52 @@ def test_engine_facade_impulse_forces(api):
     assert abs(engine.robot_states[0].v[0]) < 1e-14
 
 
+def test_engine_facade_profile_force_function(api):
+    """`Engine.register_profile_force(robot_name, frame_name, force_func, update_period)`: the Python function is sampled at
+    its update period (an integration breakpoint) and held in between -- against the oracle driven by hand the same way."""
+    from jiminy_b200.core import Engine
+    robot = M.build_robot_table(os.path.join(DATA, "simple_pendulum.urdf"), False)
+    engine = Engine(api_=api)
+    engine.add_robot(robot)
+    opt = engine.get_options()
+    opt["stepper"].update(sensorsUpdatePeriod=0.0, controllerUpdatePeriod=0.0, odeSolver="runge_kutta_4", dtMax=1e-3)
+    engine.set_options(opt)
+    calls = []
+
+    def force(t, q, v, out):
+        calls.append(t)
+        out[:] = [30.0 * np.sin(40.0 * t), 0.0, 5.0 * q[0], 0.0, -2.0 * v[0], 0.0]
+    with pytest.raises(NotImplementedError):
+        engine.register_profile_force("", "PendulumLink", force, 0.0)
+    engine.register_profile_force("", "PendulumLink", force, 2e-3)
+    fr = robot.frames["PendulumLink"]
+    orc = OracleBatch(robot, opt, 1)
+    slot = orc.register_profile_force(fr.joint, fr.placement.p, 2e-3)
+    q0, v0 = np.array([[0.2]]), np.array([[-0.5]])
+    w = np.zeros(6)
+    force(0.0, q0[0], v0[0], w)
+    orc.set_profile_force(slot, w[None, :])
+    assert not orc.start(q0, v0).any()
+    engine.start(q0[0], v0[0])
+    for k in range(10):
+        engine.step(5e-3)                      # not a multiple of the force period: breakpoints fall inside the steps
+        t = 5e-3 * k
+        while t < 5e-3 * (k + 1) - 1e-12:      # the oracle, stopped by hand at every multiple of 2 ms
+            _, q, v, _ = orc.get_state()
+            if abs(t / 2e-3 - round(t / 2e-3)) < 1e-9:
+                force(t, q[0], v[0], w)
+                orc.set_profile_force(slot, w[None, :])
+            h = min(5e-3 * (k + 1), (np.floor(t / 2e-3 + 1e-9) + 1.0) * 2e-3) - t
+            assert not orc.step(h).any()
+            t += h
+        _, q, v, a = orc.get_state()
+        np.testing.assert_allclose([engine.robot_states[0].q[0], engine.robot_states[0].v[0]], [q[0, 0], v[0, 0]], rtol=0, atol=1e-10)
+    assert abs(engine.robot_states[0].v[0] + 0.5) > 1e-2 and len(calls) > 40
+    engine.stop()
+    engine.remove_all_forces()
+    assert engine._profile_forces == []
+
+
 def test_engine_facade_telemetry_log(api, tmp_path):
     """`Engine.log_data` / `Engine.write_log` (binary format of the reference): one line at start and per step."""
     from jiminy_b200.core import Engine, BadControlFlow
