@@ -340,7 +340,8 @@ __device__ __forceinline__ void env_step_body() {
             Ctx c0 = c; c0.flags = CTX_ZERO_U | CTX_IGNORE_BOUNDS;
             rhs(c0, false, &status);
             const bool constrained = __any_sync(c.gmask, SMF(c, KP->cons_off) != 0.0);
-            for (int it = 1; it < (constrained ? 4 : 2); ++it) rhs(c, true, &status);
+            Ctx c1 = c; c1.flags = CTX_START_FEEDBACK;
+            for (int it = 1; it < (constrained ? 4 : 2); ++it) rhs(c1, true, &status);
         } else rhs(c, false, &status);
         // forceMax > 1e5 guard (engine.cc:1310-1346)
         double fmax2 = 0.0;

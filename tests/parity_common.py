@@ -181,6 +181,34 @@ def bounds_scenario(api, data_dir, model="spring_damper", n_steps=60):
     return eng, orc
 
 
+def start_on_bounds_scenario(api, data_dir):
+    """`Engine::start` with joint-bound constraints enabled (constraint contact model: every bound starts enabled): the
+    INIT_ITERATIONS loop rebuilds u from a uInternal that carries the multipliers of the previous iteration
+    (engine.cc:1452-1461, :3770-3788), so the initial acceleration of a joint resting on its bound is the fixed point of
+    that feedback, not the plain regularised solve."""
+    import os
+    from jiminy_b200 import model as M
+    r = M.build_robot_table(os.path.join(data_dir, "simple_pendulum.urdf"), False)
+    M.attach_motor(r, "PendulumJoint", "PendulumJoint", enableVelocityLimit=False, enableEffortLimit=False)
+    r.q_upper[0], r.q_lower[0] = 0.5, -0.5
+    opt = _cons_opt(odeSolver="runge_kutta_4", dtMax=1e-3, controllerUpdatePeriod=1e-3, sensorsUpdatePeriod=1e-3)
+    opt["contacts"]["model"] = "constraint"
+    eng, orc = BatchedEngine(r, opt, 4, api_=api), OracleBatch(r, opt, 4)
+    q0, v0 = np.array([[0.5], [-0.5], [0.3], [0.5]]), np.array([[0.0], [0.0], [0.0], [-1.0]])
+    for x in (eng, orc):
+        x.set_command(np.zeros((4, 1)))
+    eng.start(q0, v0)
+    assert not orc.start(q0, v0).any()
+    a1, a0 = eng.get_state()[3], orc.get_state()[3]
+    np.testing.assert_allclose(a1, a0, rtol=1e-12, atol=1e-13)
+    assert abs(a0[1, 0]) < 1e-4 and abs(a0[2, 0]) > 1.0          # held on its lower bound / free inside the bounds
+    for _ in range(5):
+        eng.step(0.002)
+        assert not orc.step(0.002).any()
+        compare(eng, orc, 1e-11, 1e-9)
+    return eng, orc
+
+
 def point_mass_constraint_scenario(api, data_dir, n_steps=40, torsion=0.0, solver="runge_kutta_4", impulse=False):
     """A free-flying mass on the ground with the constraint contact model: resting, sliding (Coulomb cone) and
     spinning envs; contact / force sensors and f_external included in the comparison."""
@@ -322,6 +350,76 @@ def atlas_bounds_and_contacts_scenario(api, n_env=2, n_steps=6, tol_state=1e-8, 
         hit = hit or bool((eng.get_status() & 8).any())
     assert hit and not (eng.get_status() & ~8).any()
     return eng, orc
+
+
+def atlas_reference_neutral(robot):
+    """`AtlasJiminyEnv._neutral` (atlas.py:147-166) clipped to the joint limits as `_sample_state` does
+    (generic.py:1300-1335; two shoulder angles exceed the rounded URDF limits by 2e-7), base lifted so that the feet
+    touch the ground, zero velocity.  The knees and the shoulders sit exactly on position bounds."""
+    import json
+    import os
+    from jiminy_b200 import robots as R
+    with open(os.path.join(os.path.dirname(os.path.abspath(R.__file__)), "robots", "atlas.json")) as fh:
+        q = np.array(json.load(fh)["meta"]["neutral"])
+    q[7:] = np.clip(q[7:], robot.q_lower[7:], robot.q_upper[7:])
+    return R.ground_base_height(robot, q)
+
+
+ATLAS_PIPELINE = dict(joint_velocity_limit=4.0, joint_acceleration_limit=30.0, order=1, mahony=(0.75, 0.057),
+                      safety=dict(kp=50.0, kd=0.15, soft_position_margin=0.0, soft_velocity_max=4.0))    # atlas.py:28-37, :239-295
+
+
+def atlas_pd_standing_on_oracle(t_end=9.0):
+    """The reference's acceptance test of the PD pipeline (gym_jiminy/unit_py/test_pipeline_control.py:46-113):
+    `AtlasPDControlJiminyEnv` in evaluation mode, zero target motor velocities for 9 s.  Returns per env-step the
+    largest |target velocity| and the largest |generalised velocity|, and the oracle."""
+    from jiminy_b200.blocks import pd_adapter
+    sc = scenarios.make("atlas", 1, seed=0, contact_model="constraint", solver="euler_explicit", dt_max=0.005)
+    rob, nm = sc.robot, sc.robot.nmotors
+    iq = np.array([rob.idx_q[m.joint] for m in rob.motors])
+    v_hw = np.array([m.velocity_limit for m in rob.motors])
+    vel = np.minimum(v_hw, ATLAS_PIPELINE["joint_velocity_limit"])
+    acc = np.full(nm, ATLAS_PIPELINE["joint_acceleration_limit"])
+    lower, upper = np.stack([rob.q_lower[iq], -vel, -acc]), np.stack([rob.q_upper[iq], vel, acc])
+    sf = ATLAS_PIPELINE["safety"]
+    table = np.stack([np.full(nm, sf["kp"]), np.full(nm, sf["kd"]), rob.q_lower[iq], rob.q_upper[iq], np.minimum(v_hw, sf["soft_velocity_max"])])
+    orc = OracleBatch(rob, sc.options, 1)
+    orc.set_pd_controller_full(sc.kp, sc.kd, lower, upper, table)
+    orc.set_mahony_filter(*ATLAS_PIPELINE["mahony"])
+    orc.set_command(np.zeros((1, nm)))
+    q0 = atlas_reference_neutral(rob)[None, :]
+    assert not orc.start(q0, np.zeros((1, rob.nv))).any()
+    action, deadband = np.zeros((1, nm)), np.zeros(nm)       # evaluation mode: dead band enabled, 0 wide
+    v_target, v_robot = [], []
+    for _ in range(int(round(t_end / sc.step_dt))):
+        st, out = orc.get_pd_controller_state(), np.zeros((1, nm))
+        pd_adapter(action.copy(), 1, st, lower, upper, False, deadband, sc.step_dt, out)
+        orc.set_command(out)
+        assert not orc.step(sc.step_dt).any()
+        v_target.append(np.abs(orc.get_pd_controller_state()[0, 1]).max())
+        v_robot.append(np.abs(orc.get_state()[2]).max())
+    return np.array(v_target), np.array(v_robot), orc, sc
+
+
+def atlas_pd_standing_on_device(api, t_end, tol_state=1e-8):
+    """Same run through `PDControlBatchedEnv` (evaluation mode) on the device path; compared with the oracle at the end."""
+    from jiminy_b200.envs import PDControlBatchedEnv
+    v_target, v_robot, orc, sc = atlas_pd_standing_on_oracle(t_end)
+    sc.q0, sc.v0 = atlas_reference_neutral(sc.robot)[None, :], np.zeros((1, sc.robot.nv))
+    env = PDControlBatchedEnv(sc, training=False, api_=api, **ATLAS_PIPELINE)
+    env.reset()
+    v_dev = []
+    for _ in range(len(v_robot)):
+        obs, reward, terminated, truncated, info = env.step(np.zeros((1, sc.robot.nmotors)))
+        assert not terminated.any() and not truncated.any()
+        v_dev.append(np.abs(obs["states"]["agent"]["v"]).max())
+    (_, q1, v1, _), (_, q0, v0, _) = env.engine.get_state(), orc.get_state()
+    np.testing.assert_allclose(q1, q0, rtol=0, atol=tol_state)
+    np.testing.assert_allclose(v1, v0, rtol=0, atol=10 * tol_state)
+    np.testing.assert_allclose(env.engine.get_pd_controller_state(), orc.get_pd_controller_state(), rtol=0, atol=tol_state)
+    assert (env.engine.get_status() & 8).all()          # bound constraints were active (knees / shoulders on their bounds)
+    env.close()
+    return np.array(v_dev), v_robot, sc
 
 
 def pd_adapter_scenario(api, name="anymal", n_env=3, n_steps=3, order=0, instantaneous=False):

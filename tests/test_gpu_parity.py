@@ -149,6 +149,10 @@ def test_joint_bounds_constraint_path(model):
     pc.bounds_scenario(None, DATA, model)
 
 
+def test_start_on_joint_bounds():
+    pc.start_on_bounds_scenario(None, DATA)
+
+
 def test_constraint_contact_matches_oracle():
     """contacts.model = "constraint" (boxed PGS): point mass (rest / slide / spin, torsion), 40 ANYmal envs,
     Atlas (78 constraint rows at most)."""
@@ -174,6 +178,14 @@ def test_constraint_solver_variants(monkeypatch, robot, toggle):
 @pytest.mark.parametrize("robot", ["atlas", "anymal"])
 def test_masked_restart_with_constraint_contacts(robot):
     pc.masked_restart_constraint_scenario(None, robot, n_env=21, tol_state=1e-7, tol_sens=1e-5)
+
+
+def test_atlas_pd_standing_like_the_reference_test():
+    """gym_jiminy/unit_py/test_pipeline_control.py:46-113 on the device: 9 s of zero target velocities, then every
+    generalised velocity of the last second below 1e-3 (and the final state equal to the oracle's)."""
+    v_dev, v_orc, sc = pc.atlas_pd_standing_on_device(None, 9.0, tol_state=1e-6)
+    last = int(round(1.0 / sc.step_dt))
+    assert np.all(v_dev[-last:] < 1.0e-3), v_dev[-last:].max()
 
 
 def test_atlas_bounds_and_contacts_together():

@@ -445,6 +445,10 @@ def test_joint_bounds_constraint_path(api, model):
     pc.bounds_scenario(api, DATA, model)
 
 
+def test_start_on_joint_bounds(api):
+    pc.start_on_bounds_scenario(api, DATA)
+
+
 def test_constraint_contact_point_mass(api):
     pc.point_mass_constraint_scenario(api, DATA)
     pc.point_mass_constraint_scenario(api, DATA, n_steps=15, torsion=0.05)
@@ -552,6 +556,12 @@ def test_gpu_like_rounding_stays_within_the_gpu_tolerances():
     pc.atlas_bounds_and_contacts_scenario(api_fma, n_env=4, n_steps=6, tol_state=1e-10, tol_sens=1e-8)
     pc.robot_constraint_scenario("anymal", 8, 2, api_fma, seed=2, tol_state=1e-10, tol_sens=1e-8)
     pc.pd_adapter_scenario(api_fma, n_env=8, n_steps=3, order=0)
+
+
+def test_atlas_pd_standing_first_steps(api):
+    """The reference's Atlas PD-standing test (tests/test_oracle_analytic.py, 9 s on the oracle): its first 0.4 s on the
+    device path against the oracle -- neutral posture with knees and shoulders on their bounds, full block pipeline."""
+    pc.atlas_pd_standing_on_device(api, 0.4)
 
 
 def test_atlas_bounds_and_contacts_together(api):

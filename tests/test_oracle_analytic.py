@@ -326,3 +326,18 @@ def test_joint_bound_stops_pendulum(model):
     # the bound holds the gravity torque m g l sin(q): reported in u (engine.cc:3770-3788)
     np.testing.assert_allclose(abs(u[0, 0]), 5.0 * 9.81 * np.sin(q[0, 0]), rtol=2e-3)
     assert o.get_status()[0] & 8
+
+
+def test_atlas_pd_pipeline_stands_still_like_the_reference_test():
+    """gym_jiminy/unit_py/test_pipeline_control.py:46-113 (`test_pid_standing`, Atlas): after 9 s of zero target motor
+    velocities the velocity targets of the last second are below 1e-9 and every generalised velocity below 1e-3.
+    Restated on the oracle with the reference's neutral posture, option file and block arguments: constraint contacts,
+    knees and shoulders on their position bounds, safety limits, PD controller, adapter and Mahony filter together."""
+    import parity_common as pc
+    v_target, v_robot, orc, sc = pc.atlas_pd_standing_on_oracle()
+    last = int(round(1.0 / sc.step_dt))
+    assert np.all(v_target[-last:] < 1.0e-9)
+    assert np.all(v_robot[-last:] < 1.0e-3), v_robot[-last:].max()
+    assert v_robot[:5].max() > 0.05                                   # it did settle from somewhere
+    q = orc.get_state()[1][0]
+    assert abs(q[2] - pc.atlas_reference_neutral(sc.robot)[2]) < 5e-3 and (orc.get_status() & ~8 == 0).all()
