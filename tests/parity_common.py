@@ -422,6 +422,32 @@ def atlas_pd_standing_on_device(api, t_end, tol_state=1e-8):
     return np.array(v_dev), v_robot, sc
 
 
+def atlas_repeatability_scenario(api, steps=(0, 5, 20, 10, 0), n_env=2):
+    """gym_jiminy/unit_py/test_pipeline_control.py:315-330 (`test_repeatability`): restarting from the same state after
+    any number of steps must give exactly the same initial acceleration -- nothing of the previous episode (constraint
+    multipliers and enabled set, controller targets, filter state, solver workspace) may survive `start`."""
+    from jiminy_b200.envs import PDControlBatchedEnv
+    sc = scenarios.make("atlas", n_env, seed=0, contact_model="constraint", solver="euler_explicit", dt_max=0.005)
+    sc.q0 = np.tile(atlas_reference_neutral(sc.robot), (n_env, 1))
+    sc.q0[1:, 7:] = np.clip(sc.q0[1:, 7:] + 0.01, sc.robot.q_lower[7:], sc.robot.q_upper[7:])    # a second, different env
+    sc.v0 = np.zeros((n_env, sc.robot.nv))
+    env = PDControlBatchedEnv(sc, training=False, api_=api, **ATLAS_PIPELINE)
+    a_prev = None
+    for n in steps:
+        env.engine.set_command(np.zeros((n_env, sc.robot.nmotors)))
+        env.engine.start(sc.q0, sc.v0)
+        a = env.engine.get_state()[3].copy()
+        s = env.engine.get_sensors().copy()
+        if a_prev is None:
+            a_prev, s_prev = a, s
+        np.testing.assert_array_equal(a, a_prev)
+        np.testing.assert_array_equal(s, s_prev)
+        env._started = True
+        for _ in range(n):
+            env.step(np.zeros((n_env, sc.robot.nmotors)))
+    env.close()
+
+
 def pd_adapter_scenario(api, name="anymal", n_env=3, n_steps=3, order=0, instantaneous=False):
     """`PDAdapter` -> `PDController` pipeline (the `*-pid` envs of gym_jiminy): the host-side adapter of
     jiminy_b200/blocks.py drives the device block through the command-state getter / setter; the same adapter function

@@ -188,6 +188,10 @@ def test_atlas_pd_standing_like_the_reference_test():
     assert np.all(v_dev[-last:] < 1.0e-3), v_dev[-last:].max()
 
 
+def test_restart_is_exactly_repeatable():
+    pc.atlas_repeatability_scenario(None, n_env=9)
+
+
 def test_atlas_bounds_and_contacts_together():
     pc.atlas_bounds_and_contacts_scenario(None, n_env=16, n_steps=8, tol_state=1e-7, tol_sens=1e-5)
 

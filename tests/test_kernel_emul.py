@@ -564,6 +564,10 @@ def test_atlas_pd_standing_first_steps(api):
     pc.atlas_pd_standing_on_device(api, 0.4)
 
 
+def test_restart_is_exactly_repeatable(api):
+    pc.atlas_repeatability_scenario(api, steps=(0, 3, 5, 2, 0))
+
+
 def test_atlas_bounds_and_contacts_together(api):
     pc.atlas_bounds_and_contacts_scenario(api)
 
