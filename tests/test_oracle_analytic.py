@@ -341,3 +341,48 @@ def test_atlas_pd_pipeline_stands_still_like_the_reference_test():
     assert v_robot[:5].max() > 0.05                                   # it did settle from somewhere
     q = orc.get_state()[1][0]
     assert abs(q[2] - pc.atlas_reference_neutral(sc.robot)[2]) < 5e-3 and (orc.get_status() & ~8 == 0).all()
+
+
+def test_pd_controller_targets_like_the_reference_test():
+    """gym_jiminy/unit_py/test_pipeline_control.py:258-313 (`test_pd_controller`): Atlas PD pipeline with the acceleration
+    limits lifted and random target velocities for 2 s.  The logged targets of the last motor must satisfy: the target
+    velocity reaches the commanded one at the end of every adapter period; finite differences of target position /
+    velocity reproduce the logged velocity / acceleration (shifted by one controller period, as the reference checks
+    them); position and velocity targets stay within the motor limits."""
+    import parity_common as pc
+    from jiminy_b200 import scenarios
+    from jiminy_b200.blocks import pd_adapter
+    from oracle.oracle import OracleBatch
+    sc = scenarios.make("atlas", 1, seed=0, contact_model="constraint", solver="euler_explicit", dt_max=0.005)
+    rob, nm = sc.robot, sc.robot.nmotors
+    iq = np.array([rob.idx_q[m.joint] for m in rob.motors])
+    v_hw = np.array([m.velocity_limit for m in rob.motors])
+    vel = np.minimum(v_hw, pc.ATLAS_PIPELINE["joint_velocity_limit"])
+    lower = np.stack([rob.q_lower[iq], -vel, np.full(nm, -1e300)])        # controller._command_state_lower[2] = -inf
+    upper = np.stack([rob.q_upper[iq], vel, np.full(nm, 1e300)])
+    sf = pc.ATLAS_PIPELINE["safety"]
+    table = np.stack([np.full(nm, sf["kp"]), np.full(nm, sf["kd"]), rob.q_lower[iq], rob.q_upper[iq], np.minimum(v_hw, sf["soft_velocity_max"])])
+    orc = OracleBatch(rob, sc.options, 1)
+    orc.set_pd_controller_full(sc.kp, sc.kd, lower, upper, table)
+    orc.set_command(np.zeros((1, nm)))
+    assert not orc.start(pc.atlas_reference_neutral(rob)[None, :], np.zeros((1, rob.nv))).any()
+    rng = np.random.default_rng(0)
+    control_dt = sc.options["stepper"]["controllerUpdatePeriod"]
+    update_ratio = int(round(sc.step_dt / control_dt))
+    pos, velo, acc, cmd = [], [], [], []
+    for _ in range(int(round(2.0 / sc.step_dt))):
+        action = 0.2 * rng.uniform(lower[1], upper[1])[None, :]             # 0.2 * action_space.sample()
+        state, out = orc.get_pd_controller_state(), np.zeros((1, nm))
+        pd_adapter(action.copy(), 1, state, lower, upper, False, np.zeros(nm), sc.step_dt, out)
+        orc.set_command(out)
+        for _ in range(update_ratio):
+            assert not orc.step(control_dt).any()
+            s = orc.get_pd_controller_state()[0]
+            pos.append(s[0, -1]); velo.append(s[1, -1]); acc.append(s[2, -1]); cmd.append(action[0, -1])
+    pos, velo, acc, cmd = map(np.array, (pos, velo, acc, cmd))
+    TOLERANCE = 1.0e-6                                                       # the reference's
+    np.testing.assert_allclose(velo[update_ratio - 1::update_ratio], cmd[update_ratio - 1::update_ratio], atol=TOLERANCE)
+    np.testing.assert_allclose((np.diff(velo) / control_dt)[:-1], acc[1:-1], atol=TOLERANCE)
+    np.testing.assert_allclose((np.diff(pos) / control_dt)[:-1], velo[1:-1], atol=TOLERANCE)
+    assert np.all((rob.q_lower[iq][-1] <= pos) & (pos <= rob.q_upper[iq][-1])) and np.all(np.abs(velo) <= v_hw[-1])
+    assert np.abs(velo).max() > 0.05
