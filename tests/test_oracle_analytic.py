@@ -386,3 +386,54 @@ def test_pd_controller_targets_like_the_reference_test():
     np.testing.assert_allclose((np.diff(pos) / control_dt)[:-1], velo[1:-1], atol=TOLERANCE)
     assert np.all((rob.q_lower[iq][-1] <= pos) & (pos <= rob.q_upper[iq][-1])) and np.all(np.abs(velo) <= v_hw[-1])
     assert np.abs(velo).max() > 0.05
+
+
+def test_mahony_filter_tracks_the_imu_like_the_reference_test():
+    """gym_jiminy/unit_py/test_pipeline_control.py:135-190 (`test_mahony_filter_plus_body_observer`, the variant where
+    the twist is measured): Atlas PD pipeline with a Mahony filter at kp = ki = 0 and exact initialisation; a constant
+    action swings the upper body (back joints at 0.4 / 0.08 / 0.08 rad/s, sign flipped every 50 steps) for 200 steps;
+    the roll-pitch-yaw of the estimated IMU orientation must stay within 5e-3 rad of the true orientation of the IMU
+    frame (the reference's tolerance; the gyro integration at 5 ms leaves 4.9e-3 here)."""
+    import parity_common as pc
+    from jiminy_b200 import scenarios, robots as R
+    from jiminy_b200.blocks import pd_adapter
+    from oracle.oracle import OracleBatch
+    sc = scenarios.make("atlas", 1, seed=0, contact_model="constraint", solver="euler_explicit", dt_max=0.005)
+    rob, nm = sc.robot, sc.robot.nmotors
+    iq = np.array([rob.idx_q[m.joint] for m in rob.motors])
+    v_hw = np.array([m.velocity_limit for m in rob.motors])
+    vel = np.minimum(v_hw, pc.ATLAS_PIPELINE["joint_velocity_limit"])
+    acc = np.full(nm, pc.ATLAS_PIPELINE["joint_acceleration_limit"])
+    lower, upper = np.stack([rob.q_lower[iq], -vel, -acc]), np.stack([rob.q_upper[iq], vel, acc])
+    sf = pc.ATLAS_PIPELINE["safety"]
+    table = np.stack([np.full(nm, sf["kp"]), np.full(nm, sf["kd"]), rob.q_lower[iq], rob.q_upper[iq], np.minimum(v_hw, sf["soft_velocity_max"])])
+    orc = OracleBatch(rob, sc.options, 1)
+    orc.set_pd_controller_full(sc.kp, sc.kd, lower, upper, table)
+    orc.set_mahony_filter(0.0, 0.0)
+    orc.set_command(np.zeros((1, nm)))
+    assert not orc.start(pc.atlas_reference_neutral(rob)[None, :], np.zeros((1, rob.nv))).any()
+    names = [m.name for m in rob.motors]
+    action = np.zeros((1, nm))
+    for name, value in (("back_bkz", 0.4), ("back_bky", 0.08), ("back_bkx", 0.08)):
+        action[0, names.index(name)] = value
+
+    def quat_to_matrix(q):
+        x, y, z, w = q
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                         [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                         [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+    def matrix_to_rpy(m):
+        return np.array([np.arctan2(m[2, 1], m[2, 2]), -np.arcsin(m[2, 0]), np.arctan2(m[1, 0], m[0, 0])])
+    frame, swing = rob.imu_frames[0], 0.0
+    for i in range(200):
+        a = action * (1 - 2 * ((i // 50) % 2))
+        state, out = orc.get_pd_controller_state(), np.zeros((1, nm))
+        pd_adapter(a.copy(), 1, state, lower, upper, False, None, sc.step_dt, out)
+        orc.set_command(out)
+        assert not orc.step(sc.step_dt).any()
+        rpy_true = matrix_to_rpy(R.frame_placements(rob, orc.get_state()[1][0], [frame])[frame].R)
+        rpy_est = matrix_to_rpy(quat_to_matrix(orc.get_mahony_filter()[0, 0, :4]))
+        np.testing.assert_allclose(rpy_true, rpy_est, atol=5e-3)
+        swing = max(swing, np.abs(rpy_true).max())
+    assert swing > 0.3
