@@ -553,9 +553,9 @@ def test_gpu_like_rounding_stays_within_the_gpu_tolerances():
     if not host_has_fma():
         pytest.skip("host CPU without FMA")
     api_fma = emul_api(fma=True)
-    pc.atlas_bounds_and_contacts_scenario(api_fma, n_env=4, n_steps=6, tol_state=1e-10, tol_sens=1e-8)
-    pc.robot_constraint_scenario("anymal", 8, 2, api_fma, seed=2, tol_state=1e-10, tol_sens=1e-8)
-    pc.pd_adapter_scenario(api_fma, n_env=8, n_steps=3, order=0)
+    pc.atlas_bounds_and_contacts_scenario(api_fma, n_env=2, n_steps=4, tol_state=1e-10, tol_sens=1e-8)
+    pc.robot_constraint_scenario("anymal", 4, 1, api_fma, seed=2, tol_state=1e-10, tol_sens=1e-8)
+    pc.pd_adapter_scenario(api_fma, n_env=4, n_steps=2, order=0)
 
 
 def test_atlas_pd_standing_first_steps(api):
@@ -565,7 +565,7 @@ def test_atlas_pd_standing_first_steps(api):
 
 
 def test_restart_is_exactly_repeatable(api):
-    pc.atlas_repeatability_scenario(api, steps=(0, 3, 5, 2, 0))
+    pc.atlas_repeatability_scenario(api, steps=(0, 2, 4, 0))
 
 
 def test_atlas_bounds_and_contacts_together(api):
