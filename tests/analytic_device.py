@@ -37,6 +37,40 @@ def armature_spring(api=None):
         np.testing.assert_allclose(np.c_[qs[:, e], vs[:, e]], xa, rtol=1e-5, atol=1e-7)
 
 
+def velocity_bounds_criteria(ts, vel, acc, motor, tau=50.0, inertia=5.0, v_max=15.0, slope=0.5, tol=1e-7):
+    """The assertions of test_simple_pendulum.py:143-211 (`test_velocity_bounds`): a constant command against
+    SimpleMotor's velocity-dependent effort limit (basic_motors.cc:98-128)."""
+    assert np.all(np.abs(vel) < v_max)                          # never beyond the limit ...
+    assert v_max - abs(vel[-1]) < 1e-6 and abs(acc[-1]) < tol   # ... which is reached, where the acceleration vanishes
+    acc_thr = tau / inertia
+    start = next(i for i, a in enumerate(acc) if a < acc_thr)
+    end = next(i for i, a in enumerate(acc) if a < 0.1)
+    rate = np.diff(np.log(acc[start:end] / acc_thr)) / np.diff(ts[start:end])
+    assert end - start > 5 and np.all(np.abs(rate - rate.mean()) < 1e-5)      # exponential decay of the acceleration
+    v_th_max = max(motor.velocity_limit - slope * motor.effort_limit, 0.0)
+    v_th = motor.velocity_limit - (tau / motor.effort_limit) * (motor.velocity_limit - v_th_max)
+    assert vel[start - 1] < v_th < vel[start]                   # the taper starts where expected
+
+
+def velocity_bounds_robot():
+    r = M.build_robot_table(os.path.join(DATA, "simple_pendulum.urdf"), False)
+    M.attach_motor(r, "PendulumJoint", "PendulumJoint", enableEffortLimit=True, enableVelocityLimit=True,
+                   velocityEffortInvSlope=0.5, velocityLimitFromUrdf=False, velocityLimit=15.0)
+    r.q_lower[:], r.q_upper[:] = -1000.0, 1000.0
+    opt = _opt(odeSolver="runge_kutta_dopri", tolAbs=1e-12, tolRel=1e-12)
+    opt["world"]["gravity"] = [0.0] * 6
+    return r, opt
+
+
+def velocity_bounds(api=None):
+    r, opt = velocity_bounds_robot()
+    eng = BatchedEngine(r, opt, 2, api_=api)
+    eng.set_command(np.array([[50.0], [0.0]]))
+    ts, qs, vs, as_ = eng.simulate(4.0, np.zeros((2, 1)), np.zeros((2, 1)))
+    velocity_bounds_criteria(ts[:, 0], vs[:, 0, 0], as_[:, 0, 0], r.motors[0])
+    assert np.abs(vs[:, 1]).max() == 0.0                        # env 1: no command, nothing moves
+
+
 def two_masses(api=None, period=1e-3, t_end=1.0):
     """test_double_spring_mass.py:85-130 (prismatic chain, discrete periods, adaptive DOPRI)."""
     r = M.build_robot_table(os.path.join(DATA, "linear_two_masses.urdf"), False)

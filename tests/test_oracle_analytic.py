@@ -7,6 +7,8 @@ hand-written fixtures:
   5. unit_py/test_simple_mass.py:113-176, :248-344 .... spring-damper contact equilibrium, friction steady state
   6. unit_py/test_simple_mass.py:183-246 .............. contact / force sensor == external force in frame
   7. unit_py/test_simulator.py:26-109 ................. Euler finite difference of v equals a; IMU reads g at rest
+  8. unit_py/test_simple_pendulum.py:143-211 .......... SimpleMotor velocity-dependent effort limit
+  9. gym_jiminy/unit_py/test_pipeline_control.py ...... PD pipeline: Atlas stands still, target consistency, Mahony filter
 The reference binary itself cannot run here, so these analytical pins are what anchors the oracle.
 """
 import os
@@ -437,3 +439,15 @@ def test_mahony_filter_tracks_the_imu_like_the_reference_test():
         np.testing.assert_allclose(rpy_true, rpy_est, atol=5e-3)
         swing = max(swing, np.abs(rpy_true).max())
     assert swing > 0.3
+
+
+def test_motor_velocity_bounds_like_the_reference_test():
+    """unit_py/test_simple_pendulum.py:143-211 (`test_velocity_bounds`): constant command against the velocity-dependent
+    effort limit of `SimpleMotor` -- the velocity saturates at the limit, the acceleration decays exponentially from the
+    velocity where the taper starts."""
+    import analytic_device as ad
+    r, opt = ad.velocity_bounds_robot()
+    o = OracleBatch(r, opt)
+    o.set_command(np.array([[50.0]]))
+    ts, qs, vs, as_ = o.simulate(4.0, [0.0], [0.0])
+    ad.velocity_bounds_criteria(np.asarray(ts).reshape(len(ts), -1)[:, 0], vs[:, 0], as_[:, 0], r.motors[0])
