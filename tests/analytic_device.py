@@ -71,6 +71,57 @@ def velocity_bounds(api=None):
     assert np.abs(vs[:, 1]).max() == 0.0                        # env 1: no command, nothing moves
 
 
+def foot_pendulum_robot():
+    """The robot of unit_py/test_foot_pendulum.py (hand-written fixture tests/data/foot_pendulum.urdf): contact points
+    at the vertices of the foot's collision box, sensors as in its hardware file."""
+    r = M.build_robot_table(os.path.join(DATA, "foot_pendulum.urdf"), True)
+    box = r.links["Foot"].collision_boxes[0]
+    names = []
+    for i, xyz in enumerate(np.stack(np.meshgrid(*[0.5 * v * np.array([-1.0, 1.0]) for v in box.size], indexing="ij"), -1).reshape(-1, 3)):
+        names.append(f"Foot_CollisionBox_0_{i}")
+        r.add_frame(names[-1], "Foot", M.SE3(np.eye(3), xyz))
+    r.add_contact_points(names)
+    M.attach_motor(r, "PendulumJoint", "PendulumJoint")
+    M.attach_sensor(r, "ImuSensor", "Foot", frame_name="Foot")
+    M.attach_sensor(r, "ForceSensor", "Foot", frame_name="Foot")
+    for i in (0, 2, 4, 6):
+        M.attach_sensor(r, "ContactSensor", names[i], frame_name=names[i])
+    opt = M.default_engine_options()
+    opt["stepper"].update(odeSolver="runge_kutta_4", dtMax=1e-5, sensorsUpdatePeriod=0.0, controllerUpdatePeriod=1e-3)
+    opt["contacts"].update(model="constraint", stabilizationFreq=0.0)
+    opt["constraints"]["regularization"] = 1e-9
+    return r, opt
+
+
+def foot_pendulum_criteria(engine, r, t_end=1.0, tol=1.0e-5):
+    """test_foot_pendulum.py:25-107 (`test_init_and_consistency`, its TOLERANCE = 1e-5): started exactly on its unstable
+    equilibrium the pendulum does not move; no discontinuity at initialisation; IMU, force and contact sensors read the
+    static values.  `engine`: an oracle or a BatchedEngine with one env."""
+    q0 = np.array([[0.0, 0.0, 0.005, 0.0, 0.0, 0.0, 1.0, 0.0]])
+    engine.set_command(np.zeros((1, 1)))
+    rc = engine.start(q0, np.zeros((1, r.nv)))
+    assert rc is None or not np.any(rc)
+    a = engine.get_state()[3]
+    assert np.all(np.abs(a) < tol)
+    s, lay = engine.get_sensors()[0], r.sensor_layout()
+    imu, force, contact = (s[lay[k][0]:lay[k][0] + lay[k][1] * lay[k][2]] for k in ("ImuSensor", "ForceSensor", "ContactSensor"))
+    mass = float(r.inertia[1:, 0].sum())
+    assert np.allclose(imu[:3], 0.0, atol=tol) and np.allclose(imu[3:], [0.0, 0.0, 9.81], atol=tol)
+    assert np.allclose(force, [0.0, 0.0, 9.81 * mass, 0.0, 0.0, 0.0], atol=tol)
+    c = contact.reshape(3, 4)                                       # field-major: FX, FY, FZ of the four sensors
+    for i in range(3):
+        assert np.allclose(c[:, i], c[:, i + 1], atol=tol)
+    assert abs(c[2].sum() - 9.81 * mass) < 1e-3                     # the four bottom vertices carry the weight
+    engine.step(t_end)
+    _, q, v, a = engine.get_state()
+    assert np.all(np.abs(v) < tol) and np.all(np.abs(a) < tol)
+
+
+def foot_pendulum(api=None, t_end=1.0):
+    r, opt = foot_pendulum_robot()
+    foot_pendulum_criteria(BatchedEngine(r, opt, 1, api_=api), r, t_end)
+
+
 def two_masses(api=None, period=1e-3, t_end=1.0):
     """test_double_spring_mass.py:85-130 (prismatic chain, discrete periods, adaptive DOPRI)."""
     r = M.build_robot_table(os.path.join(DATA, "linear_two_masses.urdf"), False)

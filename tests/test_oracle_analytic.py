@@ -8,7 +8,8 @@ hand-written fixtures:
   6. unit_py/test_simple_mass.py:183-246 .............. contact / force sensor == external force in frame
   7. unit_py/test_simulator.py:26-109 ................. Euler finite difference of v equals a; IMU reads g at rest
   8. unit_py/test_simple_pendulum.py:143-211 .......... SimpleMotor velocity-dependent effort limit
-  9. gym_jiminy/unit_py/test_pipeline_control.py ...... PD pipeline: Atlas stands still, target consistency, Mahony filter
+  9. unit_py/test_foot_pendulum.py:25-107 ............. redundant contact constraints at an unstable equilibrium
+ 10. gym_jiminy/unit_py/test_pipeline_control.py ...... PD pipeline: Atlas stands still, target consistency, Mahony filter
 The reference binary itself cannot run here, so these analytical pins are what anchors the oracle.
 """
 import os
@@ -451,3 +452,11 @@ def test_motor_velocity_bounds_like_the_reference_test():
     o.set_command(np.array([[50.0]]))
     ts, qs, vs, as_ = o.simulate(4.0, [0.0], [0.0])
     ad.velocity_bounds_criteria(np.asarray(ts).reshape(len(ts), -1)[:, 0], vs[:, 0], as_[:, 0], r.motors[0])
+
+
+def test_foot_pendulum_holds_its_equilibrium_like_the_reference_test():
+    """unit_py/test_foot_pendulum.py:25-107: inverted pendulum on a square foot, `constraint` contacts with four redundant
+    contact points, no Baumgarte stabilisation, regularisation 1e-9."""
+    import analytic_device as ad
+    r, opt = ad.foot_pendulum_robot()
+    ad.foot_pendulum_criteria(OracleBatch(r, opt), r)
