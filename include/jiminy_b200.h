@@ -192,6 +192,15 @@ int jb_describe(JbBatch* batch, char* buf, int32_t len);
  * non-NULL, joint_lane[njoints] (-1 = trunk joint shared by all lanes).  lanes = 0: automatic. */
 int jb_plan_describe(const JbModelDesc* model, int32_t lanes, char* buf, int32_t len, int32_t* joint_lane);
 
+/* Replaces: the constraint objects of `robot.constraints` read back by user code and tests -- `bounds_joints[...]`
+ * and `contact_frames[...]`, their `is_enabled` and `lambda_c` (python/jiminy_pywrap/src/constraints.cc;
+ * AbstractConstraintBase::getIsEnabled / lambda_, core/include/jiminy/core/constraints/abstract_constraint.h).
+ * joint_enabled [n_env][njoints] and joint_lambda [n_env][njoints] are indexed by joint (0 for joints without a bound
+ * constraint), contact_enabled [n_env][ncontacts], contact_lambda [n_env][ncontacts][4] (x, y, z, torsion) by contact
+ * frame.  Any pointer may be NULL.  State after the last dynamics evaluation of each env. */
+int jb_get_constraints(JbBatch* batch, uint8_t* joint_enabled, double* joint_lambda, uint8_t* contact_enabled,
+                       double* contact_lambda);
+
 /* Replaces: Engine::start(q, v) (engine.cc:952-1533) for every env with mask[i] != 0 (NULL mask =
  * all).  q0 is [n_env][nq], v0 is [n_env][nv] (rows of unmasked envs are ignored).  Normalises q,
  * runs forward kinematics, the initial contact-force guard, the INIT_ITERATIONS fixed-point loop

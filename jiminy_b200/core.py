@@ -55,7 +55,7 @@ class Api:
                "jb_register_profile_force", "jb_set_profile_force", "jb_remove_all_forces",
                "jb_peer_obs_create", "jb_peer_obs_connect", "jb_peer_obs_wait", "jb_peer_obs_view",
                "jb_set_pd_controller_full", "jb_set_mahony_filter", "jb_get_mahony_filter",
-               "jb_get_pd_controller_state", "jb_set_pd_controller_state")
+               "jb_get_pd_controller_state", "jb_set_pd_controller_state", "jb_get_constraints")
 
     def __init__(self, cdll: C.CDLL):
         self.dll = L = cdll
@@ -100,6 +100,7 @@ class Api:
         L.jb_remove_all_forces.argtypes = [vp]
         L.jb_set_pd_controller_full.argtypes = [vp] + [c_double_p] * 5
         L.jb_get_pd_controller_state.argtypes = [vp, c_double_p]
+        L.jb_get_constraints.argtypes = [vp, c_uint8_p, c_double_p, c_uint8_p, c_double_p]
         L.jb_set_pd_controller_state.argtypes = [vp, c_double_p]
         L.jb_set_mahony_filter.argtypes = [vp, C.c_double, C.c_double]
         L.jb_get_mahony_filter.argtypes = [vp, c_double_p]
@@ -262,6 +263,16 @@ class BatchedEngine:
         sf = safety_table(safety, self.robot)
         self._api.check(self._api.dll.jb_set_pd_controller_full(self._h, dptr(kp), dptr(kd), dptr(lo), dptr(hi),
                                                                 None if sf is None else dptr(sf)))
+
+    def get_constraints(self):
+        """(joint_enabled [n_env, njoints], joint_lambda [n_env, njoints], contact_enabled [n_env, ncontacts],
+        contact_lambda [n_env, ncontacts, 4]): `is_enabled` / `lambda_c` of the bound and contact constraints."""
+        nc = max(len(self.robot.contact_frame_names), 1)
+        je, jl = np.zeros((self.n_env, self.nj), dtype=np.uint8), np.zeros((self.n_env, self.nj))
+        ce, cl = np.zeros((self.n_env, nc), dtype=np.uint8), np.zeros((self.n_env, nc, 4))
+        self._api.check(self._api.dll.jb_get_constraints(self._h, je.ctypes.data_as(c_uint8_p), dptr(jl), ce.ctypes.data_as(c_uint8_p), dptr(cl)))
+        n = len(self.robot.contact_frame_names)
+        return je.astype(bool), jl, ce[:, :n].astype(bool), cl[:, :n]
 
     def get_pd_controller_state(self) -> np.ndarray:
         """Target motor position / velocity / acceleration of the `PDController` block, [n_env, 3, nmotors]."""

@@ -66,6 +66,7 @@ struct JbBatch {
     size_t smem_bytes = 0;
     int base_fields = 0;           // plan fields + constraint bookkeeping, before the external-force slots
     int32_t* d_needs_full = nullptr;
+    std::vector<int32_t> jc_joint;  // joint of each joint-bound constraint (constraint path)
     // observation exchange over peer memory
     int peer_world = 0, peer_rank = 0;
     char* d_peer_buf = nullptr;                 // [2][world][n_env][width] doubles, then flags [2][world] int64
@@ -476,6 +477,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
                     kp.lb_on = 1; kp.lb_nt = nt; kp.lb_nl = nl; kp.lb_ml = ml; kp.lw_total = lw_total; kp.lb_dof0 = d_dof0; kp.lwork = d_lwk;
                 }
             }
+            b->jc_joint = jc_joint;
             kp.jmap = d_jmap; kp.cmap = d_cmap; kp.jc_joint = d_jcj; kp.jc_of_joint = d_jcof; kp.cstate = d_cst; kp.cwork = d_cwk;
         }
     }
@@ -617,6 +619,33 @@ int jb_get_mahony_filter(JbBatch* b, double* out) {
     CU(cudaSetDevice(b->device));
     CU(cudaMemcpyAsync(out, b->d_mahony, sizeof(double) * b->n_env * b->nimu * 10, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
+    return JB_OK;
+}
+
+int jb_get_constraints(JbBatch* b, uint8_t* joint_enabled, double* joint_lambda, uint8_t* contact_enabled, double* contact_lambda) {
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!b->kp.cons_on) return fail(JB_ERR_NOT_IMPLEMENTED, "no constraint state for this robot (more than 64 degrees of freedom)");
+    CU(cudaSetDevice(b->device));
+    const size_t cs = b->kp.cs_total, n = b->n_env;
+    std::vector<double> h(cs * n);
+    CU(cudaMemcpyAsync(h.data(), b->kp.cstate, sizeof(double) * cs * n, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    const int nj = b->njoints, ncc = b->kp.n_cc;
+    if (joint_enabled) std::memset(joint_enabled, 0, n * nj);
+    if (joint_lambda) std::fill(joint_lambda, joint_lambda + n * nj, 0.0);
+    for (size_t e = 0; e < n; ++e) {
+        const double* row = h.data() + e * cs;
+        for (size_t k = 0; k < b->jc_joint.size(); ++k) {
+            const double* c = row + CS_JOINT0 + CS_JOINT_SIZE * k;
+            if (joint_enabled) joint_enabled[e * nj + b->jc_joint[k]] = c[0] != 0.0;
+            if (joint_lambda) joint_lambda[e * nj + b->jc_joint[k]] = c[3];
+        }
+        for (int k = 0; k < ncc; ++k) {
+            const double* c = row + CS_JOINT0 + CS_JOINT_SIZE * b->jc_joint.size() + CS_CONTACT_SIZE * k;
+            if (contact_enabled) contact_enabled[e * ncc + k] = c[0] != 0.0;
+            if (contact_lambda) std::memcpy(contact_lambda + (e * ncc + k) * 4, c + 1, 4 * sizeof(double));
+        }
+    }
     return JB_OK;
 }
 

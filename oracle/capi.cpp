@@ -148,6 +148,23 @@ void orc_set_pd_state(OrcBatch* b, const double* in) {
     const size_t n = 3 * static_cast<size_t>(b->nmotors);
     for (size_t i = 0; i < b->envs.size(); ++i) b->envs[i]->pdf_state.assign(in + i * n, in + (i + 1) * n);
 }
+// is_enabled / lambda of the bound constraints (by joint) and of the contact constraints (by contact frame)
+void orc_get_constraints(OrcBatch* b, uint8_t* joint_enabled, double* joint_lambda, uint8_t* contact_enabled, double* contact_lambda) {
+    for (size_t e = 0; e < b->envs.size(); ++e) {
+        const auto& E = *b->envs[e];
+        const int nj = E.model.njoints, ncc = E.model.ncontacts;
+        for (int j = 0; j < nj; ++j) { if (joint_enabled) joint_enabled[e * nj + j] = 0; if (joint_lambda) joint_lambda[e * nj + j] = 0.0; }
+        for (const auto& c : E.constraints) {
+            if (c.kind == 0) {
+                if (joint_enabled) joint_enabled[e * nj + c.joint] = c.enabled;
+                if (joint_lambda) joint_lambda[e * nj + c.joint] = c.lambda[0];
+            } else {
+                if (contact_enabled) contact_enabled[e * ncc + c.contact] = c.enabled;
+                if (contact_lambda) for (int k = 0; k < 4; ++k) contact_lambda[(e * ncc + c.contact) * 4 + k] = c.lambda[k];
+            }
+        }
+    }
+}
 void orc_set_mahony(OrcBatch* b, double kp, double ki) {
     for (auto& e : b->envs) { e->mahony_enabled = kp >= 0.0; e->mahony_kp = kp; e->mahony_ki = ki; }
 }

@@ -179,6 +179,15 @@ class OracleBatch:
         sf = safety_table(safety, self.robot)
         lib().orc_set_pd_full(self._h, dptr(kp), dptr(kd), dptr(lower), dptr(upper), None if sf is None else dptr(sf))
 
+    def get_constraints(self):
+        nj, nc = self.robot.njoints, max(len(self.robot.contact_frame_names), 1)
+        je, jl = np.zeros((self.n, nj), dtype=np.uint8), np.zeros((self.n, nj))
+        ce, cl = np.zeros((self.n, nc), dtype=np.uint8), np.zeros((self.n, nc, 4))
+        lib().orc_get_constraints.argtypes = [C.c_void_p, c_uint8_p, c_double_p, c_uint8_p, c_double_p]
+        lib().orc_get_constraints(self._h, je.ctypes.data_as(c_uint8_p), dptr(jl), ce.ctypes.data_as(c_uint8_p), dptr(cl))
+        n = len(self.robot.contact_frame_names)
+        return je.astype(bool), jl, ce[:, :n].astype(bool), cl[:, :n]
+
     def get_pd_controller_state(self) -> np.ndarray:
         out = np.zeros((self.n, 3, self.nm))
         lib().orc_get_pd_state.argtypes = [C.c_void_p, c_double_p]

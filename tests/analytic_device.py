@@ -122,6 +122,48 @@ def foot_pendulum(api=None, t_end=1.0):
     foot_pendulum_criteria(BatchedEngine(r, opt, 1, api_=api), r, t_end)
 
 
+def joint_position_limits_robot():
+    r = M.build_robot_table(os.path.join(DATA, "simple_pendulum.urdf"), False)
+    M.attach_motor(r, "PendulumJoint", "PendulumJoint", enableVelocityLimit=False)
+    r.q_lower[0], r.q_upper[0] = -0.002, 0.002
+    opt = M.default_engine_options()
+    opt["stepper"].update(odeSolver="euler_explicit", dtMax=1e-5, tolAbs=1e-9, tolRel=1e-8)
+    opt["constraints"]["regularization"] = 0.0
+    opt["contacts"]["transitionEps"] = 1e-4
+    return r, opt, 0.002, 1e-4
+
+
+def joint_position_limits_criteria(engine, joint_limit, transition_eps, t_end=0.05, step_dt=1e-5):
+    """unit_py/test_dense_pole.py:160-199 (`test_joint_position_limits`): the bound constraint of a joint thrown at its
+    limits must be enabled beyond the limit, keep its state inside the transition band, be disabled farther inside --
+    and the run must visit all five cases."""
+    engine.set_command(np.zeros((1, 1)))
+    rc = engine.start(np.array([[0.0]]), np.array([[1.0]]))
+    assert rc is None or not np.any(rc)
+    branches = set()
+    is_enabled = bool(engine.get_constraints()[0][0, 1])
+    for _ in range(int(np.round(t_end / step_dt))):
+        engine.step(step_dt)
+        theta = engine.get_state()[1][0, 0]
+        now = bool(engine.get_constraints()[0][0, 1])
+        if joint_limit - abs(theta) <= 0.0:
+            assert now
+            branches.add(0 if is_enabled else 1)
+        elif joint_limit - abs(theta) < transition_eps:
+            assert now == is_enabled
+            branches.add(2 if is_enabled else 3)
+        else:
+            assert not now
+            branches.add(4)
+        is_enabled = now
+    assert branches == {0, 1, 2, 3, 4}
+
+
+def joint_position_limits(api=None):
+    r, opt, lim, eps = joint_position_limits_robot()
+    joint_position_limits_criteria(BatchedEngine(r, opt, 1, api_=api), lim, eps)
+
+
 def two_masses(api=None, period=1e-3, t_end=1.0):
     """test_double_spring_mass.py:85-130 (prismatic chain, discrete periods, adaptive DOPRI)."""
     r = M.build_robot_table(os.path.join(DATA, "linear_two_masses.urdf"), False)

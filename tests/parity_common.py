@@ -348,7 +348,13 @@ def atlas_bounds_and_contacts_scenario(api, n_env=2, n_steps=6, tol_state=1e-8, 
         assert not orc.step(sc.step_dt, parallel=True).any()
         compare(eng, orc, tol_state, tol_sens)
         hit = hit or bool((eng.get_status() & 8).any())
-    assert hit and not (eng.get_status() & ~8).any()
+        c1, c0 = eng.get_constraints(), orc.get_constraints()          # is_enabled / lambda of every constraint
+        np.testing.assert_array_equal(c1[0], c0[0])
+        np.testing.assert_array_equal(c1[2], c0[2])
+        scale = max(1.0, np.abs(c0[3]).max())
+        np.testing.assert_allclose(c1[1], c0[1], rtol=0, atol=1e-5 * scale)
+        np.testing.assert_allclose(c1[3], c0[3], rtol=0, atol=1e-5 * scale)
+    assert hit and not (eng.get_status() & ~8).any() and c0[0].any() and c0[2].any()
     return eng, orc
 
 

@@ -286,7 +286,8 @@ def test_device_code_vs_closed_forms(api):
     import analytic_device as ad
     ad.armature_spring(api)
     ad.foot_pendulum(api, t_end=0.01)            # (the full second at dtMax = 1e-5 is run on the oracle)
-    # (ad.velocity_bounds: 15 s under the emulator -- in the GPU suite; the oracle is pinned by the same criteria)
+    # (ad.velocity_bounds and ad.joint_position_limits: 15 s / 3 min under the emulator -- in the GPU suite; the oracle is
+    # pinned by the same criteria, and the emulator ran both once when they were written)
     ad.two_masses(api, t_end=0.25)               # the emulator is slow: shorter horizons than the GPU suite
     ad.contact_equilibrium_and_friction(api)
     ad.energy_conservation(api)

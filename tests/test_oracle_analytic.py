@@ -9,7 +9,8 @@ hand-written fixtures:
   7. unit_py/test_simulator.py:26-109 ................. Euler finite difference of v equals a; IMU reads g at rest
   8. unit_py/test_simple_pendulum.py:143-211 .......... SimpleMotor velocity-dependent effort limit
   9. unit_py/test_foot_pendulum.py:25-107 ............. redundant contact constraints at an unstable equilibrium
- 10. gym_jiminy/unit_py/test_pipeline_control.py ...... PD pipeline: Atlas stands still, target consistency, Mahony filter
+ 10. unit_py/test_dense_pole.py:160-199 ............... joint-bound constraint enable / disable hysteresis
+ 11. gym_jiminy/unit_py/test_pipeline_control.py ...... PD pipeline: Atlas stands still, target consistency, Mahony filter
 The reference binary itself cannot run here, so these analytical pins are what anchors the oracle.
 """
 import os
@@ -460,3 +461,11 @@ def test_foot_pendulum_holds_its_equilibrium_like_the_reference_test():
     import analytic_device as ad
     r, opt = ad.foot_pendulum_robot()
     ad.foot_pendulum_criteria(OracleBatch(r, opt), r)
+
+
+def test_joint_position_limits_like_the_reference_test():
+    """unit_py/test_dense_pole.py:160-199: enable / keep / disable logic of a joint-bound constraint (hysteresis band
+    `transitionEps`), all five cases visited."""
+    import analytic_device as ad
+    r, opt, lim, eps = ad.joint_position_limits_robot()
+    ad.joint_position_limits_criteria(OracleBatch(r, opt), lim, eps)
