@@ -133,7 +133,7 @@ def test_cuda_path_vs_closed_forms():
     import analytic_device as ad
     ad.armature_spring()
     ad.joint_position_limits()
-    ad.foot_pendulum(t_end=0.05)                 # (5000 RK4 steps of a single env: the full second is run on the oracle)
+    ad.foot_pendulum(t_end=0.02)                 # (2000 RK4 steps of a single env: the full second is run on the oracle)
     ad.velocity_bounds()
     ad.two_masses()
     ad.contact_equilibrium_and_friction()
