@@ -209,50 +209,11 @@ def run_gpu(args):
     obs_host = torch.empty((n_env, max(width, 1)), dtype=torch.float64).pin_memory()
     obs_np = obs_host.numpy()
     sens_ptr, _ = eng.device_views()
-    # multi-GPU: the only collective of the path is the end-of-step observation all-gather
-    gather_out = gather_in = None
-    use_p2p = world > 1 and not args.nccl_gather
-    obs_gather = "none (1 GPU)"
-    if world > 1:
-        gather_in = torch.empty((n_env, width), dtype=torch.float64, device=f"cuda:{local_rank}")
-        gather_out = torch.empty((world * n_env, width), dtype=torch.float64, device=f"cuda:{local_rank}")
-        obs_gather = "nccl all_gather_into_tensor after the step"
-    if use_p2p:
-        # every env writes its sensor row into every rank's gathered buffer from inside the step kernel (stores over
-        # NVLink / NVSwitch peer memory): the exchange overlaps the physics, no collective is left on the path.
-        # If the IPC mapping is not available on this box, every rank falls back to the NCCL all-gather together.
-        ok = 1
-        try:
-            handle = eng.peer_obs_create(world, rank)
-        except Exception as e:   # noqa: BLE001
-            print(f"[bench] rank {rank}: peer_obs_create failed: {e}", file=sys.stderr)
-            handle, ok = b"", 0
-        handles = [None] * world
-        dist.all_gather_object(handles, handle)
-        if ok and all(len(h) == 64 for h in handles):
-            try:
-                eng.peer_obs_connect(handles)
-            except Exception as e:   # noqa: BLE001
-                print(f"[bench] rank {rank}: peer_obs_connect failed: {e}", file=sys.stderr)
-                ok = 0
-        else:
-            ok = 0
-        flag = torch.tensor([ok], device=f"cuda:{local_rank}")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 1:
-            obs_gather = "in-kernel stores into peer memory (IPC-mapped gathered buffers), signal + wait kernels"
-        else:
-            use_p2p = False
-            obs_gather += " (peer-memory exchange unavailable on this box)"
-            if ok:   # this rank did connect: rebuild the engine without the peer buffers so that all ranks run alike
-                eng.close()
-                eng = core.BatchedEngine(sc.robot, sc.options, n_env, device=local_rank)
-                if sc.kp is not None:
-                    eng.set_pd_controller(sc.kp, sc.kd)
-                eng.set_command(sc.target0)
-                eng.start(sc.q0, sc.v0)
-                stream = torch.cuda.ExternalStream(eng.stream(), device=local_rank)
-                sens_ptr, _ = eng.device_views()
+    # multi-GPU: the only exchange of the path is the end-of-step observation concat
+    from jiminy_b200.parallel import ObservationExchange
+    xch = ObservationExchange(eng, rank, world, local_rank, prefer_peer=not args.nccl_gather)
+    use_p2p = xch.mode == "peer"
+    obs_gather = xch.note
     flush = torch.empty(160 * 1024 * 1024 // 8, dtype=torch.float64, device=f"cuda:{local_rank}")  # > 126 MB L2
 
     def barrier():
@@ -260,27 +221,8 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    class _DevArray:   # zero-copy torch view of a raw device pointer
-        def __init__(self, ptr, shape):
-            self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (ptr, False), "version": 3}
-
-    def peer_view():
-        return torch.as_tensor(_DevArray(eng.peer_obs_view(), (world * n_env, width)), device=f"cuda:{local_rank}")
-
     def gather_obs():
-        if use_p2p:
-            eng.peer_obs_wait()      # the rows were published by the step kernel itself
-        elif world > 1:
-            eng.copy_sensors_to(gather_in.data_ptr())
-            ev = torch.cuda.Event()
-            ev.record(stream)
-            torch.cuda.current_stream().wait_event(ev)
-            dist.all_gather_into_tensor(gather_out, gather_in)
-            # the step kernel fills every SM's shared memory (4 CTAs x 55 KB): a concurrent NCCL kernel
-            # would push CTAs into a second wave, so the next step is ordered after the gather
-            done = torch.cuda.Event()
-            done.record(torch.cuda.current_stream())
-            stream.wait_event(done)
+        xch.gather()
 
     # ---------------- HBM-resident arm: `value`
     for k in range(args.warmup):
@@ -288,14 +230,11 @@ def run_gpu(args):
         eng.step(sc.step_dt)
         gather_obs()
     barrier()
+    eng.synchronize()       # raises PeerTimeout if a rank's completion signal never arrived during the warm-up
     if use_p2p:
         # the peer-memory exchange against the plain NCCL all-gather of the same step: must be identical
-        eng.copy_sensors_to(gather_in.data_ptr())
-        torch.cuda.synchronize()
-        dist.all_gather_into_tensor(gather_out, gather_in)
-        torch.cuda.synchronize()
-        got = peer_view()
-        same = torch.tensor([1 if torch.equal(got, gather_out) else 0], device=f"cuda:{local_rank}")
+        got = xch.view().clone()
+        same = torch.tensor([1 if torch.equal(got, xch.reference_gather()) else 0], device=f"cuda:{local_rank}")
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         if int(same.item()) != 1:
             raise RuntimeError("peer-memory observation exchange differs from the NCCL all-gather (rerun with --nccl-gather)")
@@ -321,6 +260,7 @@ def run_gpu(args):
         ev[k][1].record(stream)
     t_end.record(stream)
     barrier()
+    eng.synchronize()       # PeerTimeout here = a signal of the timed region never arrived: no number is printed
     launches = eng.launch_count() - launches0
     clocks = sampler.stop()
     kernel_ms = [a.elapsed_time(b) for (a, _), b in zip(ev, evk)]      # step kernel alone (roofline)

@@ -31,6 +31,7 @@ extern "C" {
 #define JB_ERR_RUNTIME (-3)          /* reference: std::runtime_error -> RuntimeError       */
 #define JB_ERR_NOT_IMPLEMENTED (-4)  /* reference: jiminy::not_implemented_error            */
 #define JB_ERR_CUDA (-5)             /* no CUDA device / CUDA runtime failure (never a CPU fallback) */
+#define JB_ERR_PEER_TIMEOUT (-6)     /* multi-GPU observation exchange: a rank never signalled its step     */
 
 /* Per-env status bits written by the device scheduler (jb_get_status).  The reference raises
  * from Engine::step for the first three (engine.cc:1742-1747, :2341-2378). */
@@ -324,12 +325,17 @@ int jb_copy_sensors_device(JbBatch* batch, double* dst_dev);
  * warps and costs no collective.  Protocol: each rank calls jb_peer_obs_create (allocates its buffer, returns
  * the 64-byte CUDA IPC handle), the handles are exchanged out of band (e.g. torch.distributed
  * all_gather_object), each rank calls jb_peer_obs_connect with all of them.  From then on jb_step publishes and
- * signals; jb_peer_obs_wait enqueues (on the batch stream) the wait for every rank's signal of the last step;
+ * signals; jb_peer_obs_wait enqueues (on the batch stream) the wait for every rank's signal of the last step
+ * (it gives up after JB_PEER_TIMEOUT_S seconds, default 2: the next synchronising call -- jb_synchronize,
+ * jb_get_sensors -- then returns JB_ERR_PEER_TIMEOUT naming the silent rank);
  * jb_peer_obs_view returns the gathered buffer of that step (two buffers alternate, so a fast rank never
  * overwrites what a slower one is still reading). */
 int jb_peer_obs_create(JbBatch* batch, int32_t world, int32_t rank, uint8_t handle_out[64]);
 int jb_peer_obs_connect(JbBatch* batch, const uint8_t* handles /* [world][64], rank order */);
 int jb_peer_obs_wait(JbBatch* batch);
+/* on = 0: jb_step stops publishing / signalling (a rank that connected while another could not -- all ranks then
+ * use the plain all-gather); on = 1 resumes.  Every rank must hold the same setting. */
+int jb_peer_obs_enable(JbBatch* batch, int32_t on);
 int jb_peer_obs_view(JbBatch* batch, double** obs_dev /* [world][n_env][width] */);
 
 /* Stream the batch launches on (a `cudaStream_t` cast to void*), for CUDA-event timing. */

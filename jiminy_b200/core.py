@@ -20,6 +20,7 @@ from ._ctypes_abi import (JbModelDesc, JbOptions, JbSensorLayout, ModelDescHolde
 
 JB_OK = 0
 JB_ERR_INVALID_ARGUMENT, JB_ERR_BAD_CONTROL_FLOW, JB_ERR_RUNTIME, JB_ERR_NOT_IMPLEMENTED, JB_ERR_CUDA = -1, -2, -3, -4, -5
+JB_ERR_PEER_TIMEOUT = -6
 JB_ENV_OK, JB_ENV_NAN, JB_ENV_ITER_FAILED, JB_ENV_DT_UNDERFLOW = 0, 1, 2, 4
 JB_ENV_JOINT_LIMIT, JB_ENV_NOT_STARTED, JB_ENV_CONTACT_FORCE = 8, 16, 32
 
@@ -32,8 +33,12 @@ class CudaUnavailable(RuntimeError):
     """No CUDA device / runtime failure.  jiminy_b200 never falls back to a CPU implementation."""
 
 
+class PeerTimeout(RuntimeError):
+    """Multi-GPU observation exchange: a rank never signalled its step (JB_ERR_PEER_TIMEOUT)."""
+
+
 _EXC = {JB_ERR_INVALID_ARGUMENT: ValueError, JB_ERR_BAD_CONTROL_FLOW: BadControlFlow, JB_ERR_RUNTIME: RuntimeError,
-        JB_ERR_NOT_IMPLEMENTED: NotImplementedError, JB_ERR_CUDA: CudaUnavailable}
+        JB_ERR_NOT_IMPLEMENTED: NotImplementedError, JB_ERR_CUDA: CudaUnavailable, JB_ERR_PEER_TIMEOUT: PeerTimeout}
 
 _LIB_NAME = "libjiminy_b200.so"
 
@@ -53,7 +58,7 @@ class Api:
                "jb_launch_count", "jb_synchronize", "jb_set_joint_springs", "jb_set_pd_controller", "jb_copy_sensors_device", "jb_describe",
                "jb_plan_describe", "jb_stop", "jb_register_impulse_force", "jb_set_impulse_force",
                "jb_register_profile_force", "jb_set_profile_force", "jb_remove_all_forces",
-               "jb_peer_obs_create", "jb_peer_obs_connect", "jb_peer_obs_wait", "jb_peer_obs_view",
+               "jb_peer_obs_create", "jb_peer_obs_connect", "jb_peer_obs_wait", "jb_peer_obs_view", "jb_peer_obs_enable",
                "jb_set_pd_controller_full", "jb_set_mahony_filter", "jb_get_mahony_filter",
                "jb_get_pd_controller_state", "jb_set_pd_controller_state", "jb_get_constraints")
 
@@ -107,6 +112,7 @@ class Api:
         L.jb_peer_obs_create.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p]
         L.jb_peer_obs_connect.argtypes = [vp, C.c_char_p]
         L.jb_peer_obs_wait.argtypes = [vp]
+        L.jb_peer_obs_enable.argtypes = [vp, C.c_int32]
         L.jb_peer_obs_view.argtypes = [vp, C.POINTER(vp)]
 
     def check(self, rc: int) -> None:
@@ -310,6 +316,9 @@ class BatchedEngine:
     def peer_obs_wait(self) -> None:
         """Enqueues (on the batch stream) the wait for every rank's rows of the last step."""
         self._api.check(self._api.dll.jb_peer_obs_wait(self._h))
+
+    def peer_obs_enable(self, on: bool) -> None:
+        self._api.check(self._api.dll.jb_peer_obs_enable(self._h, 1 if on else 0))
 
     def peer_obs_view(self) -> int:
         """Device pointer of the gathered observations `[world][n_env][width]` of the last step."""

@@ -54,13 +54,14 @@ struct JbBatch {
     double *d_qin = nullptr, *d_vin = nullptr, *d_aout = nullptr, *d_fext = nullptr, *d_u = nullptr, *d_umotor = nullptr;
     double* d_springs = nullptr;
     double *d_pd = nullptr, *d_cmd_torque = nullptr, *d_pdf = nullptr, *d_pdf_state = nullptr, *d_mahony = nullptr;
+    double *d_pdf_snap = nullptr, *d_mahony_snap = nullptr;
     int nimu = 0;
     uint8_t* d_mask = nullptr;
     double* d_stage = nullptr;  // staging for SoA -> AoS getters
     // pinned host staging
     double* h_stage = nullptr;
     size_t h_stage_bytes = 0;
-    int64_t launches = 0;
+    int64_t launches = 0, param_uploads = 0;
     bool any_started = false;
     bool no_fast_kernel = false;   // JB_NO_FAST_KERNEL: always the full kernel (development / tests)
     size_t smem_bytes = 0;
@@ -73,8 +74,11 @@ struct JbBatch {
     size_t peer_obs_doubles = 0;                // doubles of ONE parity buffer
     std::vector<void*> peer_opened;             // mapped buffers of the other ranks
     char* peer_base[8] = {nullptr};
-    int* d_peer_timeout = nullptr;
+    int* h_peer_timeout = nullptr;             // host-mapped: set by the wait kernel when a rank never signalled
+    int* d_peer_timeout = nullptr;             // device alias of the same word
+    double peer_timeout_s = 2.0;
     long long step_id = 0;
+    bool peer_enabled = true;                   // jb_peer_obs_enable
     // external forces: frames (slots), impulse table mirror, profile periods
     struct ExtFrame { int joint; double p[3]; };
     std::vector<ExtFrame> eframes;
@@ -95,6 +99,16 @@ static int raise_smem_attr(int device, size_t bytes) {
     if (e != cudaSuccess) return fail(JB_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     g_smem_attr[device] = bytes;
 #endif
+    return JB_OK;
+}
+
+// After a stream synchronisation: did a peer-exchange wait give up?  (the wait kernel writes the host-mapped word)
+static int check_peer_timeout(JbBatch* b) {
+    if (b->h_peer_timeout && *b->h_peer_timeout != 0) {
+        const int who = *b->h_peer_timeout - 1;
+        return fail(JB_ERR_PEER_TIMEOUT, "observation exchange: rank " + std::to_string(who) + " never signalled step " +
+                    std::to_string(b->step_id) + " within " + std::to_string(b->peer_timeout_s) + " s (rank dead, or steps out of lockstep)");
+    }
     return JB_OK;
 }
 
@@ -125,56 +139,58 @@ static int ensure_host_stage(JbBatch* b, size_t bytes) {
     return JB_OK;
 }
 
-// One launch of the step kernel.  `fast`: the hot-path instantiation; `only_flagged`: the full kernel as the fix-up
-// pass behind it (envs the fast kernel left untouched).
-static int launch_one(JbBatch* b, KParams kp, bool fast) {
+// One launch of the step kernel.  The persistent parameter block lives in constant memory, one per device: it is
+// re-uploaded only when it differs from what the device holds (another batch launched in between, or a setter
+// changed it), ordered after every earlier launch on that device.  What changes at every launch (mode, step size,
+// peer-exchange step) travels as the kernel parameter.
+#ifndef JB_HOST_EMUL
+static KParams g_kp_on_device[64];
+static bool g_kp_valid[64] = {};
+#endif
+static int launch(JbBatch* b, int mode, double step_dt, const uint8_t* d_mask = nullptr) {
+    KParams kp = b->kp;
+    // static plan signatures carry no external-force / constraint-contact code
+    if (kp.n_eslot > 0 || kp.opt.contact_model == JB_CONTACT_CONSTRAINT) kp.sig_id = 0;
+    LaunchArgs la{};
+    la.mode = mode; la.step_dt = step_dt; la.mask = d_mask;
+    if (mode == MODE_STEP && b->peer_world > 1 && !b->peer_opened.empty() && b->peer_enabled) {
+        ++b->step_id;
+        la.peer_on = 1;
+        la.peer_parity = static_cast<int32_t>(b->step_id & 1);
+        la.peer_step = b->step_id;
+    }
+    // the hot-path kernel hands envs that leave the hot path over to the full body inside the same launch
+    const bool fast = mode == MODE_STEP && kp.n_eslot == 0 && kp.opt.contact_model == JB_CONTACT_SPRING_DAMPER &&
+                      kp.opt.ode_solver != JB_SOLVER_RUNGE_KUTTA_DOPRI && !b->no_fast_kernel;
     const int epw = 32 / b->plan.L;
     const int nblocks = (b->n_env + epw - 1) / epw;
 #ifdef JB_HOST_EMUL
     emul::current_L = b->plan.L;
     g_kp_host = kp;
-    if (fast) JB_LAUNCH(env_step_kernel_t<true>, nblocks, 32, b->smem_bytes, b->stream);
-    else JB_LAUNCH(env_step_kernel_t<false>, nblocks, 32, b->smem_bytes, b->stream);
+    if (fast) JB_LAUNCH(env_step_kernel_t<true>, nblocks, 32, b->smem_bytes, b->stream, la);
+    else JB_LAUNCH(env_step_kernel_t<false>, nblocks, 32, b->smem_bytes, b->stream, la);
 #else
     {
-        // one constant-memory parameter block per device: order this launch after the previous one
         std::lock_guard<std::mutex> lock(g_launch_mutex);
         cudaEvent_t& evt = g_last_launch[b->device];
         if (!evt) CU(cudaEventCreateWithFlags(&evt, cudaEventDisableTiming));
-        else CU(cudaStreamWaitEvent(b->stream, evt, 0));
-        CU(cudaMemcpyToSymbolAsync(g_kp, &kp, sizeof kp, 0, cudaMemcpyHostToDevice, b->stream));
-        if (fast) JB_LAUNCH(env_step_kernel_t<true>, nblocks, 32, b->smem_bytes, b->stream);
-        else JB_LAUNCH(env_step_kernel_t<false>, nblocks, 32, b->smem_bytes, b->stream);
+        if (!g_kp_valid[b->device] || std::memcmp(&g_kp_on_device[b->device], &kp, sizeof kp) != 0) {
+            if (g_kp_valid[b->device]) CU(cudaStreamWaitEvent(b->stream, evt, 0));
+            g_kp_valid[b->device] = false;
+            // (the copy is staged by the runtime before the call returns: `kp` may live on this stack)
+            CU(cudaMemcpyToSymbolAsync(g_kp, &kp, sizeof kp, 0, cudaMemcpyHostToDevice, b->stream));
+            std::memcpy(&g_kp_on_device[b->device], &kp, sizeof kp);
+            g_kp_valid[b->device] = true;
+            ++b->param_uploads;
+        }
+        if (fast) JB_LAUNCH(env_step_kernel_t<true>, nblocks, 32, b->smem_bytes, b->stream, la);
+        else JB_LAUNCH(env_step_kernel_t<false>, nblocks, 32, b->smem_bytes, b->stream, la);
         CU(cudaEventRecord(evt, b->stream));
     }
 #endif
     CU(cudaGetLastError());
     ++b->launches;
     return JB_OK;
-}
-
-static int launch(JbBatch* b, int mode, double step_dt) {
-    KParams kp = b->kp;
-    kp.mode = mode;
-    kp.step_dt = step_dt;
-    kp.only_flagged = 0;
-    // static plan signatures carry no external-force / constraint-contact code
-    if (kp.n_eslot > 0 || kp.opt.contact_model == JB_CONTACT_CONSTRAINT) kp.sig_id = 0;
-    if (mode == MODE_STEP && b->peer_world > 1 && !b->peer_opened.empty()) {
-        ++b->step_id;
-        kp.peer_parity = static_cast<int32_t>(b->step_id & 1);
-        kp.peer_step = b->step_id;
-    } else kp.peer_n = 0;
-    kp.peer_signal = 0;
-    const bool fast_ok = mode == MODE_STEP && kp.n_eslot == 0 && kp.opt.contact_model == JB_CONTACT_SPRING_DAMPER &&
-                         kp.opt.ode_solver != JB_SOLVER_RUNGE_KUTTA_DOPRI && !b->no_fast_kernel;
-    // the full kernel is always the last launch of a step: its last block signals the other ranks
-    if (!fast_ok) { kp.peer_signal = kp.peer_n > 0; return launch_one(b, kp, false); }
-    int rc = launch_one(b, kp, true);
-    if (rc) return rc;
-    kp.only_flagged = 1;
-    kp.peer_signal = kp.peer_n > 0;
-    return launch_one(b, kp, false);
 }
 
 extern "C" {
@@ -237,6 +253,9 @@ int jb_batch_destroy(JbBatch* b) {
 #endif
     for (void* p : b->allocs) cudaFree(p);
     if (b->h_stage) cudaFreeHost(b->h_stage);
+#ifndef JB_HOST_EMUL
+    if (b->h_peer_timeout) cudaFreeHost(b->h_peer_timeout);
+#endif
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
     return JB_OK;
@@ -336,7 +355,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
     kp.pd_gains = nullptr; kp.cmd_torque = b->d_cmd_torque; kp.pdf = nullptr; kp.pdf_state = nullptr; kp.pdf_safety = 0; kp.mahony = nullptr; kp.mahony_kp = 1.0; kp.mahony_ki = 0.1;
     kp.q = b->d_q; kp.v = b->d_v; kp.a = b->d_a; kp.sched = b->d_sched; kp.iters = b->d_iters; kp.status = b->d_status;
     kp.command = b->d_cmd; kp.sensors = b->d_sensors; kp.qv_out = b->d_qv;
-    kp.q_in = b->d_qin; kp.v_in = b->d_vin; kp.mask = nullptr;
+    kp.q_in = b->d_qin; kp.v_in = b->d_vin;
     kp.a_out = b->d_aout; kp.fext_out = b->d_fext; kp.u_out = b->d_u;
     kp.eff_u = b->d_u; kp.eff_umotor = b->d_umotor; kp.eff_fext = b->d_fext;
     {
@@ -419,7 +438,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
             const size_t cw_rows = std::min<size_t>(N, static_cast<size_t>(n_sm) * blocks_per_sm * (32 / P.L));
             unsigned int* d_slots;
             ALLOC(d_slots, n_sm);
-            kp.cw_slots = d_slots; kp.cw_blocks_per_sm = blocks_per_sm;
+            kp.cw_slots = d_slots; kp.cw_blocks_per_sm = blocks_per_sm; kp.cw_n_sm = n_sm;
             ALLOC(d_cst, static_cast<size_t>(cs_fields) * N); ALLOC(d_cwk, static_cast<size_t>(w.total) * std::max<size_t>(cw_rows, static_cast<size_t>(n_sm) * blocks_per_sm * (32 / P.L)));
             cudaMemcpyAsync(d_jmap, jmap.data(), jmap.size() * sizeof(JointMap), cudaMemcpyHostToDevice, b->stream);
             cudaMemcpyAsync(d_cmap, cmap.data(), cmap.size() * sizeof(ContactMap), cudaMemcpyHostToDevice, b->stream);
@@ -485,7 +504,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
     b->smem_bytes = static_cast<size_t>(b->base_fields) * 32 * sizeof(double);
     if (b->smem_bytes > 227 * 1024) { jb_batch_destroy(b); return fail(JB_ERR_NOT_IMPLEMENTED, "robot too large: per-warp working set exceeds shared memory (" + P.describe() + ")"); }
     ALLOC(b->d_needs_full, N);
-    kp.needs_full = b->d_needs_full; kp.only_flagged = 0;
+    kp.needs_full = b->d_needs_full;
     if (const char* s = std::getenv("JB_NO_FAST_KERNEL")) b->no_fast_kernel = std::atoi(s) != 0;
     if (raise_smem_attr(device, b->smem_bytes)) { jb_batch_destroy(b); return JB_ERR_CUDA; }
     e = cudaStreamSynchronize(b->stream);
@@ -561,6 +580,8 @@ int jb_set_pd_controller_full(JbBatch* b, const double* kp, const double* kd, co
         if (rc) return rc;
         rc = dev_alloc(b, &b->d_pdf_state, static_cast<size_t>(b->n_env) * 3 * nm);
         if (rc) return rc;
+        rc = dev_alloc(b, &b->d_pdf_snap, static_cast<size_t>(b->n_env) * 3 * nm);
+        if (rc) return rc;
     }
     std::vector<double> h(13 * nm, 0.0);
     std::memcpy(h.data(), kp, sizeof(double) * nm);
@@ -573,7 +594,7 @@ int jb_set_pd_controller_full(JbBatch* b, const double* kp, const double* kd, co
     }
     CU(cudaMemcpyAsync(b->d_pdf, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, b->stream));
     CU(cudaStreamSynchronize(b->stream));
-    b->kp.pdf = b->d_pdf; b->kp.pdf_state = b->d_pdf_state; b->kp.pdf_safety = safety ? 1 : 0;
+    b->kp.pdf = b->d_pdf; b->kp.pdf_state = b->d_pdf_state; b->kp.pdf_snap = b->d_pdf_snap; b->kp.pdf_safety = safety ? 1 : 0;
     b->kp.pd_gains = nullptr;
     return JB_OK;
 }
@@ -607,9 +628,11 @@ int jb_set_mahony_filter(JbBatch* b, double kp, double ki) {
     if (!b->d_mahony) {
         int rc = dev_alloc(b, &b->d_mahony, static_cast<size_t>(b->n_env) * b->nimu * 10);
         if (rc) return rc;
+        rc = dev_alloc(b, &b->d_mahony_snap, static_cast<size_t>(b->n_env) * b->nimu * 10);
+        if (rc) return rc;
         CU(cudaStreamSynchronize(b->stream));
     }
-    b->kp.mahony = b->d_mahony; b->kp.mahony_kp = kp; b->kp.mahony_ki = ki;
+    b->kp.mahony = b->d_mahony; b->kp.mahony_snap = b->d_mahony_snap; b->kp.mahony_kp = kp; b->kp.mahony_ki = ki;
     return JB_OK;
 }
 
@@ -668,12 +691,8 @@ int jb_start(JbBatch* b, const uint8_t* mask, const double* q0, const double* v0
     }
     CU(cudaMemcpyAsync(b->d_qin, q0, sizeof(double) * b->n_env * b->nq, cudaMemcpyHostToDevice, b->stream));
     CU(cudaMemcpyAsync(b->d_vin, v0, sizeof(double) * b->n_env * b->nv, cudaMemcpyHostToDevice, b->stream));
-    if (mask) {
-        CU(cudaMemcpyAsync(b->d_mask, mask, b->n_env, cudaMemcpyHostToDevice, b->stream));
-        b->kp.mask = b->d_mask;
-    } else b->kp.mask = nullptr;
-    int rc = launch(b, MODE_START, 0.0);
-    b->kp.mask = nullptr;
+    if (mask) CU(cudaMemcpyAsync(b->d_mask, mask, b->n_env, cudaMemcpyHostToDevice, b->stream));
+    int rc = launch(b, MODE_START, 0.0, mask ? b->d_mask : nullptr);
     if (rc) return rc;
     CU(cudaStreamSynchronize(b->stream));
     b->any_started = true;
@@ -908,7 +927,7 @@ int jb_get_sensors(JbBatch* b, double* out) {
     CU(cudaSetDevice(b->device));
     if (b->width) CU(cudaMemcpyAsync(out, b->d_sensors, sizeof(double) * b->n_env * b->width, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
-    return JB_OK;
+    return check_peer_timeout(b);
 }
 
 int jb_sensor_layout(JbBatch* b, JbSensorLayout* out) {
@@ -977,8 +996,10 @@ int jb_peer_obs_create(JbBatch* b, int32_t world, int32_t rank, uint8_t handle_o
     CU(cudaMemset(raw, 0, bytes));
     b->allocs.push_back(raw);
     b->d_peer_buf = static_cast<char*>(raw);
-    int rc = dev_alloc(b, &b->d_peer_timeout, 1);
-    if (rc) return rc;
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&b->h_peer_timeout), sizeof(int), cudaHostAllocMapped));
+    *b->h_peer_timeout = 0;
+    CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&b->d_peer_timeout), b->h_peer_timeout, 0));
+    if (const char* e = std::getenv("JB_PEER_TIMEOUT_S")) b->peer_timeout_s = std::max(0.01, std::atof(e));
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, raw));
     std::memcpy(handle_out, &h, 64);
@@ -1005,7 +1026,7 @@ int jb_peer_obs_connect(JbBatch* b, const uint8_t* handles) {
         b->peer_opened.push_back(ptr);
         b->peer_base[p] = static_cast<char*>(ptr);
     }
-    b->kp.peer_n = b->peer_world; b->kp.peer_rank = b->peer_rank; b->kp.peer_parity = 0;
+    b->kp.peer_n = b->peer_world; b->kp.peer_rank = b->peer_rank;
     const size_t flag_off = 2 * b->peer_obs_doubles * sizeof(double);
     for (int p = 0; p < b->peer_world; ++p) {
         b->kp.peer_obs[p] = reinterpret_cast<double*>(b->peer_base[p]);
@@ -1020,16 +1041,26 @@ int jb_peer_obs_connect(JbBatch* b, const uint8_t* handles) {
 #endif
 }
 
+int jb_peer_obs_enable(JbBatch* b, int32_t on) {
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (b->peer_opened.empty()) return fail(JB_ERR_BAD_CONTROL_FLOW, "not connected (jb_peer_obs_connect)");
+    b->peer_enabled = on != 0;
+    return JB_OK;
+}
+
 int jb_peer_obs_wait(JbBatch* b) {
 #ifdef JB_HOST_EMUL
     return fail(JB_ERR_NOT_IMPLEMENTED, "peer memory needs CUDA devices");
 #else
     if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
-    if (b->peer_opened.empty() || b->step_id == 0) return fail(JB_ERR_BAD_CONTROL_FLOW, "no published step to wait for");
+    if (b->peer_opened.empty() || !b->peer_enabled || b->step_id == 0) return fail(JB_ERR_BAD_CONTROL_FLOW, "no published step to wait for");
     CU(cudaSetDevice(b->device));
     const int parity = static_cast<int>(b->step_id & 1);
     volatile long long* mine = reinterpret_cast<volatile long long*>(b->d_peer_buf + 2 * b->peer_obs_doubles * sizeof(double));
-    JB_LAUNCH(peer_wait_kernel, 1, 1, 0, b->stream, mine, b->peer_world, parity, b->step_id, b->d_peer_timeout);
+    int khz = 1965000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, b->device);
+    const long long cycles = static_cast<long long>(b->peer_timeout_s * 1e3 * khz);
+    JB_LAUNCH(peer_wait_kernel, 1, 1, 0, b->stream, mine, b->peer_world, parity, b->step_id, cycles, b->d_peer_timeout);
     CU(cudaGetLastError());
     ++b->launches;
     return JB_OK;
@@ -1055,7 +1086,7 @@ int jb_synchronize(JbBatch* b) {
     if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
     CU(cudaSetDevice(b->device));
     CU(cudaStreamSynchronize(b->stream));
-    return JB_OK;
+    return check_peer_timeout(b);
 }
 
 // Host-side introspection of the lane planner (no device needed): used by the CPU test-suite.

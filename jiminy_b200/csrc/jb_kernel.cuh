@@ -150,6 +150,25 @@ __device__ __noinline__ void update_pd_commands(const Ctx c, bool running) {
     }
 }
 
+// Copy (restore = false) or put back (restore = true) the per-env state of the device-side PDController / MahonyFilter
+// blocks.  Called by every lane of the env; the L lanes share the copy.
+__device__ __noinline__ void snapshot_blocks(const Ctx c, const int L, const bool restore) {
+    if (restore) __syncwarp(c.gmask);   // the owner lanes' writes to the live state come first
+    if (KP->pdf != nullptr) {
+        const size_t n = 3 * static_cast<size_t>(KP->nmotors);
+        double* live = KP->pdf_state + static_cast<size_t>(c.env) * n;
+        double* snap = KP->pdf_snap + static_cast<size_t>(c.env) * n;
+        for (size_t k = c.sub; k < n; k += L) { if (restore) live[k] = snap[k]; else snap[k] = live[k]; }
+    }
+    if (KP->mahony != nullptr) {
+        const size_t n = 10 * static_cast<size_t>(KP->nimu);
+        double* live = KP->mahony + static_cast<size_t>(c.env) * n;
+        double* snap = KP->mahony_snap + static_cast<size_t>(c.env) * n;
+        for (size_t k = c.sub; k < n; k += L) { if (restore) live[k] = snap[k]; else snap[k] = live[k]; }
+    }
+    __syncwarp(c.gmask);
+}
+
 __device__ __noinline__ void store_outputs(const Ctx c) {
     if (!c.valid) return;
     const int L = KP->L;
@@ -258,10 +277,10 @@ __device__ __noinline__ void store_dynamics(const Ctx c) {
 }
 
 // FAST = true: the product hot path only (MODE_STEP, Euler / RK4, spring-damper contacts, no external forces,
-// no enabled constraint).  An env that needs anything else leaves untouched and is stepped by the full kernel,
-// launched right behind as a fix-up pass (KParams::only_flagged).
+// no enabled constraint).  An env that needs anything else leaves untouched (needs_full raised) and is stepped by the
+// full body right behind, inside the same launch (`only_flagged`).
 template <bool FAST>
-__device__ __forceinline__ void env_step_body() {
+__device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool only_flagged) {
     Ctx c;
     c.lane = threadIdx.x & 31;
     const int L = KP->L;
@@ -273,16 +292,21 @@ __device__ __forceinline__ void env_step_body() {
     c.flags = 0;
     c.gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (c.lane - c.sub));
     const size_t N = KP->n_pad, col = c.env;
-    const int mode = KP->mode;
+    const int mode = la.mode;
     int status = KP->status[c.env];
 
-    const bool masked_out = (mode == MODE_START) && KP->mask != nullptr && KP->mask[c.env] == 0;
+    const bool masked_out = (mode == MODE_START) && la.mask != nullptr && la.mask[c.env] == 0;
     if (masked_out) return;   // whole env (all its lanes) leaves: group masks keep the others safe
     if (mode == MODE_STEP && (status & (JB_ENV_NOT_STARTED | JB_ENV_NAN | JB_ENV_ITER_FAILED | JB_ENV_DT_UNDERFLOW | JB_ENV_SOLVER_FAILED))) return;
     int32_t* const needs_full = KP->needs_full + (blockIdx.x * epw + c.lane / L);   // own row, also for padding envs
     if constexpr (FAST) { if (*needs_full != 0) return; }
-    else if (mode == MODE_STEP && KP->only_flagged && *needs_full == 0) return;
+    else if (mode == MODE_STEP && only_flagged && *needs_full == 0) return;
 
+    // The stateful device blocks (PDController targets, MahonyFilter) advance inside the launch; an env handed over to
+    // the full body is replayed from the top of the step, so the fast body keeps a copy to put back.
+    if constexpr (FAST) {
+        if (c.valid && (KP->pdf != nullptr || KP->mahony != nullptr)) snapshot_blocks(c, L, false);
+    }
     // ---------------- load state into the lane records
     for (int r = 0; r < KP->nrec; ++r) {
         const RecInt* ri = KP->rint + (r * L + c.sub);
@@ -365,7 +389,7 @@ __device__ __forceinline__ void env_step_body() {
 
         // ------------- Engine::step (engine.cc:1724-2417)
         const JbOptions& opt = KP->opt;
-        double stepSize = KP->step_dt;
+        double stepSize = la.step_dt;
         if (stepSize < D_EPS) {
             if (opt.controller_update_period > D_EPS) stepSize = opt.controller_update_period;
             else if (opt.sensors_update_period > D_EPS) stepSize = opt.sensors_update_period;
@@ -510,24 +534,25 @@ __device__ __forceinline__ void env_step_body() {
 
     // ---------------- store
     if constexpr (FAST) {
-        if (__any_sync(c.gmask, (status & ENV_RETRY_FULL) != 0)) {   // nothing of this launch is kept: the full kernel redoes the env
+        if (__any_sync(c.gmask, (status & ENV_RETRY_FULL) != 0)) {   // nothing of this pass is kept: the full body redoes the env
+            if (c.valid && (KP->pdf != nullptr || KP->mahony != nullptr)) snapshot_blocks(c, L, true);
             if (c.sub == 0) *needs_full = 1;
             return;
         }
     } else if (KP->cons_on) {
-        // envs that still own enabled constraints stay with the full kernel
+        // envs that still own enabled constraints stay with the full body
         const bool any = __any_sync(c.gmask, SMF(c, KP->cons_off) != 0.0);
         if (c.sub == 0) *needs_full = any ? 1 : 0;
-    }
+    } else if (c.sub == 0) *needs_full = 0;   // bounds are only flagged for this robot (JB_ENV_JOINT_LIMIT): back to the hot path
     if (KP->extra_energy != nullptr && !(status & (JB_ENV_NAN | JB_ENV_NOT_STARTED))) extra_terms(c);
     store_outputs(c);
 #ifndef JB_HOST_EMUL
     // multi-GPU: publish the sensor rows into every rank's gathered buffer (stores over NVLink / NVSwitch).  The rows
     // of a warp's envs are contiguous: when the whole warp is here it copies them with coalesced 16-byte stores,
     // otherwise (some env of the warp failed or was handed to the full kernel) every env copies its own row.
-    if (KP->peer_n > 0) {
+    if (la.peer_on) {
         const int width = KP->lay.width;
-        const size_t slot = (static_cast<size_t>(KP->peer_parity) * KP->peer_n + KP->peer_rank) * KP->n_env;
+        const size_t slot = (static_cast<size_t>(la.peer_parity) * KP->peer_n + KP->peer_rank) * KP->n_env;
         const unsigned act = __activemask();
         if (act == 0xffffffffu && (width & 1) == 0) {
             __syncwarp();
@@ -577,19 +602,15 @@ JB_DI unsigned int jb_smid() {
 #endif
 }
 
-template <bool FAST>
-__global__ void __launch_bounds__(32) env_step_kernel_t() {
-    // constraint workspace: one slot per resident block of this SM, taken for the lifetime of the block
+// The full body: every mode, every stepper, the constraint path.  Out of line, so that the hot-path kernel carries one
+// call to it instead of a second copy of the code.
+__device__ __noinline__ void env_step_full(const LaunchArgs la, const bool only_flagged) {
+    // constraint workspace: one slot per resident block of this SM, taken for the lifetime of the call
     int my_bit = -1;
     unsigned int my_sm = 0;
-    if (!FAST && KP->only_flagged && KP->mode == MODE_STEP) {
-        // fix-up pass behind the fast kernel: nothing to do unless an env of this warp was handed over
-        const int flag = KP->needs_full[blockIdx.x * (32 / KP->L) + (threadIdx.x & 31) / KP->L];
-        if (!__any_sync(0xffffffffu, flag != 0)) return;
-    }
-    if (!FAST && KP->cons_on) {
+    if (KP->cons_on) {
         if (threadIdx.x == 0) {
-            my_sm = jb_smid();
+            my_sm = jb_smid() % static_cast<unsigned int>(KP->cw_n_sm);
             for (int tries = 0; my_bit < 0; ++tries) {
                 const int bit = tries % KP->cw_blocks_per_sm;
                 const unsigned int old = atomicOr(KP->cw_slots + my_sm, 1u << bit);
@@ -599,15 +620,28 @@ __global__ void __launch_bounds__(32) env_step_kernel_t() {
         }
         __syncwarp();
     }
-    env_step_body<FAST>();
-    if (!FAST && KP->cons_on) {
+    env_step_body<false>(la, only_flagged);
+    if (KP->cons_on) {
         __syncwarp();
         if (threadIdx.x == 0) atomicAnd(KP->cw_slots + my_sm, ~(1u << my_bit));
     }
+}
+
+// One launch = one Engine::step (or start / single evaluation) of every env.  FAST: the hot-path body first; the envs it
+// handed over (a joint left its bounds now, or constraints still enabled from an earlier step) go through the full
+// body in the same launch, so a step is always exactly one kernel.
+template <bool FAST>
+__global__ void __launch_bounds__(32) env_step_kernel_t(const LaunchArgs la) {
+    if constexpr (FAST) {
+        env_step_body<true>(la, false);
+        __syncwarp();   // needs_full is written by sub-lane 0 of each env
+        const int flag = KP->needs_full[blockIdx.x * (32 / KP->L) + (threadIdx.x & 31) / KP->L];
+        if (__any_sync(0xffffffffu, flag != 0)) env_step_full(la, true);
+    } else env_step_full(la, false);
 #ifndef JB_HOST_EMUL
-    // observation exchange over peer memory: the last block of the last launch of a step tells the other ranks
-    // that every row of this rank has been published (release: fence, then the flags)
-    if (!FAST && KP->peer_signal) {
+    // observation exchange over peer memory: EVERY block arrives here, whatever its envs did; the last one tells the
+    // other ranks that every row of this rank has been published (release: fence, then the flags)
+    if (la.peer_on) {
         __syncwarp();
         if (threadIdx.x == 0) {
             __threadfence_system();
@@ -615,7 +649,7 @@ __global__ void __launch_bounds__(32) env_step_kernel_t() {
             if (done == gridDim.x - 1) {
                 *KP->peer_counter = 0u;
                 __threadfence_system();
-                for (int p = 0; p < KP->peer_n; ++p) KP->peer_flags[p][KP->peer_parity * KP->peer_n + KP->peer_rank] = KP->peer_step;
+                for (int p = 0; p < KP->peer_n; ++p) KP->peer_flags[p][la.peer_parity * KP->peer_n + KP->peer_rank] = la.peer_step;
             }
         }
     }
@@ -624,11 +658,13 @@ __global__ void __launch_bounds__(32) env_step_kernel_t() {
 
 // ---- observation exchange over peer memory: the consumer's wait (one thread)
 #ifndef JB_HOST_EMUL
-__global__ void peer_wait_kernel(volatile long long* mine, int world, int parity, long long step, int* timed_out) {
+// `timed_out` is host-mapped: the host checks it at its next synchronisation point (JB_ERR_PEER_TIMEOUT).
+__global__ void peer_wait_kernel(volatile long long* mine, int world, int parity, long long step, long long timeout_cycles,
+                                 volatile int* timed_out) {
     const long long t0 = clock64();
     for (int p = 0; p < world; ++p)
         while (mine[parity * world + p] < step)
-            if (clock64() - t0 > 20000000000LL) { *timed_out = 1; return; }   // ~10 s: a rank died
+            if (clock64() - t0 > timeout_cycles) { *timed_out = p + 1; __threadfence_system(); return; }   // rank p never signalled
     __threadfence_system();
 }
 #endif

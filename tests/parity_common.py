@@ -520,6 +520,46 @@ def bounds_handoff_scenario(api, n_env=9, n_steps=3, tol_state=1e-8):
     return eng, orc
 
 
+def stateful_handoff_scenario(api, n_env=6, n_steps=6, tol_state=1e-8):
+    """Hand-off from the hot-path body to the full body with the STATEFUL device blocks enabled (PDController targets
+    integrated by integrate_zoh, MahonyFilter): every third env drives its hip targets beyond the joint bounds, so its
+    step is aborted midway and replayed from the top -- the replay must not see targets / filter states that the
+    aborted pass already advanced."""
+    sc = scenarios.make("anymal", n_env, seed=8)
+    rob = sc.robot
+    nm = rob.nmotors
+    iq = np.array([rob.idx_q[m.joint] for m in rob.motors])
+    haa = [k for k, m in enumerate(rob.motors) if "HAA" in m.name]
+    lower = np.stack([rob.q_lower[iq] - 0.5, np.full(nm, -4.0), np.full(nm, -40.0)])
+    upper = np.stack([rob.q_upper[iq] + 0.5, np.full(nm, 4.0), np.full(nm, 40.0)])     # targets may leave the joint bounds
+    eng, orc = BatchedEngine(rob, sc.options, n_env, api_=api), OracleBatch(rob, sc.options, n_env)
+    rng = np.random.default_rng(12)
+    act = np.zeros((n_env, nm))
+    for x in (eng, orc):
+        x.set_pd_controller_full(sc.kp, sc.kd, lower, upper, None)
+        x.set_mahony_filter(1.0, 0.1)
+        x.set_command(act)
+    eng.start(sc.q0, sc.v0)
+    assert not orc.start(sc.q0, sc.v0).any()
+    compare(eng, orc, 1e-13, 1e-11)
+    hit_any = False
+    for k in range(n_steps):
+        act = rng.uniform(-3.0, 3.0, size=(n_env, nm))
+        for j in haa:
+            act[::3, j] = 40.0        # the hip targets accelerate towards (and beyond) the upper bound
+        eng.set_command(act)
+        orc.set_command(act)
+        eng.step(sc.step_dt)
+        assert not orc.step(sc.step_dt, parallel=True).any()
+        compare(eng, orc, tol_state, 1e-6)
+        np.testing.assert_allclose(eng.get_pd_controller_state(), orc.get_pd_controller_state(), rtol=0, atol=1e-9)
+        np.testing.assert_allclose(eng.get_mahony_filter(), orc.get_mahony_filter(), rtol=0, atol=1e-8)
+        hit_any = hit_any or bool((eng.get_status() & 8).any())
+    st = eng.get_status()
+    assert hit_any and (st[::3] & 8).all() and not (st[1::3] & 8).any()
+    return eng, orc
+
+
 def mahony_scenario(api, name="anymal", n_env=3, n_steps=3):
     """Device-side MahonyFilter observer against the oracle's (pinned by golden vectors of the reference's own
     `mahony_filter` / `matrices_to_quat`): exact initialisation at start, one iteration per sensor refresh."""

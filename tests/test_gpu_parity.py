@@ -246,6 +246,10 @@ def test_bounds_handoff_between_kernels_at_scale():
     pc.bounds_handoff_scenario(None, n_env=600, n_steps=5)
 
 
+def test_handoff_with_stateful_blocks_at_scale():
+    pc.stateful_handoff_scenario(None, n_env=300, n_steps=7)
+
+
 def test_mahony_filter_observer():
     pc.mahony_scenario(None, "anymal", n_env=70, n_steps=4)
     pc.mahony_scenario(None, "atlas", n_env=5, n_steps=1)

@@ -669,6 +669,10 @@ def test_bounds_handoff_between_kernels(api):
     pc.bounds_handoff_scenario(api, n_env=9, n_steps=4)
 
 
+def test_handoff_with_stateful_blocks(api):
+    pc.stateful_handoff_scenario(api, n_env=6, n_steps=6)
+
+
 def test_mahony_filter_observer(api):
     pc.mahony_scenario(api, "anymal")
     pc.mahony_scenario(api, "atlas", n_env=1, n_steps=1)
