@@ -288,6 +288,18 @@ int jb_compute_dynamics(JbBatch* batch, const double* q, const double* v, const 
  * be NULL.  t [n_env], q [n_env][nq], v/a [n_env][nv]. */
 int jb_get_state(JbBatch* batch, double* t, double* q, double* v, double* a);
 
+/* Checkpoint / restore of a running batch.  Replaces: the remaining fields of `StepperState` a resumed rollout needs
+ * besides (t, q, v, a) -- `dt`, `dtLargest`, the Kahan error `tError`, ... (core/include/jiminy/core/engine/engine.h:216-250;
+ * the reference serialises them nowhere: a simulation can only be replayed from t = 0) -- and the command held since
+ * the last controller update (RobotState.command).  sched [n_env][6] = (t, dt, dtLargest, dtLargestPrev, tError,
+ * tPrev); command_held [n_env][nmotors].  jb_set_stepper_state overwrites whichever arrays are non-NULL (q [n_env][nq],
+ * v / a [n_env][nv], iter / iter_failed [n_env]); contact forces, sensors and extra terms are rebuilt from (q, v, a)
+ * by the next jb_step.  Constraint multipliers and the states of the device controller blocks are not touched (they
+ * have their own getters / setters). */
+int jb_get_stepper_state(JbBatch* batch, double* sched, double* command_held);
+int jb_set_stepper_state(JbBatch* batch, const double* sched, const double* q, const double* v, const double* a,
+                         const int64_t* iter, const int64_t* iter_failed, const double* command_held);
+
 /* Replaces: RobotState.{u, u_motor, command, f_external} views (pywrap engine.cc:175-187).
  * u [n_env][nv], u_motor [n_env][nmotors], command [n_env][nmotors], fext [n_env][njoints][6]. */
 int jb_get_efforts(JbBatch* batch, double* u, double* u_motor, double* command, double* fext);

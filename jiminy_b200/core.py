@@ -60,7 +60,8 @@ class Api:
                "jb_register_profile_force", "jb_set_profile_force", "jb_remove_all_forces",
                "jb_peer_obs_create", "jb_peer_obs_connect", "jb_peer_obs_wait", "jb_peer_obs_view", "jb_peer_obs_enable",
                "jb_set_pd_controller_full", "jb_set_mahony_filter", "jb_get_mahony_filter",
-               "jb_get_pd_controller_state", "jb_set_pd_controller_state", "jb_get_constraints")
+               "jb_get_pd_controller_state", "jb_set_pd_controller_state", "jb_get_constraints",
+               "jb_get_stepper_state", "jb_set_stepper_state")
 
     def __init__(self, cdll: C.CDLL):
         self.dll = L = cdll
@@ -82,6 +83,8 @@ class Api:
         L.jb_compute_dynamics.argtypes = [vp] + [c_double_p] * 6
         L.jb_get_state.argtypes = [vp] + [c_double_p] * 4
         L.jb_get_efforts.argtypes = [vp] + [c_double_p] * 4
+        L.jb_get_stepper_state.argtypes = [vp, c_double_p, c_double_p]
+        L.jb_set_stepper_state.argtypes = [vp] + [c_double_p] * 4 + [c_int64_p, c_int64_p, c_double_p]
         L.jb_get_sensors.argtypes = [vp, c_double_p]
         L.jb_sensor_layout.argtypes = [vp, C.POINTER(JbSensorLayout)]
         L.jb_get_extra_terms.argtypes = [vp] + [c_double_p] * 3
@@ -374,6 +377,26 @@ class BatchedEngine:
         q, v, a = np.zeros((self.n_env, self.nq)), np.zeros((self.n_env, self.nv)), np.zeros((self.n_env, self.nv))
         self._api.check(self._api.dll.jb_get_state(self._h, dptr(t), dptr(q), dptr(v), dptr(a)))
         return t, q, v, a
+
+    def get_stepper_state(self):
+        """(sched [n_env, 6] = t, dt, dtLargest, dtLargestPrev, tError, tPrev; command held since the last controller update)."""
+        sched, cmd = np.zeros((self.n_env, 6)), np.zeros((self.n_env, max(self.nm, 1)))
+        self._api.check(self._api.dll.jb_get_stepper_state(self._h, dptr(sched), dptr(cmd)))
+        return sched, cmd[:, :self.nm]
+
+    def set_stepper_state(self, sched=None, q=None, v=None, a=None, iters=None, iters_failed=None, command_held=None) -> None:
+        """Checkpoint restore: overwrites the given parts of the running state of every env."""
+        def arr(x, shape, dtype=np.float64):
+            if x is None:
+                return None
+            x = np.ascontiguousarray(x, dtype=dtype)
+            assert x.shape == shape, (x.shape, shape)
+            return x
+        n = self.n_env
+        keep = [arr(sched, (n, 6)), arr(q, (n, self.nq)), arr(v, (n, self.nv)), arr(a, (n, self.nv)),
+                arr(iters, (n,), np.int64), arr(iters_failed, (n,), np.int64), arr(command_held, (n, self.nm))]
+        ptr = [None if x is None else (x.ctypes.data_as(c_int64_p) if x.dtype == np.int64 else dptr(x)) for x in keep]
+        self._api.check(self._api.dll.jb_set_stepper_state(self._h, *ptr))
 
     def get_efforts(self):
         u, um = np.zeros((self.n_env, self.nv)), np.zeros((self.n_env, max(self.nm, 1)))

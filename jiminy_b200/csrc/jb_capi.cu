@@ -130,6 +130,14 @@ __global__ void soa_to_aos_kernel(const double* __restrict__ in, double* __restr
     out[i] = in[k * n_pad + env];
 }
 
+// AoS [env][width] -> SoA [k][n_pad] (padding envs replicate the last one)
+__global__ void aos_to_soa_kernel(const double* __restrict__ in, double* __restrict__ out, int n_env, int n_pad, int width) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= static_cast<size_t>(n_pad) * width) return;
+    const size_t k = i / n_pad, env = i % n_pad;
+    out[i] = in[(env < static_cast<size_t>(n_env) ? env : static_cast<size_t>(n_env - 1)) * width + k];
+}
+
 static int ensure_host_stage(JbBatch* b, size_t bytes) {
     if (bytes <= b->h_stage_bytes) return JB_OK;
     if (b->h_stage) cudaFreeHost(b->h_stage);
@@ -908,6 +916,51 @@ int jb_get_state(JbBatch* b, double* t, double* q, double* v, double* a) {
     if (q && (rc = fetch_soa(b, b->d_q, b->nq, q))) return rc;
     if (v && (rc = fetch_soa(b, b->d_v, b->nv, v))) return rc;
     if (a && (rc = fetch_soa(b, b->d_a, b->nv, a))) return rc;
+    return JB_OK;
+}
+
+static int store_soa(JbBatch* b, const double* host_src, int width, double* d_dst) {
+    const size_t total = static_cast<size_t>(b->n_env) * width;
+    if (!total) return JB_OK;
+    CU(cudaMemcpyAsync(b->d_stage, host_src, total * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    const size_t padded = static_cast<size_t>(b->n_pad) * width;
+    JB_LAUNCH(aos_to_soa_kernel, static_cast<unsigned>((padded + 255) / 256), 256, 0, b->stream, b->d_stage, d_dst, b->n_env, b->n_pad, width);
+    CU(cudaGetLastError());
+    ++b->launches;
+    CU(cudaStreamSynchronize(b->stream));   // d_stage and host_src are free again
+    return JB_OK;
+}
+
+int jb_get_stepper_state(JbBatch* b, double* sched, double* command_held) {
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(b->device));
+    int rc;
+    if (sched && (rc = fetch_soa(b, b->d_sched, SCH_N, sched))) return rc;
+    if (command_held && b->nmotors) {
+        const double* src = (b->kp.pd_gains || b->kp.pdf) ? b->d_cmd_torque : b->d_cmd;
+        CU(cudaMemcpyAsync(command_held, src, sizeof(double) * b->n_env * b->nmotors, cudaMemcpyDeviceToHost, b->stream));
+        CU(cudaStreamSynchronize(b->stream));
+    }
+    return JB_OK;
+}
+
+int jb_set_stepper_state(JbBatch* b, const double* sched, const double* q, const double* v, const double* a,
+                         const int64_t* iter, const int64_t* iter_failed, const double* command_held) {
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!b->any_started) return fail(JB_ERR_BAD_CONTROL_FLOW, "No simulation running. Please start one before restoring its state.");
+    CU(cudaSetDevice(b->device));
+    int rc;
+    if (sched && (rc = store_soa(b, sched, SCH_N, b->d_sched))) return rc;
+    if (q && (rc = store_soa(b, q, b->nq, b->d_q))) return rc;
+    if (v && (rc = store_soa(b, v, b->nv, b->d_v))) return rc;
+    if (a && (rc = store_soa(b, a, b->nv, b->d_a))) return rc;
+    if (iter) CU(cudaMemcpyAsync(b->d_iters, iter, sizeof(int64_t) * b->n_env, cudaMemcpyHostToDevice, b->stream));
+    if (iter_failed) CU(cudaMemcpyAsync(b->d_iters + b->n_pad, iter_failed, sizeof(int64_t) * b->n_env, cudaMemcpyHostToDevice, b->stream));
+    if (command_held && b->nmotors) {
+        double* dst = (b->kp.pd_gains || b->kp.pdf) ? b->d_cmd_torque : b->d_cmd;
+        CU(cudaMemcpyAsync(dst, command_held, sizeof(double) * b->n_env * b->nmotors, cudaMemcpyHostToDevice, b->stream));
+    }
+    CU(cudaStreamSynchronize(b->stream));
     return JB_OK;
 }
 

@@ -200,6 +200,14 @@ void orc_get_state(OrcBatch* b, double* t, double* q, double* v, double* a) {
         if (a) std::memcpy(a + i * b->nv, e.a.data(), sizeof(double) * b->nv);
     }
 }
+// StepperState fields besides (t, q, v, a) and the command held since the last controller update
+void orc_get_stepper_state(OrcBatch* b, double* sched, double* command_held) {
+    for (size_t i = 0; i < b->envs.size(); ++i) {
+        Engine& e = *b->envs[i];
+        if (sched) { double* s = sched + 6 * i; s[0] = e.t; s[1] = e.dt; s[2] = e.dtLargest; s[3] = e.dtLargestPrev; s[4] = e.tError; s[5] = e.tPrev; }
+        if (command_held && b->nmotors) std::memcpy(command_held + i * b->nmotors, e.state.command.data(), sizeof(double) * b->nmotors);
+    }
+}
 void orc_get_efforts(OrcBatch* b, double* u, double* u_motor, double* command, double* fext) {
     for (size_t i = 0; i < b->envs.size(); ++i) {
         Engine& e = *b->envs[i];

@@ -72,6 +72,7 @@ def lib():
         L.orc_step.argtypes = [C.c_void_p, C.c_double, C.c_int, c_int32_p]
         L.orc_get_state.argtypes = [C.c_void_p] + [c_double_p] * 4
         L.orc_get_efforts.argtypes = [C.c_void_p] + [c_double_p] * 4
+        L.orc_get_stepper_state.argtypes = [C.c_void_p, c_double_p, c_double_p]
         L.orc_get_sensors.argtypes = [C.c_void_p, c_double_p]
         L.orc_get_extra_terms.argtypes = [C.c_void_p] + [c_double_p] * 3
         L.orc_get_status.argtypes = [C.c_void_p, c_int32_p]
@@ -252,6 +253,11 @@ class OracleBatch:
         q, v, a = np.zeros((self.n, self.nq)), np.zeros((self.n, self.nv)), np.zeros((self.n, self.nv))
         lib().orc_get_state(self._h, dptr(t), dptr(q), dptr(v), dptr(a))
         return t, q, v, a
+
+    def get_stepper_state(self):
+        sched, cmd = np.zeros((self.n, 6)), np.zeros((self.n, max(self.nm, 1)))
+        lib().orc_get_stepper_state(self._h, dptr(sched), dptr(cmd))
+        return sched, cmd[:, :self.nm]
 
     def get_efforts(self):
         u, um = np.zeros((self.n, self.nv)), np.zeros((self.n, max(self.nm, 1)))

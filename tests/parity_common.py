@@ -68,6 +68,56 @@ def run_scenario(name, n_env, n_steps, api=None, tol_state=1e-9, tol_sens=1e-7, 
     return eng, orc, sc
 
 
+def rel_state_error(q1, v1, q0, v0):
+    """Per-env relative deviation of (q, v): max |x1 - x0| / max(1, max |x0|), the larger of the two blocks."""
+    eq = np.abs(q1 - q0).max(axis=1) / np.maximum(1.0, np.abs(q0).max(axis=1))
+    ev = np.abs(v1 - v0).max(axis=1) / np.maximum(1.0, np.abs(v0).max(axis=1))
+    return np.maximum(eq, ev)
+
+
+def resync_long_horizon_scenario(name, n_env, n_steps, api=None, tol_rel=1e-10, free_running=True, seed=21, **kw):
+    """Long horizons without the chaotic amplification: after every env-step the device is handed the ORACLE's state
+    (jb_set_stepper_state: q, v, a, scheduler scalars, iteration counters, held command), so that each step is compared
+    from identical inputs -- `resync[k]` is the error the device path adds in ONE env-step, at every point of a long
+    trajectory.  A second, free-running device engine records how a rounding-level difference grows when nothing is
+    re-synchronised (`free[k]`, a property of the dynamics: stiff contacts amplify any perturbation).
+    Returns (resync [n_steps, n_env], free [n_steps, n_env])."""
+    sc = scenarios.make(name, n_env, seed=seed, **kw)
+    eng, orc = make_pair(sc, api)
+    free = None
+    if free_running:
+        free = BatchedEngine(sc.robot, sc.options, sc.n_env, api_=api)
+        if sc.kp is not None:
+            free.set_pd_controller(sc.kp, sc.kd)
+        free.set_command(sc.target0)
+        free.start(sc.q0, sc.v0)
+    resync, growth = [], []
+    for k in range(n_steps):
+        act = sc.sample_targets(k)
+        for x in (eng, orc) + ((free,) if free is not None else ()):
+            x.set_command(act)
+        eng.step(sc.step_dt)
+        assert not orc.step(sc.step_dt, parallel=True).any()
+        (t1, q1, v1, a1), (t0, q0, v0, a0) = eng.get_state(), orc.get_state()
+        e = rel_state_error(q1, v1, q0, v0)
+        resync.append(e)
+        assert e.max() <= tol_rel, f"{name}: env-step {k}: one-step relative deviation {e.max():.3e} > {tol_rel:.1e} (env {int(e.argmax())})"
+        np.testing.assert_allclose(t1, t0, rtol=0, atol=1e-15)
+        np.testing.assert_array_equal(eng.get_iters()[0], orc.get_iters()[0])
+        np.testing.assert_array_equal(eng.get_status(), orc.get_status())
+        s1, s0 = eng.get_sensors(), orc.get_sensors()
+        if s0.size:
+            np.testing.assert_allclose(s1, s0, rtol=0, atol=1e4 * tol_rel * max(1.0, np.abs(s0).max()))
+        if free is not None:
+            free.step(sc.step_dt)
+            _, qf, vf, _ = free.get_state()
+            growth.append(rel_state_error(qf, vf, q0, v0))
+        sched, held = orc.get_stepper_state()
+        it, itf = orc.get_iters()
+        eng.set_stepper_state(sched, q0, v0, a0, it, itf, held)
+    return np.array(resync), np.array(growth)
+
+
 def compare_extra_terms(eng, orc, tol=1e-9):
     """computeExtraTerms outputs: energies, joint spatial accelerations, joint internal wrenches."""
     e1, a1, f1 = eng.get_extra_terms()

@@ -14,7 +14,7 @@ from jiminy_b200.core import BatchedEngine, plan_describe
 from oracle.oracle import OracleBatch
 
 from conftest import DATA
-from emul import emul_api
+from emul import emul_api, host_has_fma
 import parity_common as pc
 
 
@@ -667,6 +667,16 @@ def test_pd_control_pipeline_env(api):
 
 def test_bounds_handoff_between_kernels(api):
     pc.bounds_handoff_scenario(api, n_env=9, n_steps=4)
+
+
+def test_long_horizon_resynchronised_gpu_like_rounding():
+    """Short version of the `-m gpu` long-horizon test on the emulator build that contracts multiply-adds like nvcc."""
+    if not host_has_fma():
+        pytest.skip("host CPU without FMA")
+    fma = emul_api(fma=True)
+    resync, free = pc.resync_long_horizon_scenario("anymal", 4, 25, api=fma, tol_rel=1e-11)
+    assert free.max() < 1e-10
+    pc.resync_long_horizon_scenario("atlas", 2, 4, api=fma, tol_rel=1e-11, free_running=False)
 
 
 def test_handoff_with_stateful_blocks(api):
