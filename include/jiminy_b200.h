@@ -315,6 +315,14 @@ int jb_sensor_layout(JbBatch* batch, JbSensorLayout* out);
  * `joint_f` [n_env][njoints][6] (data.f).  Any pointer may be NULL. */
 int jb_get_extra_terms(JbBatch* batch, double* energy, double* joint_a, double* joint_f);
 
+/* Replaces: the centroidal quantities of the same function (engine.cc:817-832, :890-904), read by user code through
+ * `robot.pinocchio_data.{Ycrb, com, vcom, hg, dhg}`: subtree inertias `ycrb` [n_env][njoints][10] (mass, lever[3],
+ * inertia about the subtree centre of mass xx xy yy xz yz zz -- Pinocchio's `Inertia`; row 0 unused), subtree centres
+ * of mass `com` [n_env][njoints][3] in the joint frames (row 0: whole robot, world frame) and their velocities `vcom`
+ * [n_env][njoints][3] (h[j].linear / mass[j]), centroidal momentum `hg` [n_env][6] and its derivative `dhg` [n_env][6]
+ * (linear, angular about the centre of mass).  Any pointer may be NULL. */
+int jb_get_centroidal(JbBatch* batch, double* ycrb, double* com, double* vcom, double* hg, double* dhg);
+
 /* Replaces: the exceptions Engine::step raises per robot; here one word per env (JB_ENV_*). */
 int jb_get_status(JbBatch* batch, int32_t* status);
 

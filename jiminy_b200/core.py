@@ -61,7 +61,7 @@ class Api:
                "jb_peer_obs_create", "jb_peer_obs_connect", "jb_peer_obs_wait", "jb_peer_obs_view", "jb_peer_obs_enable",
                "jb_set_pd_controller_full", "jb_set_mahony_filter", "jb_get_mahony_filter",
                "jb_get_pd_controller_state", "jb_set_pd_controller_state", "jb_get_constraints",
-               "jb_get_stepper_state", "jb_set_stepper_state")
+               "jb_get_stepper_state", "jb_set_stepper_state", "jb_get_centroidal")
 
     def __init__(self, cdll: C.CDLL):
         self.dll = L = cdll
@@ -84,6 +84,7 @@ class Api:
         L.jb_get_state.argtypes = [vp] + [c_double_p] * 4
         L.jb_get_efforts.argtypes = [vp] + [c_double_p] * 4
         L.jb_get_stepper_state.argtypes = [vp, c_double_p, c_double_p]
+        L.jb_get_centroidal.argtypes = [vp] + [c_double_p] * 5
         L.jb_set_stepper_state.argtypes = [vp] + [c_double_p] * 4 + [c_int64_p, c_int64_p, c_double_p]
         L.jb_get_sensors.argtypes = [vp, c_double_p]
         L.jb_sensor_layout.argtypes = [vp, C.POINTER(JbSensorLayout)]
@@ -377,6 +378,14 @@ class BatchedEngine:
         q, v, a = np.zeros((self.n_env, self.nq)), np.zeros((self.n_env, self.nv)), np.zeros((self.n_env, self.nv))
         self._api.check(self._api.dll.jb_get_state(self._h, dptr(t), dptr(q), dptr(v), dptr(a)))
         return t, q, v, a
+
+    def get_centroidal(self):
+        """`pinocchio_data.{Ycrb, com, vcom, hg, dhg}` after the last step: (ycrb [n_env, njoints, 10], com [n_env, njoints, 3],
+        vcom [n_env, njoints, 3], hg [n_env, 6], dhg [n_env, 6])."""
+        n, nj = self.n_env, self.robot.njoints
+        y, c, vc, hg, dhg = np.zeros((n, nj, 10)), np.zeros((n, nj, 3)), np.zeros((n, nj, 3)), np.zeros((n, 6)), np.zeros((n, 6))
+        self._api.check(self._api.dll.jb_get_centroidal(self._h, dptr(y), dptr(c), dptr(vc), dptr(hg), dptr(dhg)))
+        return y, c, vc, hg, dhg
 
     def get_stepper_state(self):
         """(sched [n_env, 6] = t, dt, dtLargest, dtLargestPrev, tError, tPrev; command held since the last controller update)."""

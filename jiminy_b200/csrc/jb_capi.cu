@@ -371,6 +371,10 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
         ALLOC2(d_en, 2 * static_cast<size_t>(n_env)); ALLOC2(d_ea, static_cast<size_t>(n_env) * m->njoints * 6);
         ALLOC2(d_ef, static_cast<size_t>(n_env) * m->njoints * 6);
         kp.extra_energy = d_en; kp.extra_a = d_ea; kp.extra_f = d_ef;
+        double *d_y, *d_c, *d_vc, *d_hg;
+        ALLOC2(d_y, static_cast<size_t>(n_env) * m->njoints * 10); ALLOC2(d_c, static_cast<size_t>(n_env) * m->njoints * 3);
+        ALLOC2(d_vc, static_cast<size_t>(n_env) * m->njoints * 3); ALLOC2(d_hg, static_cast<size_t>(n_env) * 12);
+        kp.extra_ycrb = d_y; kp.extra_com = d_c; kp.extra_vcom = d_vc; kp.extra_hg = d_hg; kp.total_mass = P.total_mass;
     }
 
     if (SigQuadruped::matches(kp) && !std::getenv("JB_NO_STATIC_PLAN")) kp.sig_id = SigQuadruped::ID;
@@ -996,6 +1000,19 @@ int jb_get_extra_terms(JbBatch* b, double* energy, double* joint_a, double* join
     if (energy) CU(cudaMemcpyAsync(energy, b->kp.extra_energy, sizeof(double) * 2 * b->n_env, cudaMemcpyDeviceToHost, b->stream));
     if (joint_a) CU(cudaMemcpyAsync(joint_a, b->kp.extra_a, sizeof(double) * nj6, cudaMemcpyDeviceToHost, b->stream));
     if (joint_f) CU(cudaMemcpyAsync(joint_f, b->kp.extra_f, sizeof(double) * nj6, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return JB_OK;
+}
+
+int jb_get_centroidal(JbBatch* b, double* ycrb, double* com, double* vcom, double* hg, double* dhg) {
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(b->device));
+    const size_t n = b->n_env, nj = b->njoints;
+    if (ycrb) CU(cudaMemcpyAsync(ycrb, b->kp.extra_ycrb, sizeof(double) * n * nj * 10, cudaMemcpyDeviceToHost, b->stream));
+    if (com) CU(cudaMemcpyAsync(com, b->kp.extra_com, sizeof(double) * n * nj * 3, cudaMemcpyDeviceToHost, b->stream));
+    if (vcom) CU(cudaMemcpyAsync(vcom, b->kp.extra_vcom, sizeof(double) * n * nj * 3, cudaMemcpyDeviceToHost, b->stream));
+    if (hg) CU(cudaMemcpy2DAsync(hg, 6 * sizeof(double), b->kp.extra_hg, 12 * sizeof(double), 6 * sizeof(double), n, cudaMemcpyDeviceToHost, b->stream));
+    if (dhg) CU(cudaMemcpy2DAsync(dhg, 6 * sizeof(double), b->kp.extra_hg + 6, 12 * sizeof(double), 6 * sizeof(double), n, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
     return JB_OK;
 }

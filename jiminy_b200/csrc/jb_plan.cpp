@@ -195,6 +195,10 @@ Plan build_plan(const JbModelDesc& m, int lanes, int n_hist) {
     P.nfields = off;
 
     // ---- tables
+    std::vector<double> subtree_mass(m.njoints, 0.0);
+    for (int j = 1; j < m.njoints; ++j) subtree_mass[j] = m.inertia[10 * j];
+    for (int j = m.njoints - 1; j > 0; --j) subtree_mass[m.parent[j]] += subtree_mass[j];
+    P.total_mass = subtree_mass[0];
     P.rint.assign(static_cast<size_t>(P.nrec) * L, RecInt{});
     P.rdbl.assign(static_cast<size_t>(P.nrec) * L, RecDbl{});
     P.cslots.assign(static_cast<size_t>(P.ncslot) * L, ContactSlot{});
@@ -264,6 +268,7 @@ Plan build_plan(const JbModelDesc& m, int lanes, int n_hist) {
                         throw std::invalid_argument("rotor inertia on free-flyer dofs is not supported");
             }
             rd.enc_reduction = 1.0;
+            rd.subtree_mass = subtree_mass[j];
             for (int mm = 0; mm < m.nmotors; ++mm)
                 if (m.motor_joint[mm] == j) {
                     if (ri.motor >= 0) throw std::invalid_argument("several motors on one joint are not supported");

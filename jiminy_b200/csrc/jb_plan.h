@@ -61,7 +61,10 @@ struct RecDbl {
     double motor[10];      // SimpleMotor params (see jiminy_b200.h)
     double enc_reduction;
     double pad;            // velocity taper threshold of the motor (velocityLimit - effortLimit * velocityEffortInvSlope, >= 0)
+    double subtree_mass;   // mass of the subtree rooted at this joint (pinocchio `data.mass[j]`, model.cc:269)
+    double pad2;           // keeps rows 16-byte aligned
 };
+static_assert(sizeof(RecDbl) % 16 == 0, "RecDbl rows are read with 16-byte loads");
 constexpr int REC_DBL_STRIDE = sizeof(RecDbl) / sizeof(double);
 
 struct ContactSlot {  // per lane contact slot (rows[(c * L + s)])
@@ -121,6 +124,7 @@ struct Plan {
     std::vector<RecDbl> rdbl;           // [nrec * L]
     std::vector<ContactSlot> cslots;    // [ncslot * L]
     std::vector<int32_t> joint_lane;    // [njoints] owning sub-lane (-1 trunk)
+    double total_mass = 0.0;            // pinocchio `data.mass[0]`
     std::string describe() const;
 };
 

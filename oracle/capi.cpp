@@ -232,6 +232,25 @@ void orc_get_extra_terms(OrcBatch* b, double* energy, double* joint_a, double* j
         }
     }
 }
+// ycrb [n][njoints][10] (mass, lever, inertia about the subtree CoM), com / vcom [n][njoints][3], hg / dhg [n][6]
+void orc_get_centroidal(OrcBatch* b, double* ycrb, double* com, double* vcom, double* hg, double* dhg) {
+    const int nj = b->njoints;
+    for (size_t i = 0; i < b->envs.size(); ++i) {
+        const Engine& e = *b->envs[i];
+        for (int j = 0; j < nj; ++j) {
+            if (ycrb) {
+                double* o = ycrb + (i * nj + j) * 10;
+                const orc::Inertia& Y = e.data.Ycrb[j];
+                o[0] = Y.mass; o[1] = Y.c.x; o[2] = Y.c.y; o[3] = Y.c.z;
+                for (int k = 0; k < 6; ++k) o[4 + k] = Y.I[k];
+            }
+            if (com) { double* o = com + (i * nj + j) * 3; o[0] = e.data.com[j].x; o[1] = e.data.com[j].y; o[2] = e.data.com[j].z; }
+            if (vcom) { double* o = vcom + (i * nj + j) * 3; o[0] = e.data.vcom[j].x; o[1] = e.data.vcom[j].y; o[2] = e.data.vcom[j].z; }
+        }
+        if (hg) { double* o = hg + 6 * i; const orc::Force& f = e.data.hg; o[0] = f.lin.x; o[1] = f.lin.y; o[2] = f.lin.z; o[3] = f.ang.x; o[4] = f.ang.y; o[5] = f.ang.z; }
+        if (dhg) { double* o = dhg + 6 * i; const orc::Force& f = e.data.dhg; o[0] = f.lin.x; o[1] = f.lin.y; o[2] = f.lin.z; o[3] = f.ang.x; o[4] = f.ang.y; o[5] = f.ang.z; }
+    }
+}
 void orc_get_status(OrcBatch* b, int32_t* status) {
     for (size_t i = 0; i < b->envs.size(); ++i) status[i] = b->envs[i]->status;
 }

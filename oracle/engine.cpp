@@ -64,6 +64,11 @@ Engine::Engine(const JbModelDesc& d, const JbOptions& o) : model(make_model(d)) 
     data.liMi.assign(n, SE3::identity()); data.oMi.assign(n, SE3::identity());
     data.v.assign(n, Motion{}); data.a.assign(n, Motion{}); data.a_gf.assign(n, Motion{});
     data.f.assign(n, Force{}); data.h.assign(n, Force{});
+    data.Ycrb.assign(n, Inertia{}); data.com.assign(n, V3()); data.vcom.assign(n, V3());
+    // subtree masses: data.mass as left by pinocchio::centerOfMass(model, data, qNeutral) (model.cc:269); mass[0] = total
+    data.mass.assign(n, 0.0);
+    for (int i = 1; i < n; ++i) data.mass[i] = model.inertia[i].mass;
+    for (int i = n - 1; i > 0; --i) data.mass[model.parent[i]] += data.mass[i];
     data.Yaba.assign(n, M6::zero()); data.joints.resize(n);
     data.u.assign(nv, 0.0); data.ddq.assign(nv, 0.0);
     auto init_state = [&](RobotState& s) {
@@ -633,6 +638,23 @@ void Engine::computeExtraTerms() {
         data.h[p] += act(data.liMi[i], data.h[i]);
         if (p > 0) data.f[p] += act(data.liMi[i], data.f[i]);
     }
+    // subtree (composite) inertias (engine.cc:817-832; with constraints the reference's CRBA leaves the same quantity)
+    for (int i = 1; i < n; ++i) data.Ycrb[i] = model.inertia[i];
+    for (int i = n - 1; i > 0; --i) {
+        const int p = model.parent[i];
+        if (p > 0) add_inertia(data.Ycrb[p], act(data.liMi[i], data.Ycrb[i]));
+    }
+    // position and velocity of the centre of mass of each subtree (engine.cc:890-898)
+    for (int i = 0; i < n; ++i) {
+        if (i > 0) data.com[i] = data.Ycrb[i].c;
+        data.vcom[i] = V3(data.h[i].lin.x / data.mass[i], data.h[i].lin.y / data.mass[i], data.h[i].lin.z / data.mass[i]);
+    }
+    data.com[0] = n > 1 ? act_point(data.liMi[1], data.com[1]) : V3();
+    // centroidal momentum and its derivative (engine.cc:900-904)
+    data.hg = data.h[0];
+    data.hg.ang += cross(data.hg.lin, data.com[0]);
+    data.dhg = fExt[0];
+    data.dhg.ang += cross(data.dhg.lin, data.com[0]);
 }
 
 // syncAccelerationsAndForces (engine.cc:920-950)

@@ -102,6 +102,12 @@ struct Data {
     std::vector<JointData> joints;
     std::vector<double> u, ddq;
     double kinetic_energy = 0, potential_energy = 0;
+    // computeExtraTerms (engine.cc:817-832, :890-904): subtree inertias, subtree centres of mass and their velocities,
+    // centroidal momentum and its derivative; `mass` = subtree masses (pinocchio::centerOfMass at model set-up, model.cc:269)
+    std::vector<Inertia> Ycrb;
+    std::vector<V3> com, vcom;
+    std::vector<double> mass;
+    Force hg, dhg;
 };
 
 struct RobotState {

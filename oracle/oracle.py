@@ -76,6 +76,7 @@ def lib():
         L.orc_get_sensors.argtypes = [C.c_void_p, c_double_p]
         L.orc_get_extra_terms.argtypes = [C.c_void_p] + [c_double_p] * 3
         L.orc_get_status.argtypes = [C.c_void_p, c_int32_p]
+        L.orc_get_centroidal.argtypes = [C.c_void_p] + [c_double_p] * 5
         L.orc_get_iters.argtypes = [C.c_void_p, c_int64_p, c_int64_p]
         L.orc_rhs_count.argtypes = [C.c_void_p]
         L.orc_rhs_count.restype = C.c_int64
@@ -275,6 +276,13 @@ class OracleBatch:
         e, ja, jf = np.zeros((self.n, 2)), np.zeros((self.n, self.nj, 6)), np.zeros((self.n, self.nj, 6))
         lib().orc_get_extra_terms(self._h, dptr(e), dptr(ja), dptr(jf))
         return e, ja, jf
+
+    def get_centroidal(self):
+        """(Ycrb [n, njoints, 10], com [n, njoints, 3], vcom [n, njoints, 3], hg [n, 6], dhg [n, 6])."""
+        y, c, vc = np.zeros((self.n, self.nj, 10)), np.zeros((self.n, self.nj, 3)), np.zeros((self.n, self.nj, 3))
+        hg, dhg = np.zeros((self.n, 6)), np.zeros((self.n, 6))
+        lib().orc_get_centroidal(self._h, dptr(y), dptr(c), dptr(vc), dptr(hg), dptr(dhg))
+        return y, c, vc, hg, dhg
 
     def get_status(self) -> np.ndarray:
         s = np.zeros(self.n, dtype=np.int32)

@@ -124,6 +124,37 @@ inline double vtiv(const Inertia& Y, const Motion& v) {  // v^T I v
     return Y.mass * dot(d, d) + dot(v.ang, sym_mul(Y.I, v.ang));
 }
 
+// InertiaTpl::se3Action_impl: Y expressed in the parent frame (pinocchio/spatial/inertia.hpp)
+inline Inertia act(const SE3& M, const Inertia& Y) {
+    Inertia r;
+    r.mass = Y.mass;
+    r.c = M.p + M.R * Y.c;
+    // Symmetric3::rotate: R S R^T
+    M3 S;
+    S.m[0] = Y.I[0]; S.m[1] = Y.I[1]; S.m[2] = Y.I[3];
+    S.m[3] = Y.I[1]; S.m[4] = Y.I[2]; S.m[5] = Y.I[4];
+    S.m[6] = Y.I[3]; S.m[7] = Y.I[4]; S.m[8] = Y.I[5];
+    const M3 T = M.R * S * transpose(M.R);
+    r.I[0] = T.m[0]; r.I[1] = T.m[1]; r.I[2] = T.m[4]; r.I[3] = T.m[2]; r.I[4] = T.m[5]; r.I[5] = T.m[8];
+    return r;
+}
+// InertiaTpl::__pequ__: composite of two rigid bodies expressed in the same frame
+inline void add_inertia(Inertia& Ya, const Inertia& Yb) {
+    const double mab = Ya.mass + Yb.mass;
+    const double mab_inv = 1.0 / std::max(mab, 2.220446049250313e-16);
+    const V3 AB = Ya.c - Yb.c;
+    Ya.c = (Ya.mass * mab_inv) * Ya.c + (Yb.mass * mab_inv) * Yb.c;
+    // I += Ib - (ma mb / mab) [AB]x^2,  [v]x^2 = v v^T - |v|^2 1
+    const double k = Ya.mass * Yb.mass * mab_inv, n2 = dot(AB, AB);
+    Ya.I[0] += Yb.I[0] - k * (AB.x * AB.x - n2);
+    Ya.I[1] += Yb.I[1] - k * (AB.x * AB.y);
+    Ya.I[2] += Yb.I[2] - k * (AB.y * AB.y - n2);
+    Ya.I[3] += Yb.I[3] - k * (AB.x * AB.z);
+    Ya.I[4] += Yb.I[4] - k * (AB.y * AB.z);
+    Ya.I[5] += Yb.I[5] - k * (AB.z * AB.z - n2);
+    Ya.mass = mab;
+}
+
 struct M6 {
     double m[36];  // row-major, rows/cols: [lin(3), ang(3)]
     double operator()(int i, int j) const { return m[6 * i + j]; }

@@ -125,6 +125,9 @@ def compare_extra_terms(eng, orc, tol=1e-9):
     np.testing.assert_allclose(e1, e0, rtol=0, atol=tol * max(1.0, np.abs(e0).max()))
     np.testing.assert_allclose(a1, a0, rtol=0, atol=tol * max(1.0, np.abs(a0).max()))
     np.testing.assert_allclose(f1, f0, rtol=0, atol=tol * max(1.0, np.abs(f0).max()))
+    # subtree inertias / centres of mass / their velocities, centroidal momentum and its derivative (engine.cc:817-832, :890-904)
+    for x1, x0 in zip(eng.get_centroidal(), orc.get_centroidal()):
+        np.testing.assert_allclose(x1, x0, rtol=0, atol=tol * max(1.0, np.abs(x0).max()))
 
 
 def _force_pair(sc, api):

@@ -469,3 +469,46 @@ def test_joint_position_limits_like_the_reference_test():
     import analytic_device as ad
     r, opt, lim, eps = ad.joint_position_limits_robot()
     ad.joint_position_limits_criteria(OracleBatch(r, opt), lim, eps)
+
+
+def test_centroidal_terms_against_first_principles():
+    """computeExtraTerms (engine.cc:817-832, :890-904) on the oracle, checked against quantities derived independently
+    of any spatial algebra: the whole-robot centre of mass from a numpy forward kinematics (sum of m_i * oMi c_i), the
+    subtree masses, Newton's law for the centroidal momentum derivative (dhg.linear = M g + sum of the contact forces;
+    a robot in free fall has dhg = (M g, 0) exactly) and hg.linear = M * d(com)/dt by finite differences."""
+    from jiminy_b200 import scenarios
+    sc = scenarios.make("anymal", 2, seed=2)
+    rob = sc.robot
+    q0 = sc.q0.copy()
+    q0[1, 2] += 0.5                      # env 1 starts in the air: free fall, no contact
+    v0 = np.zeros_like(sc.v0)
+    v0[1, 3:6] = [0.4, -0.3, 0.2]        # ... tumbling
+    orc = OracleBatch(rob, sc.options, 2)
+    orc.set_pd_controller(sc.kp, sc.kd)
+    orc.set_command(sc.target0)
+    assert not orc.start(q0, v0).any()
+    Mtot = rob.mass
+    g = np.array(sc.options["world"]["gravity"][:3])
+    coms = []
+    for k in range(3):
+        orc.step(1e-3)
+        _, q, v, _ = orc.get_state()
+        ycrb, com, vcom, hg, dhg = orc.get_centroidal()
+        for e in range(2):
+            oMi = R.forward_kinematics(rob, q[e])
+            c = sum(rob.inertia[j, 0] * (oMi[j].R @ rob.inertia[j, 1:4] + oMi[j].p) for j in range(1, rob.njoints)) / Mtot
+            np.testing.assert_allclose(com[e, 0], c, rtol=0, atol=1e-13)
+            np.testing.assert_allclose(ycrb[e, 1, 0], Mtot, rtol=1e-14)
+            np.testing.assert_allclose(hg[e, :3], Mtot * vcom[e, 0], rtol=0, atol=1e-11)
+        # free fall: total external force = weight, no moment about the centre of mass
+        np.testing.assert_allclose(dhg[1, :3], Mtot * g, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(dhg[1, 3:], 0.0, atol=1e-9)
+        # standing: weight + contact forces (world frame) = d(hg)/dt
+        fext = orc.get_efforts()[3][0]                      # per joint wrench in the joint frame
+        oMi = R.forward_kinematics(rob, q[0])
+        f_world = sum(oMi[j].R @ fext[j, :3] for j in range(1, rob.njoints))
+        np.testing.assert_allclose(dhg[0, :3], Mtot * g + f_world, rtol=0, atol=1e-8 * max(1.0, np.abs(f_world).max()))
+        coms.append((orc.get_state()[0][1], com[1, 0].copy(), vcom[1, 0].copy()))
+    # finite difference of the free-falling CoM against vcom (world-frame velocity of the centre of mass)
+    (t0, c0, _), (t1, c1, w1), (t2, c2, _) = coms
+    np.testing.assert_allclose((c2 - c0) / (t2 - t0), w1, rtol=0, atol=1e-5)
