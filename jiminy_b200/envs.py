@@ -53,12 +53,13 @@ class BatchedJiminyEnv:
     # ------------------------------------------------------------------ helpers
     def _observation(self) -> Dict[str, Any]:
         t, q, v, _ = self.engine.get_state()
-        self.engine.get_sensors(self._sens)
+        sens = np.empty_like(self._sens)      # a fresh matrix per observation: earlier observations stay valid
+        self.engine.get_sensors(sens)
         meas = {}
         for name, nf in SENSOR_FIELDS.items():
             off, _, ns = self._layout[name]
             if ns:
-                meas[name] = self._sens[:, off:off + nf * ns].reshape(self.n_env, nf, ns)
+                meas[name] = sens[:, off:off + nf * ns].reshape(self.n_env, nf, ns)
         return {"t": t, "states": {"agent": {"q": q, "v": v}}, "measurements": meas}
 
     def _sample_state(self, n: int) -> Tuple[np.ndarray, np.ndarray]:
@@ -101,7 +102,10 @@ class BatchedJiminyEnv:
         info = {"status": status}
         done = terminated | truncated
         if done.any():
-            self.reset(mask=done.astype(np.uint8))
+            # gymnasium vector-env convention: finished envs return their first observation after the restart, the
+            # terminal one goes to info["final_observation"] (valid where info["_final_observation"])
+            info["final_observation"], info["_final_observation"] = obs, done
+            obs, _ = self.reset(mask=done.astype(np.uint8))
         return obs, reward, terminated, truncated, info
 
     def close(self) -> None:
@@ -199,9 +203,11 @@ class PDControlBatchedEnv(BatchedJiminyEnv):
         truncated = ((status & ~core.JB_ENV_JOINT_LIMIT) != 0) | (self.num_steps * self.step_dt >= self.simulation_duration_max)
         reward = np.where(terminated, 0.0, 1.0)
         done = terminated | truncated
+        info = {"status": status}
         if done.any():
-            self.reset(mask=done.astype(np.uint8))
-        return obs, reward, terminated, truncated, {"status": status}
+            info["final_observation"], info["_final_observation"] = obs, done
+            obs, _ = self.reset(mask=done.astype(np.uint8))
+        return obs, reward, terminated, truncated, info
 
 
 def flatten_observation(obs: Dict[str, Any], nested_keys, low=None, high=None) -> np.ndarray:

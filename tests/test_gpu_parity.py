@@ -277,3 +277,26 @@ def test_handoff_with_stateful_blocks_at_scale():
 def test_mahony_filter_observer():
     pc.mahony_scenario(None, "anymal", n_env=70, n_steps=4)
     pc.mahony_scenario(None, "atlas", n_env=5, n_steps=1)
+
+
+# ---- the single-env `Engine` facade on the CUDA library (the same test bodies the CPU suite runs on the emulator)
+def test_engine_facade_python_controller_on_device():
+    import test_kernel_emul as tke
+    tke.test_engine_facade_python_controller(None)
+
+
+def test_engine_facade_forces_on_device():
+    import test_kernel_emul as tke
+    tke.test_engine_facade_impulse_forces(None)
+    tke.test_engine_facade_profile_force_function(None)
+
+
+def test_engine_facade_telemetry_log_on_device(tmp_path):
+    import test_kernel_emul as tke
+    tke.test_engine_facade_telemetry_log(None, tmp_path)
+
+
+def test_batched_env_reset_step_autoreset_on_device():
+    import test_kernel_emul as tke
+    tke.test_batched_env_reset_step_autoreset(None)
+    tke.test_pd_control_pipeline_env(None)

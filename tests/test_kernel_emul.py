@@ -195,6 +195,12 @@ def test_batched_env_reset_step_autoreset(api):
     obs, rew, term, trunc, info = env.step(sc.sample_targets(3))
     assert trunc.all()                              # duration limit reached -> every env is restarted
     np.testing.assert_allclose(env.engine.get_state()[0], 0.0)
+    # the returned observation is the one after the restart; the terminal one is kept aside, untouched by the restart
+    np.testing.assert_allclose(obs["t"], 0.0)
+    fin = info["final_observation"]
+    assert info["_final_observation"].all() and np.allclose(fin["t"], 0.16)
+    assert np.abs(fin["measurements"]["ForceSensor"][:, :3, :]).sum() > 0.0
+    assert not np.shares_memory(fin["measurements"]["ForceSensor"], obs["measurements"]["ForceSensor"])
     env.close()
 
 
