@@ -77,6 +77,7 @@ struct JbBatch {
     int* h_peer_timeout = nullptr;             // host-mapped: set by the wait kernel when a rank never signalled
     int* d_peer_timeout = nullptr;             // device alias of the same word
     double peer_timeout_s = 2.0;
+    long long peer_timeout_cycles = 4000000000LL;
     long long step_id = 0;
     bool peer_enabled = true;                   // jb_peer_obs_enable
     // external forces: frames (slots), impulse table mirror, profile periods
@@ -378,6 +379,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
     }
 
     if (SigQuadruped::matches(kp) && !std::getenv("JB_NO_STATIC_PLAN")) kp.sig_id = SigQuadruped::ID;
+    kp.rhs_variant = (std::getenv("JB_QUADRUPED_ABA") && std::atoi(std::getenv("JB_QUADRUPED_ABA"))) ? 0 : 1;
     // ---- constraint path: lookup tables, persistent state and workspace (jb_constraints.cuh)
     {
         std::vector<JointMap> jmap(m->njoints);
@@ -1070,6 +1072,11 @@ int jb_peer_obs_create(JbBatch* b, int32_t world, int32_t rank, uint8_t handle_o
     *b->h_peer_timeout = 0;
     CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&b->d_peer_timeout), b->h_peer_timeout, 0));
     if (const char* e = std::getenv("JB_PEER_TIMEOUT_S")) b->peer_timeout_s = std::max(0.01, std::atof(e));
+    {   // (queried once: the clock-rate attribute is a slow driver call)
+        int khz = 1965000;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, b->device);
+        b->peer_timeout_cycles = static_cast<long long>(b->peer_timeout_s * 1e3 * khz);
+    }
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, raw));
     std::memcpy(handle_out, &h, 64);
@@ -1127,10 +1134,7 @@ int jb_peer_obs_wait(JbBatch* b) {
     CU(cudaSetDevice(b->device));
     const int parity = static_cast<int>(b->step_id & 1);
     volatile long long* mine = reinterpret_cast<volatile long long*>(b->d_peer_buf + 2 * b->peer_obs_doubles * sizeof(double));
-    int khz = 1965000;
-    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, b->device);
-    const long long cycles = static_cast<long long>(b->peer_timeout_s * 1e3 * khz);
-    JB_LAUNCH(peer_wait_kernel, 1, 1, 0, b->stream, mine, b->peer_world, parity, b->step_id, cycles, b->d_peer_timeout);
+    JB_LAUNCH(peer_wait_kernel, 1, 1, 0, b->stream, mine, b->peer_world, parity, b->step_id, b->peer_timeout_cycles, b->d_peer_timeout);
     CU(cudaGetLastError());
     ++b->launches;
     return JB_OK;
