@@ -110,15 +110,15 @@ class ClockSampler(threading.Thread):
         return out
 
 
-def cpu_baseline(sc_name, threads_all=True, budget_s=12.0, contact_model=None, solver=None, dt_max=None):
+def cpu_baseline(sc_name, threads_all=True, budget_s=12.0, contact_model=None, solver=None, dt_max=None, **kw):
     """The oracle (a C++ restatement of the reference's CPU path) on this box's host cores: a bounded
     sample of the same workload.  Returns env-steps/s single-thread and with all OpenMP threads."""
     from jiminy_b200 import scenarios
     from oracle.oracle import OracleBatch
     ncores = OracleBatch.use_all_cores()
-    out = {}
+    out = {"usable": OracleBatch.usable_cores()}
     for label, n_env, par in (("single_thread", 8, False), ("all_threads", 32 * ncores, True)):
-        sc = scenarios.make(sc_name, n_env, contact_model=contact_model, solver=solver, dt_max=dt_max)
+        sc = scenarios.make(sc_name, n_env, contact_model=contact_model, solver=solver, dt_max=dt_max, **kw)
         orc = OracleBatch(sc.robot, sc.options, n_env)
         if sc.kp is not None:
             orc.set_pd_controller(sc.kp, sc.kd)
@@ -130,11 +130,33 @@ def cpu_baseline(sc_name, threads_all=True, budget_s=12.0, contact_model=None, s
         # (the cartpole's random-force policy would walk the cart into its +-10 m position bound after ~200 steps)
         while time.perf_counter() - t0 < budget_s / 2 and k < (80 if sc_name == "cartpole" else 200):
             orc.set_command(sc.sample_targets(k + 1))
-            assert not orc.step(sc.step_dt, parallel=par).any()
+            rc = orc.step(sc.step_dt, parallel=par)
+            assert kw.get("action", "pd") == "torque" or not rc.any()     # (raw torques: an explicit stepper may diverge, see tools/stability_sweep.py)
             k += 1
         dt = time.perf_counter() - t0
         out[label] = {"value": n_env * k / dt, "n_env": n_env, "steps": k, "seconds": dt}
     return ncores, out
+
+
+PORT_NOTE = ("kind=port: a scalar C++ restatement of the reference path (oracle/), not jiminy itself (it cannot be built here); on "
+             "the one setting the reference publishes (Atlas, Euler 5 ms, constraint contacts: 3.65 k env-steps/s on one thread, "
+             "Python pipeline included) the port does 1.3 k single-thread, i.e. it is >= 2.8x slower than real jiminy")
+
+
+def workload_name(args, sc):
+    """The same string in both arms (the driver compares them)."""
+    return f"{args.workload}: {args.n_env} envs per GPU, one Engine::step({sc.step_dt}) per step"
+
+
+def kernel_source_sha():
+    """Identity of the device code the profile numbers belong to."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "jiminy_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".cpp", ".h")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def run_reference(args):
@@ -148,7 +170,8 @@ def run_reference(args):
     from oracle.oracle import OracleBatch
     ncores = OracleBatch.use_all_cores()
     n_env = min(args.n_env, 64 * ncores)        # bounded sample of the 4096-env batch
-    sc = scenarios.make(args.workload, n_env, contact_model=args.contact_model, solver=args.ode_solver, dt_max=args.dt_max)
+    sc = scenarios.make(args.workload, n_env, contact_model=args.contact_model, solver=args.ode_solver, dt_max=args.dt_max,
+                        action=args.action, flagged_fraction=args.flagged_fraction)
     orc = OracleBatch(sc.robot, sc.options, n_env)
     if sc.kp is not None:
         orc.set_pd_controller(sc.kp, sc.kd)
@@ -161,17 +184,18 @@ def run_reference(args):
     for k in range(args.steps):
         orc.set_command(sc.sample_targets(args.warmup + k))
         rc = orc.step(sc.step_dt, parallel=True)
-        assert not rc.any()
+        assert args.action == "torque" or not rc.any()
     dt = time.perf_counter() - t0
     value = n_env * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {n_env}-env sample of the {args.n_env}-env batch, same scenario as the GPU arm",
-                   "scenario": sc.description, "step_dt": sc.step_dt},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "port",
-                         "sample": f"{n_env} envs x {args.steps} env-steps, OpenMP over envs"},
+        "config": {"workload": workload_name(args, sc), "scenario": sc.description, "step_dt": sc.step_dt,
+                   "sample": f"{n_env}-env sample of the {args.n_env}-env batch, same scenario as the GPU arm"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "port", "usable_cores": OracleBatch.usable_cores(),
+                         "sample": f"{n_env} envs x {args.steps} env-steps, OpenMP over envs",
+                         "note": PORT_NOTE},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -192,7 +216,8 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_env = args.n_env                                   # per GPU (weak scaling: envs are independent)
-    sc = scenarios.make(args.workload, n_env, seed=rank, contact_model=args.contact_model, solver=args.ode_solver, dt_max=args.dt_max)
+    sc = scenarios.make(args.workload, n_env, seed=rank, contact_model=args.contact_model, solver=args.ode_solver, dt_max=args.dt_max,
+                        action=args.action, flagged_fraction=args.flagged_fraction)
     eng = core.BatchedEngine(sc.robot, sc.options, n_env, device=local_rank)
     if sc.kp is not None:
         eng.set_pd_controller(sc.kp, sc.kd)
@@ -276,7 +301,8 @@ def run_gpu(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_path_ms = float(tt.item())
     status = eng.get_status()
-    n_bad = int((status != 0).sum())
+    n_bad = int(((status & ~8) != 0).sum())            # failed envs (8 = JB_ENV_JOINT_LIMIT is informational)
+    n_bounds = int(((status & 8) != 0).sum())          # envs whose joint-bound constraints have been active: stepped by the full body
 
     # ---------------- end-to-end arm: host buffers through the C ABI every step
     barrier()
@@ -296,9 +322,9 @@ def run_gpu(args):
         tt = torch.tensor([e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_ms = float(tt.item())
-        bad = torch.tensor([n_bad], device=f"cuda:{local_rank}")
+        bad = torch.tensor([n_bad, n_bounds], device=f"cuda:{local_rank}")
         dist.all_reduce(bad)
-        n_bad = int(bad.item())
+        n_bad, n_bounds = int(bad[0].item()), int(bad[1].item())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -309,33 +335,37 @@ def run_gpu(args):
     e2e_value = total_envs * args.steps / (e2e_ms * 1e-3)
     peaks, peak_kind = read_peaks()
     bytes_per_launch = sc.algorithmic_bytes_per_env_step() * n_env
-    traffic, fp64_pct = None, None
+    # `traffic` and the FP64-pipe figure come from the committed ncu capture of THIS device code (profiles/ncu_traffic.json is
+    # written by tools/ncu_traffic.py with the hash of jiminy_b200/csrc): a stale capture reports null, never an old number
+    traffic, fp64_pct, prof_src = None, None, None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
-            rec = json.load(fh).get(args.workload) if (args.contact_model in (None, "spring_damper") and args.ode_solver is None and args.dt_max is None) else None
-        if rec and rec["n_env"] == n_env:
-            traffic, fp64_pct = rec["traffic_bytes"], rec["fp64_pipe_active_pct"]
+            default = (args.contact_model in (None, "spring_damper") and args.ode_solver is None and args.dt_max is None and
+                       args.action == "pd" and args.flagged_fraction == 0.0)
+            rec = json.load(fh).get(args.workload) if default else None
+        if rec and rec["n_env"] == n_env and rec.get("kernel_source_sha") == kernel_source_sha():
+            traffic, fp64_pct, prof_src = rec["traffic_bytes"], rec["fp64_pipe_active_pct"], rec.get("source")
     except Exception:
         pass
     achieved_gbs = bytes_per_launch / (step_ms_dev * 1e-3) / 1e9
     ncores, cpu = (None, None)
     if not args.no_cpu_baseline:
-        ncores, cpu = cpu_baseline(args.workload, contact_model=args.contact_model, solver=args.ode_solver, dt_max=args.dt_max)
+        ncores, cpu = cpu_baseline(args.workload, contact_model=args.contact_model, solver=args.ode_solver, dt_max=args.dt_max,
+                                   action=args.action, flagged_fraction=args.flagged_fraction)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_path_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {n_env} envs per GPU, {world} GPU(s), one Engine::step({sc.step_dt}) per step",
-                   "scenario": sc.description, "envs_total": total_envs, "lane_plan": eng.describe(),
+        "config": {"workload": workload_name(args, sc), "scenario": sc.description, "envs_total": total_envs, "lane_plan": eng.describe(),
                    "l2": "160 MB buffer rewritten between timed steps (flush)", "obs_all_gather_ms": gather_ms, "obs_exchange": obs_gather,
-                   "envs_flagged": n_bad, "timed_region_wall_ms": wall_ms},
+                   "envs_failed": n_bad, "envs_flagged": n_bounds, "timed_region_wall_ms": wall_ms},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_env * nm * 8 * world),
                 "d2h_bytes_per_step": int(n_env * width * 8 * world), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
-                     "fp64_pipe_active_pct_ncu": fp64_pct,
+                     "fp64_pipe_active_pct_ncu": fp64_pct, "ncu_capture": prof_src, "kernel_source_sha": kernel_source_sha(),
                      "kernel": "env_step_kernel", "kernel_ms": step_ms_dev,
                      "algorithmic_bytes_per_launch": bytes_per_launch,
                      "note": "fp64-pipe / latency bound by construction (state stays on chip for the whole "
@@ -345,7 +375,7 @@ def run_gpu(args):
         line["cpu_baseline"] = {"value": cpu["all_threads"]["value"], "unit": UNIT, "cores": ncores, "kind": "port",
                                 "sample": f"{cpu['all_threads']['n_env']} envs x {cpu['all_threads']['steps']} env-steps, "
                                           f"OpenMP over envs ({cpu['all_threads']['seconds']:.1f} s)",
-                                "single_thread_value": cpu["single_thread"]["value"]}
+                                "single_thread_value": cpu["single_thread"]["value"], "usable_cores": cpu["usable"], "note": PORT_NOTE}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -367,6 +397,10 @@ def main():
     ap.add_argument("--contact-model", default=None, choices=["spring_damper", "constraint"],
                     help="override contacts.model of the scenario (the BASELINE metric is quoted on spring_damper)")
     ap.add_argument("--n-env", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--action", default="pd", choices=["pd", "torque"],
+                    help="legged robots: PD position targets around the standing posture (default) or raw torque actions U(-20, 20) Nm")
+    ap.add_argument("--flagged-fraction", type=float, default=0.0,
+                    help="PD mode: share of the envs driven through their hip joint bounds (stepped by the full body with joint-bound constraints)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -60,6 +60,8 @@ class Scenario:
     seed: int
     description: str = ""
     _motor_q: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int64))
+    torque_amplitude: float = 0.0     # > 0: raw effort actions U(-amplitude, amplitude) (SURVEY.md 8d config 3 as written)
+    flagged_fraction: float = 0.0     # PD mode: this share of the envs drives its hip-abduction targets beyond the joint bounds
 
     def sample_targets(self, k: int) -> np.ndarray:
         """Action of env-step k, reproducible: position targets (PD mode) or efforts."""
@@ -68,9 +70,19 @@ class Scenario:
             # per env random element of {-limit, 0, +limit} (cartpole.py:139-147)
             lim = self.robot.motors[0].effort_limit
             return rng.integers(-1, 2, size=(self.n_env, 1)).astype(np.float64) * lim
+        if self.torque_amplitude > 0.0:
+            return rng.uniform(-self.torque_amplitude, self.torque_amplitude, size=(self.n_env, max(self.robot.nmotors, 1)))
         if self.kp is None:
             return np.zeros((self.n_env, max(self.robot.nmotors, 1)))
-        return self.target0 + rng.uniform(-self.action_noise, self.action_noise, size=self.target0.shape)
+        act = self.target0 + rng.uniform(-self.action_noise, self.action_noise, size=self.target0.shape)
+        if self.flagged_fraction > 0.0:
+            # every (1/fraction)-th env pushes its hip-abduction joints through their position bounds: those envs leave
+            # the hot path and are stepped by the full body with their joint-bound constraints (spread over the warps)
+            stride = max(1, int(round(1.0 / self.flagged_fraction)))
+            haa = [k for k, m in enumerate(self.robot.motors) if "HAA" in m.name.upper() or "shx" in m.name]
+            for j in haa:
+                act[::stride, j] = self.robot.q_upper[self._motor_q[j]] + 0.3
+        return act
 
     def algorithmic_bytes_per_env_step(self) -> int:
         """compulsory HBM traffic of one env-step: read (q, v, a, command), write
@@ -100,7 +112,7 @@ def standing_posture(name: str, robot: RobotTable) -> np.ndarray:
 
 
 def make(name: str, n_env: int, seed: int = 0, dt_max: Optional[float] = None, solver: Optional[str] = None,
-         contact_model: Optional[str] = None) -> Scenario:
+         contact_model: Optional[str] = None, action: str = "pd", flagged_fraction: float = 0.0) -> Scenario:
     robot, base = R.load_robot(name)
     opt = R.baseline_options(name, copy.deepcopy(base))
     if dt_max is not None:
@@ -131,13 +143,20 @@ def make(name: str, n_env: int, seed: int = 0, dt_max: Optional[float] = None, s
             kp = np.array([_gain(_ATLAS_KP, m.name) for m in robot.motors])
             kd = np.array([_gain(_ATLAS_KD, m.name) for m in robot.motors])
         target0 = np.tile(qs[mq], (n_env, 1))
+        if action == "torque":
+            # SURVEY.md 8(d) config 3 as written: raw effort actions U(-20, 20) Nm, zero-order held over the env-step
+            return Scenario(name, robot, opt, n_env, 0.04, q0, v0, None, None, np.zeros((n_env, robot.nmotors)), 0.0, seed,
+                            f"{name}: raw torque actions U(-20, 20) Nm per env-step, {opt['stepper']['odeSolver']} "
+                            f"dtMax={opt['stepper']['dtMax']}, contacts.model={opt['contacts']['model']}", _motor_q=mq,
+                            torque_amplitude=20.0)
         return Scenario(name, robot, opt, n_env, 0.04, q0, v0, kp, kd, target0, 0.02, seed,
                         f"{name}: PD standing (reference gains), targets = posture + U(-0.02, 0.02) rad per env-step, "
                         f"{opt['stepper']['odeSolver']} dtMax={opt['stepper']['dtMax']}, " +
                         (f"spring-damper contact k={opt['contacts']['stiffness']:g} c={opt['contacts']['damping']:g} "
                          if opt["contacts"]["model"] == "spring_damper" else "constraint contact (PGS) ") +
-                        f"mu={opt['contacts']['friction']:g}",
-                        _motor_q=mq)
+                        f"mu={opt['contacts']['friction']:g}" +
+                        (f"; {flagged_fraction:g} of the envs driven through their hip joint bounds" if flagged_fraction > 0 else ""),
+                        _motor_q=mq, flagged_fraction=flagged_fraction)
     if name == "cartpole":
         # x, theta, dx, dtheta ~ U(-0.05, 0.05) (cartpole.py:184-199); q = (x, cos, sin)
         x = rng.uniform(-0.05, 0.05, size=(n_env, 4))

@@ -112,10 +112,32 @@ class OracleBatch:
     def use_all_cores() -> int:
         """OpenMP thread count = the cores this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it
         to 1 for its workers)."""
-        import os
-        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        n = OracleBatch.usable_cores()["threads"]
         lib().orc_set_threads(int(n))
         return lib().orc_max_threads()
+
+    @staticmethod
+    def usable_cores() -> dict:
+        """What this process may actually use: the affinity mask AND the cgroup CPU quota (a container that shows 128
+        CPUs in its affinity mask may be throttled to a handful by `cpu.max`).  `threads` = min of the two."""
+        import math
+        import os
+        aff = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        quota = None
+        try:   # cgroup v2, then v1
+            txt = open("/sys/fs/cgroup/cpu.max").read().split()
+            if txt[0] != "max":
+                quota = float(txt[0]) / float(txt[1])
+        except Exception:
+            try:
+                q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+                per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    quota = q / per
+            except Exception:
+                pass
+        threads = aff if quota is None else max(1, min(aff, int(math.ceil(quota))))
+        return {"affinity": aff, "cgroup_quota_cpus": quota, "threads": threads}
 
     def set_options(self, options: dict) -> None:
         self._opt = make_options(options)
