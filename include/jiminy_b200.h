@@ -309,6 +309,25 @@ int jb_get_efforts(JbBatch* batch, double* u, double* u_motor, double* command, 
 int jb_get_sensors(JbBatch* batch, double* out);
 int jb_sensor_layout(JbBatch* batch, JbSensorLayout* out);
 
+/* Replaces: AbstractSensorBase::setOptions with the options every sensor shares -- `noiseStd`, `bias`, `delay`, `jitter`,
+ * `delayInterpolationOrder` (core/include/jiminy/core/hardware/abstract_sensor.h:66-100) -- i.e. the measurement pipeline
+ * applied on top of the true value at every sensor refresh: the value `delay` (+ uniform jitter) seconds ago from a
+ * ring of past true values, zero-order hold or linear interpolation (abstract_sensor.hxx:305-430, :445-522), plus white
+ * noise, plus bias (abstract_sensor.cc:71-85).  `type`: 0 ImuSensor, 1 ForceSensor, 2 EncoderSensor, 3 EffortSensor,
+ * 4 ContactSensor; `index`: attach order within the type; noise_std / bias: one value per field of the type (6, 6, 2, 1,
+ * 3), NULL = none.  Once any sensor has options, jb_get_sensors returns MEASUREMENTS (what `robot.sensor_measurements`
+ * holds) and jb_get_sensor_data the true values (`sensor.data`); without options both are the true values and the step
+ * path is bit-unchanged.  Only between episodes (after jb_stop / before the first jb_start), like the reference; needs
+ * a discrete sensorsUpdatePeriod. */
+int jb_set_sensor_options(JbBatch* batch, int32_t type, int32_t index, const double* noise_std, const double* bias,
+                          double delay, double jitter, int32_t delay_interpolation_order);
+/* Replaces: `stepper.randomSeedSeq` of each env's engine (engine.h:331, Engine::reset engine.cc:756-763), one 32-bit
+ * seed per env: jb_start derives from it the generator of every sensor of the (re)started envs with the reference's
+ * chain -- PCG32(seed_seq{seed}) -> one draw per sensor type -> seed_seq expansion -> PCG32(seed) per sensor
+ * (abstract_sensor.hxx:213-226, random.cc:10-37).  Default: 0 for every env. */
+int jb_set_seeds(JbBatch* batch, const uint32_t* seeds /* [n_env] */);
+int jb_get_sensor_data(JbBatch* batch, double* out /* [n_env][width] true values */);
+
 /* Replaces: the quantities Engine::computeExtraTerms leaves in pinocchio::Data after each
  * successful step (engine.cc:800-905): per env kinetic+potential energy `energy` [n_env][2],
  * joint spatial accelerations `joint_a` [n_env][njoints][6] (data.a) and joint internal wrenches

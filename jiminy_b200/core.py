@@ -61,7 +61,8 @@ class Api:
                "jb_peer_obs_create", "jb_peer_obs_connect", "jb_peer_obs_wait", "jb_peer_obs_view", "jb_peer_obs_enable",
                "jb_set_pd_controller_full", "jb_set_mahony_filter", "jb_get_mahony_filter",
                "jb_get_pd_controller_state", "jb_set_pd_controller_state", "jb_get_constraints",
-               "jb_get_stepper_state", "jb_set_stepper_state", "jb_get_centroidal")
+               "jb_get_stepper_state", "jb_set_stepper_state", "jb_get_centroidal",
+               "jb_set_sensor_options", "jb_set_seeds", "jb_get_sensor_data")
 
     def __init__(self, cdll: C.CDLL):
         self.dll = L = cdll
@@ -85,6 +86,9 @@ class Api:
         L.jb_get_efforts.argtypes = [vp] + [c_double_p] * 4
         L.jb_get_stepper_state.argtypes = [vp, c_double_p, c_double_p]
         L.jb_get_centroidal.argtypes = [vp] + [c_double_p] * 5
+        L.jb_set_sensor_options.argtypes = [vp, C.c_int32, C.c_int32, c_double_p, c_double_p, C.c_double, C.c_double, C.c_int32]
+        L.jb_set_seeds.argtypes = [vp, C.POINTER(C.c_uint32)]
+        L.jb_get_sensor_data.argtypes = [vp, c_double_p]
         L.jb_set_stepper_state.argtypes = [vp] + [c_double_p] * 4 + [c_int64_p, c_int64_p, c_double_p]
         L.jb_get_sensors.argtypes = [vp, c_double_p]
         L.jb_sensor_layout.argtypes = [vp, C.POINTER(JbSensorLayout)]
@@ -378,6 +382,29 @@ class BatchedEngine:
         q, v, a = np.zeros((self.n_env, self.nq)), np.zeros((self.n_env, self.nv)), np.zeros((self.n_env, self.nv))
         self._api.check(self._api.dll.jb_get_state(self._h, dptr(t), dptr(q), dptr(v), dptr(a)))
         return t, q, v, a
+
+    SENSOR_TYPES = ("ImuSensor", "ForceSensor", "EncoderSensor", "EffortSensor", "ContactSensor")
+
+    def set_sensor_options(self, sensor_type: str, index: int, noise_std=None, bias=None, delay: float = 0.0,
+                           jitter: float = 0.0, delay_interpolation_order: int = 1) -> None:
+        """`sensor.set_options({"noiseStd", "bias", "delay", "jitter", "delayInterpolationOrder"})` of one sensor
+        (abstract_sensor.h:66-100): afterwards `get_sensors` returns measurements, `get_sensor_data` the true values."""
+        ns = None if noise_std is None else np.ascontiguousarray(noise_std, dtype=np.float64)
+        bs = None if bias is None else np.ascontiguousarray(bias, dtype=np.float64)
+        self._api.check(self._api.dll.jb_set_sensor_options(
+            self._h, self.SENSOR_TYPES.index(sensor_type), int(index), None if ns is None else dptr(ns),
+            None if bs is None else dptr(bs), float(delay), float(jitter), int(delay_interpolation_order)))
+
+    def set_seeds(self, seeds) -> None:
+        """One engine seed per env (`stepper.randomSeedSeq = [seed]`): consumed at the next start of each env."""
+        s = np.ascontiguousarray(seeds, dtype=np.uint32)
+        assert s.shape == (self.n_env,)
+        self._api.check(self._api.dll.jb_set_seeds(self._h, s.ctypes.data_as(C.POINTER(C.c_uint32))))
+
+    def get_sensor_data(self) -> np.ndarray:
+        out = np.zeros((self.n_env, max(self.width, 1)))
+        self._api.check(self._api.dll.jb_get_sensor_data(self._h, dptr(out)))
+        return out[:, :self.width]
 
     def get_centroidal(self):
         """`pinocchio_data.{Ycrb, com, vcom, hg, dhg}` after the last step: (ycrb [n_env, njoints, 10], com [n_env, njoints, 3],

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -55,6 +56,16 @@ struct JbBatch {
     double* d_springs = nullptr;
     double *d_pd = nullptr, *d_cmd_torque = nullptr, *d_pdf = nullptr, *d_pdf_state = nullptr, *d_mahony = nullptr;
     double *d_pdf_snap = nullptr, *d_mahony_snap = nullptr;
+    // sensor measurement pipeline (jb_set_sensor_options / jb_set_seeds)
+    std::vector<SensorDesc> sdesc;
+    std::vector<uint32_t> seeds;
+    bool sp_dirty = false;
+    int sp_cap_alloc = 0;
+    SensorDesc* d_sdesc = nullptr;
+    unsigned long long *d_sp_rng = nullptr, *d_sp_rng_init = nullptr, *d_sp_snap_rng = nullptr;
+    int32_t *d_sp_count = nullptr, *d_sp_snap_count = nullptr;
+    double *d_sp_times = nullptr, *d_sp_ring = nullptr, *d_sens_true = nullptr;
+    double *d_cmd_dyn = nullptr, *d_cstate_save = nullptr;   // jb_compute_dynamics: command of the evaluation, saved constraint state
     int nimu = 0;
     uint8_t* d_mask = nullptr;
     double* d_stage = nullptr;  // staging for SoA -> AoS getters
@@ -156,12 +167,12 @@ static int ensure_host_stage(JbBatch* b, size_t bytes) {
 static KParams g_kp_on_device[64];
 static bool g_kp_valid[64] = {};
 #endif
-static int launch(JbBatch* b, int mode, double step_dt, const uint8_t* d_mask = nullptr) {
+static int launch(JbBatch* b, int mode, double step_dt, const uint8_t* d_mask = nullptr, const double* d_command = nullptr) {
     KParams kp = b->kp;
     // static plan signatures carry no external-force / constraint-contact code
     if (kp.n_eslot > 0 || kp.opt.contact_model == JB_CONTACT_CONSTRAINT) kp.sig_id = 0;
     LaunchArgs la{};
-    la.mode = mode; la.step_dt = step_dt; la.mask = d_mask;
+    la.mode = mode; la.step_dt = step_dt; la.mask = d_mask; la.command = d_command;
     if (mode == MODE_STEP && b->peer_world > 1 && !b->peer_opened.empty() && b->peer_enabled) {
         ++b->step_id;
         la.peer_on = 1;
@@ -686,6 +697,164 @@ int jb_get_constraints(JbBatch* b, uint8_t* joint_enabled, double* joint_lambda,
     return JB_OK;
 }
 
+// ---- sensor measurement pipeline ---------------------------------------------------------------------------
+static const int kSensorFields[5] = {6, 6, 2, 1, 3};
+
+int jb_set_sensor_options(JbBatch* b, int32_t type, int32_t index, const double* noise_std, const double* bias, double delay,
+                          double jitter, int32_t delay_interpolation_order) {
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (b->any_started) return fail(JB_ERR_BAD_CONTROL_FLOW, "Robot already locked, probably because a simulation is running. Please stop it before setting sensor options.");
+    const int counts[5] = {b->kp.nimu, b->kp.nforce, b->kp.nenc, b->kp.neff, b->kp.ncs};
+    const int offs[5] = {b->kp.lay.imu_offset, b->kp.lay.force_offset, b->kp.lay.encoder_offset, b->kp.lay.effort_offset, b->kp.lay.contact_offset};
+    if (type < 0 || type > 4 || index < 0 || index >= counts[type]) return fail(JB_ERR_INVALID_ARGUMENT, "unknown sensor");
+    if (delay < 0.0 || jitter < 0.0) return fail(JB_ERR_INVALID_ARGUMENT, "delay and jitter must be positive");
+    if (delay_interpolation_order != 0 && delay_interpolation_order != 1) return fail(JB_ERR_NOT_IMPLEMENTED, "`delayInterpolationOrder` must be either 0 or 1.");
+    if (!(b->kp.opt.sensors_update_period > 2.3e-16))
+        return fail(JB_ERR_NOT_IMPLEMENTED, "the device measurement pipeline needs a discrete sensorsUpdatePeriod (the delay buffer is sized from it)");
+    if (b->sdesc.empty()) {
+        for (int ty = 0; ty < 5; ++ty)
+            for (int k = 0; k < counts[ty]; ++k) {
+                SensorDesc d{};
+                d.type = ty; d.index = k; d.nf = kSensorFields[ty]; d.ns = counts[ty]; d.offset = offs[ty]; d.order = 1;
+                b->sdesc.push_back(d);
+            }
+    }
+    for (SensorDesc& d : b->sdesc) {
+        if (d.type != type || d.index != index) continue;
+        d.has_noise = noise_std != nullptr; d.has_bias = bias != nullptr;
+        for (int f = 0; f < d.nf; ++f) { d.noise_std[f] = noise_std ? noise_std[f] : 0.0; d.bias[f] = bias ? bias[f] : 0.0; }
+        d.delay = delay; d.jitter = jitter; d.order = delay_interpolation_order;
+    }
+    b->sp_dirty = true;
+    return JB_OK;
+}
+
+int jb_set_seeds(JbBatch* b, const uint32_t* seeds) {
+    if (!b || !seeds) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    b->seeds.assign(seeds, seeds + b->n_env);
+    return JB_OK;
+}
+
+// Tables, buffers and start states of the pipeline, (re)built at jb_start when options changed
+static int prepare_sensor_pipeline(JbBatch* b, const uint8_t* mask) {
+    if (b->sdesc.empty()) return JB_OK;
+    KParams& kp = b->kp;
+    const int ns = static_cast<int>(b->sdesc.size());
+    if (b->sp_dirty || !kp.sp_on) {
+        double dmax_all = 0.0;
+        for (int ty = 0; ty < 5; ++ty) kp.sp_delay_max[ty] = 0.0;
+        for (const SensorDesc& d : b->sdesc) {
+            kp.sp_delay_max[d.type] = std::max(kp.sp_delay_max[d.type], d.delay + d.jitter);
+            dmax_all = std::max(dmax_all, d.delay + d.jitter);
+        }
+        const int cap = static_cast<int>(std::floor((dmax_all + 0.02) / kp.opt.sensors_update_period)) + 8;
+        if (cap > 4096) return fail(JB_ERR_NOT_IMPLEMENTED, "sensor delay too long for the sensor update period (more than 4096 samples)");
+        if (!b->d_sdesc) {
+            int rc;
+            if ((rc = dev_alloc(b, &b->d_sdesc, ns))) return rc;
+            if ((rc = dev_alloc(b, &b->d_sp_rng, static_cast<size_t>(b->n_env) * ns))) return rc;
+            if ((rc = dev_alloc(b, &b->d_sp_rng_init, static_cast<size_t>(b->n_env) * ns))) return rc;
+            if ((rc = dev_alloc(b, &b->d_sp_snap_rng, static_cast<size_t>(b->n_env) * ns))) return rc;
+            if ((rc = dev_alloc(b, &b->d_sp_count, static_cast<size_t>(b->n_env) * 6))) return rc;
+            if ((rc = dev_alloc(b, &b->d_sp_snap_count, static_cast<size_t>(b->n_env) * 6))) return rc;
+            // ziggurat tables of the normal sampler (random.cc:62-98), computed with the host's libm like the reference does
+            std::vector<uint32_t> kn(128, 0); std::vector<float> fn(128, 0.f), wn(128, 0.f);
+            {
+                const double m1 = 2147483648.0, vn = 9.91256303526217e-03;
+                double dn = 3.442619855899, tn = dn;
+                const double q = vn / std::exp(-0.5 * dn * dn);
+                kn[0] = static_cast<uint32_t>((dn / q) * m1); kn[1] = 0;
+                wn[0] = static_cast<float>(q / m1); wn[127] = static_cast<float>(dn / m1);
+                fn[0] = 1.0F; fn[127] = static_cast<float>(std::exp(-0.5 * dn * dn));
+                for (int i = 126; 1 <= i; i--) {
+                    dn = std::sqrt(-2.0 * std::log(vn / dn + std::exp(-0.5 * dn * dn)));
+                    kn[i + 1] = static_cast<uint32_t>((dn / tn) * m1);
+                    tn = dn;
+                    fn[i] = static_cast<float>(std::exp(-0.5 * dn * dn));
+                    wn[i] = static_cast<float>(dn / m1);
+                }
+            }
+            uint32_t* d_kn; float *d_fn, *d_wn;
+            if ((rc = dev_alloc(b, &d_kn, 128)) || (rc = dev_alloc(b, &d_fn, 128)) || (rc = dev_alloc(b, &d_wn, 128))) return rc;
+            CU(cudaMemcpyAsync(d_kn, kn.data(), 128 * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
+            CU(cudaMemcpyAsync(d_fn, fn.data(), 128 * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+            CU(cudaMemcpyAsync(d_wn, wn.data(), 128 * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+            CU(cudaStreamSynchronize(b->stream));
+            kp.zig_kn = d_kn; kp.zig_fn = d_fn; kp.zig_wn = d_wn;
+        }
+        if (cap > b->sp_cap_alloc) {
+            int rc;
+            if ((rc = dev_alloc(b, &b->d_sp_times, static_cast<size_t>(b->n_env) * cap))) return rc;
+            if ((rc = dev_alloc(b, &b->d_sp_ring, static_cast<size_t>(b->n_env) * cap * std::max(b->width, 1)))) return rc;
+            b->sp_cap_alloc = cap;
+        }
+        CU(cudaMemcpyAsync(b->d_sdesc, b->sdesc.data(), sizeof(SensorDesc) * ns, cudaMemcpyHostToDevice, b->stream));
+        CU(cudaStreamSynchronize(b->stream));
+        kp.sp_on = 1; kp.sp_cap = cap; kp.sp_nsens = ns; kp.sp_desc = b->d_sdesc;
+        kp.sp_rng = b->d_sp_rng; kp.sp_rng_init = b->d_sp_rng_init; kp.sp_snap_rng = b->d_sp_snap_rng;
+        kp.sp_count = b->d_sp_count; kp.sp_snap_count = b->d_sp_snap_count; kp.sp_times = b->d_sp_times; kp.sp_ring = b->d_sp_ring;
+        b->sp_dirty = false;
+    }
+    // Start states of the generators: Engine::reset seeds the engine's PCG32 from stepper.randomSeedSeq (engine.cc:756-757),
+    // Robot::reset draws one seed per sensor type (robot.cc:137-144; fixed type order Imu, Force, Encoder, Effort, Contact here,
+    // the reference iterates an unordered_map), resetAll expands it with a seed_seq into one seed per sensor
+    // (abstract_sensor.hxx:213-226) and PCG32(seed) sets state = seed | 3 (random.cc:10-13).
+    if (b->seeds.empty()) b->seeds.assign(b->n_env, 0u);
+    std::vector<unsigned long long> init(static_cast<size_t>(b->n_env) * ns, 0ULL);
+    const int counts[5] = {kp.nimu, kp.nforce, kp.nenc, kp.neff, kp.ncs};
+    for (int e = 0; e < b->n_env; ++e) {
+        if (mask && !mask[e]) continue;
+        std::seed_seq seq{b->seeds[e]};
+        uint32_t buf[2];
+        seq.generate(buf, buf + 2);
+        unsigned long long st = (static_cast<unsigned long long>(buf[0]) | (static_cast<unsigned long long>(buf[1]) << 32)) | 3ULL;
+        size_t col = 0;
+        for (int ty = 0; ty < 5; ++ty) {
+            if (!counts[ty]) continue;
+            st *= 6364136223846793005ULL;
+            unsigned long long sx = st;
+            const unsigned rshift = static_cast<unsigned>(sx >> 61) & 7u;
+            sx ^= sx >> 22;
+            const uint32_t type_seed = static_cast<uint32_t>(sx >> (22 + rshift));
+            std::seed_seq tseq{type_seed};
+            std::vector<uint32_t> sub(counts[ty]);
+            tseq.generate(sub.begin(), sub.end());
+            for (int k = 0; k < counts[ty]; ++k) init[static_cast<size_t>(e) * ns + col++] = static_cast<unsigned long long>(sub[k]) | 3ULL;
+        }
+    }
+    if (mask) {
+        // rows of the envs that are not restarted keep what the device holds
+        for (int e = 0; e < b->n_env; ++e)
+            if (mask[e]) CU(cudaMemcpyAsync(b->d_sp_rng_init + static_cast<size_t>(e) * ns, init.data() + static_cast<size_t>(e) * ns, sizeof(unsigned long long) * ns, cudaMemcpyHostToDevice, b->stream));
+    } else CU(cudaMemcpyAsync(b->d_sp_rng_init, init.data(), sizeof(unsigned long long) * init.size(), cudaMemcpyHostToDevice, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return JB_OK;
+}
+
+__global__ void gather_true_sensors_kernel(const double* __restrict__ ring, const int32_t* __restrict__ count, double* __restrict__ out,
+                                           int n_env, int cap, int width) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= static_cast<size_t>(n_env) * width) return;
+    const size_t env = i / width, k = i % width;
+    out[i] = ring[(env * cap + count[env * 6]) * width + k];
+}
+
+int jb_get_sensor_data(JbBatch* b, double* out) {
+    if (!b || !out) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!b->kp.sp_on) return jb_get_sensors(b, out);
+    CU(cudaSetDevice(b->device));
+    const size_t total = static_cast<size_t>(b->n_env) * b->width;
+    if (!total) return JB_OK;
+    if (!b->d_sens_true) { int rc = dev_alloc(b, &b->d_sens_true, total); if (rc) return rc; }
+    JB_LAUNCH(gather_true_sensors_kernel, static_cast<unsigned>((total + 255) / 256), 256, 0, b->stream, b->d_sp_ring, b->d_sp_count, b->d_sens_true,
+              b->n_env, b->kp.sp_cap, b->width);
+    CU(cudaGetLastError());
+    ++b->launches;
+    CU(cudaMemcpyAsync(out, b->d_sens_true, total * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return JB_OK;
+}
+
 int jb_start(JbBatch* b, const uint8_t* mask, const double* q0, const double* v0) {
     if (!b || !q0 || !v0) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
     CU(cudaSetDevice(b->device));
@@ -706,7 +875,9 @@ int jb_start(JbBatch* b, const uint8_t* mask, const double* q0, const double* v0
     CU(cudaMemcpyAsync(b->d_qin, q0, sizeof(double) * b->n_env * b->nq, cudaMemcpyHostToDevice, b->stream));
     CU(cudaMemcpyAsync(b->d_vin, v0, sizeof(double) * b->n_env * b->nv, cudaMemcpyHostToDevice, b->stream));
     if (mask) CU(cudaMemcpyAsync(b->d_mask, mask, b->n_env, cudaMemcpyHostToDevice, b->stream));
-    int rc = launch(b, MODE_START, 0.0, mask ? b->d_mask : nullptr);
+    int rc = prepare_sensor_pipeline(b, mask);
+    if (rc) return rc;
+    rc = launch(b, MODE_START, 0.0, mask ? b->d_mask : nullptr);
     if (rc) return rc;
     CU(cudaStreamSynchronize(b->stream));
     b->any_started = true;
@@ -893,9 +1064,20 @@ int jb_compute_dynamics(JbBatch* b, const double* q, const double* v, const doub
     CU(cudaSetDevice(b->device));
     CU(cudaMemcpyAsync(b->d_qin, q, sizeof(double) * b->n_env * b->nq, cudaMemcpyHostToDevice, b->stream));
     CU(cudaMemcpyAsync(b->d_vin, v, sizeof(double) * b->n_env * b->nv, cudaMemcpyHostToDevice, b->stream));
-    if (cmd && b->nmotors) CU(cudaMemcpyAsync(b->d_cmd, cmd, sizeof(double) * b->n_env * b->nmotors, cudaMemcpyHostToDevice, b->stream));
-    int rc = launch(b, MODE_DYNAMICS, 0.0);
+    // the evaluation must leave the running envs alone: its command goes to a buffer of its own, and the persistent
+    // constraint state (a joint outside its bounds in `q` would enable its constraint) is put back afterwards
+    if (cmd && b->nmotors) {
+        if (!b->d_cmd_dyn) { int rc0 = dev_alloc(b, &b->d_cmd_dyn, static_cast<size_t>(b->n_env) * b->nmotors); if (rc0) return rc0; }
+        CU(cudaMemcpyAsync(b->d_cmd_dyn, cmd, sizeof(double) * b->n_env * b->nmotors, cudaMemcpyHostToDevice, b->stream));
+    }
+    const size_t cs_bytes = b->kp.cons_on ? sizeof(double) * static_cast<size_t>(b->kp.cs_total) * b->n_pad : 0;
+    if (cs_bytes) {
+        if (!b->d_cstate_save) { int rc0 = dev_alloc(b, &b->d_cstate_save, cs_bytes / sizeof(double)); if (rc0) return rc0; }
+        CU(cudaMemcpyAsync(b->d_cstate_save, b->kp.cstate, cs_bytes, cudaMemcpyDeviceToDevice, b->stream));
+    }
+    int rc = launch(b, MODE_DYNAMICS, 0.0, nullptr, (cmd && b->nmotors) ? b->d_cmd_dyn : nullptr);
     if (rc) return rc;
+    if (cs_bytes) CU(cudaMemcpyAsync(b->kp.cstate, b->d_cstate_save, cs_bytes, cudaMemcpyDeviceToDevice, b->stream));
     CU(cudaMemcpyAsync(a, b->d_aout, sizeof(double) * b->n_env * b->nv, cudaMemcpyDeviceToHost, b->stream));
     if (fext) CU(cudaMemcpyAsync(fext, b->d_fext, sizeof(double) * b->n_env * b->njoints * 6, cudaMemcpyDeviceToHost, b->stream));
     if (u) CU(cudaMemcpyAsync(u, b->d_u, sizeof(double) * b->n_env * b->nv, cudaMemcpyDeviceToHost, b->stream));

@@ -166,6 +166,15 @@ __device__ __noinline__ void snapshot_blocks(const Ctx c, const int L, const boo
         double* snap = KP->mahony_snap + static_cast<size_t>(c.env) * n;
         for (size_t k = c.sub; k < n; k += L) { if (restore) live[k] = snap[k]; else snap[k] = live[k]; }
     }
+    if (KP->sp_on) {
+        // sensor measurement pipeline: sample counts and generator states (ring slots written by the aborted pass are rewritten)
+        int32_t* lc = KP->sp_count + static_cast<size_t>(c.env) * 6;
+        int32_t* sc = KP->sp_snap_count + static_cast<size_t>(c.env) * 6;
+        for (int k = c.sub; k < 6; k += L) { if (restore) lc[k] = sc[k]; else sc[k] = lc[k]; }
+        unsigned long long* lr = KP->sp_rng + static_cast<size_t>(c.env) * KP->sp_nsens;
+        unsigned long long* sr = KP->sp_snap_rng + static_cast<size_t>(c.env) * KP->sp_nsens;
+        for (int k = c.sub; k < KP->sp_nsens; k += L) { if (restore) lr[k] = sr[k]; else sr[k] = lr[k]; }
+    }
     __syncwarp(c.gmask);
 }
 
@@ -305,7 +314,7 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
     // The stateful device blocks (PDController targets, MahonyFilter) advance inside the launch; an env handed over to
     // the full body is replayed from the top of the step, so the fast body keeps a copy to put back.
     if constexpr (FAST) {
-        if (c.valid && (KP->pdf != nullptr || KP->mahony != nullptr)) snapshot_blocks(c, L, false);
+        if (c.valid && (KP->pdf != nullptr || KP->mahony != nullptr || KP->sp_on)) snapshot_blocks(c, L, false);
     }
     // ---------------- load state into the lane records
     for (int r = 0; r < KP->nrec; ++r) {
@@ -320,7 +329,8 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
         }
         if (ri->kind != REC_FREE) {
             // torque command: the action itself, or (PD mode) the torque held since the last breakpoint
-            const double* cmd_src = ((KP->pd_gains != nullptr || KP->pdf != nullptr) && mode == MODE_STEP) ? KP->cmd_torque : KP->command;
+            const double* cmd_src = ((KP->pd_gains != nullptr || KP->pdf != nullptr) && mode == MODE_STEP) ? KP->cmd_torque
+                                    : ((mode == MODE_DYNAMICS && la.command != nullptr) ? la.command : KP->command);
             RP(R1_CMD) = (ri->motor >= 0) ? cmd_src[col * KP->nmotors + ri->motor] : 0.0;
             RP(R1_UMOTOR) = 0.0;
         }
@@ -380,7 +390,7 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
         bool bad = accel_has_nan(c);
         bad = __any_sync(c.gmask, bad);
         if (bad) status |= JB_ENV_NAN;
-        write_sensors(c, true);
+        write_sensors(c, true, 0.0);
     } else {
         t = KP->sched[SCH_T * N + col]; dt = KP->sched[SCH_DT * N + col];
         dtLargest = KP->sched[SCH_DTLARGEST * N + col]; dtLargestPrev = KP->sched[SCH_DTLARGESTPREV * N + col];
@@ -527,7 +537,7 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
             const double sp = opt.sensors_update_period;
             bool mustUpdateSensors = sp < D_EPS;
             if (!mustUpdateSensors) mustUpdateSensors = period_hit(t, sp);
-            if (mustUpdateSensors) write_sensors(c, false);
+            if (mustUpdateSensors) write_sensors(c, false, t);
         }
         if (!failed) t = tEnd;
     }
@@ -535,7 +545,7 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
     // ---------------- store
     if constexpr (FAST) {
         if (__any_sync(c.gmask, (status & ENV_RETRY_FULL) != 0)) {   // nothing of this pass is kept: the full body redoes the env
-            if (c.valid && (KP->pdf != nullptr || KP->mahony != nullptr)) snapshot_blocks(c, L, true);
+            if (c.valid && (KP->pdf != nullptr || KP->mahony != nullptr || KP->sp_on)) snapshot_blocks(c, L, true);
             if (c.sub == 0) *needs_full = 1;
             return;
         }

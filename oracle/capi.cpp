@@ -220,7 +220,24 @@ void orc_get_efforts(OrcBatch* b, double* u, double* u_motor, double* command, d
 }
 void orc_get_sensors(OrcBatch* b, double* out) {
     for (size_t i = 0; i < b->envs.size(); ++i)
+        std::memcpy(out + i * b->width, b->envs[i]->sensorOutput().data(), sizeof(double) * b->width);
+}
+// true values behind the measurements (AbstractSensorTpl::data())
+void orc_get_sensor_data(OrcBatch* b, double* out) {
+    for (size_t i = 0; i < b->envs.size(); ++i)
         std::memcpy(out + i * b->width, b->envs[i]->sensors.data(), sizeof(double) * b->width);
+}
+void orc_set_sensor_options(OrcBatch* b, int type, int index, const double* noise_std, const double* bias, double delay, double jitter, int order) {
+    for (auto& e : b->envs) e->setSensorOptions(type, index, noise_std, bias, delay, jitter, static_cast<uint32_t>(order));
+}
+void orc_set_seeds(OrcBatch* b, const uint32_t* seeds) {
+    for (size_t i = 0; i < b->envs.size(); ++i) b->envs[i]->engineSeed = seeds[i];
+}
+// raw generator access for the distribution tests: n draws of normal(0, 1) / uniform01 / raw 32-bit words from PCG32(seed_seq{seed})
+void orc_random_draws(uint32_t seed, int kind, int n, double* out) {
+    std::seed_seq seq{seed};
+    orc::PCG32 g = orc::pcg32_from_seed_seq(seq);
+    for (int i = 0; i < n; ++i) out[i] = kind == 0 ? static_cast<double>(orc::normal(g)) : (kind == 1 ? static_cast<double>(orc::uniform01(g)) : static_cast<double>(g()));
 }
 void orc_get_extra_terms(OrcBatch* b, double* energy, double* joint_a, double* joint_f) {
     for (size_t i = 0; i < b->envs.size(); ++i) {

@@ -566,6 +566,44 @@ void Engine::computeSensorMeasurements(const double* qv, const double* vv, const
         s[L.contact_offset + 1 * model.ncs + k] = f.y;
         s[L.contact_offset + 2 * model.ncs + k] = f.z;
     }
+    if (sensorPipeline) measureSensors();
+}
+
+// ---- measurement pipeline: Robot::reset -> resetAll seeds, setAll ring, interpolateData + measureData (sensor_noise.hpp)
+void Engine::setSensorOptions(int type, int index, const double* noiseStd, const double* bias, double delay, double jitter, uint32_t order) {
+    const int counts[N_SENSOR_TYPES] = {model.nimu, model.nforce, model.nenc, model.neff, model.ncs};
+    const int offs[N_SENSOR_TYPES] = {model.layout.imu_offset, model.layout.force_offset, model.layout.encoder_offset,
+                                      model.layout.effort_offset, model.layout.contact_offset};
+    if (!sensorPipeline) {
+        for (int t = 0; t < N_SENSOR_TYPES; ++t) {
+            SensorGroup& g = sensorGroups[t];
+            g.nf = SENSOR_FIELDS[t]; g.ns = counts[t]; g.offset = offs[t];
+            g.opt.assign(g.ns, SensorOptions{});
+        }
+        measurements.assign(sensors.size(), 0.0);
+        sensorPipeline = true;
+    }
+    SensorOptions& o = sensorGroups[type].opt.at(index);
+    const int nf = SENSOR_FIELDS[type];
+    o.noiseStd.clear(); o.bias.clear();
+    if (noiseStd) o.noiseStd.assign(noiseStd, noiseStd + nf);
+    if (bias) o.bias.assign(bias, bias + nf);
+    o.delay = delay; o.jitter = jitter; o.delayInterpolationOrder = order;
+}
+void Engine::resetSensorPipeline() {
+    // Engine::reset: generator_.seed(seed_seq(randomSeedSeq)) (engine.cc:756-757), robot->reset(generator_) (:763): one
+    // draw per sensor type that has sensors (robot.cc:137-144), in the fixed type order documented in sensor_noise.hpp
+    std::seed_seq seq{engineSeed};
+    PCG32 g = pcg32_from_seed_seq(seq);
+    for (SensorGroup& grp : sensorGroups)
+        if (grp.ns > 0) grp.reset(g());
+}
+void Engine::measureSensors() {
+    for (SensorGroup& grp : sensorGroups) {
+        if (!grp.ns) continue;
+        grp.push(sensorClock, sensors.data() + grp.offset);
+        for (int k = 0; k < grp.ns; ++k) grp.measure(k, measurements.data() + grp.offset);
+    }
 }
 
 // ============================================================================ RHS
@@ -914,7 +952,7 @@ void Engine::mahonyInit() {
 void Engine::mahonyUpdate() {
     const int M = model.nimu;
     if (!M) return;
-    const double* s = sensors.data() + model.layout.imu_offset;   // [6][nimu]: gyro (3), accel (3)
+    const double* s = sensorOutput().data() + model.layout.imu_offset;   // [6][nimu]: gyro (3), accel (3), as measured
     mahony_filter(mahony_q.data(), mahony_omega.data(), s, s + 3 * M, mahony_bias.data(), M, mahony_kp, mahony_ki, opt.sensors_update_period);
 }
 
@@ -929,6 +967,8 @@ int Engine::start(const double* q0, const double* v0) {
     }
     normalize(qn.data());
     simStarted = false;   // is_simulation_running becomes true at the very end of Engine::start (engine.cc:1532)
+    if (sensorPipeline) resetSensorPipeline();
+    sensorClock = 0.0;
     q = qn; v.assign(v0, v0 + nv); a.assign(nv, 0.0);
     iter = 0; iterFailed = 0; t = 0.0; tPrev = 0.0; tError = 0.0;
     dt = SIMULATION_MIN_TIMESTEP; dtLargest = dt; dtLargestPrev = dt;
@@ -1136,6 +1176,7 @@ int Engine::step(double stepSize) {
             mustUpdateSensors = dtNextSensorsUpdatePeriod < SIMULATION_MIN_TIMESTEP ||
                                 sp - dtNextSensorsUpdatePeriod < STEPPER_MIN_TIMESTEP;
         if (mustUpdateSensors) {
+            sensorClock = t;
             computeSensorMeasurements(state.q.data(), state.v.data(), state.uMotor);
             if (mahony_enabled) mahonyUpdate();
         }

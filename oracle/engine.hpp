@@ -28,6 +28,7 @@
 
 #include "../include/jiminy_b200.h"
 #include "spatial.hpp"
+#include "sensor_noise.hpp"
 
 namespace orc {
 
@@ -135,7 +136,18 @@ struct Engine {
     std::vector<Force> contactForcesPrev, fPrev;
     std::vector<Motion> aPrev;
     std::vector<Force> fExtBuffer;          // `fPrev_` argument of computeExtraTerms used as fExt buffer
-    std::vector<double> sensors;
+    std::vector<double> sensors;            // true values written by the sensors' set() (AbstractSensorTpl::data())
+    // measurement pipeline (oracle/sensor_noise.hpp): off until a sensor option is set; `measurements` = what
+    // robot.sensor_measurements exposes (delayed, noisy, biased), `sensors` keeps the true values
+    bool sensorPipeline = false;
+    uint32_t engineSeed = 0;                // stepper.randomSeedSeq = [engineSeed]
+    std::array<SensorGroup, N_SENSOR_TYPES> sensorGroups;
+    std::vector<double> measurements;
+    double sensorClock = 0.0;               // time of the refresh in progress
+    void setSensorOptions(int type, int index, const double* noiseStd, const double* bias, double delay, double jitter, uint32_t order);
+    void resetSensorPipeline();
+    void measureSensors();
+    const std::vector<double>& sensorOutput() const { return sensorPipeline ? measurements : sensors; }
     // ---- kinematic constraints (oracle/constraints.cpp)
     struct Constraint {
         int kind = 0;          // 0: JointConstraint (bounds), 1: FrameConstraint {x, y, z, rot z} (contact frame)

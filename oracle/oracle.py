@@ -74,6 +74,10 @@ def lib():
         L.orc_get_efforts.argtypes = [C.c_void_p] + [c_double_p] * 4
         L.orc_get_stepper_state.argtypes = [C.c_void_p, c_double_p, c_double_p]
         L.orc_get_sensors.argtypes = [C.c_void_p, c_double_p]
+        L.orc_get_sensor_data.argtypes = [C.c_void_p, c_double_p]
+        L.orc_set_sensor_options.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p, C.c_double, C.c_double, C.c_int]
+        L.orc_set_seeds.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+        L.orc_random_draws.argtypes = [C.c_uint32, C.c_int, C.c_int, c_double_p]
         L.orc_get_extra_terms.argtypes = [C.c_void_p] + [c_double_p] * 3
         L.orc_get_status.argtypes = [C.c_void_p, c_int32_p]
         L.orc_get_centroidal.argtypes = [C.c_void_p] + [c_double_p] * 5
@@ -85,6 +89,16 @@ def lib():
         L.orc_difference.argtypes = [C.c_void_p] + [c_double_p] * 3
         _lib = L
     return _lib
+
+
+SENSOR_TYPES = ("ImuSensor", "ForceSensor", "EncoderSensor", "EffortSensor", "ContactSensor")
+
+
+def random_draws(seed: int, kind: str, n: int) -> np.ndarray:
+    """n draws of the restated generator PCG32(seed_seq{seed}): kind = 'normal' | 'uniform' | 'raw'."""
+    out = np.zeros(n)
+    lib().orc_random_draws(int(seed), {"normal": 0, "uniform": 1, "raw": 2}[kind], int(n), dptr(out))
+    return out
 
 
 class OracleBatch:
@@ -293,6 +307,26 @@ class OracleBatch:
         if self.width:
             lib().orc_get_sensors(self._h, dptr(out))
         return out[:, :self.width]
+
+    def get_sensor_data(self) -> np.ndarray:
+        """True values behind the measurements (what `sensor.data` holds in the reference)."""
+        out = np.zeros((self.n, max(self.width, 1)))
+        if self.width:
+            lib().orc_get_sensor_data(self._h, dptr(out))
+        return out[:, :self.width]
+
+    def set_sensor_options(self, sensor_type: str, index: int, noise_std=None, bias=None, delay: float = 0.0,
+                           jitter: float = 0.0, delay_interpolation_order: int = 1) -> None:
+        t = SENSOR_TYPES.index(sensor_type)
+        ns = None if noise_std is None else np.ascontiguousarray(noise_std, dtype=np.float64)
+        bs = None if bias is None else np.ascontiguousarray(bias, dtype=np.float64)
+        lib().orc_set_sensor_options(self._h, t, int(index), None if ns is None else dptr(ns), None if bs is None else dptr(bs),
+                                     float(delay), float(jitter), int(delay_interpolation_order))
+
+    def set_seeds(self, seeds) -> None:
+        s = np.ascontiguousarray(seeds, dtype=np.uint32)
+        assert s.shape == (self.n,)
+        lib().orc_set_seeds(self._h, s.ctypes.data_as(C.POINTER(C.c_uint32)))
 
     def get_extra_terms(self):
         e, ja, jf = np.zeros((self.n, 2)), np.zeros((self.n, self.nj, 6)), np.zeros((self.n, self.nj, 6))

@@ -300,3 +300,11 @@ def test_batched_env_reset_step_autoreset_on_device():
     import test_kernel_emul as tke
     tke.test_batched_env_reset_step_autoreset(None)
     tke.test_pd_control_pipeline_env(None)
+
+
+def test_sensor_measurement_pipeline_matches_oracle():
+    """Delay ring / jitter / white noise / bias of every sensor type on the device against the oracle's restatement
+    (abstract_sensor.hxx:305-522): identical noise draws, delayed values within the physics tolerance; restart of one env
+    with the same seed reproduces its noise."""
+    import sensor_pipeline_common as spc
+    spc.pipeline_scenario(None, n_env=48, n_steps=3)

@@ -692,3 +692,28 @@ def test_handoff_with_stateful_blocks(api):
 def test_mahony_filter_observer(api):
     pc.mahony_scenario(api, "anymal")
     pc.mahony_scenario(api, "atlas", n_env=1, n_steps=1)
+
+
+def test_compute_dynamics_leaves_the_running_state_alone(api):
+    """`compute_dynamics` on arbitrary states (out-of-bounds joints included) between two steps must not change the
+    running envs: neither their held command nor their constraint state."""
+    sc = scenarios.make("anymal", 3, seed=9)
+    runs = []
+    for probe in (False, True):
+        eng = BatchedEngine(sc.robot, sc.options, 3, api_=api)
+        eng.set_pd_controller(sc.kp, sc.kd)
+        eng.set_command(sc.target0)
+        eng.start(sc.q0, sc.v0)
+        for k in range(2):
+            eng.set_command(sc.sample_targets(k))
+            if probe:
+                rng = np.random.default_rng(k)
+                q, v = pc.random_states(sc.robot, 3, rng)
+                q[:, 7] = sc.robot.q_upper[7] + 0.2          # a hip joint beyond its upper bound
+                eng.compute_dynamics(q, v, rng.uniform(-30, 30, size=(3, sc.robot.nmotors)))
+            eng.step(sc.step_dt)
+        runs.append((eng.get_state(), eng.get_status(), eng.get_constraints()[0].copy()))
+    for x, y in zip(runs[0][0], runs[1][0]):
+        np.testing.assert_array_equal(x, y)
+    np.testing.assert_array_equal(runs[0][1], runs[1][1])
+    np.testing.assert_array_equal(runs[0][2], runs[1][2])
