@@ -449,17 +449,12 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
             const int cs_fields = CS_JOINT0 + CS_JOINT_SIZE * kp.n_jc + CS_CONTACT_SIZE * kp.n_cc;
             const CwLayout w = cw_layout(m->njoints, m->nv, kp.m_max);
             ALLOC(d_jmap, jmap.size()); ALLOC(d_cmap, cmap.size()); ALLOC(d_jcj, std::max<size_t>(jc_joint.size(), 1)); ALLOC(d_jcof, jc_of_joint.size());
-            // the workspace is scratch of one dynamics evaluation: sized for the blocks that can be resident at once
+            // the workspace is scratch of one dynamics evaluation, one row per block of the launch
             int n_sm = 1, blocks_per_sm = 1;
-#ifndef JB_HOST_EMUL
-            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
-            const size_t smem_guess = static_cast<size_t>(b->base_fields) * 32 * sizeof(double);
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, env_step_kernel_t<false>, 32, smem_guess) != cudaSuccess || blocks_per_sm < 1) {
-                cudaGetLastError();
-                blocks_per_sm = 32;
+            {
+                const int epw_ = 32 / P.L;
+                n_sm = (n_env + epw_ - 1) / epw_;      // (historical names: rows = n_sm * blocks_per_sm blocks)
             }
-            blocks_per_sm = std::min(blocks_per_sm, 32);
-#endif
             const size_t cw_rows = std::min<size_t>(N, static_cast<size_t>(n_sm) * blocks_per_sm * (32 / P.L));
             unsigned int* d_slots;
             ALLOC(d_slots, n_sm);
@@ -540,7 +535,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
 
 int jb_describe(JbBatch* b, char* buf, int32_t len) {
     if (!b || !buf) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
-    std::snprintf(buf, len, "%s; constraints: %s", b->plan.describe().c_str(),
+    std::snprintf(buf, len, "%s; workspace slots/SM %d; constraints: %s", b->plan.describe().c_str(), b->kp.cons_on ? b->kp.cw_blocks_per_sm : 0,
                   !b->kp.cons_on ? "flag only" : (b->kp.cq_on ? (b->kp.lb_on ? "structured quadruped solver + lane-block solver" : "structured quadruped solver + generic")
                                                  : (b->kp.bd_on ? "body-space contact solver + lane-block solver" : (b->kp.lb_on ? "lane-block solver" : "generic solver"))));
     return JB_OK;

@@ -371,6 +371,9 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) conv = conv && (fabs(Y[r] - YP[r]) < tol);
         ok = __all_sync(c.gmask, conv);
+#ifdef JB_DEBUG_COUNTS
+        if (c.sub == 0) { extern long long jb_dbg_counts[8]; ++jb_dbg_counts[4]; if (!ok && iter == CONS_PGS_MAX_ITER - 1) ++jb_dbg_counts[5]; }
+#endif
     }
     // ---------------- accelerations: ddq_t = ddq_free_t + S^-1 z = ddq_free_t + sum_r h_r lambda_r ;
     //                  ddq_l = ddq_free_l + M_ll^-1 J_l^T lambda - W (ddq_t - ddq_free_t)

@@ -615,26 +615,12 @@ JB_DI unsigned int jb_smid() {
 // The full body: every mode, every stepper, the constraint path.  Out of line, so that the hot-path kernel carries one
 // call to it instead of a second copy of the code.
 __device__ __noinline__ void env_step_full(const LaunchArgs la, const bool only_flagged) {
-    // constraint workspace: one slot per resident block of this SM, taken for the lifetime of the call
-    int my_bit = -1;
-    unsigned int my_sm = 0;
-    if (KP->cons_on) {
-        if (threadIdx.x == 0) {
-            my_sm = jb_smid() % static_cast<unsigned int>(KP->cw_n_sm);
-            for (int tries = 0; my_bit < 0; ++tries) {
-                const int bit = tries % KP->cw_blocks_per_sm;
-                const unsigned int old = atomicOr(KP->cw_slots + my_sm, 1u << bit);
-                if (!(old & (1u << bit))) my_bit = bit;
-            }
-            jb_cw_slot = static_cast<int>(my_sm) * KP->cw_blocks_per_sm + my_bit;
-        }
-        __syncwarp();
-    }
+    // constraint workspace of this block: one row per block of the launch.  (A pool of per-SM slots taken with an atomic
+    // spin by lane 0 kept the workspace L2-resident, but left the warp's env groups running one after the other in the
+    // constraint solvers -- 3.7x on ANYmal with constraint contacts; profiles/r02_bisect_constraint_regression.txt.)
+    if (threadIdx.x == 0) jb_cw_slot = static_cast<int>(blockIdx.x);
+    __syncwarp();
     env_step_body<false>(la, only_flagged);
-    if (KP->cons_on) {
-        __syncwarp();
-        if (threadIdx.x == 0) atomicAnd(KP->cw_slots + my_sm, ~(1u << my_bit));
-    }
 }
 
 // One launch = one Engine::step (or start / single evaluation) of every env.  FAST: the hot-path body first; the envs it
