@@ -391,6 +391,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
 
     if (SigQuadruped::matches(kp) && !std::getenv("JB_NO_STATIC_PLAN")) kp.sig_id = SigQuadruped::ID;
     kp.rhs_variant = (std::getenv("JB_QUADRUPED_ABA") && std::atoi(std::getenv("JB_QUADRUPED_ABA"))) ? 0 : 1;
+    kp.fast_bounds = 0;   // set below, once the constraint tables exist
     // ---- constraint path: lookup tables, persistent state and workspace (jb_constraints.cuh)
     {
         std::vector<JointMap> jmap(m->njoints);
@@ -520,6 +521,8 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
             kp.jmap = d_jmap; kp.cmap = d_cmap; kp.jc_joint = d_jcj; kp.jc_of_joint = d_jcof; kp.cstate = d_cst; kp.cwork = d_cwk;
         }
     }
+    kp.fast_bounds = (kp.sig_id == SigQuadruped::ID && kp.rhs_variant == 1 && kp.cons_on &&
+                      !(std::getenv("JB_NO_FAST_BOUNDS") && std::atoi(std::getenv("JB_NO_FAST_BOUNDS")))) ? 1 : 0;
     kp.n_eslot = 0; kp.n_imp = 0; kp.n_prof = 0; kp.ext_off = b->base_fields;
     b->smem_bytes = static_cast<size_t>(b->base_fields) * 32 * sizeof(double);
     if (b->smem_bytes > 227 * 1024) { jb_batch_destroy(b); return fail(JB_ERR_NOT_IMPLEMENTED, "robot too large: per-warp working set exceeds shared memory (" + P.describe() + ")"); }

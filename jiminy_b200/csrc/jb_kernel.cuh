@@ -337,6 +337,17 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
     }
     for (int k = 0; k < CSLOT_SIZE * KP->ncslot; ++k) SMF(c, KP->cslot_off + k) = 0.0;
     for (int k = 0; k < IMUSLOT_SIZE * KP->nimuslot; ++k) SMF(c, KP->imu_off + k) = 0.0;
+    if constexpr (FAST) {
+        if (KP->fast_bounds) {
+            // joint-bound constraint state of this lane's leg joints (persistent in cstate like the reference's constraint objects)
+            for (int r = 1; r < 4; ++r) {
+                const int o = cs_joint(KP->jc_of_joint[(KP->rint + (r * L + c.sub))->joint]);
+                double* const rp = jb_smem + KP->rec_off[r] * 32 + c.lane;
+                RP(R1_BEN) = CST(o); RP(R1_BREV) = CST(o + 1); RP(R1_BQREF) = CST(o + 2); RP(R1_BLAM) = CST(o + 3);
+            }
+            SMF(c, KP->rec_off[1] + R1_BFAIL) = CST(CS_SOLVE_FAILED);
+        }
+    }
     if constexpr (!FAST) {
         for (int k = 0; k < ESLOT_SIZE * KP->n_eslot; ++k) SMF(c, KP->ext_off + k) = 0.0;
         if (KP->cons_on) {
@@ -531,6 +542,8 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
             if (successiveIterFailed > failedMax) { status |= JB_ENV_ITER_FAILED; failed = true; break; }
             if constexpr (!FAST) {
                 if (KP->cons_on && __any_sync(c.gmask, c.sub == 0 && CST(CS_SOLVE_FAILED) > failedMax)) { status |= JB_ENV_SOLVER_FAILED; failed = true; break; }
+            } else if (KP->fast_bounds) {
+                if (__any_sync(c.gmask, SMF(c, KP->rec_off[1] + R1_BFAIL) > failedMax)) { status |= JB_ENV_SOLVER_FAILED; failed = true; break; }
             }
             if (dt < STEPPER_MIN_TIMESTEP) { status |= JB_ENV_DT_UNDERFLOW; failed = true; break; }
             // sensors refresh (engine.cc:2386-2410)
@@ -552,8 +565,21 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
     } else if (KP->cons_on) {
         // envs that still own enabled constraints stay with the full body
         const bool any = __any_sync(c.gmask, SMF(c, KP->cons_off) != 0.0);
-        if (c.sub == 0) *needs_full = any ? 1 : 0;
+        // (the hot-path evaluation of the quadruped signature solves joint bounds itself: nothing to keep the env here for)
+        if (c.sub == 0) *needs_full = (any && !(KP->fast_bounds && KP->opt.contact_model == JB_CONTACT_SPRING_DAMPER)) ? 1 : 0;
     } else if (c.sub == 0) *needs_full = 0;   // bounds are only flagged for this robot (JB_ENV_JOINT_LIMIT): back to the hot path
+    if constexpr (FAST) {
+        if (KP->fast_bounds && c.valid) {
+            bool any_en = false;
+            for (int r = 1; r < 4; ++r) {
+                const int o = cs_joint(KP->jc_of_joint[(KP->rint + (r * L + c.sub))->joint]);
+                const double* const rp = jb_smem + KP->rec_off[r] * 32 + c.lane;
+                CST(o) = RP(R1_BEN); CST(o + 1) = RP(R1_BREV); CST(o + 2) = RP(R1_BQREF); CST(o + 3) = RP(R1_BLAM);
+                any_en = any_en || RP(R1_BEN) != 0.0;
+            }
+            if (c.sub == 0) CST(CS_SOLVE_FAILED) = SMF(c, KP->rec_off[1] + R1_BFAIL);
+        }
+    }
     if (KP->extra_energy != nullptr && !(status & (JB_ENV_NAN | JB_ENV_NOT_STARTED))) extra_terms(c);
     store_outputs(c);
 #ifndef JB_HOST_EMUL
