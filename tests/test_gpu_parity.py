@@ -265,12 +265,19 @@ def test_pd_adapter_pipeline(order, instantaneous):
     pc.pd_adapter_scenario(None, n_env=40, n_steps=4, order=order, instantaneous=instantaneous)
 
 
-def test_bounds_handoff_between_kernels_at_scale():
-    """600 ANYmal envs, every third pushed into its joint bounds: fast kernel / full kernel hand-off inside warps."""
+@pytest.mark.parametrize("in_kernel", [True, False])
+def test_joint_bounds_at_scale(monkeypatch, in_kernel):
+    """600 ANYmal envs, every third pushed into its joint bounds: solved inside the hot-path evaluation, or (the path of
+    every robot without a static signature) aborted and replayed by the full body inside the same launch."""
+    if not in_kernel:
+        monkeypatch.setenv("JB_NO_FAST_BOUNDS", "1")
     pc.bounds_handoff_scenario(None, n_env=600, n_steps=5)
 
 
-def test_handoff_with_stateful_blocks_at_scale():
+@pytest.mark.parametrize("in_kernel", [True, False])
+def test_handoff_with_stateful_blocks_at_scale(monkeypatch, in_kernel):
+    if not in_kernel:
+        monkeypatch.setenv("JB_NO_FAST_BOUNDS", "1")
     pc.stateful_handoff_scenario(None, n_env=300, n_steps=7)
 
 

@@ -671,7 +671,12 @@ def test_pd_control_pipeline_env(api):
     env.close()
 
 
-def test_bounds_handoff_between_kernels(api):
+@pytest.mark.parametrize("in_kernel", [True, False])
+def test_joint_bounds_on_the_hot_path_and_by_handoff(api, monkeypatch, in_kernel):
+    """ANYmal envs driven through their hip bounds: solved inside the hot-path evaluation (default for the quadruped
+    signature), or -- JB_NO_FAST_BOUNDS=1, the path every other robot takes -- aborted and replayed by the full body."""
+    if not in_kernel:
+        monkeypatch.setenv("JB_NO_FAST_BOUNDS", "1")
     pc.bounds_handoff_scenario(api, n_env=9, n_steps=4)
 
 
@@ -685,7 +690,10 @@ def test_long_horizon_resynchronised_gpu_like_rounding():
     pc.resync_long_horizon_scenario("atlas", 2, 4, api=fma, tol_rel=1e-11, free_running=False)
 
 
-def test_handoff_with_stateful_blocks(api):
+@pytest.mark.parametrize("in_kernel", [True, False])
+def test_handoff_with_stateful_blocks(api, monkeypatch, in_kernel):
+    if not in_kernel:
+        monkeypatch.setenv("JB_NO_FAST_BOUNDS", "1")
     pc.stateful_handoff_scenario(api, n_env=6, n_steps=6)
 
 
