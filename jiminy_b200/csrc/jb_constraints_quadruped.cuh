@@ -26,10 +26,10 @@
 constexpr int CQ_SIZE = 0;
 JB_DI double cq_bcast_sum4(const Ctx& c, double x) {   // sum over the 4 lanes of the env, same order on every lane
     const int l0 = c.lane - c.sub;
-    double s = __shfl_sync(c.gmask, x, l0);
-    s += __shfl_sync(c.gmask, x, l0 + 1);
-    s += __shfl_sync(c.gmask, x, l0 + 2);
-    s += __shfl_sync(c.gmask, x, l0 + 3);
+    double s = jb_shfl(c, x, l0);
+    s += jb_shfl(c, x, l0 + 1);
+    s += jb_shfl(c, x, l0 + 2);
+    s += jb_shfl(c, x, l0 + 3);
     return s;
 }
 
@@ -86,7 +86,7 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
     const int kc = ct->contact;                        // contact index == constraint index among the contact frames
     const int cso = cs_contact(kc);
     const bool en = CST(cso) != 0.0;
-    __syncwarp(c.gmask);
+    jb_syncwarp(c);
     // ---------------- kinematics along the chain, composite inertias, inertia blocks
     Xf oM; Mot v, aD;
     {
@@ -312,11 +312,11 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
                 // otherwise); no coupling between contacts, so all lanes do it at once
                 const double d3 = -LA[3];
                 LA[3] = 0.0;
-                if (__any_sync(c.gmask, d3 != 0.0)) {
+                if (jb_any(c, d3 != 0.0)) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
 #pragma unroll
-                        for (int d = 0; d < 6; ++d) z[d] += __shfl_sync(c.gmask, G[3][d] * d3, lane0 + own_of[k]);
+                        for (int d = 0; d < 6; ++d) z[d] += jb_shfl(c, G[3][d] * d3, lane0 + own_of[k]);
                 }
                 continue;
             }
@@ -360,17 +360,17 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
                     }
                 }
 #pragma unroll
-                for (int d = 0; d < 6; ++d) z[d] += __shfl_sync(c.gmask, dz[d], lane0 + own_of[k]);
+                for (int d = 0; d < 6; ++d) z[d] += jb_shfl(c, dz[d], lane0 + own_of[k]);
             }
         }
         // stopping criterion on the stagnation of the residuals (constraint_solvers.cc:256-274)
         double ymax = fmax(fmax(fabs(Y[0]), fabs(Y[1])), fmax(fabs(Y[2]), fabs(Y[3])));
-        for (int o = 1; o < L; o <<= 1) ymax = fmax(ymax, __shfl_xor_sync(c.gmask, ymax, o));
+        for (int o = 1; o < L; o <<= 1) ymax = fmax(ymax, jb_shfl_xor(c, ymax, o));
         const double tol = opt.tol_abs + opt.tol_rel * ymax + D_EPS;
         bool conv = true;
 #pragma unroll
         for (int r = 0; r < 4; ++r) conv = conv && (fabs(Y[r] - YP[r]) < tol);
-        ok = __all_sync(c.gmask, conv);
+        ok = jb_all(c, conv);
 #ifdef JB_DEBUG_COUNTS
         if (c.sub == 0) { extern long long jb_dbg_counts[8]; ++jb_dbg_counts[4]; if (!ok && iter == CONS_PGS_MAX_ITER - 1) ++jb_dbg_counts[5]; }
 #endif
@@ -419,7 +419,7 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
         }
         if (c.sub == 0) CST(CS_SOLVE_FAILED) = ok ? 0.0 : CST(CS_SOLVE_FAILED) + 1.0;
     }
-    __syncwarp(c.gmask);
+    jb_syncwarp(c);
     cons_refresh_accelerations(c);
     (void)status;
     return ok;

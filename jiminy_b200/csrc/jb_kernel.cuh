@@ -139,7 +139,7 @@ __device__ __noinline__ void update_pd_commands(const Ctx c, bool running) {
         RP(R1_CMD) = fmin(fmax(tau, -lim), lim);
     }
     if (KP->pdf != nullptr) {
-        __syncwarp(c.gmask);
+        jb_syncwarp(c);
         double* st = KP->pdf_state + static_cast<size_t>(c.env) * 3 * nm;
         for (int r = 0; r < KP->nrec; ++r) {
             const RecInt* ri = KP->rint + (r * L + c.sub);
@@ -153,7 +153,7 @@ __device__ __noinline__ void update_pd_commands(const Ctx c, bool running) {
 // Copy (restore = false) or put back (restore = true) the per-env state of the device-side PDController / MahonyFilter
 // blocks.  Called by every lane of the env; the L lanes share the copy.
 __device__ __noinline__ void snapshot_blocks(const Ctx c, const int L, const bool restore) {
-    if (restore) __syncwarp(c.gmask);   // the owner lanes' writes to the live state come first
+    if (restore) jb_syncwarp(c);   // the owner lanes' writes to the live state come first
     if (KP->pdf != nullptr) {
         const size_t n = 3 * static_cast<size_t>(KP->nmotors);
         double* live = KP->pdf_state + static_cast<size_t>(c.env) * n;
@@ -175,7 +175,7 @@ __device__ __noinline__ void snapshot_blocks(const Ctx c, const int L, const boo
         unsigned long long* sr = KP->sp_snap_rng + static_cast<size_t>(c.env) * KP->sp_nsens;
         for (int k = c.sub; k < KP->sp_nsens; k += L) { if (restore) lr[k] = sr[k]; else sr[k] = lr[k]; }
     }
-    __syncwarp(c.gmask);
+    jb_syncwarp(c);
 }
 
 __device__ __noinline__ void store_outputs(const Ctx c) {
@@ -338,7 +338,7 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
     for (int k = 0; k < CSLOT_SIZE * KP->ncslot; ++k) SMF(c, KP->cslot_off + k) = 0.0;
     for (int k = 0; k < IMUSLOT_SIZE * KP->nimuslot; ++k) SMF(c, KP->imu_off + k) = 0.0;
     if constexpr (FAST) {
-        if (KP->fast_bounds) {
+        if (KP->fast_bounds_io) {
             // joint-bound constraint state of this lane's leg joints (persistent in cstate like the reference's constraint objects)
             for (int r = 1; r < 4; ++r) {
                 const int o = cs_joint(KP->jc_of_joint[(KP->rint + (r * L + c.sub))->joint]);
@@ -384,7 +384,7 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
             cons_reset(c);
             Ctx c0 = c; c0.flags = CTX_ZERO_U | CTX_IGNORE_BOUNDS;
             rhs(c0, false, &status);
-            const bool constrained = __any_sync(c.gmask, SMF(c, KP->cons_off) != 0.0);
+            const bool constrained = jb_any(c, SMF(c, KP->cons_off) != 0.0);
             Ctx c1 = c; c1.flags = CTX_START_FEEDBACK;
             for (int it = 1; it < (constrained ? 4 : 2); ++it) rhs(c1, true, &status);
         } else rhs(c, false, &status);
@@ -396,10 +396,10 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
             const double fx = CO(0), fy = CO(1), fz = CO(2);
             fmax2 = fmax(fmax2, fx * fx + fy * fy + fz * fz);
         }
-        for (int o = 1; o < L; o <<= 1) fmax2 = fmax(fmax2, __shfl_xor_sync(c.gmask, fmax2, o));
+        for (int o = 1; o < L; o <<= 1) fmax2 = fmax(fmax2, jb_shfl_xor(c, fmax2, o));
         if (fmax2 > 1e10) status |= JB_ENV_CONTACT_FORCE | JB_ENV_NOT_STARTED;
         bool bad = accel_has_nan(c);
-        bad = __any_sync(c.gmask, bad);
+        bad = jb_any(c, bad);
         if (bad) status |= JB_ENV_NAN;
         write_sensors(c, true, 0.0);
     } else {
@@ -446,13 +446,13 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
                 // one vote for the two rare events of a step: NaN in the new acceleration, or a joint that left its
                 // position bounds (this env is then re-done by the full kernel)
                 const bool bad = accel_has_nan(c), retry = (status & ENV_RETRY_FULL) != 0;
-                if (__any_sync(c.gmask, bad || retry)) {
-                    if (__any_sync(c.gmask, retry)) { status |= ENV_RETRY_FULL; failed = true; }
-                    if (__any_sync(c.gmask, bad)) rc = 2;
+                if (jb_any(c, bad || retry)) {
+                    if (jb_any(c, retry)) { status |= ENV_RETRY_FULL; failed = true; }
+                    if (jb_any(c, bad)) rc = 2;
                 }
             } else if (rc == 0 && opt.ode_solver != JB_SOLVER_RUNGE_KUTTA_DOPRI) {
                 bool bad = accel_has_nan(c);
-                bad = __any_sync(c.gmask, bad);
+                bad = jb_any(c, bad);
                 if (bad) rc = 2;
             }
             if (rc == 0) {
@@ -541,9 +541,9 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
             if (failed) break;
             if (successiveIterFailed > failedMax) { status |= JB_ENV_ITER_FAILED; failed = true; break; }
             if constexpr (!FAST) {
-                if (KP->cons_on && __any_sync(c.gmask, c.sub == 0 && CST(CS_SOLVE_FAILED) > failedMax)) { status |= JB_ENV_SOLVER_FAILED; failed = true; break; }
+                if (KP->cons_on && jb_any(c, c.sub == 0 && CST(CS_SOLVE_FAILED) > failedMax)) { status |= JB_ENV_SOLVER_FAILED; failed = true; break; }
             } else if (KP->fast_bounds) {
-                if (__any_sync(c.gmask, SMF(c, KP->rec_off[1] + R1_BFAIL) > failedMax)) { status |= JB_ENV_SOLVER_FAILED; failed = true; break; }
+                if (jb_any(c, SMF(c, KP->rec_off[1] + R1_BFAIL) > failedMax)) { status |= JB_ENV_SOLVER_FAILED; failed = true; break; }
             }
             if (dt < STEPPER_MIN_TIMESTEP) { status |= JB_ENV_DT_UNDERFLOW; failed = true; break; }
             // sensors refresh (engine.cc:2386-2410)
@@ -557,19 +557,19 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
 
     // ---------------- store
     if constexpr (FAST) {
-        if (__any_sync(c.gmask, (status & ENV_RETRY_FULL) != 0)) {   // nothing of this pass is kept: the full body redoes the env
+        if (jb_any(c, (status & ENV_RETRY_FULL) != 0)) {   // nothing of this pass is kept: the full body redoes the env
             if (c.valid && (KP->pdf != nullptr || KP->mahony != nullptr || KP->sp_on)) snapshot_blocks(c, L, true);
             if (c.sub == 0) *needs_full = 1;
             return;
         }
     } else if (KP->cons_on) {
         // envs that still own enabled constraints stay with the full body
-        const bool any = __any_sync(c.gmask, SMF(c, KP->cons_off) != 0.0);
+        const bool any = jb_any(c, SMF(c, KP->cons_off) != 0.0);
         // (the hot-path evaluation of the quadruped signature solves joint bounds itself: nothing to keep the env here for)
         if (c.sub == 0) *needs_full = (any && !(KP->fast_bounds && KP->opt.contact_model == JB_CONTACT_SPRING_DAMPER)) ? 1 : 0;
     } else if (c.sub == 0) *needs_full = 0;   // bounds are only flagged for this robot (JB_ENV_JOINT_LIMIT): back to the hot path
     if constexpr (FAST) {
-        if (KP->fast_bounds && c.valid) {
+        if (KP->fast_bounds_io && c.valid) {
             bool any_en = false;
             for (int r = 1; r < 4; ++r) {
                 const int o = cs_joint(KP->jc_of_joint[(KP->rint + (r * L + c.sub))->joint]);
@@ -601,7 +601,7 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
                 for (int i = c.lane; i < n2; i += 32) out[i] = src[i];
             }
         } else if (c.valid) {
-            __syncwarp(c.gmask);   // the row was written by the owner lanes of the env
+            jb_syncwarp(c);   // the row was written by the owner lanes of the env
             const double* row = KP->sensors + col * width;
             for (int p = 0; p < KP->peer_n; ++p) {
                 double* out = KP->peer_obs[p] + (slot + col) * width;
@@ -624,7 +624,7 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
         KP->iters[col] = iter; KP->iters[N + col] = iterFailed;
     }
     // status bits can be raised by any lane of the env
-    for (int o = 1; o < L; o <<= 1) status |= __shfl_xor_sync(c.gmask, status, o);
+    for (int o = 1; o < L; o <<= 1) status |= jb_shfl_xor(c, status, o);
     if (c.valid && c.sub == 0) KP->status[c.env] = status;
 }
 
