@@ -524,6 +524,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
     kp.fast_bounds = (kp.sig_id == SigQuadruped::ID && kp.rhs_variant == 1 && kp.cons_on &&
                       !(std::getenv("JB_NO_FAST_BOUNDS") && std::atoi(std::getenv("JB_NO_FAST_BOUNDS")))) ? 1 : 0;
     kp.fast_bounds_io = kp.fast_bounds;
+    kp.uniform_solver = (std::getenv("JB_NO_UNIFORM_SOLVER") && std::atoi(std::getenv("JB_NO_UNIFORM_SOLVER"))) ? 0 : 1;
     if (const char* e = std::getenv("JB_FAST_BOUNDS_MODE")) { const int m_ = std::atoi(e); if (m_ == 2) kp.fast_bounds = 0; if (m_ == 3) kp.fast_bounds_io = 0; }
     kp.n_eslot = 0; kp.n_imp = 0; kp.n_prof = 0; kp.ext_off = b->base_fields;
     b->smem_bytes = static_cast<size_t>(b->base_fields) * 32 * sizeof(double);

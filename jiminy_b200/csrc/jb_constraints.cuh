@@ -347,7 +347,7 @@ __device__ __noinline__ void cons_refresh_accelerations(const Ctx c) {
         if (ri->imu_slot >= 0) sm_store_mot(c, KP->imu_off + IMUSLOT_SIZE * ri->imu_slot + 6, ag);
         agc = ag;
     }
-    jb_syncwarp(c);
+    __syncwarp(c.gmask);
 }
 
 // ---- the solve -----------------------------------------------------------------------------------------
@@ -358,7 +358,7 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
     const CwLayout w = cw_layout(nj, nv, ld);
     const JbOptions& opt = KP->opt;
     double* const cw = KP->cwork + CW_ROW(c) * KP->cw_total;
-    jb_syncwarp(c);
+    __syncwarp(c.gmask);
     // ---------------- 1. tree quantities, joint-space inertia and its Cholesky factor (sub-lane 0)
     if (c.sub == 0) {
         for (int j = 1; j < nj; ++j) {
@@ -445,7 +445,7 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
         }
         if (!cw_llt(cw, w.MM, nv, nv)) *status |= JB_ENV_NAN;
     }
-    jb_syncwarp(c);
+    __syncwarp(c.gmask);
     // ---------------- 2. rows of J, drift, rows of L^-1 J^T: constraints dealt round-robin to the lanes
     int m = 0, n_active = 0;
     {
@@ -530,7 +530,7 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
             }
         }
     }
-    jb_syncwarp(c);
+    __syncwarp(c.gmask);
     // ---------------- 3. rows of A = J M^-1 J^T + regularisation, b = -gamma - J ddq_free
     {
         int count = 0, row = 0;
@@ -556,7 +556,7 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
             }
         }
     }
-    jb_syncwarp(c);
+    __syncwarp(c.gmask);
     // ---------------- 4. multipliers, accelerations, contact wrenches (sub-lane 0)
     bool ok = true;
     if (c.sub == 0) {
@@ -607,7 +607,7 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
         }
         CST(CS_SOLVE_FAILED) = ok ? 0.0 : CST(CS_SOLVE_FAILED) + 1.0;
     }
-    jb_syncwarp(c);
+    __syncwarp(c.gmask);
     cons_refresh_accelerations(c);
     return ok;
 }

@@ -48,8 +48,8 @@ JB_HD LbLayout lb_layout(int nrec, int ntrunk, int nl, int nt, int ml, int nact)
 #define LBW(off) (lw[(off)])
 JB_DI double lb_sum_lanes(const Ctx& c, double x) {   // sum over the lanes of the env, same order on every lane
     const int l0 = c.lane - c.sub;
-    double s = jb_shfl(c, x, l0);
-    for (int k = 1; k < KP->L; ++k) s += jb_shfl(c, x, l0 + k);
+    double s = __shfl_sync(c.gmask, x, l0);
+    for (int k = 1; k < KP->L; ++k) s += __shfl_sync(c.gmask, x, l0 + k);
     return s;
 }
 // Small dense factorisations and solves run on a copy in local memory: it is cached write-back in L1, whereas a
@@ -276,7 +276,7 @@ __device__ __noinline__ bool cons_solve_blocks(const Ctx c, int* status) {
     const int lane0 = c.lane - c.sub;
     const double omega = 2.0 * 3.14159265358979323846 * opt.contact_stabilization_freq;
     const double kp = omega * omega, kd = 2.0 * omega;
-    jb_syncwarp(c);
+    __syncwarp(c.gmask);
     auto ndof = [&](int r) { return lb_ndof(rint, r, L); };
     lb_prepare(c, w, lw, status);
     // ---------------- 5. sweep list (replicated on every lane) and the rows this lane owns
@@ -470,7 +470,7 @@ __device__ __noinline__ bool cons_solve_blocks(const Ctx c, int* status) {
                     }
                 }
                 // the owner's change of z reaches every lane of the env
-                if (!jb_any(c, d0 != 0.0 || d1 != 0.0)) continue;
+                if (!__any_sync(c.gmask, d0 != 0.0 || d1 != 0.0)) continue;
 #pragma unroll
                 for (int t = 0; t < LB_MAX_NT; ++t) {
                     if (t < nt) {
@@ -479,18 +479,18 @@ __device__ __noinline__ bool cons_solve_blocks(const Ctx c, int* status) {
                             dz = LBW(w.GG + r0 * nt + t) * d0;
                             if (r1 >= 0) dz += LBW(w.GG + r1 * nt + t) * d1;
                         }
-                        z[t] += jb_shfl(c, dz, lane0 + owner);
+                        z[t] += __shfl_sync(c.gmask, dz, lane0 + owner);
                     }
                 }
             }
         }
         double ymax = 0.0;
         for (int r = 0; r < my_rows; ++r) ymax = fmax(ymax, fabs(LBW(w.YV + r)));
-        for (int o2 = 1; o2 < L; o2 <<= 1) ymax = fmax(ymax, jb_shfl_xor(c, ymax, o2));
+        for (int o2 = 1; o2 < L; o2 <<= 1) ymax = fmax(ymax, __shfl_xor_sync(c.gmask, ymax, o2));
         const double tol = opt.tol_abs + opt.tol_rel * ymax + D_EPS;
         bool conv = true;
         for (int r = 0; r < my_rows; ++r) conv = conv && (fabs(LBW(w.YV + r) - LBW(w.YP + r)) < tol);
-        ok = jb_all(c, conv);
+        ok = __all_sync(c.gmask, conv);
     }
     // ---------------- 8. accelerations: ddq_t += S^-1 z ; ddq_l += sum_r x_r lambda_r - W S^-1 z
 #pragma unroll
@@ -530,7 +530,7 @@ __device__ __noinline__ bool cons_solve_blocks(const Ctx c, int* status) {
         if (owner == c.sub)
             for (int e = 0; e < 4; ++e) { l4[e] = LBW(w.LA + start + e); CST(o + 1 + e) = l4[e]; }
         if (cm.trunk)   // a contact frame on a trunk joint is replicated in every lane's slot list
-            for (int e = 0; e < 4; ++e) l4[e] = jb_shfl(c, l4[e], lane0 + owner);
+            for (int e = 0; e < 4; ++e) l4[e] = __shfl_sync(c.gmask, l4[e], lane0 + owner);
         if (owner == c.sub || cm.trunk) {
             const Xf oM = lb_load_xf(lw + w.KI + 24 * KP->jmap[cm.joint].rec);
             const V3 Fl = rtmul(oM.R, mk(l4[0], l4[1], l4[2]));
@@ -540,7 +540,7 @@ __device__ __noinline__ bool cons_solve_blocks(const Ctx c, int* status) {
         }
     }
     if (c.sub == 0) CST(CS_SOLVE_FAILED) = ok ? 0.0 : CST(CS_SOLVE_FAILED) + 1.0;
-    jb_syncwarp(c);
+    __syncwarp(c.gmask);
     cons_refresh_accelerations(c);
     return ok;
 }

@@ -74,7 +74,7 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
     for (int k = 0; k < n_cc; ++k) body_bits |= static_cast<unsigned>(KP->bd_of_contact[k]) << (2 * k);
     double pl_all[12 * BD_MAX_CONTACTS];   // per contact: lambda (4), y (4), y_prev (4)
     double Fv[6 * BD_MAX_BODIES];
-    jb_syncwarp(c);      // the enabled flags below were written by the lanes owning the contact frames
+    __syncwarp(c.gmask);      // the enabled flags below were written by the lanes owning the contact frames
     unsigned enabled = 0;
     for (int k = 0; k < n_cc; ++k) if (CST(cs_contact(k)) != 0.0) enabled |= 1u << k;
     lb_prepare(c, w, lw, status);
@@ -128,7 +128,7 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
             cb[wl.CF + k] = jd;
         }
     }
-    jb_syncwarp(c);
+    __syncwarp(c.gmask);
     // Omega: same-lane part by the owner, trunk-coupled part dealt round-robin
     for (int b = 0; b < nb; ++b) {
         if (KP->bd_owner[b] != c.sub) continue;
@@ -144,14 +144,14 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
                 }
         }
     }
-    jb_syncwarp(c);
+    __syncwarp(c.gmask);
     for (int e = c.sub; e < D * D; e += L) {
         const int i = e / D, j = e - i * D;
         double s = SHW(ws.OM + e);
         for (int t = 0; t < nt; ++t) s += SHW(ws.GS + i * nt + t) * SHW(ws.HS + j * nt + t);
         SHW(ws.OM + e) = s;
     }
-    jb_syncwarp(c);
+    __syncwarp(c.gmask);
     // ---------------- C. per enabled contact (owner lane): lever, drift, b, diagonal of A
     for (int k = 0; k < n_cc; ++k) {
         const int o = cs_contact(k);
@@ -204,7 +204,7 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
     }
     // ---------------- D. warm start: private lambda, F, then a = Omega F (rows shared out)
     for (int e = 0; e < D; ++e) Fv[e] = 0.0;
-    jb_syncwarp(c);
+    __syncwarp(c.gmask);
     for (int k = 0; k < n_cc; ++k) {
         const int o = cs_contact(k);
         if (!(enabled >> k & 1u)) continue;
@@ -225,7 +225,7 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
         for (int j = 0; j < D; ++j) s += SHW(ws.OM + i * D + j) * Fv[j];
         AVS(0, i) = s;
     }
-    jb_syncwarp(c);
+    __syncwarp(c.gmask);
     // ---------------- E. projected Gauss-Seidel sweep (constraint_solvers.cc:107-318), redundantly on every lane
     bool ok = false;
     for (int iter = 0; iter < CONS_PGS_MAX_ITER && !ok; ++iter) {
@@ -306,7 +306,7 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
                     }
                 }
                 cur = 1 - cur;
-                jb_syncwarp(c);
+                __syncwarp(c.gmask);
             }
         }
         double ymax = 0.0;
@@ -368,7 +368,7 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
         }
     }
     if (c.sub == 0) CST(CS_SOLVE_FAILED) = ok ? 0.0 : CST(CS_SOLVE_FAILED) + 1.0;
-    jb_syncwarp(c);
+    __syncwarp(c.gmask);
     cons_refresh_accelerations(c);
     return ok;
 }

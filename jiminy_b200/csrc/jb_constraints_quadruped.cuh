@@ -24,14 +24,18 @@
 //   W (3 x 6) and M_ll^-1 (6) in the U / Dinv / u fields of the three leg records, the world rotation of the foot
 //   joint (9) and J_l (4 x 3) in the trunk's pool entry.
 constexpr int CQ_SIZE = 0;
-JB_DI double cq_bcast_sum4(const Ctx& c, double x) {   // sum over the 4 lanes of the env, same order on every lane
+JB_DI double cq_bcast_sum4(const Ctx& c, double x, unsigned mask) {   // sum over the 4 lanes of the env, same order on every lane
     const int l0 = c.lane - c.sub;
-    double s = jb_shfl(c, x, l0);
-    s += jb_shfl(c, x, l0 + 1);
-    s += jb_shfl(c, x, l0 + 2);
-    s += jb_shfl(c, x, l0 + 3);
+    double s = __shfl_sync(mask, x, l0);
+    s += __shfl_sync(mask, x, l0 + 1);
+    s += __shfl_sync(mask, x, l0 + 2);
+    s += __shfl_sync(mask, x, l0 + 3);
     return s;
 }
+JB_DI double cq_bcast_sum4(const Ctx& c, double x) { return cq_bcast_sum4(c, x, c.gmask); }
+// votes among the lanes of the env under either kind of mask (a ballot restricted to the group's bits)
+JB_DI bool cq_any(unsigned mask, const Ctx& c, bool p) { return (__ballot_sync(mask, p) & c.gmask) != 0u; }
+JB_DI bool cq_all(unsigned mask, const Ctx& c, bool p) { return (__ballot_sync(mask, p) & c.gmask) == c.gmask; }
 
 struct Spd6 { double Ai[6], T[9], Si[6]; };
 JB_DI void spd6_factor(const SymY& Y, Spd6& f) {
@@ -79,6 +83,11 @@ static bool cons_quadruped_matches(const KParams& kp, const Plan& P, const JbMod
 
 // Called by the four lanes of the env after the ABA sweeps, when only contact constraints are enabled.
 __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
+    // CTX_UNIFORM_WARP: all 32 lanes of the warp are in this call together (decided by the caller): every collective below
+    // then uses the full mask -- a primitive whose mask differs from lane to lane is executed one mask after the other --
+    // and the sweep loop keeps every env of the warp inside until the last one has converged
+    const bool uni = (c.flags & CTX_UNIFORM_WARP) != 0;
+    const unsigned M = uni ? 0xffffffffu : c.gmask;
     constexpr int L = 4;
     const JbOptions& opt = KP->opt;
     const RecDbl* rd0 = KP->rdbl + (0 * L + c.sub);
@@ -86,7 +95,7 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
     const int kc = ct->contact;                        // contact index == constraint index among the contact frames
     const int cso = cs_contact(kc);
     const bool en = CST(cso) != 0.0;
-    jb_syncwarp(c);
+    __syncwarp(M);
     // ---------------- kinematics along the chain, composite inertias, inertia blocks
     Xf oM; Mot v, aD;
     {
@@ -190,9 +199,9 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
         SymY S;
         inertia_to_sym(rd0->inertia[0], ld3(rd0->inertia + 1), rd0->inertia + 4, S);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { S.A[k] += cq_bcast_sum4(c, Tl.A[k]); S.D[k] += cq_bcast_sum4(c, Tl.D[k]); }
+        for (int k = 0; k < 6; ++k) { S.A[k] += cq_bcast_sum4(c, Tl.A[k], M); S.D[k] += cq_bcast_sum4(c, Tl.D[k], M); }
 #pragma unroll
-        for (int k = 0; k < 9; ++k) S.B[k] += cq_bcast_sum4(c, Tl.B[k]);
+        for (int k = 0; k < 9; ++k) S.B[k] += cq_bcast_sum4(c, Tl.B[k], M);
         spd6_factor(S, sf);
     }
     // ---------------- constraint rows of this lane's contact frame (FrameConstraint::computeJacobianAndDrift)
@@ -277,8 +286,8 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
     }
     // z = sum over all rows of g_r lambda_r (all-reduce in fixed order)
     double z[6];
-    z[0] = cq_bcast_sum4(c, zpart.l.x); z[1] = cq_bcast_sum4(c, zpart.l.y); z[2] = cq_bcast_sum4(c, zpart.l.z);
-    z[3] = cq_bcast_sum4(c, zpart.a.x); z[4] = cq_bcast_sum4(c, zpart.a.y); z[5] = cq_bcast_sum4(c, zpart.a.z);
+    z[0] = cq_bcast_sum4(c, zpart.l.x, M); z[1] = cq_bcast_sum4(c, zpart.l.y, M); z[2] = cq_bcast_sum4(c, zpart.l.z, M);
+    z[3] = cq_bcast_sum4(c, zpart.a.x, M); z[4] = cq_bcast_sum4(c, zpart.a.y, M); z[5] = cq_bcast_sum4(c, zpart.a.z, M);
     // ---------------- projected Gauss-Seidel sweep (constraint_solvers.cc:107-318)
     // Sweep order = contact index order; the lane owning contact k updates its multipliers from the current z and
     // broadcasts the change of z to the other lanes of the env with shuffles.  Everything the sweep touches is in
@@ -295,7 +304,8 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) own_of[k] = KP->cmap[k].sub;
     bool ok = false;
-    for (int iter = 0; iter < CONS_PGS_MAX_ITER && !ok; ++iter) {
+    for (int iter = 0; uni ? __any_sync(0xffffffffu, iter < CONS_PGS_MAX_ITER && !ok) : (iter < CONS_PGS_MAX_ITER && !ok); ++iter) {
+        const bool live = !ok && iter < CONS_PGS_MAX_ITER;   // (uniform warp: an env that is done keeps exchanging zeros)
 #pragma unroll
         for (int r = 0; r < 4; ++r) YP[r] = Y[r];
         const double ratio = (static_cast<double>(CONS_PGS_MAX_ITER - CONS_RELAX_MIN_ITER) - iter) /
@@ -312,18 +322,18 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
                 // otherwise); no coupling between contacts, so all lanes do it at once
                 const double d3 = -LA[3];
                 LA[3] = 0.0;
-                if (jb_any(c, d3 != 0.0)) {
+                if (uni ? __any_sync(0xffffffffu, d3 != 0.0) : __any_sync(c.gmask, d3 != 0.0)) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
 #pragma unroll
-                        for (int d = 0; d < 6; ++d) z[d] += jb_shfl(c, G[3][d] * d3, lane0 + own_of[k]);
+                        for (int d = 0; d < 6; ++d) z[d] += __shfl_sync(M, G[3][d] * d3, lane0 + own_of[k]);
                 }
                 continue;
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 double dz[6] = {0, 0, 0, 0, 0, 0};
-                if (own_of[k] == c.sub && en) {
+                if (own_of[k] == c.sub && en && live) {
                     if (pass == 0) {
                         const double y = residual(2);
                         Y[2] = y;
@@ -360,17 +370,18 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
                     }
                 }
 #pragma unroll
-                for (int d = 0; d < 6; ++d) z[d] += jb_shfl(c, dz[d], lane0 + own_of[k]);
+                for (int d = 0; d < 6; ++d) z[d] += __shfl_sync(M, dz[d], lane0 + own_of[k]);
             }
         }
         // stopping criterion on the stagnation of the residuals (constraint_solvers.cc:256-274)
         double ymax = fmax(fmax(fabs(Y[0]), fabs(Y[1])), fmax(fabs(Y[2]), fabs(Y[3])));
-        for (int o = 1; o < L; o <<= 1) ymax = fmax(ymax, jb_shfl_xor(c, ymax, o));
+        for (int o = 1; o < L; o <<= 1) ymax = fmax(ymax, __shfl_xor_sync(M, ymax, o));
         const double tol = opt.tol_abs + opt.tol_rel * ymax + D_EPS;
         bool conv = true;
 #pragma unroll
         for (int r = 0; r < 4; ++r) conv = conv && (fabs(Y[r] - YP[r]) < tol);
-        ok = jb_all(c, conv);
+        const bool all_conv = cq_all(M, c, conv || !live);   // (one call site: every lane of the mask takes part)
+        if (live) ok = all_conv;
 #ifdef JB_DEBUG_COUNTS
         if (c.sub == 0) { extern long long jb_dbg_counts[8]; ++jb_dbg_counts[4]; if (!ok && iter == CONS_PGS_MAX_ITER - 1) ++jb_dbg_counts[5]; }
 #endif
@@ -385,7 +396,7 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
             for (int d = 0; d < 6; ++d) xp[d] += H[r][d] * LA[r];
         double xv[6];
 #pragma unroll
-        for (int d = 0; d < 6; ++d) xv[d] = cq_bcast_sum4(c, xp[d]);
+        for (int d = 0; d < 6; ++d) xv[d] = cq_bcast_sum4(c, xp[d], M);
         double* const r0 = jb_smem + KP->rec_off[0] * 32 + c.lane;
 #pragma unroll
         for (int d = 0; d < 6; ++d) r0[(RF_A + d) * 32] += xv[d];
@@ -419,7 +430,7 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
         }
         if (c.sub == 0) CST(CS_SOLVE_FAILED) = ok ? 0.0 : CST(CS_SOLVE_FAILED) + 1.0;
     }
-    jb_syncwarp(c);
+    __syncwarp(M);
     cons_refresh_accelerations(c);
     (void)status;
     return ok;

@@ -85,6 +85,15 @@ inline bool __any_sync(unsigned mask, bool p) {
     return r;
 }
 inline bool __all_sync(unsigned mask, bool p) { return !__any_sync(mask, !p); }
+inline unsigned __ballot_sync(unsigned mask, bool p) {
+    emul::warp->islot[emul::lane_id] = p ? 1 : 0;
+    emul::sync_group(mask);
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l)
+        if ((mask & (1u << l)) && emul::warp->islot[l] != 0) r |= 1u << l;
+    emul::sync_group(mask);
+    return r;
+}
 // blocks run one after the other in the emulator: plain read-modify-write is enough
 inline unsigned int atomicOr(unsigned int* p, unsigned int v) { const unsigned int o = *p; *p = o | v; return o; }
 inline unsigned int atomicAnd(unsigned int* p, unsigned int v) { const unsigned int o = *p; *p = o & v; return o; }
