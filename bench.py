@@ -149,12 +149,12 @@ def workload_name(args, sc):
 
 
 def kernel_source_sha():
-    """Identity of the device code the profile numbers belong to."""
+    """Identity of the device code of the step kernel (the .cuh files) the profile numbers belong to."""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "jiminy_b200", "csrc")
     for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh", ".cpp", ".h")):
+        if f.endswith(".cuh"):
             h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
 

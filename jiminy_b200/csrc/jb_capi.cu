@@ -541,7 +541,9 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
 
 int jb_describe(JbBatch* b, char* buf, int32_t len) {
     if (!b || !buf) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
-    std::snprintf(buf, len, "%s; workspace slots/SM %d; constraints: %s", b->plan.describe().c_str(), b->kp.cons_on ? b->kp.cw_blocks_per_sm : 0,
+    std::snprintf(buf, len, "%s; hot path: %s%s; constraints: %s", b->plan.describe().c_str(),
+                  b->kp.sig_id == SigQuadruped::ID ? (b->kp.rhs_variant == 1 ? "quadruped signature, composite-rigid-body evaluation" : "quadruped signature, ABA sweeps") : "ABA sweeps (dynamic plan)",
+                  b->kp.fast_bounds ? ", joint bounds solved in the evaluation" : "",
                   !b->kp.cons_on ? "flag only" : (b->kp.cq_on ? (b->kp.lb_on ? "structured quadruped solver + lane-block solver" : "structured quadruped solver + generic")
                                                  : (b->kp.bd_on ? "body-space contact solver + lane-block solver" : (b->kp.lb_on ? "lane-block solver" : "generic solver"))));
     return JB_OK;
