@@ -282,6 +282,16 @@ int64_t orc_pgs_iterations(OrcBatch* b) {
     for (auto& e : b->envs) n += e->pgsIterations;
     return n;
 }
+// diagnostics: iteration count of every PGS solve of one env since the history was switched on
+void orc_pgs_history_enable(OrcBatch* b, int32_t on) {
+    for (auto& e : b->envs) { e->keepPgsHistory = on != 0; e->pgsHistory.clear(); }
+}
+int64_t orc_pgs_history(OrcBatch* b, int32_t env, int32_t* out, int64_t cap) {
+    const auto& h = b->envs[env]->pgsHistory;
+    const int64_t n = std::min<int64_t>(cap, static_cast<int64_t>(h.size()));
+    for (int64_t i = 0; i < n; ++i) out[i] = h[i];
+    return static_cast<int64_t>(h.size());
+}
 int64_t orc_rhs_count(OrcBatch* b) {
     int64_t s = 0;
     for (auto& e : b->envs) s += e->rhs_count;

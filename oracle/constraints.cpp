@@ -390,8 +390,9 @@ bool Engine::pgsSolve(int m, const std::vector<double>& A, const double* b, doub
         bool converged = true;
         for (int k = 0; k < rowsMax; ++k) if (!(std::fabs(solverY[k] - solverYPrev[k]) < tol)) { converged = false; break; }
         ++pgsIterations;
-        if (converged) return true;
+        if (converged) { if (keepPgsHistory) pgsHistory.push_back(static_cast<int32_t>(iter + 1)); return true; }
     }
+    if (keepPgsHistory) pgsHistory.push_back(static_cast<int32_t>(PGS_MAX_ITERATIONS));
     return false;
 }
 

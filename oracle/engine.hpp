@@ -165,6 +165,8 @@ struct Engine {
     int rowsMax = 0;
     uint32_t successiveSolveFailed = 0;
     int64_t pgsIterations = 0;
+    std::vector<int32_t> pgsHistory;            // iterations of every solve (diagnostics: tools/pgs_iteration_stats.py)
+    bool keepPgsHistory = false;
     std::vector<double> Mmat, Mchol, Jworld, nle, torqueResidual;
     std::vector<Motion> aDrift;
     std::vector<double> solverJ, solverGamma, solverLambda, solverB, solverY, solverYPrev, solverA;

@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
+#include <mutex>
 #include <memory>
 #include <thread>
 #include <vector>
@@ -42,14 +44,26 @@ struct Warp {
     int islot[32];
     std::vector<std::unique_ptr<std::barrier<>>> bars;   // indexed by group id for the current L
     std::unique_ptr<std::barrier<>> full;                 // whole-warp barrier (mask 0xffffffff)
+    std::map<unsigned, std::unique_ptr<std::barrier<>>> other;   // any other mask (unions of groups: the scheduler's votes)
+    std::mutex other_mutex;
     int L = 1;
 };
 extern thread_local Warp* warp;
 extern thread_local int lane_id;
 inline int group_of(unsigned mask) { return __builtin_ctz(mask) / warp->L; }
 inline void sync_group(unsigned mask) {
-    if (mask == 0xffffffffu && warp->L < 32) warp->full->arrive_and_wait();
-    else warp->bars[group_of(mask)]->arrive_and_wait();
+    if (mask == 0xffffffffu && warp->L < 32) { warp->full->arrive_and_wait(); return; }
+    const int g = group_of(mask);
+    const unsigned gm = warp->L >= 32 ? 0xffffffffu : (((1u << warp->L) - 1u) << (g * warp->L));
+    if (mask == gm) { warp->bars[g]->arrive_and_wait(); return; }
+    std::barrier<>* b;
+    {
+        std::lock_guard<std::mutex> lock(warp->other_mutex);
+        auto& slot = warp->other[mask];
+        if (!slot) slot.reset(new std::barrier<>(__builtin_popcount(mask)));
+        b = slot.get();
+    }
+    b->arrive_and_wait();
 }
 }  // namespace emul
 
