@@ -353,6 +353,22 @@ int jb_get_iters(JbBatch* batch, int64_t* iter, int64_t* iter_failed);
  * is the buffer a multi-GPU rollout all-gathers. */
 int jb_device_views(JbBatch* batch, double** sensors_dev, double** qv_dev);
 
+/* Stable zero-copy views of the state, like the `StepperState` / `RobotState` members the reference exposes to Python as
+ * array views of the engine's own memory (python/jiminy_pywrap/include/jiminy/python/functors.h:57-68, generic.py:688-690:
+ * a gym env reads `q`, `v`, the sensor matrix every step without a getter call).  The first call with `host` non-null
+ * allocates pinned host mirrors; from then on every jb_start / jb_step refreshes them behind the kernel on the batch
+ * stream (contents valid after jb_synchronize or any synchronising getter); the addresses never change.  `device`
+ * (optional) receives the device buffers of the same layout (`a` only once host mirrors exist).  Rows are env-major:
+ * t [n_env], qv [n_env][nq + nv] (q then v), a [n_env][nv], sensors [n_env][width]. */
+typedef struct JbStateViews {
+    const double* t;
+    const double* qv;
+    const double* a;
+    const double* sensors;
+    int32_t n_env, nq, nv, width;
+} JbStateViews;
+int jb_state_ptrs(JbBatch* batch, JbStateViews* host, JbStateViews* device);
+
 /* Asynchronous device-to-device copy (on the batch stream) of the sensor matrix `[n_env][width]` into a
  * caller-owned device buffer, e.g. the send buffer of the observation all-gather. */
 int jb_copy_sensors_device(JbBatch* batch, double* dst_dev);

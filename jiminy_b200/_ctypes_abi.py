@@ -56,6 +56,12 @@ class JbSensorLayout(C.Structure):
                 ("effort_offset", C.c_int32), ("contact_offset", C.c_int32), ("width", C.c_int32)]
 
 
+class JbStateViews(C.Structure):
+    _fields_ = [("t", C.POINTER(C.c_double)), ("qv", C.POINTER(C.c_double)), ("a", C.POINTER(C.c_double)),
+                ("sensors", C.POINTER(C.c_double)), ("n_env", C.c_int32), ("nq", C.c_int32), ("nv", C.c_int32),
+                ("width", C.c_int32)]
+
+
 SOLVERS = {"euler_explicit": 0, "runge_kutta_4": 1, "runge_kutta_dopri": 2}
 CONTACT_MODELS = {"spring_damper": 0, "constraint": 1}
 

@@ -15,7 +15,7 @@ from typing import Any, Dict, Optional, Sequence, Tuple
 import numpy as np
 
 from . import model as M
-from ._ctypes_abi import (JbModelDesc, JbOptions, JbSensorLayout, ModelDescHolder, c_double_p, c_int32_p,
+from ._ctypes_abi import (JbModelDesc, JbOptions, JbSensorLayout, JbStateViews, ModelDescHolder, c_double_p, c_int32_p,
                           c_int64_p, c_uint8_p, dptr, make_options, safety_table)
 
 JB_OK = 0
@@ -54,7 +54,7 @@ class Api:
     SYMBOLS = ("jb_last_error", "jb_version", "jb_default_options", "jb_batch_create", "jb_batch_destroy",
                "jb_set_options", "jb_start", "jb_set_command", "jb_set_command_device", "jb_step",
                "jb_compute_dynamics", "jb_get_state", "jb_get_efforts", "jb_get_sensors", "jb_sensor_layout",
-               "jb_get_extra_terms", "jb_get_status", "jb_get_iters", "jb_device_views", "jb_get_stream",
+               "jb_get_extra_terms", "jb_get_status", "jb_get_iters", "jb_device_views", "jb_state_ptrs", "jb_get_stream",
                "jb_launch_count", "jb_synchronize", "jb_set_joint_springs", "jb_set_pd_controller", "jb_copy_sensors_device", "jb_describe",
                "jb_plan_describe", "jb_stop", "jb_register_impulse_force", "jb_set_impulse_force",
                "jb_register_profile_force", "jb_set_profile_force", "jb_remove_all_forces",
@@ -96,6 +96,7 @@ class Api:
         L.jb_get_status.argtypes = [vp, c_int32_p]
         L.jb_get_iters.argtypes = [vp, c_int64_p, c_int64_p]
         L.jb_device_views.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+        L.jb_state_ptrs.argtypes = [vp, C.POINTER(JbStateViews), C.POINTER(JbStateViews)]
         L.jb_get_stream.argtypes = [vp, C.POINTER(vp)]
         L.jb_launch_count.argtypes = [vp]
         L.jb_launch_count.restype = C.c_int64
@@ -477,6 +478,25 @@ class BatchedEngine:
         s, qv = C.c_void_p(), C.c_void_p()
         self._api.check(self._api.dll.jb_device_views(self._h, C.byref(s), C.byref(qv)))
         return s.value, qv.value
+
+    def state_views(self) -> Dict[str, np.ndarray]:
+        """Zero-copy views of the state (`jb_state_ptrs`): numpy arrays over pinned host memory that every `start` /
+        `step` refreshes behind the kernel -- the batched counterpart of the array views the reference hands out for
+        `stepper_state.q`, `robot_state.v`, `robot.sensor_measurements` (functors.h:57-68).  The arrays are created
+        once and keep their address; read them after `synchronize()` (or any getter).  Keys: t [n], q [n, nq],
+        v [n, nv], a [n, nv], sensors [n, width]; treat them as read-only."""
+        if getattr(self, "_views", None) is None:
+            hv = JbStateViews()
+            self._api.check(self._api.dll.jb_state_ptrs(self._h, C.byref(hv), None))
+            n = self.n_env
+            qv = np.ctypeslib.as_array(hv.qv, shape=(n, self.nq + self.nv))
+            self._views = {
+                "t": np.ctypeslib.as_array(hv.t, shape=(n,)),
+                "q": qv[:, :self.nq], "v": qv[:, self.nq:],
+                "a": np.ctypeslib.as_array(hv.a, shape=(n, max(self.nv, 1)))[:, :self.nv],
+                "sensors": np.ctypeslib.as_array(hv.sensors, shape=(n, max(self.width, 1)))[:, :self.width],
+            }
+        return self._views
 
     def stream(self) -> int:
         s = C.c_void_p()

@@ -52,6 +52,8 @@ struct JbBatch {
     long long* d_iters = nullptr;
     int32_t* d_status = nullptr;
     double *d_cmd = nullptr, *d_sensors = nullptr, *d_qv = nullptr;
+    // jb_state_ptrs: pinned host mirrors refreshed behind every start / step launch (stable addresses, zero-copy views)
+    double *h_mirror = nullptr, *hm_t = nullptr, *hm_qv = nullptr, *hm_a = nullptr, *hm_sensors = nullptr, *d_a_aos = nullptr;
     double *d_qin = nullptr, *d_vin = nullptr, *d_aout = nullptr, *d_fext = nullptr, *d_u = nullptr, *d_umotor = nullptr;
     double* d_springs = nullptr;
     double *d_pd = nullptr, *d_cmd_torque = nullptr, *d_pdf = nullptr, *d_pdf_state = nullptr, *d_mahony = nullptr;
@@ -210,6 +212,19 @@ static int launch(JbBatch* b, int mode, double step_dt, const uint8_t* d_mask = 
 #endif
     CU(cudaGetLastError());
     ++b->launches;
+    if (b->h_mirror && (mode == MODE_STEP || mode == MODE_START)) {
+        // behind the step on the same stream: the views hold the new state once the stream has been synchronised
+        CU(cudaMemcpyAsync(b->hm_t, b->d_sched + static_cast<size_t>(SCH_T) * b->n_pad, sizeof(double) * b->n_env, cudaMemcpyDeviceToHost, b->stream));
+        CU(cudaMemcpyAsync(b->hm_qv, b->d_qv, sizeof(double) * b->n_env * (b->nq + b->nv), cudaMemcpyDeviceToHost, b->stream));
+        const size_t na = static_cast<size_t>(b->n_env) * b->nv;
+        if (na) {
+            JB_LAUNCH(soa_to_aos_kernel, static_cast<unsigned>((na + 255) / 256), 256, 0, b->stream, b->d_a, b->d_a_aos, b->n_env, b->n_pad, b->nv);
+            CU(cudaGetLastError());
+            ++b->launches;
+            CU(cudaMemcpyAsync(b->hm_a, b->d_a_aos, sizeof(double) * na, cudaMemcpyDeviceToHost, b->stream));
+        }
+        if (b->width) CU(cudaMemcpyAsync(b->hm_sensors, b->d_sensors, sizeof(double) * b->n_env * b->width, cudaMemcpyDeviceToHost, b->stream));
+    }
     return JB_OK;
 }
 
@@ -273,6 +288,7 @@ int jb_batch_destroy(JbBatch* b) {
 #endif
     for (void* p : b->allocs) cudaFree(p);
     if (b->h_stage) cudaFreeHost(b->h_stage);
+    if (b->h_mirror) cudaFreeHost(b->h_mirror);
 #ifndef JB_HOST_EMUL
     if (b->h_peer_timeout) cudaFreeHost(b->h_peer_timeout);
 #endif
@@ -1340,6 +1356,38 @@ int jb_get_stream(JbBatch* b, void** stream) {
 }
 
 int64_t jb_launch_count(JbBatch* b) { return b ? b->launches : 0; }
+
+int jb_state_ptrs(JbBatch* b, JbStateViews* host, JbStateViews* device) {
+    if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(b->device));
+    if (host && !b->h_mirror) {
+        const size_t nt = b->n_env, nqv = static_cast<size_t>(b->n_env) * (b->nq + b->nv), na = static_cast<size_t>(b->n_env) * b->nv,
+                     ns = static_cast<size_t>(b->n_env) * b->width;
+        double* h = nullptr;
+        CU(cudaMallocHost(reinterpret_cast<void**>(&h), sizeof(double) * (nt + nqv + na + ns + 4)));
+        std::memset(h, 0, sizeof(double) * (nt + nqv + na + ns + 4));
+        int rc = dev_alloc(b, &b->d_a_aos, std::max<size_t>(na, 1));
+        if (rc) { cudaFreeHost(h); return rc; }
+        b->h_mirror = h; b->hm_t = h; b->hm_qv = h + nt; b->hm_a = b->hm_qv + nqv; b->hm_sensors = b->hm_a + na;
+        if (b->any_started) {
+            // a running batch: fill the views with the current state right away
+            CU(cudaMemcpyAsync(b->hm_t, b->d_sched + static_cast<size_t>(SCH_T) * b->n_pad, sizeof(double) * b->n_env, cudaMemcpyDeviceToHost, b->stream));
+            CU(cudaMemcpyAsync(b->hm_qv, b->d_qv, sizeof(double) * nqv, cudaMemcpyDeviceToHost, b->stream));
+            if (na && (rc = fetch_soa(b, b->d_a, b->nv, b->hm_a))) return rc;
+            if (ns) CU(cudaMemcpyAsync(b->hm_sensors, b->d_sensors, sizeof(double) * ns, cudaMemcpyDeviceToHost, b->stream));
+            CU(cudaStreamSynchronize(b->stream));
+        }
+    }
+    if (host) {
+        host->t = b->hm_t; host->qv = b->hm_qv; host->a = b->hm_a; host->sensors = b->hm_sensors;
+        host->n_env = b->n_env; host->nq = b->nq; host->nv = b->nv; host->width = b->width;
+    }
+    if (device) {
+        device->t = b->d_sched + static_cast<size_t>(SCH_T) * b->n_pad; device->qv = b->d_qv; device->a = b->d_a_aos; device->sensors = b->d_sensors;
+        device->n_env = b->n_env; device->nq = b->nq; device->nv = b->nv; device->width = b->width;
+    }
+    return JB_OK;
+}
 
 int jb_synchronize(JbBatch* b) {
     if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");

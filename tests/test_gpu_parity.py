@@ -315,3 +315,10 @@ def test_sensor_measurement_pipeline_matches_oracle():
     with the same seed reproduces its noise."""
     import sensor_pipeline_common as spc
     spc.pipeline_scenario(None, n_env=48, n_steps=3)
+
+
+@pytest.mark.gpu
+def test_state_views_on_device():
+    import test_kernel_emul as tke
+    tke.test_state_views_are_stable_and_current(None)
+

@@ -725,3 +725,32 @@ def test_compute_dynamics_leaves_the_running_state_alone(api):
         np.testing.assert_array_equal(x, y)
     np.testing.assert_array_equal(runs[0][1], runs[1][1])
     np.testing.assert_array_equal(runs[0][2], runs[1][2])
+
+
+def test_state_views_are_stable_and_current(api):
+    """`jb_state_ptrs` / `BatchedEngine.state_views`: the arrays are created once (same memory for the life of the batch)
+    and hold, after a synchronise, what the getters return -- start, steps, and a masked restart included."""
+    sc = scenarios.make("anymal", 5, seed=4)
+    eng = BatchedEngine(sc.robot, sc.options, 5, api_=api)
+    eng.set_pd_controller(sc.kp, sc.kd)
+    eng.set_command(sc.target0)
+    eng.start(sc.q0, sc.v0)
+    views = eng.state_views()                      # enabled on a running batch: filled right away
+    addr = {k: a.__array_interface__["data"][0] for k, a in views.items()}
+
+    def check():
+        eng.synchronize()
+        t, q, v, a = eng.get_state()
+        for key, ref in (("t", t), ("q", q), ("v", v), ("a", a), ("sensors", eng.get_sensors())):
+            np.testing.assert_array_equal(views[key], ref)
+        assert eng.state_views() is views
+        assert {k: a.__array_interface__["data"][0] for k, a in views.items()} == addr
+    check()
+    for k in range(3):
+        eng.set_command(sc.sample_targets(k))
+        eng.step(sc.step_dt)
+        check()
+    mask = np.array([1, 0, 0, 1, 0], dtype=bool)
+    eng.start(sc.q0, sc.v0, mask=mask)
+    check()
+    assert (views["t"][mask] == 0.0).all() and (views["t"][~mask] > 0.0).all()
