@@ -348,6 +348,19 @@ def run_gpu(args):
     except Exception:
         pass
     achieved_gbs = bytes_per_launch / (step_ms_dev * 1e-3) / 1e9
+    # supplementary (never the reported metric): the same steps back to back WITHOUT the L2 flush -- what a rollout loop
+    # that does nothing else between two steps sees; for the small configs the cold misses of the flushed timing are most of it
+    warm_ms = None
+    if world == 1:
+        nw = min(args.steps, 20)
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record(stream)
+        for k in range(nw):
+            eng.set_command_device(acts_dev[args.warmup + k].data_ptr())
+            eng.step(sc.step_dt)
+        w1.record(stream)
+        eng.synchronize()
+        warm_ms = w0.elapsed_time(w1) / nw
     ncores, cpu = (None, None)
     if not args.no_cpu_baseline:
         ncores, cpu = cpu_baseline(args.workload, contact_model=args.contact_model, solver=args.ode_solver, dt_max=args.dt_max,
@@ -357,7 +370,7 @@ def run_gpu(args):
         "ms_per_step": t_path_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args, sc), "scenario": sc.description, "envs_total": total_envs, "lane_plan": eng.describe(),
-                   "l2": "160 MB buffer rewritten between timed steps (flush)", "obs_all_gather_ms": gather_ms, "obs_exchange": obs_gather,
+                   "l2": "160 MB buffer rewritten between timed steps (flush)", "ms_per_step_warm_l2_back_to_back": warm_ms, "obs_all_gather_ms": gather_ms, "obs_exchange": obs_gather,
                    "envs_failed": n_bad, "envs_flagged": n_bounds, "timed_region_wall_ms": wall_ms},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_env * nm * 8 * world),

@@ -353,6 +353,16 @@ int jb_get_iters(JbBatch* batch, int64_t* iter, int64_t* iter_failed);
  * is the buffer a multi-GPU rollout all-gathers. */
 int jb_device_views(JbBatch* batch, double** sensors_dev, double** qv_dev);
 
+/* Model randomisation: `Model::addBiasedToExtendedModel` (core/src/robot/model.cc:1166-1236; options
+ * `centerOfMassPositionBodiesBiasStd`, `massBodiesBiasStd`, `inertiaBodiesBiasStd`, `relativePositionBodiesBiasStd`)
+ * re-draws the body inertias and joint placements of a robot at every `Engine::reset`.  A batch holds `n_variants` such
+ * draws of the model it was created with -- same kinematic tree, hardware and frames, other numbers (anything else is
+ * rejected) -- and assigns them per GROUP of jb_envs_per_group() consecutive envs (the envs that share a warp):
+ * `variant_of_group[g]` in [0, n_variants), g < ceil(n_env / jb_envs_per_group()).  Takes effect at the next launch;
+ * call it before jb_start (or restart the envs afterwards, as the reference's reset does). */
+int jb_set_model_variants(JbBatch* batch, int32_t n_variants, const JbModelDesc* models, const int32_t* variant_of_group);
+int jb_envs_per_group(JbBatch* batch);
+
 /* Stable zero-copy views of the state, like the `StepperState` / `RobotState` members the reference exposes to Python as
  * array views of the engine's own memory (python/jiminy_pywrap/include/jiminy/python/functors.h:57-68, generic.py:688-690:
  * a gym env reads `q`, `v`, the sensor matrix every step without a getter call).  The first call with `host` non-null

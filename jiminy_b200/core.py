@@ -54,7 +54,7 @@ class Api:
     SYMBOLS = ("jb_last_error", "jb_version", "jb_default_options", "jb_batch_create", "jb_batch_destroy",
                "jb_set_options", "jb_start", "jb_set_command", "jb_set_command_device", "jb_step",
                "jb_compute_dynamics", "jb_get_state", "jb_get_efforts", "jb_get_sensors", "jb_sensor_layout",
-               "jb_get_extra_terms", "jb_get_status", "jb_get_iters", "jb_device_views", "jb_state_ptrs", "jb_get_stream",
+               "jb_get_extra_terms", "jb_get_status", "jb_get_iters", "jb_device_views", "jb_state_ptrs", "jb_set_model_variants", "jb_envs_per_group", "jb_get_stream",
                "jb_launch_count", "jb_synchronize", "jb_set_joint_springs", "jb_set_pd_controller", "jb_copy_sensors_device", "jb_describe",
                "jb_plan_describe", "jb_stop", "jb_register_impulse_force", "jb_set_impulse_force",
                "jb_register_profile_force", "jb_set_profile_force", "jb_remove_all_forces",
@@ -97,6 +97,8 @@ class Api:
         L.jb_get_iters.argtypes = [vp, c_int64_p, c_int64_p]
         L.jb_device_views.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
         L.jb_state_ptrs.argtypes = [vp, C.POINTER(JbStateViews), C.POINTER(JbStateViews)]
+        L.jb_set_model_variants.argtypes = [vp, C.c_int32, C.POINTER(JbModelDesc), c_int32_p]
+        L.jb_envs_per_group.argtypes = [vp]
         L.jb_get_stream.argtypes = [vp, C.POINTER(vp)]
         L.jb_launch_count.argtypes = [vp]
         L.jb_launch_count.restype = C.c_int64
@@ -208,6 +210,25 @@ class BatchedEngine:
         d = np.ascontiguousarray(damping, dtype=np.float64)
         assert k.shape == (self.nv,) and d.shape == (self.nv,)
         self._api.check(self._api.dll.jb_set_joint_springs(self._h, dptr(k), dptr(d)))
+
+    # ---- model randomisation (Model::addBiasedToExtendedModel, model.cc:1166-1236)
+    @property
+    def envs_per_group(self) -> int:
+        """How many consecutive envs share one model variant (the envs of a warp)."""
+        return int(self._api.dll.jb_envs_per_group(self._h))
+
+    def set_model_variants(self, robots: Sequence[M.RobotTable], variant_of_group: Sequence[int]) -> None:
+        """Give every group of `envs_per_group` consecutive envs one of `robots` -- draws of `model.biased_robot` on the
+        robot the batch was built with (same tree, hardware and frames; other inertias / joint placements).  The
+        batched form of the per-reset model randomisation of the reference; takes effect at the next `start`."""
+        holders = [ModelDescHolder(r) for r in robots]
+        descs = (JbModelDesc * len(robots))(*[h.desc for h in holders])
+        ngroups = -(-self.n_env // self.envs_per_group)
+        vog = np.ascontiguousarray(variant_of_group, dtype=np.int32)
+        if vog.shape != (ngroups,):
+            raise ValueError(f"variant_of_group must have one entry per group of {self.envs_per_group} envs ({ngroups})")
+        self._api.check(self._api.dll.jb_set_model_variants(self._h, len(robots), descs, vog.ctypes.data_as(c_int32_p)))
+        self._variants = (list(robots), vog)
 
     # ---- external forces (Engine.register_impulse_force / register_profile_force / remove_all_forces)
     def stop(self) -> None:

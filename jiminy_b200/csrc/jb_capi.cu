@@ -575,6 +575,50 @@ int jb_set_options(JbBatch* b, const JbOptions* o) {
     return JB_OK;
 }
 
+// Model randomisation (Model::addBiasedToExtendedModel, core/src/robot/model.cc:1166-1236): a reset of the reference
+// re-draws the inertias and joint placements of ONE robot; a batch holds n_variants such draws of the same kinematic tree
+// and every group of envs that shares a warp uses one of them (a table base per block: nothing on the hot path changes).
+int jb_set_model_variants(JbBatch* b, int32_t n_variants, const JbModelDesc* models, const int32_t* variant_of_group) {
+    if (!b || !models || !variant_of_group || n_variants < 1) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaSetDevice(b->device));
+    const Plan& P0 = b->plan;
+    const int epw = 32 / P0.L, ngroups = (b->n_env + epw - 1) / epw;
+    std::vector<RecDbl> rows;
+    std::vector<double> mass(n_variants);
+    for (int v = 0; v < n_variants; ++v) {
+        Plan P;
+        try { P = build_plan(models[v], P0.L, b->kp.n_hist); }
+        catch (const std::exception& ex) { return fail(JB_ERR_INVALID_ARGUMENT, std::string("lane planner (variant): ") + ex.what()); }
+        // same tree, same hardware: everything but the numbers in the double tables must be what the batch was built with
+        bool same = P.L == P0.L && P.nrec == P0.nrec && P.nfields == P0.nfields && P.rint.size() == P0.rint.size() &&
+                    P.cslots.size() == P0.cslots.size() && models[v].nq == b->nq && models[v].nv == b->nv && models[v].nmotors == b->nmotors;
+        if (same) same = std::memcmp(P.rint.data(), P0.rint.data(), P.rint.size() * sizeof(RecInt)) == 0;
+        if (same && !P.cslots.empty()) same = std::memcmp(P.cslots.data(), P0.cslots.data(), P.cslots.size() * sizeof(ContactSlot)) == 0;
+        if (!same) return fail(JB_ERR_INVALID_ARGUMENT, "a model variant must have the kinematic tree, hardware and frames of the batch's model (only inertias and joint placements may differ)");
+        rows.insert(rows.end(), P.rdbl.begin(), P.rdbl.end());
+        mass[v] = P.total_mass;
+    }
+    std::vector<int32_t> vob(ngroups);
+    std::vector<double> bm(ngroups);
+    for (int g = 0; g < ngroups; ++g) {
+        if (variant_of_group[g] < 0 || variant_of_group[g] >= n_variants) return fail(JB_ERR_INVALID_ARGUMENT, "variant index out of range");
+        vob[g] = variant_of_group[g]; bm[g] = mass[vob[g]];
+    }
+    RecDbl* d_rows; int32_t* d_vob; double* d_bm;
+    int rc;
+    if ((rc = dev_alloc(b, &d_rows, rows.size())) || (rc = dev_alloc(b, &d_vob, vob.size())) || (rc = dev_alloc(b, &d_bm, bm.size()))) return rc;
+    CU(cudaMemcpyAsync(d_rows, rows.data(), rows.size() * sizeof(RecDbl), cudaMemcpyHostToDevice, b->stream));
+    CU(cudaMemcpyAsync(d_vob, vob.data(), vob.size() * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
+    CU(cudaMemcpyAsync(d_bm, bm.data(), bm.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    CU(cudaStreamSynchronize(b->stream));   // the host vectors go away
+    b->kp.rdbl = d_rows; b->kp.n_variants = n_variants > 1 ? n_variants : 2;   // (a single variant still replaces the table: keep the indirection on)
+    b->kp.rdbl_rows = static_cast<int32_t>(P0.rdbl.size());
+    b->kp.variant_of_block = d_vob; b->kp.block_mass = d_bm;
+    return JB_OK;
+}
+
+int jb_envs_per_group(JbBatch* b) { return b ? 32 / b->plan.L : 0; }
+
 // Linear internal dynamics u_custom = -k q - d v on 1-dof joints: the device-side stand-in for the
 // `internalDynamics` functor of FunctionalController (controller_functor.h:27-80).
 int jb_set_joint_springs(JbBatch* b, const double* k, const double* d) {

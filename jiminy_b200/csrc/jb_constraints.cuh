@@ -168,7 +168,7 @@ __device__ __noinline__ void cons_update_bounds(const Ctx c, int* status) {
         if (ri->kind == REC_PAD || ri->kind == REC_FREE || !ri->owner || !ri->has_limit) continue;
         const int k = KP->jc_of_joint[ri->joint];
         if (k < 0) continue;
-        const RecDbl* rd = KP->rdbl + (r * L + c.sub);
+        const RecDbl* rd = JB_RDBL + (r * L + c.sub);
         const double q = SMF(c, KP->rec_off[r] + R1_QS), lo = rd->q_lo, hi = rd->q_hi;
         const int o = cs_joint(k);
         const bool was = CST(o) != 0.0;
@@ -327,7 +327,7 @@ __device__ __noinline__ void cons_refresh_accelerations(const Ctx c) {
         const RecInt* ri = KP->rint + (r * L + c.sub);
         const int kind = ri->kind;
         if (kind == REC_PAD) continue;
-        const RecDbl* rd = KP->rdbl + (r * L + c.sub);
+        const RecDbl* rd = JB_RDBL + (r * L + c.sub);
         const int base = KP->rec_off[r];
         double* const rp = jb_smem + base * 32 + c.lane;
         if (ri->parent_rec < 0) {
@@ -364,7 +364,7 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
         for (int j = 1; j < nj; ++j) {
             const JointMap jm = KP->jmap[j];
             const double* rq = rec_of(c, jm);
-            const RecDbl* rd = KP->rdbl + (jm.rec * L + jm.sub);
+            const RecDbl* rd = JB_RDBL + (jm.rec * L + jm.sub);
             const Xf li = ld_xf32(rq);
             const V3 ax = ld3(rd->axis);
             Mot vJ = mzero();
@@ -408,7 +408,7 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
         // composite-rigid-body algorithm (pinocchio_overload::crba, overload.h:99-124)
         for (int j = nj - 1; j > 0; --j) {
             const JointMap jm = KP->jmap[j];
-            const RecDbl* rd = KP->rdbl + (jm.rec * L + jm.sub);
+            const RecDbl* rd = JB_RDBL + (jm.rec * L + jm.sub);
             const V3 ax = ld3(rd->axis);
             SymY Y;
 #pragma unroll
@@ -424,7 +424,7 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
                     G = force_act(ld_xf32(rec_of(c, KP->jmap[jj])), G);
                     jj = KP->jmap[jj].parent;
                     const JointMap jp = KP->jmap[jj];
-                    const V3 axp = ld3((KP->rdbl + (jp.rec * L + jp.sub))->axis);
+                    const V3 axp = ld3((JB_RDBL + (jp.rec * L + jp.sub))->axis);
                     for (int e = 0; e < jp.nvj; ++e) {
                         const double val = mdot(subspace_col(jp.kind, axp, e), G);
                         CWK(w.MM + (jp.idx_v + e) * nv + jm.idx_v + d) = val;
@@ -484,7 +484,7 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
                 const V3 pf = oM.p + rmul(oM.R, P.p);
                 for (int jj = j; jj > 0; jj = KP->jmap[jj].parent) {
                     const JointMap jp = KP->jmap[jj];
-                    const V3 axp = ld3((KP->rdbl + (jp.rec * L + jp.sub))->axis);
+                    const V3 axp = ld3((JB_RDBL + (jp.rec * L + jp.sub))->axis);
                     Xf oMj;
 #pragma unroll
                     for (int e = 0; e < 9; ++e) oMj.R[e] = CWK(w.OM + 12 * jj + e);

@@ -146,7 +146,7 @@ JB_DI Xf lb_limi(const Ctx& c, int r) { Xf li; sm_load_xf(c, KP->rec_off[r], li)
 __device__ __noinline__ void lb_prepare(const Ctx c, const LbLayout w, double* const lw, int* status) {
     const int L = KP->L, nrec = KP->nrec, ntrunk = KP->ntrunk, nt = KP->lb_nt, nl = KP->lb_nl;
     const RecInt* const rint = KP->rint + c.sub;
-    const RecDbl* const rdbl = KP->rdbl + c.sub;
+    const RecDbl* const rdbl = JB_RDBL + c.sub;
     const int32_t* const dof0 = KP->lb_dof0 + c.sub;
     const int my_nl = KP->lb_nl_of[c.sub];
     auto ndof = [&](int r) { return lb_ndof(rint, r, L); };
@@ -270,7 +270,7 @@ __device__ __noinline__ bool cons_solve_blocks(const Ctx c, int* status) {
     const LbLayout w = lb_layout(nrec, ntrunk, nl, nt, ml, n_cons);
     double* const lw = KP->lwork + (CW_ROW(c) * L + c.sub) * static_cast<size_t>(KP->lw_total);
     const RecInt* const rint = KP->rint + c.sub;
-    const RecDbl* const rdbl = KP->rdbl + c.sub;
+    const RecDbl* const rdbl = JB_RDBL + c.sub;
     const int32_t* const dof0 = KP->lb_dof0 + c.sub;
     const int my_nl = KP->lb_nl_of[c.sub];
     const int lane0 = c.lane - c.sub;

@@ -60,7 +60,7 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
     double* const lw = KP->lwork + (CW_ROW(c) * L + c.sub) * static_cast<size_t>(KP->lw_total);
     double* const sh = KP->cwork + CW_ROW(c) * static_cast<size_t>(KP->cw_total);
     const RecInt* const rint = KP->rint + c.sub;
-    const RecDbl* const rdbl = KP->rdbl + c.sub;
+    const RecDbl* const rdbl = JB_RDBL + c.sub;
     const int32_t* const dof0 = KP->lb_dof0 + c.sub;
     const int my_nl = KP->lb_nl_of[c.sub];
     const double omega = 2.0 * 3.14159265358979323846 * opt.contact_stabilization_freq;

@@ -90,7 +90,7 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
     const unsigned M = uni ? 0xffffffffu : c.gmask;
     constexpr int L = 4;
     const JbOptions& opt = KP->opt;
-    const RecDbl* rd0 = KP->rdbl + (0 * L + c.sub);
+    const RecDbl* rd0 = JB_RDBL + (0 * L + c.sub);
     const ContactSlot* ct = KP->cslots + c.sub;       // contact slot 0 of this lane
     const int kc = ct->contact;                        // contact index == constraint index among the contact frames
     const int cso = cs_contact(kc);
@@ -109,7 +109,7 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
     V3 wax[3], parm[3];        // world axes and world positions of the three leg joints
 #pragma unroll
     for (int i = 1; i <= 3; ++i) {
-        const RecDbl* rd = KP->rdbl + (i * L + c.sub);
+        const RecDbl* rd = JB_RDBL + (i * L + c.sub);
         const int base = KP->rec_off[i];
         Xf li; sm_load_xf(c, base + R1_LIMI, li);
         Xf o2;
@@ -132,7 +132,7 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
         Mot F[3];
 #pragma unroll
         for (int i = 3; i >= 1; --i) {
-            const RecDbl* rd = KP->rdbl + (i * L + c.sub);
+            const RecDbl* rd = JB_RDBL + (i * L + c.sub);
             const V3 ax = ld3(rd->axis);
             SymY Yi;
             inertia_to_sym(rd->inertia[0], ld3(rd->inertia + 1), rd->inertia + 4, Yi);

@@ -100,7 +100,7 @@ __device__ __noinline__ void update_pd_commands(const Ctx c, bool running) {
     for (int r = 0; r < KP->nrec; ++r) {
         const RecInt* ri = KP->rint + (r * L + c.sub);
         if (ri->kind == REC_PAD || ri->kind == REC_FREE || ri->motor < 0) continue;
-        const RecDbl* rd = KP->rdbl + (r * L + c.sub);
+        const RecDbl* rd = JB_RDBL + (r * L + c.sub);
         const int base = KP->rec_off[r];
         double* const rp = jb_smem + base * 32 + c.lane;
         const double red = rd->motor[0], lim = rd->motor[1];
@@ -185,7 +185,7 @@ __device__ __noinline__ void store_outputs(const Ctx c) {
     for (int r = 0; r < KP->nrec; ++r) {
         const RecInt* ri = KP->rint + (r * L + c.sub);
         if (ri->kind == REC_PAD || !ri->owner) continue;
-        const RecDbl* rd = KP->rdbl + (r * L + c.sub);
+        const RecDbl* rd = JB_RDBL + (r * L + c.sub);
         const int base = KP->rec_off[r];
         double* const rp = jb_smem + base * 32 + c.lane;
         double* qv = KP->qv_out ? KP->qv_out + col * (KP->nq + KP->nv) : nullptr;
@@ -249,7 +249,7 @@ __device__ __noinline__ void store_dynamics(const Ctx c) {
     for (int r = 0; r < KP->nrec; ++r) {
         const RecInt* ri = KP->rint + (r * L + c.sub);
         if (ri->kind == REC_PAD || !ri->owner) continue;
-        const RecDbl* rd = KP->rdbl + (r * L + c.sub);
+        const RecDbl* rd = JB_RDBL + (r * L + c.sub);
         const int base = KP->rec_off[r];
         double* const rp = jb_smem + base * 32 + c.lane;
         if (ri->kind == REC_FREE) {
@@ -298,7 +298,7 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
     const int env_raw = blockIdx.x * epw + c.lane / L;
     c.valid = env_raw < KP->n_env;
     c.env = c.valid ? env_raw : (KP->n_env - 1);
-    c.flags = 0;
+    c.flags = KP->n_variants > 1 ? (KP->variant_of_block[blockIdx.x] * KP->rdbl_rows) << CTX_ROW_SHIFT : 0;
     c.gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (c.lane - c.sub));
     const size_t N = KP->n_pad, col = c.env;
     const int mode = la.mode;
@@ -382,10 +382,10 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
             // zero joint efforts and solves the enabled constraints as equalities, the next three run the boxed
             // solver warm-started on an up-to-date state
             cons_reset(c);
-            Ctx c0 = c; c0.flags = CTX_ZERO_U | CTX_IGNORE_BOUNDS;
+            Ctx c0 = c; c0.flags |= CTX_ZERO_U | CTX_IGNORE_BOUNDS;
             rhs(c0, false, &status);
             const bool constrained = jb_any(c, SMF(c, KP->cons_off) != 0.0);
-            Ctx c1 = c; c1.flags = CTX_START_FEEDBACK;
+            Ctx c1 = c; c1.flags |= CTX_START_FEEDBACK;
             for (int it = 1; it < (constrained ? 4 : 2); ++it) rhs(c1, true, &status);
         } else rhs(c, false, &status);
         // forceMax > 1e5 guard (engine.cc:1310-1346)

@@ -723,3 +723,53 @@ def robot_table_from_dict(d: dict) -> RobotTable:
                 "contact_sensor_names", "contact_sensor_index"):
         setattr(r, key, list(d[key]))
     return r
+
+
+# --------------------------------------------------------------------------- model randomisation
+def _exp3(w: np.ndarray) -> np.ndarray:
+    """Rotation matrix of a rotation vector (pinocchio::exp3)."""
+    th = float(np.linalg.norm(w))
+    K = np.array([[0.0, -w[2], w[1]], [w[2], 0.0, -w[0]], [-w[1], w[0], 0.0]])
+    if th < 1e-12:
+        return np.eye(3) + K
+    return np.eye(3) + math.sin(th) / th * K + (1.0 - math.cos(th)) / (th * th) * (K @ K)
+
+
+def biased_robot(robot: RobotTable, rng: np.random.Generator, *, mass_std: float = 0.0, com_std: float = 0.0,
+                 inertia_std: float = 0.0, relative_position_std: float = 0.0) -> RobotTable:
+    """One draw of `Model::addBiasedToExtendedModel` (core/src/robot/model.cc:1166-1236) with the model options
+    `massBodiesBiasStd`, `centerOfMassPositionBodiesBiasStd`, `inertiaBodiesBiasStd`, `relativePositionBodiesBiasStd`:
+    for every mechanical joint (not the root free-flyer), in the reference's order, the centre of mass is scaled
+    component-wise by N(1, std), the mass by N(1, std) (never below min(mass, 1 g)), the principal moments of inertia by
+    N(1, std) after the principal axes have been turned by a random rotation vector N(0, std), and the translation of the
+    joint placement by N(1, std) (rotation untouched).  Draws are single precision like the reference's; the stream is
+    numpy's, not the engine's PCG32 (and Eigen's eigenvector signs are not reproduced): equal in distribution, not draw by
+    draw.  Returns a new table; everything but `inertia` and `placement` is shared with `robot`."""
+    import copy
+    EPS = 2.220446049250313e-16
+    out = copy.copy(robot)
+    out.inertia = np.array(robot.inertia, dtype=np.float64, copy=True)
+    out.placement = np.array(robot.placement, dtype=np.float64, copy=True)
+
+    def normal(n, mean, std):
+        return (np.float32(mean) + np.float32(std) * rng.standard_normal(n, dtype=np.float32)).astype(np.float64)
+    for j in range(1, robot.njoints):
+        if int(robot.joint_type[j]) == JB_JOINT_FREEFLYER:
+            continue
+        if com_std > EPS:
+            out.inertia[j, 1:4] *= normal(3, 1.0, com_std)
+        if mass_std > EPS:
+            m = out.inertia[j, 0]
+            out.inertia[j, 0] = max(m * float(normal(1, 1.0, mass_std)[0]), min(m, 1.0e-3))
+        if inertia_std > EPS:
+            xx, xy, yy, xz, yz, zz = out.inertia[j, 4:10]
+            I = np.array([[xx, xy, xz], [xy, yy, yz], [xz, yz, zz]])
+            moments, axes = np.linalg.eigh(I)
+            axes = axes @ _exp3(normal(3, 0.0, inertia_std))
+            moments = moments * normal(3, 1.0, inertia_std)
+            I = axes @ np.diag(moments) @ axes.T
+            out.inertia[j, 4:10] = [I[0, 0], I[0, 1], I[1, 1], I[0, 2], I[1, 2], I[2, 2]]
+        if relative_position_std > EPS:
+            out.placement[j, 9:12] *= normal(3, 1.0, relative_position_std)
+    return out
+

@@ -322,3 +322,9 @@ def test_state_views_on_device():
     import test_kernel_emul as tke
     tke.test_state_views_are_stable_and_current(None)
 
+
+@pytest.mark.gpu
+def test_model_variants_on_device():
+    import test_kernel_emul as tke
+    tke.test_model_variants_match_per_variant_oracles(None)
+

@@ -754,3 +754,58 @@ def test_state_views_are_stable_and_current(api):
     eng.start(sc.q0, sc.v0, mask=mask)
     check()
     assert (views["t"][mask] == 0.0).all() and (views["t"][~mask] > 0.0).all()
+
+
+def test_model_variants_match_per_variant_oracles(api):
+    """Model randomisation (`jb_set_model_variants`): three draws of `biased_robot` (mass, centre of mass, inertia, joint
+    placement) over four groups of envs; every group follows the oracle built on ITS variant, centroidal terms included."""
+    from jiminy_b200 import model as M
+    n = 26                                         # ANYmal: 8 envs per group -> 4 groups, the last one partial
+    sc = scenarios.make("anymal", n, seed=6)
+    rng = np.random.default_rng(11)
+    robots = [sc.robot] + [M.biased_robot(sc.robot, rng, mass_std=0.05, com_std=0.05, inertia_std=0.05, relative_position_std=0.002)
+                           for _ in range(2)]
+    assert abs(robots[1].mass - sc.robot.mass) > 1e-3 and not np.array_equal(robots[1].placement, sc.robot.placement)
+    np.testing.assert_array_equal(robots[1].placement[:, :9], sc.robot.placement[:, :9])      # rotations untouched
+    eng = BatchedEngine(sc.robot, sc.options, n, api_=api)
+    assert eng.envs_per_group == 8
+    vog = np.array([1, 0, 2, 1], dtype=np.int32)
+    eng.set_model_variants(robots, vog)
+    with pytest.raises(ValueError):
+        eng.set_model_variants(robots, vog[:2])
+    eng.set_pd_controller(sc.kp, sc.kd)
+    eng.set_command(sc.target0)
+    eng.start(sc.q0, sc.v0)
+    for k in range(2):
+        eng.set_command(sc.sample_targets(k))
+        eng.step(sc.step_dt)
+    t, q, v, a = eng.get_state()
+    cen = eng.get_centroidal()
+    worst = 0.0
+    for g, var in enumerate(vog):
+        rows = slice(8 * g, min(8 * g + 8, n))
+        m = rows.stop - rows.start
+        orc = OracleBatch(robots[var], sc.options, m)
+        orc.set_pd_controller(sc.kp, sc.kd)
+        orc.set_command(sc.target0[rows])
+        orc.start(sc.q0[rows], sc.v0[rows])
+        for k in range(2):
+            orc.set_command(sc.sample_targets(k)[rows])
+            orc.step(sc.step_dt)
+        to, qo, vo, ao = orc.get_state()
+        np.testing.assert_allclose(q[rows], qo, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(v[rows], vo, rtol=0, atol=1e-8)
+        np.testing.assert_allclose(a[rows], ao, rtol=1e-7, atol=1e-6)
+        for x, y in zip(cen, orc.get_centroidal()):
+            np.testing.assert_allclose(np.asarray(x)[rows], y, rtol=1e-8, atol=1e-8)
+        worst = max(worst, float(np.abs(q[rows] - qo).max()))
+    # the variants really differ: group 0 (variant 1) against the unbiased model
+    orc0 = OracleBatch(sc.robot, sc.options, 8)
+    orc0.set_pd_controller(sc.kp, sc.kd); orc0.set_command(sc.target0[:8]); orc0.start(sc.q0[:8], sc.v0[:8])
+    for k in range(2):
+        orc0.set_command(sc.sample_targets(k)[:8]); orc0.step(sc.step_dt)
+    assert np.abs(orc0.get_state()[1] - q[:8]).max() > 1e4 * max(worst, 1e-13)
+    # a variant with another tree is refused
+    other = scenarios.make("atlas", 1).robot
+    with pytest.raises(Exception):
+        eng.set_model_variants([other], np.zeros(4, dtype=np.int32))

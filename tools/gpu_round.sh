@@ -1,36 +1,13 @@
 #!/bin/bash
-# One GPU session: parity tests, smoke, bench, launch list and one full ncu capture of the step kernel.
-# Usage (from the repo root, on the GPU box): bash tools/gpu_round.sh [tag]
-TAG=${1:-r01}
+# full GPU suite + headline bench + secondary workloads (no ncu): the check after a device-code change
+TAG=${1:-r02_round}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 export PYTHONUNBUFFERED=1
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit,memory.total --format=csv > $OUT/gpu.csv 2>&1
-nproc > $OUT/nproc.txt
-echo "== pytest -m gpu" | tee $OUT/pytest_gpu.log
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -40 | tee -a $OUT/pytest_gpu.log
-echo "== bench" | tee $OUT/bench.log
-timeout 600 python bench.py --gpus 1 --steps 20 --warmup 3 2> $OUT/bench.err | tee -a $OUT/bench.log
-tail -5 $OUT/bench.err
-for W in atlas cartpole; do
-  timeout 300 python bench.py --workload $W --steps 10 --warmup 3 --no-cpu-baseline 2>> $OUT/bench.err | tee -a $OUT/bench_$W.log
-done
-# the other BASELINE configs at their own sizes, and the constraint contact model (the reference's default)
-timeout 300 python bench.py --workload cartpole --n-env 512 --steps 50 --warmup 5 2>> $OUT/bench.err | tee -a $OUT/bench_cartpole512.log
-timeout 300 python bench.py --workload double_pendulum --n-env 1 --steps 50 --warmup 5 2>> $OUT/bench.err | tee -a $OUT/bench_double_pendulum1.log
-timeout 300 python bench.py --workload anymal --contact-model constraint --steps 5 --warmup 3 2>> $OUT/bench.err | tee -a $OUT/bench_anymal_constraint.log
-timeout 300 python bench.py --workload atlas --contact-model constraint --n-env 512 --steps 3 --warmup 3 --no-cpu-baseline 2>> $OUT/bench.err | tee -a $OUT/bench_atlas_constraint512.log
-# the reference's own Atlas settings (atlas_options.toml; the config of its only published timing): Euler 5 ms, constraint contacts
-timeout 300 python bench.py --workload atlas --contact-model constraint --ode-solver euler_explicit --dt-max 0.005 --steps 5 --warmup 3 2>> $OUT/bench.err | tee -a $OUT/bench_atlas_reference_settings.log
-# the published benchmark restated: AtlasPDControlJiminyEnv pipeline + observation wrappers, wall clock around env.step
-timeout 300 python tools/bench_pipeline.py --n-env 4096 --steps 10 --warmup 3 2>> $OUT/bench.err | tee -a $OUT/bench_atlas_pd_pipeline.log
-echo "== reference arm" | tee $OUT/bench_ref.log
-timeout 300 python bench.py --impl reference --steps 5 --warmup 1 2>> $OUT/bench.err | tee -a $OUT/bench_ref.log
-echo "== ncu launch list"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches.csv \
-    python bench.py --steps 3 --warmup 1 --no-cpu-baseline > $OUT/ncu_launch_run.log 2>&1
-echo "== ncu full capture of env_step_kernel"
-# launches: 0 = start (full kernel), then per step: fast kernel, full kernel as fix-up pass -> odd indices are the hot kernel
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:env_step_kernel -s 5 -c 1 -f -o $OUT/prof_step \
-    python bench.py --steps 3 --warmup 1 --no-cpu-baseline > $OUT/ncu_full_run.log 2>&1
-ls -la $OUT
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 | tee $OUT/pytest_gpu.log
+B="timeout 600 python bench.py --no-cpu-baseline"
+$B --steps 20 --warmup 3 2>> $OUT/bench.err | tee -a $OUT/bench.log
+$B --steps 20 --warmup 3 2>> $OUT/bench.err | tee -a $OUT/bench.log
+$B --workload anymal --contact-model constraint --steps 4 --warmup 3 2>> $OUT/bench.err | tee -a $OUT/bench_anymal_constraint.log
+$B --flagged-fraction 0.1 --steps 5 --warmup 3 2>> $OUT/bench.err | tee -a $OUT/bench_flagged.log
+tail -3 $OUT/bench.err
