@@ -171,8 +171,8 @@ static bool g_kp_valid[64] = {};
 #endif
 static int launch(JbBatch* b, int mode, double step_dt, const uint8_t* d_mask = nullptr, const double* d_command = nullptr) {
     KParams kp = b->kp;
-    // static plan signatures carry no external-force / constraint-contact code
-    if (kp.n_eslot > 0 || kp.opt.contact_model == JB_CONTACT_CONSTRAINT) kp.sig_id = 0;
+    // static plan signatures carry no external-force code
+    if (kp.n_eslot > 0) kp.sig_id = 0;
     LaunchArgs la{};
     la.mode = mode; la.step_dt = step_dt; la.mask = d_mask; la.command = d_command;
     if (mode == MODE_STEP && b->peer_world > 1 && !b->peer_opened.empty() && b->peer_enabled) {
@@ -540,6 +540,17 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
     kp.fast_bounds = (kp.sig_id == SigQuadruped::ID && kp.rhs_variant == 1 && kp.cons_on &&
                       !(std::getenv("JB_NO_FAST_BOUNDS") && std::atoi(std::getenv("JB_NO_FAST_BOUNDS")))) ? 1 : 0;
     kp.fast_bounds_io = kp.fast_bounds;
+    static_assert(CONS_PGS_MAX_ITER == sizeof(kp.pgs_relax) / sizeof(double), "relaxation table");
+    for (int iter = 0; iter < CONS_PGS_MAX_ITER; ++iter) {
+        const double ratio = (static_cast<double>(CONS_PGS_MAX_ITER - CONS_RELAX_MIN_ITER) - iter) /
+                             (CONS_PGS_MAX_ITER - CONS_RELAX_MIN_ITER - CONS_RELAX_MAX_ITER);
+        double wr = CONS_RELAX_MAX;
+        if (ratio < 1.0) {
+            wr = CONS_RELAX_MIN;
+            if (ratio > 0.0) wr += (CONS_RELAX_MAX - CONS_RELAX_MIN) * (ratio * ratio);
+        }
+        kp.pgs_relax[iter] = wr;
+    }
     kp.uniform_solver = (std::getenv("JB_NO_UNIFORM_SOLVER") && std::atoi(std::getenv("JB_NO_UNIFORM_SOLVER"))) ? 0 : 1;
     if (const char* e = std::getenv("JB_FAST_BOUNDS_MODE")) { const int m_ = std::atoi(e); if (m_ == 2) kp.fast_bounds = 0; if (m_ == 3) kp.fast_bounds_io = 0; }
     kp.n_eslot = 0; kp.n_imp = 0; kp.n_prof = 0; kp.ext_off = b->base_fields;
@@ -1432,6 +1443,20 @@ int jb_state_ptrs(JbBatch* b, JbStateViews* host, JbStateViews* device) {
     }
     return JB_OK;
 }
+
+#if defined(JB_PROFILE_CLOCKS) && !defined(JB_HOST_EMUL)
+// development build only: read and clear the cycle counters of the full body (see jb_device.cuh)
+int jb_debug_prof(JbBatch* b, double* out16) {
+    CU(cudaSetDevice(b->device));
+    CU(cudaStreamSynchronize(b->stream));
+    unsigned long long h[16];
+    CU(cudaMemcpyFromSymbol(h, jb_prof, sizeof h));
+    for (int i = 0; i < 16; ++i) out16[i] = static_cast<double>(h[i]);
+    std::memset(h, 0, sizeof h);
+    CU(cudaMemcpyToSymbol(jb_prof, h, sizeof h));
+    return JB_OK;
+}
+#endif
 
 int jb_synchronize(JbBatch* b) {
     if (!b) return fail(JB_ERR_INVALID_ARGUMENT, "null argument");

@@ -82,12 +82,16 @@ static bool cons_quadruped_matches(const KParams& kp, const Plan& P, const JbMod
 }
 
 // Called by the four lanes of the env after the ABA sweeps, when only contact constraints are enabled.
-__device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
-    // CTX_UNIFORM_WARP: all 32 lanes of the warp are in this call together (decided by the caller): every collective below
-    // then uses the full mask -- a primitive whose mask differs from lane to lane is executed one mask after the other --
-    // and the sweep loop keeps every env of the warp inside until the last one has converged
-    const bool uni = (c.flags & CTX_UNIFORM_WARP) != 0;
-    const unsigned M = uni ? 0xffffffffu : c.gmask;
+// UNI (CTX_UNIFORM_WARP): all 32 lanes of the warp are in this call together (decided by the caller): every collective
+// below then uses the full mask as a compile-time constant -- a primitive whose mask is a run-time value is compiled into
+// a converge-and-retry sequence, one whose mask differs from lane to lane is executed one mask after the other -- and the
+// sweep loop keeps every env of the warp inside until the last one has converged
+template <bool UNI>
+__device__ __noinline__ bool cons_solve_quadruped_t(const Ctx c, int* status) {
+    constexpr bool uni = UNI;
+    const unsigned M = UNI ? 0xffffffffu : c.gmask;
+    JB_PROF_T(t_setup);
+    JB_PROF_COUNT(uni ? 10 : 11, 1);                       // solves entered with / without the whole warp
     constexpr int L = 4;
     const JbOptions& opt = KP->opt;
     const RecDbl* rd0 = JB_RDBL + (0 * L + c.sub);
@@ -293,86 +297,104 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
     // broadcasts the change of z to the other lanes of the env with shuffles.  Everything the sweep touches is in
     // registers (all indices are compile-time after unrolling); divisions by the regularised diagonal are
     // multiplications by its reciprocal.
+    JB_PROF_ADD(3, t_setup);                               // solver set-up
+    JB_PROF_T(t_loop);
     const double iAmax = 1.0 / fmax(AD01[0], AD01[1]);
     auto residual = [&](int k) {
         const double s = (AL[0][k] * LA[0] + AL[1][k] * LA[1]) + (AL[2][k] * LA[2] + AL[3][k] * LA[3]);
         const double hz = (H[k][0] * z[0] + H[k][1] * z[1]) + (H[k][2] * z[2] + H[k][3] * z[3]) + (H[k][4] * z[4] + H[k][5] * z[5]);
         return B[k] - (s + hz) - RG[k] * LA[k];
     };
+    // The sweep is run some forty times per solve and what it costs is instruction fetch: straight-line code beyond the
+    // 6 KB L0 instruction cache of the scheduler is delivered at ~45 cycles per 128-byte line, every iteration again
+    // (profiles/r02_constraint_path_investigation.txt: 6.7 k cycles per iteration for ~1.1 k instructions when the twelve
+    // updates of an iteration were unrolled, each in its own divergent region).  So the loops over the contacts are real
+    // loops, the owner of a contact is a predicate, not a branch, and the relaxation schedule is a table: a few hundred
+    // instructions that stay in the L0 for the whole solve.
     const int lane0 = c.lane - c.sub;
-    int own_of[4];
+    int src_pack = 0, my_k = -1;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) own_of[k] = KP->cmap[k].sub;
+    for (int k = 0; k < 4; ++k) { const int o = KP->cmap[k].sub; src_pack |= (lane0 + o) << (8 * k); if (o == c.sub) my_k = k; }
+    const bool torsion_on = !(opt.contact_torsion < D_EPS), friction_on = !(opt.contact_friction < D_EPS);
+    const double mu = opt.contact_friction, mu_t = opt.contact_torsion;
     bool ok = false;
     for (int iter = 0; uni ? __any_sync(0xffffffffu, iter < CONS_PGS_MAX_ITER && !ok) : (iter < CONS_PGS_MAX_ITER && !ok); ++iter) {
         const bool live = !ok && iter < CONS_PGS_MAX_ITER;   // (uniform warp: an env that is done keeps exchanging zeros)
+        const bool upd = en && live;
 #pragma unroll
         for (int r = 0; r < 4; ++r) YP[r] = Y[r];
-        const double ratio = (static_cast<double>(CONS_PGS_MAX_ITER - CONS_RELAX_MIN_ITER) - iter) /
-                             (CONS_PGS_MAX_ITER - CONS_RELAX_MIN_ITER - CONS_RELAX_MAX_ITER);
-        double wr = CONS_RELAX_MAX;
-        if (ratio < 1.0) {
-            wr = CONS_RELAX_MIN;
-            if (ratio > 0.0) wr += (CONS_RELAX_MAX - CONS_RELAX_MIN) * (ratio * ratio);
-        }
+        const double wr = KP->pgs_relax[iter < CONS_PGS_MAX_ITER ? iter : CONS_PGS_MAX_ITER - 1];
+        // normal forces, contact by contact
+        JB_PROF_T(t_n);
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            const bool own = upd && k == my_k;
+            const double y = residual(2);
+            const double x = LA[2] + wr * y * iAD[2];
+            const double e = x > 0.0 ? x : 0.0;
+            const double d2 = own ? e - LA[2] : 0.0;
+            if (own) { Y[2] = y; LA[2] = e; }
+            const int src = (src_pack >> (8 * k)) & 0xff;
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-            if (pass == 1 && opt.contact_torsion < D_EPS) {
-                // torsion disabled: the multiplier is forced to zero (it is zero already unless a warm start says
-                // otherwise); no coupling between contacts, so all lanes do it at once
+            for (int d = 0; d < 6; ++d) z[d] += __shfl_sync(M, G[2][d] * d2, src);
+        }
+        JB_PROF_ADD(13, t_n);                              // normal-force loop
+        // torsion
+        if (!torsion_on) {
+            // disabled: its bounds force the multiplier to zero, after the normal forces of the iteration like in the
+            // reference.  Only a warm start can make it non-zero (the equality solve of Engine::start does), so the first
+            // iteration is the only one with anything to do
+            if (iter == 0) {
                 const double d3 = -LA[3];
                 LA[3] = 0.0;
                 if (uni ? __any_sync(0xffffffffu, d3 != 0.0) : __any_sync(c.gmask, d3 != 0.0)) {
+#pragma unroll 1
+                    for (int k = 0; k < 4; ++k) {
+                        const int src = (src_pack >> (8 * k)) & 0xff;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-#pragma unroll
-                        for (int d = 0; d < 6; ++d) z[d] += __shfl_sync(M, G[3][d] * d3, lane0 + own_of[k]);
-                }
-                continue;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                double dz[6] = {0, 0, 0, 0, 0, 0};
-                if (own_of[k] == c.sub && en && live) {
-                    if (pass == 0) {
-                        const double y = residual(2);
-                        Y[2] = y;
-                        const double e = fmax(LA[2] + wr * y * iAD[2], 0.0);
-                        const double d2 = e - LA[2];
-                        LA[2] = e;
-#pragma unroll
-                        for (int d = 0; d < 6; ++d) dz[d] = G[2][d] * d2;
-                    } else if (pass == 1) {
-                        const double y = residual(3);
-                        Y[3] = y;
-                        const double thr = opt.contact_torsion * LA[2];
-                        const double e = fmin(fmax(LA[3] + wr * y * iAD[3], -thr), thr);
-                        const double d3 = e - LA[3];
-                        LA[3] = e;
-#pragma unroll
-                        for (int d = 0; d < 6; ++d) dz[d] = G[3][d] * d3;
-                    } else {
-                        double e0, e1;
-                        if (opt.contact_friction < D_EPS) { e0 = LA[0] * 0.0; e1 = LA[1] * 0.0; }
-                        else {
-                            const double y0 = residual(0), y1 = residual(1);
-                            Y[0] = y0; Y[1] = y1;
-                            e0 = LA[0] + wr * y0 * iAmax;
-                            e1 = LA[1] + wr * y1 * iAmax;
-                            const double thr = opt.contact_friction * LA[2];
-                            const double sq = e0 * e0 + e1 * e1;
-                            if (sq > thr * thr) { const double scale = thr / sqrt(sq); e0 *= scale; e1 *= scale; }
-                        }
-                        const double d0 = e0 - LA[0], d1 = e1 - LA[1];
-                        LA[0] = e0; LA[1] = e1;
-#pragma unroll
-                        for (int d = 0; d < 6; ++d) dz[d] = G[0][d] * d0 + G[1][d] * d1;
+                        for (int d = 0; d < 6; ++d) z[d] += __shfl_sync(M, G[3][d] * d3, src);
                     }
                 }
+            }
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k) {
+                const bool own = upd && k == my_k;
+                const double y = residual(3);
+                const double thr = mu_t * LA[2];
+                const double e = fmin(fmax(LA[3] + wr * y * iAD[3], -thr), thr);
+                const double d3 = own ? e - LA[3] : 0.0;
+                if (own) { Y[3] = y; LA[3] = e; }
+                const int src = (src_pack >> (8 * k)) & 0xff;
 #pragma unroll
-                for (int d = 0; d < 6; ++d) z[d] += __shfl_sync(M, dz[d], lane0 + own_of[k]);
+                for (int d = 0; d < 6; ++d) z[d] += __shfl_sync(M, G[3][d] * d3, src);
             }
         }
+        // friction
+        JB_PROF_T(t_f);
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            const bool own = upd && k == my_k;
+            const double y0 = residual(0), y1 = residual(1);
+            double e0 = LA[0] + wr * y0 * iAmax, e1 = LA[1] + wr * y1 * iAmax;
+            const double thr = mu * LA[2];
+            const double sq = e0 * e0 + e1 * e1;
+            // projection on the friction cone: thr / sqrt(sq) as thr * rsqrt(sq), branch-free (a double-precision square
+            // root plus a division are ~500 cycles of dependent instructions, paid by every lane at every step of the sweep)
+            const double scale = sq > thr * thr ? thr * rsqrt(sq) : 1.0;
+            e0 *= scale; e1 *= scale;
+            if (!friction_on) { e0 = LA[0] * 0.0; e1 = LA[1] * 0.0; }
+            const double d0 = own ? e0 - LA[0] : 0.0, d1 = own ? e1 - LA[1] : 0.0;
+            if (own) {
+                if (friction_on) { Y[0] = y0; Y[1] = y1; }
+                LA[0] = e0; LA[1] = e1;
+            }
+            const int src = (src_pack >> (8 * k)) & 0xff;
+#pragma unroll
+            for (int d = 0; d < 6; ++d) z[d] += __shfl_sync(M, G[0][d] * d0 + G[1][d] * d1, src);
+        }
+        JB_PROF_ADD(14, t_f);                              // friction loop
+        JB_PROF_T(t_conv);
         // stopping criterion on the stagnation of the residuals (constraint_solvers.cc:256-274)
         double ymax = fmax(fmax(fabs(Y[0]), fabs(Y[1])), fmax(fabs(Y[2]), fabs(Y[3])));
         for (int o = 1; o < L; o <<= 1) ymax = fmax(ymax, __shfl_xor_sync(M, ymax, o));
@@ -382,10 +404,14 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
         for (int r = 0; r < 4; ++r) conv = conv && (fabs(Y[r] - YP[r]) < tol);
         const bool all_conv = cq_all(M, c, conv || !live);   // (one call site: every lane of the mask takes part)
         if (live) ok = all_conv;
+        JB_PROF_ADD(15, t_conv);                           // stopping criterion
+        JB_PROF_COUNT(12, 1);                              // sweep iterations
 #ifdef JB_DEBUG_COUNTS
         if (c.sub == 0) { extern long long jb_dbg_counts[8]; ++jb_dbg_counts[4]; if (!ok && iter == CONS_PGS_MAX_ITER - 1) ++jb_dbg_counts[5]; }
 #endif
     }
+    JB_PROF_ADD(4, t_loop);                                // the sweep
+    JB_PROF_T(t_post);
     // ---------------- accelerations: ddq_t = ddq_free_t + S^-1 z = ddq_free_t + sum_r h_r lambda_r ;
     //                  ddq_l = ddq_free_l + M_ll^-1 J_l^T lambda - W (ddq_t - ddq_free_t)
     {
@@ -432,6 +458,11 @@ __device__ __noinline__ bool cons_solve_quadruped(const Ctx c, int* status) {
     }
     __syncwarp(M);
     cons_refresh_accelerations(c);
+    JB_PROF_ADD(5, t_post);                                // multipliers -> accelerations, refresh
     (void)status;
     return ok;
+}
+
+JB_DI bool cons_solve_quadruped(const Ctx c, int* status) {
+    return (c.flags & CTX_UNIFORM_WARP) ? cons_solve_quadruped_t<true>(c, status) : cons_solve_quadruped_t<false>(c, status);
 }

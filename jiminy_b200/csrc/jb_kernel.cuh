@@ -654,12 +654,15 @@ __device__ __noinline__ void env_step_full(const LaunchArgs la, const bool only_
 // body in the same launch, so a step is always exactly one kernel.
 template <bool FAST>
 __global__ void __launch_bounds__(32) env_step_kernel_t(const LaunchArgs la) {
+    JB_PROF_T(t_kernel);
     if constexpr (FAST) {
         env_step_body<true>(la, false);
         __syncwarp();   // needs_full is written by sub-lane 0 of each env
         const int flag = KP->needs_full[blockIdx.x * (32 / KP->L) + (threadIdx.x & 31) / KP->L];
         if (__any_sync(0xffffffffu, flag != 0)) env_step_full(la, true);
     } else env_step_full(la, false);
+    JB_PROF_ADD(6, t_kernel);                              // the whole kernel
+    JB_PROF_COUNT(7, 1);                                   // warps
 #ifndef JB_HOST_EMUL
     // observation exchange over peer memory: EVERY block arrives here, whatever its envs did; the last one tells the
     // other ranks that every row of this rank has been published (release: fence, then the flags)
