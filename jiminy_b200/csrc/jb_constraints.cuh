@@ -298,11 +298,12 @@ JB_DI bool cons_pgs(const Ctx& c, double* const cw, const CwLayout& w, int m, in
                     const double y0 = residual(i0), y1 = residual(i1);
                     CWK(w.YV + i0) = y0; CWK(w.YV + i1) = y1;
                     const double A_max = fmax(CWK(w.AA + i0 * ld + i0), CWK(w.AA + i1 * ld + i1));
-                    double e0 = CWK(w.LA + i0) + wr * y0 / A_max;
-                    double e1 = CWK(w.LA + i1) + wr * y1 / A_max;
+                    const double iA_max = 1.0 / A_max;     // (one division instead of two on the critical path)
+                    double e0 = CWK(w.LA + i0) + wr * y0 * iA_max;
+                    double e1 = CWK(w.LA + i1) + wr * y1 * iA_max;
                     const double thr = opt.contact_friction * CWK(w.LA + start + 2);
                     const double sq = e0 * e0 + e1 * e1;
-                    if (sq > thr * thr) { const double scale = thr / sqrt(sq); e0 *= scale; e1 *= scale; }
+                    { const double scale = sq > thr * thr ? thr * rsqrt(sq) : 1.0; e0 *= scale; e1 *= scale; }   // (thr / sqrt(sq), branch-free)
                     CWK(w.LA + i0) = e0; CWK(w.LA + i1) = e1;
                 }
             }

@@ -459,11 +459,12 @@ __device__ __noinline__ bool cons_solve_blocks(const Ctx c, int* status) {
                             const double y0 = residual(r0), y1 = residual(r1);
                             LBW(w.YV + r0) = y0; LBW(w.YV + r1) = y1;
                             const double A_max = fmax(LBW(w.AD + r0), LBW(w.AD + r1));
-                            e0 = LBW(w.LA + r0) + wr * y0 / A_max;
-                            e1 = LBW(w.LA + r1) + wr * y1 / A_max;
+                            const double iA_max = 1.0 / A_max;     // (one division instead of two on the critical path)
+                            e0 = LBW(w.LA + r0) + wr * y0 * iA_max;
+                            e1 = LBW(w.LA + r1) + wr * y1 * iA_max;
                             const double thr = opt.contact_friction * LBW(w.LA + start + 2);
                             const double sq = e0 * e0 + e1 * e1;
-                            if (sq > thr * thr) { const double scale = thr / sqrt(sq); e0 *= scale; e1 *= scale; }
+                            { const double scale = sq > thr * thr ? thr * rsqrt(sq) : 1.0; e0 *= scale; e1 *= scale; }   // (thr / sqrt(sq), branch-free)
                         }
                         d0 = e0 - LBW(w.LA + r0); d1 = e1 - LBW(w.LA + r1);
                         LBW(w.LA + r0) = e0; LBW(w.LA + r1) = e1;

@@ -23,7 +23,7 @@
 
 constexpr int BD_MAX_BODIES = 4, BD_MAX_CONTACTS = 16;
 struct BdLayout { int OM, AV, GS, HS, PB, total; };
-constexpr int BD_PB = 16;   // per contact, shared: r (3), b (4), diagonal of A with regularisation (4), regularisation (4)
+constexpr int BD_PB = 16;   // per contact, shared: r (3), b (4), reciprocals of the regularised diagonal of A (4: 1/max(xx, yy), -, 1/zz, 1/tt), regularisation (4)
 JB_HD BdLayout bd_layout(int nb, int nt, int ncc) {
     BdLayout s; int o = 0;
     const int D = 6 * nb, nt1 = nt + 1;
@@ -201,6 +201,9 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
             const double reg = fmax(s * opt.constraint_regularization, CONS_MIN_REGULARIZER);
             pb[7 + q] = s + reg; pb[11 + q] = reg;
         }
+        // the sweep divides by these at every update: keep the reciprocals (a double-precision division is ~200 cycles of
+        // dependent instructions on the critical path of a Gauss-Seidel step): [7] 1 / max(A_xx, A_yy), [9] 1 / A_zz, [10] 1 / A_tt
+        pb[7] = 1.0 / fmax(pb[7], pb[8]); pb[9] = 1.0 / pb[9]; pb[10] = 1.0 / pb[10];
     }
     // ---------------- D. warm start: private lambda, F, then a = Omega F (rows shared out)
     for (int e = 0; e < D; ++e) Fv[e] = 0.0;
@@ -251,7 +254,7 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
                 if (pass == 0) {                    // normal force: lambda_z >= 0
                     const double y = pb[5] - ea.z - pb[13] * pl[2];
                     pl[6] = y;
-                    const double e = fmax(pl[2] + wr * y / pb[9], 0.0);
+                    const double e = fmax(pl[2] + wr * y * pb[9], 0.0);
                     df.z = e - pl[2];
                     pl[2] = e;
                 } else if (pass == 1) {             // torsional friction |lambda_3| <= torsion * lambda_z
@@ -261,7 +264,7 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
                         const double y = pb[6] - aa.z - pb[14] * pl[3];
                         pl[7] = y;
                         const double thr = opt.contact_torsion * pl[2];
-                        e = fmin(fmax(pl[3] + wr * y / pb[10], -thr), thr);
+                        e = fmin(fmax(pl[3] + wr * y * pb[10], -thr), thr);
                     }
                     d3 = e - pl[3];
                     pl[3] = e;
@@ -271,12 +274,12 @@ __device__ __noinline__ bool cons_solve_bodies(const Ctx c, int* status) {
                     else {
                         const double y0 = pb[3] - ea.x - pb[11] * pl[0], y1 = pb[4] - ea.y - pb[12] * pl[1];
                         pl[4] = y0; pl[5] = y1;
-                        const double A_max = fmax(pb[7], pb[8]);
-                        e0 = pl[0] + wr * y0 / A_max;
-                        e1 = pl[1] + wr * y1 / A_max;
+                        const double iA_max = pb[7];
+                        e0 = pl[0] + wr * y0 * iA_max;
+                        e1 = pl[1] + wr * y1 * iA_max;
                         const double thr = opt.contact_friction * pl[2];
                         const double sq = e0 * e0 + e1 * e1;
-                        if (sq > thr * thr) { const double scale = thr / sqrt(sq); e0 *= scale; e1 *= scale; }
+                        { const double scale = sq > thr * thr ? thr * rsqrt(sq) : 1.0; e0 *= scale; e1 *= scale; }   // (thr / sqrt(sq), branch-free)
                     }
                     df.x = e0 - pl[0]; df.y = e1 - pl[1];
                     pl[0] = e0; pl[1] = e1;
