@@ -56,7 +56,9 @@ enum {
     JB_JOINT_RUBU = 8,                                      /* RevoluteUnboundedUnaligned          */
     JB_JOINT_PX = 9, JB_JOINT_PY = 10, JB_JOINT_PZ = 11,    /* JointModelPX/PY/PZ                  */
     JB_JOINT_PU = 12,                                       /* JointModelPrismaticUnaligned        */
-    JB_JOINT_FREEFLYER = 13                                 /* JointModelFreeFlyer (nq=7, nv=6)    */
+    JB_JOINT_FREEFLYER = 13,                                /* JointModelFreeFlyer (nq=7, nv=6)    */
+    JB_JOINT_SPHERICAL = 14                                 /* JointModelSpherical (nq=4 quaternion x y z w, nv=3): the flexibility
+                                                             * joints of Model::addFlexibilityJointsToExtendedModel (model.cc:1087-1165) */
 };
 
 enum { JB_SOLVER_EULER_EXPLICIT = 0, JB_SOLVER_RUNGE_KUTTA_4 = 1, JB_SOLVER_RUNGE_KUTTA_DOPRI = 2 };
@@ -114,6 +116,11 @@ typedef struct JbModelDesc {
     const int32_t* effort_motor;      /* [neffort] motor index                                    */
     int32_t ncontact_sensor;
     const int32_t* contact_sensor_index; /* [ncontact_sensor] index into the contact frame list   */
+
+    /* Flexibility joints (modelOptions.dynamics.flexibilityConfig, Engine::computeInternalDynamics, engine.cc:3367-3391):
+     * per joint stiffness[3] then damping[3]; only the rows of JB_JOINT_SPHERICAL joints are read.  Their armature-like
+     * `inertia` goes into rotor_inertia[idx_v .. idx_v + 2] (model.cc:1136-1144).  NULL: every spherical joint is free. */
+    const double* flexibility;        /* [njoints][6] or NULL                                     */
 } JbModelDesc;
 
 /* ---------------------------------------------------------------- engine options ------ */

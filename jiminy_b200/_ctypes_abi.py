@@ -33,6 +33,7 @@ class JbModelDesc(C.Structure):
         ("nencoder", C.c_int32), ("encoder_joint", c_int32_p), ("encoder_reduction", c_double_p),
         ("neffort", C.c_int32), ("effort_motor", c_int32_p),
         ("ncontact_sensor", C.c_int32), ("contact_sensor_index", c_int32_p),
+        ("flexibility", c_double_p),
     ]
 
 
@@ -138,6 +139,9 @@ class ModelDescHolder:
         d.effort_motor = iptr(keep(_i(robot.effort_motors)))
         d.ncontact_sensor = len(robot.contact_sensor_names)
         d.contact_sensor_index = iptr(keep(_i(robot.contact_sensor_index)))
+        flex = getattr(robot, "flexibility", None)
+        if flex is not None and len(flex):
+            d.flexibility = dptr(keep(_d(flex).reshape(-1)))
         self.desc = d
 
 

@@ -32,9 +32,10 @@ JB_JOINT_RX, JB_JOINT_RY, JB_JOINT_RZ, JB_JOINT_RU = 1, 2, 3, 4
 JB_JOINT_RUBX, JB_JOINT_RUBY, JB_JOINT_RUBZ, JB_JOINT_RUBU = 5, 6, 7, 8
 JB_JOINT_PX, JB_JOINT_PY, JB_JOINT_PZ, JB_JOINT_PU = 9, 10, 11, 12
 JB_JOINT_FREEFLYER = 13
+JB_JOINT_SPHERICAL = 14
 
-JOINT_NQ = {JB_JOINT_UNIVERSE: 0, JB_JOINT_FREEFLYER: 7}
-JOINT_NV = {JB_JOINT_UNIVERSE: 0, JB_JOINT_FREEFLYER: 6}
+JOINT_NQ = {JB_JOINT_UNIVERSE: 0, JB_JOINT_FREEFLYER: 7, JB_JOINT_SPHERICAL: 4}
+JOINT_NV = {JB_JOINT_UNIVERSE: 0, JB_JOINT_FREEFLYER: 6, JB_JOINT_SPHERICAL: 3}
 for _t in (JB_JOINT_RX, JB_JOINT_RY, JB_JOINT_RZ, JB_JOINT_RU,
            JB_JOINT_PX, JB_JOINT_PY, JB_JOINT_PZ, JB_JOINT_PU):
     JOINT_NQ[_t] = 1
@@ -193,6 +194,7 @@ class Frame:
     joint: int      # parent joint index
     placement: SE3  # placement in the parent joint frame
     kind: str       # 'joint' | 'fixed_joint' | 'body' | 'op'
+    base: str = ""  # 'op' frames: the frame it was attached to (`previousFrame`)
 
 
 @dataclass
@@ -249,6 +251,9 @@ class RobotTable:
     contact_sensor_index: List[int] = field(default_factory=list)
     links: Dict[str, UrdfLink] = field(default_factory=dict, repr=False)
     urdf_path: str = ""
+    # flexibility joints (`add_flexibility_joints`): [njoints, 6] stiffness | damping, rows of the other joints zero
+    flexibility: Optional[np.ndarray] = None
+    flexibility_joint_names: List[str] = field(default_factory=list)
 
     # ---- Pinocchio-model-like accessors (what BaseJiminyEnv touches)
     @property
@@ -281,6 +286,8 @@ class RobotTable:
             t, iq = int(self.joint_type[j]), int(self.idx_q[j])
             if t == JB_JOINT_FREEFLYER:
                 q[iq + 6] = 1.0
+            elif t == JB_JOINT_SPHERICAL:
+                q[iq + 3] = 1.0
             elif t in (JB_JOINT_RUBX, JB_JOINT_RUBY, JB_JOINT_RUBZ, JB_JOINT_RUBU):
                 q[iq] = 1.0
         return q
@@ -291,7 +298,7 @@ class RobotTable:
         if name in self.frames:
             raise ValueError(f"A frame with name '{name}' already exists.")
         base = self.frames[body_name]
-        self.frames[name] = Frame(name, base.joint, base.placement * placement, "op")
+        self.frames[name] = Frame(name, base.joint, base.placement * placement, "op", body_name)
 
     def add_contact_points(self, names: Sequence[str]) -> None:
         for n in names:
@@ -726,6 +733,156 @@ def robot_table_from_dict(d: dict) -> RobotTable:
 
 
 # --------------------------------------------------------------------------- model randomisation
+# --------------------------------------------------------------------------- flexibility joints
+FLEXIBLE_JOINT_SUFFIX = "Flexibility"   # core/include/jiminy/core/robot/model.h:19
+
+
+def _inertia_from_flat(y: np.ndarray) -> Inertia:
+    I = np.array([[y[4], y[5], y[7]], [y[5], y[6], y[8]], [y[7], y[8], y[9]]])
+    return Inertia(float(y[0]), np.array(y[1:4], dtype=np.float64), I)
+
+
+def _se3_from_flat(x: np.ndarray) -> SE3:
+    return SE3(np.array(x[:9], dtype=np.float64).reshape(3, 3), np.array(x[9:12], dtype=np.float64))
+
+
+def _insert_spherical_joint(robot: RobotTable, k: int, name: str, parent: int, placement: SE3, inertia: Inertia) -> None:
+    """Insert a spherical joint at joint index `k` (every joint >= k moves up by one: the succession of
+    `swapJointIndices` at the end of the reference's insertion routines), in place."""
+    shift = lambda j: j + 1 if j >= k else j   # noqa: E731
+    iq, iv = (int(robot.idx_q[k]), int(robot.idx_v[k])) if k < robot.njoints else (robot.nq, robot.nv)
+    robot.joint_names.insert(k, name)
+    robot.joint_type = np.insert(robot.joint_type, k, JB_JOINT_SPHERICAL).astype(np.int32)
+    par = [shift(int(p)) for p in robot.parent]
+    par.insert(k, parent)
+    robot.parent = np.array(par, dtype=np.int32)
+    robot.placement = np.insert(robot.placement, k, placement.flat(), axis=0)
+    robot.axis = np.insert(robot.axis, k, np.zeros(3), axis=0)
+    robot.inertia = np.insert(robot.inertia, k, inertia.flat(), axis=0)
+    robot.rotor_inertia = np.insert(robot.rotor_inertia, iv, np.zeros(3))
+    robot.q_lower = np.insert(robot.q_lower, iq, np.full(4, -1.0 - EPS))   # model.cc:1379-1398
+    robot.q_upper = np.insert(robot.q_upper, iq, np.full(4, 1.0 + EPS))
+    robot.effort_limit = np.insert(robot.effort_limit, iv, np.full(3, INF))
+    robot.velocity_limit = np.insert(robot.velocity_limit, iv, np.full(3, INF))
+    if robot.flexibility is not None:
+        robot.flexibility = np.insert(robot.flexibility, k, np.zeros(6), axis=0)
+    idx_q, idx_v, nq, nv = [], [], 0, 0
+    for t in robot.joint_type:
+        idx_q.append(nq)
+        idx_v.append(nv)
+        nq += JOINT_NQ[int(t)]
+        nv += JOINT_NV[int(t)]
+    robot.idx_q, robot.idx_v = np.array(idx_q, dtype=np.int32), np.array(idx_v, dtype=np.int32)
+    for f in robot.frames.values():
+        f.joint = shift(f.joint)
+    for m in robot.motors:
+        m.joint = shift(m.joint)
+    robot.encoder_joints = [shift(j) for j in robot.encoder_joints]
+
+
+def add_flexibility_joints(robot: RobotTable, flexibility_config: Sequence[dict]) -> RobotTable:
+    """`Model::addFlexibilityJointsToExtendedModel` (core/src/robot/model.cc:1087-1165): one spherical joint per entry
+    of `modelOptions["dynamics"]["flexibilityConfig"]` (`frameName`, `stiffness`, `damping`, `inertia`, 3 numbers each).
+
+    * frame of a mechanical joint: `addFlexibilityJointBeforeMechanicalJoint` (utilities/pinocchio.cc:460-503) -- a
+      weightless spherical joint named `<joint>Flexibility` at the joint's placement, the joint itself re-attached to it
+      at the origin;
+    * fixed frame: `addFlexibilityJointAtFixedFrame` (utilities/pinocchio.cc:578-727) -- the composite body is split at
+      the frame: everything rigidly attached downstream of it (and the joints hanging from that) moves onto a spherical
+      joint named like the frame.
+    `inertia` is the armature-like rotor inertia of the three flexibility dofs (model.cc:1136-1144).  Returns a new
+    table (the extended model); the argument (the theoretical model) is left alone.  Engine side:
+    `Engine::computeInternalDynamics` (engine.cc:3367-3391)."""
+    import copy
+    out = copy.deepcopy(robot)
+    if out.flexibility is None:
+        out.flexibility = np.zeros((out.njoints, 6))
+    for cfg in flexibility_config:
+        if cfg["frameName"] not in robot.frames:
+            raise ValueError(f"Frame '{cfg['frameName']}' does not exists. Impossible to insert flexibility joint on it.")
+    flex_names: List[str] = []
+    for cfg in flexibility_config:
+        frame_name = cfg["frameName"]
+        fr = out.frames[frame_name]
+        if fr.kind == "joint":
+            k = out.joint_index(frame_name)
+            if k == 0 or int(out.joint_type[k]) == JB_JOINT_FREEFLYER and frame_name == "root_joint":
+                raise ValueError("Flexible joint can only be inserted at fixed or joint frames.")
+            flex_name = frame_name + FLEXIBLE_JOINT_SUFFIX
+            parent, M = int(out.parent[k]), _se3_from_flat(out.placement[k])
+            _insert_spherical_joint(out, k, flex_name, parent, M, Inertia())
+            out.parent[k + 1] = k
+            out.placement[k + 1] = SE3().flat()
+            out.frames[flex_name] = Frame(flex_name, k, SE3(), "joint")
+        elif fr.kind == "fixed_joint":
+            flex_name = frame_name
+            _, _, ujoints = parse_urdf(out.urdf_path)
+            if frame_name not in ujoints or ujoints[frame_name].type != "fixed":
+                raise ValueError("Frame must be associated with fixed joint.")
+            P, M_F = fr.joint, fr.placement
+            # links rigidly attached downstream of the frame, and the moving joints hanging from them
+            child_links, child_joints, stack = [], [], [ujoints[frame_name].child]
+            while stack:
+                link = stack.pop()
+                child_links.append(link)
+                for uj in ujoints.values():
+                    if uj.parent != link:
+                        continue
+                    if uj.name in out.joint_names:      # a moving joint, or a fixed frame that already became a flexibility joint
+                        child_joints.append(out.joint_index(uj.name))
+                    elif uj.type == "fixed":
+                        stack.append(uj.child)
+            child_inertia = Inertia()
+            for link in child_links:
+                child_inertia = child_inertia + out.links[link].inertia.transformed(out.frames[link].placement)
+            YP = _inertia_from_flat(out.inertia[P])
+            if YP.mass - child_inertia.mass < 0.0:
+                raise ValueError("Child body mass too large to be subtracted to joint mass.")
+            out.inertia[P] = (YP + Inertia(-child_inertia.mass, child_inertia.lever, -child_inertia.I)).flat()
+            k = min(child_joints) if child_joints else out.njoints
+            M_inv = M_F.inverse()
+            _insert_spherical_joint(out, k, flex_name, P, M_F, child_inertia.transformed(M_inv))
+            for c in child_joints:
+                out.parent[c + 1] = k
+                out.placement[c + 1] = (M_inv * _se3_from_flat(out.placement[c + 1])).flat()
+            moved = set(child_links) | {uj.name for uj in ujoints.values()
+                                        if uj.type == "fixed" and uj.parent in child_links and uj.name not in out.joint_names}
+            for f in out.frames.values():
+                if f.joint == P and f.name != frame_name and (f.name in moved or (f.kind == "op" and _op_base(out, f, moved))) \
+                        and f.kind != "joint":
+                    f.joint, f.placement = k, M_inv * f.placement
+            out.frames[frame_name] = Frame(frame_name, k, SE3(), "joint")
+        else:
+            raise ValueError("Flexible joint can only be inserted at fixed or joint frames.")
+        flex_names.append(flex_name)
+    for cfg, name in zip(flexibility_config, flex_names):
+        j = out.joint_index(name)
+        iv = int(out.idx_v[j])
+        out.rotor_inertia[iv:iv + 3] = np.asarray(cfg["inertia"], dtype=np.float64)
+        out.flexibility[j, :3] = np.asarray(cfg["stiffness"], dtype=np.float64)
+        out.flexibility[j, 3:] = np.asarray(cfg["damping"], dtype=np.float64)
+    for name in flex_names:   # model.cc:1146-1164
+        j = out.joint_index(name)
+        iv = int(out.idx_v[j])
+        diag = out.rotor_inertia[iv:iv + 3] + out.inertia[j, [4, 6, 9]]
+        if (diag < 1e-5).any():
+            raise ValueError(f"The subtree diagonal inertia for flexibility joint {j} must be larger than 1e-5 "
+                             f"for numerical stability: {diag}")
+    out.flexibility_joint_names = list(out.flexibility_joint_names) + flex_names
+    return out
+
+
+def _op_base(robot: RobotTable, frame: Frame, moved: set) -> bool:
+    """An operational frame added with `add_frame` follows the frame it was attached to."""
+    seen = set()
+    while frame.kind == "op" and frame.base and frame.base not in seen:
+        seen.add(frame.base)
+        if frame.base in moved:
+            return True
+        frame = robot.frames[frame.base]
+    return False
+
+
 def _exp3(w: np.ndarray) -> np.ndarray:
     """Rotation matrix of a rotation vector (pinocchio::exp3)."""
     th = float(np.linalg.norm(w))

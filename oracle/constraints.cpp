@@ -70,6 +70,7 @@ void Engine::buildConstraints() {
     constraints.clear();
     for (int i = 1; i < model.njoints; ++i) {
         if (model.jtype[i] == JB_JOINT_FREEFLYER) continue;   // 'root_joint' is not a mechanical joint
+        if (model.jtype[i] == JB_JOINT_SPHERICAL) continue;   // flexibility joints carry no bound constraint (model.cc:335-360)
         Constraint c;
         c.kind = 0; c.joint = i; c.dim = 1;
         c.jac.assign(model.nv, 0.0);

@@ -27,6 +27,7 @@ Model make_model(const JbModelDesc& d) {
     m.rotor.assign(d.rotor_inertia, d.rotor_inertia + d.nv);
     m.q_lower.assign(d.q_lower, d.q_lower + d.nq);
     m.q_upper.assign(d.q_upper, d.q_upper + d.nq);
+    if (d.flexibility) m.flexibility.assign(d.flexibility, d.flexibility + 6 * d.njoints);
     m.nmotors = d.nmotors;
     m.motor_joint.assign(d.motor_joint, d.motor_joint + d.nmotors);
     m.motor_flags.assign(d.motor_flags, d.motor_flags + d.nmotors);
@@ -174,6 +175,13 @@ void Engine::jointCalc(int i, const double* qv, const double* vv) {
         if (vv) { const double* vj = vv + model.idx_v[i]; jd.vJ = motion6(vj); }
         return;
     }
+    if (t == JB_JOINT_SPHERICAL) {
+        // JointModelSphericalTpl::calc: M = (quat.matrix(), 0), S = [0; 1_3], v = (0, omega), c = 0
+        jd.M.R = quat_to_matrix(qj);
+        for (int k = 0; k < 3; ++k) jd.S[3 + k][k] = 1.0;
+        if (vv) { const double* vj = vv + model.idx_v[i]; jd.vJ.ang = V3(vj[0], vj[1], vj[2]); }
+        return;
+    }
     const V3 ax = model.axis[i];
     const double qd = vv ? vv[model.idx_v[i]] : 0.0;
     if (Model::is_revolute(t)) {
@@ -289,9 +297,23 @@ void Engine::computeCollisionForces(std::vector<Force>& fext, bool isStateUpToDa
 }
 
 // Engine::computeInternalDynamics (engine.cc:3340-3392): joint position bounds -> JointConstraint
-// enable / disable (flexibility joints are outside the path)
-void Engine::computeInternalDynamics(const double* qv, const double* /*vv*/, std::vector<double>& /*uInternal*/) {
+// enable / disable, then the spring-damper of the flexibility joints (:3367-3391)
+void Engine::computeInternalDynamics(const double* qv, const double* vv, std::vector<double>& uInternal) {
     updateJointBoundConstraints(qv);
+    if (model.flexibility.empty()) return;
+    const double PI = 3.14159265358979323846;
+    for (int i = 1; i < model.njoints; ++i) {
+        if (model.jtype[i] != JB_JOINT_SPHERICAL) continue;
+        const int iq = model.idx_q[i], iv = model.idx_v[i];
+        const double* kd = model.flexibility.data() + 6 * i;
+        double angle;
+        const V3 angleAxis = quat_log3(qv + iq, angle);
+        if (angle > 0.95 * PI) { flexAngleError = true; }   // "Flexible joint angle must be smaller than 0.95 * pi."
+        const M3 rotJlog3 = Jlog3(angle, angleAxis);
+        const V3 t = rotJlog3 * V3(kd[0] * angleAxis.x, kd[1] * angleAxis.y, kd[2] * angleAxis.z);
+        uInternal[iv] -= t.x; uInternal[iv + 1] -= t.y; uInternal[iv + 2] -= t.z;
+        for (int k = 0; k < 3; ++k) uInternal[iv + k] -= kd[3 + k] * vv[iv + k];
+    }
 }
 
 // Engine::computeAllTerms (engine.cc:3538-3583)
@@ -719,6 +741,15 @@ void Engine::integrate(const double* q0, const double* vel, double* out) const {
             for (int k = 0; k < 4; ++k) N2 += quat[k] * quat[k];
             const double alpha = (3.0 - N2) / 2.0;  // quaternion::firstOrderNormalize
             for (int k = 0; k < 4; ++k) out[iq + 3 + k] = quat[k] * alpha;
+        } else if (t == JB_JOINT_SPHERICAL) {
+            // SpecialOrthogonalOperationTpl<3>::integrate_impl: quat * exp3(omega), firstOrderNormalize
+            double pOmega[4], quat[4];
+            quat_exp3(V3(vel[iv], vel[iv + 1], vel[iv + 2]), pOmega);
+            quat_mul(q0 + iq, pOmega, quat);
+            double N2 = 0.0;
+            for (int k = 0; k < 4; ++k) N2 += quat[k] * quat[k];
+            const double alpha = (3.0 - N2) / 2.0;
+            for (int k = 0; k < 4; ++k) out[iq + k] = quat[k] * alpha;
         } else if (Model::is_unbounded(t)) {
             const double ca = q0[iq], sa = q0[iq + 1], omega = vel[iv];
             const double cosOmega = std::cos(omega), sinOmega = std::sin(omega);
@@ -742,6 +773,13 @@ void Engine::difference(const double* q0, const double* q1, double* out) const {
             SE3 M1; M1.R = quat_to_matrix(q1 + iq + 3); M1.p = V3(q1[iq], q1[iq + 1], q1[iq + 2]);
             const Motion d = log6(se3_inverse(M0) * M1);
             to6(d, out + iv);
+        } else if (t == JB_JOINT_SPHERICAL) {
+            // SpecialOrthogonalOperationTpl<3>::difference_impl: quaternion::log3(q0.conjugate() * q1)
+            const double q0c[4] = {-q0[iq], -q0[iq + 1], -q0[iq + 2], q0[iq + 3]};
+            double dq[4], theta;
+            quat_mul(q0c, q1 + iq, dq);
+            const V3 w = quat_log3(dq, theta);
+            out[iv] = w.x; out[iv + 1] = w.y; out[iv + 2] = w.z;
         } else if (Model::is_unbounded(t)) {
             // SpecialOrthogonalOperationTpl<2>::difference_impl + log
             const double R00 = q0[iq] * q1[iq] + q0[iq + 1] * q1[iq + 1];
@@ -765,6 +803,7 @@ void Engine::neutral(double* qn) const {
         const int t = model.jtype[i], iq = model.idx_q[i];
         for (int k = 0; k < Model::nqj(t); ++k) qn[iq + k] = 0.0;
         if (t == JB_JOINT_FREEFLYER) qn[iq + 6] = 1.0;
+        else if (t == JB_JOINT_SPHERICAL) qn[iq + 3] = 1.0;
         else if (Model::is_unbounded(t)) qn[iq] = 1.0;
     }
 }
@@ -774,6 +813,7 @@ void Engine::normalize(double* qn) const {
         const int t = model.jtype[i], iq = model.idx_q[i];
         int off = -1, len = 0;
         if (t == JB_JOINT_FREEFLYER) { off = iq + 3; len = 4; }
+        else if (t == JB_JOINT_SPHERICAL) { off = iq; len = 4; }
         else if (Model::is_unbounded(t)) { off = iq; len = 2; }
         if (off < 0) continue;
         double n2 = 0.0;

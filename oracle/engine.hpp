@@ -51,6 +51,7 @@ struct Model {
     std::vector<V3> axis;
     std::vector<Inertia> inertia;
     std::vector<double> rotor, q_lower, q_upper;
+    std::vector<double> flexibility;   // [njoints][6] stiffness | damping of the spherical flexibility joints (empty: none)
     int nmotors = 0;
     std::vector<int> motor_joint, motor_flags;
     std::vector<double> motor_params;
@@ -65,10 +66,11 @@ struct Model {
     std::vector<std::vector<std::pair<int, SE3>>> force_contacts;
     JbSensorLayout layout{};
 
-    static int nvj(int t) { return t == JB_JOINT_UNIVERSE ? 0 : (t == JB_JOINT_FREEFLYER ? 6 : 1); }
+    static int nvj(int t) { return t == JB_JOINT_UNIVERSE ? 0 : (t == JB_JOINT_FREEFLYER ? 6 : (t == JB_JOINT_SPHERICAL ? 3 : 1)); }
     static int nqj(int t) {
         if (t == JB_JOINT_UNIVERSE) return 0;
         if (t == JB_JOINT_FREEFLYER) return 7;
+        if (t == JB_JOINT_SPHERICAL) return 4;
         return (t >= JB_JOINT_RUBX && t <= JB_JOINT_RUBU) ? 2 : 1;
     }
     static bool is_unbounded(int t) { return t >= JB_JOINT_RUBX && t <= JB_JOINT_RUBU; }
@@ -129,6 +131,7 @@ struct Engine {
     std::vector<double> q, v, a;  // StepperState.qSplit[0], vSplit[0], aSplit[0]
     double stepperUpdatePeriod = INF;
     bool running = false;
+    bool flexAngleError = false;   // a flexibility joint went beyond 0.95 pi (the reference throws, engine.cc:3381-3385)
     int status = JB_ENV_NOT_STARTED;
 
     std::vector<Force> contactFrameForces;  // RobotData::contactFrameForces (in parent joint frame)

@@ -330,4 +330,64 @@ inline Motion log6(const SE3& M) {
     return m;
 }
 
+// ---------------------------------------------------------------- unit-quaternion Lie group (JointModelSpherical)
+// Pinocchio 2.7.0 `explog-quaternion.hpp` and `SpecialOrthogonalOperationTpl<3>` (liegroup/special-orthogonal.hpp),
+// restated from the published algorithm (the library is not vendored in the reference); quaternions as (x, y, z, w).
+constexpr double TAYLOR_PREC2 = 6.0554544523933395e-6;  // eps^(1/3): TaylorSeriesExpansion<double>::precision<2>()
+constexpr double DBL_EPS_ = 2.220446049250313e-16;
+
+inline void quat_mul(const double a[4], const double b[4], double out[4]) {   // Eigen: a * b
+    const double x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    const double y = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+    const double z = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+    const double w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+    out[0] = x; out[1] = y; out[2] = z; out[3] = w;
+}
+// quaternion::exp3
+inline void quat_exp3(const V3& v, double out[4]) {
+    const double t2 = dot(v, v);
+    const double t = std::sqrt(t2 + DBL_EPS_ * DBL_EPS_);
+    if (t2 > TAYLOR_PREC3 * TAYLOR_PREC3) {
+        // Eigen::Quaternion(AngleAxis(t, v / t))
+        const double s = std::sin(0.5 * t), c = std::cos(0.5 * t);
+        out[0] = s * (v.x / t); out[1] = s * (v.y / t); out[2] = s * (v.z / t); out[3] = c;
+    } else {
+        const double t2_2 = t2 / 4.0;
+        const double k = 0.5 * (1.0 - t2_2 / 6.0 + t2_2 * t2_2 / 120.0);
+        out[0] = k * v.x; out[1] = k * v.y; out[2] = k * v.z;
+        out[3] = 1.0 - t2_2 / 2.0 + t2_2 * t2_2 / 24.0;
+    }
+}
+// quaternion::log3: angle-axis vector of a unit quaternion, theta in [0, pi]... [0, 2 pi) before the sign flip
+inline V3 quat_log3(const double q[4], double& theta) {
+    const double norm_squared = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+    const double norm = std::sqrt(norm_squared + DBL_EPS_ * DBL_EPS_);
+    const double pos_neg = q[3] >= 0.0 ? 1.0 : -1.0;
+    const double w = pos_neg * q[3];
+    const V3 vec(pos_neg * q[0], pos_neg * q[1], pos_neg * q[2]);
+    const double theta_2 = std::atan2(norm, w);
+    const double y_x = norm / w;
+    const double y_x_sq = norm_squared / (w * w);
+    const bool small = norm_squared < TAYLOR_PREC2;
+    theta = small ? 2.0 * (1.0 - y_x_sq / 3.0) * y_x : 2.0 * theta_2;
+    const double th2_2 = theta * theta / 4.0;
+    const double inv_sinc = small ? 2.0 * (1.0 + th2_2 / 6.0 + 7.0 / 360.0 * th2_2 * th2_2) : theta / std::sin(theta_2);
+    return inv_sinc * vec;
+}
+// pinocchio::Jlog3(theta, log, Jlog)
+inline M3 Jlog3(double theta, const V3& lg) {
+    const double st = std::sin(theta), ct = std::cos(theta);
+    const double st_1mct = st / (1.0 - ct);
+    const bool small = theta < TAYLOR_PREC3;
+    const double alpha = small ? 1.0 / 12.0 + theta * theta / 720.0 : 1.0 / (theta * theta) - st_1mct / (2.0 * theta);
+    const double diag = small ? 0.5 * (2.0 - theta * theta / 6.0) : 0.5 * (theta * st_1mct);
+    M3 J;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) J(i, j) = alpha * lg[i] * lg[j];
+    J(0, 0) += diag; J(1, 1) += diag; J(2, 2) += diag;
+    const V3 h = 0.5 * lg;   // addSkew(0.5 * log, Jlog)
+    J(0, 1) -= h.z; J(0, 2) += h.y; J(1, 0) += h.z; J(1, 2) -= h.x; J(2, 0) -= h.y; J(2, 1) += h.x;
+    return J;
+}
+
 }  // namespace orc

@@ -512,3 +512,106 @@ def test_centroidal_terms_against_first_principles():
     # finite difference of the free-falling CoM against vcom (world-frame velocity of the centre of mass)
     (t0, c0, _), (t1, c1, w1), (t2, c2, _) = coms
     np.testing.assert_allclose((c2 - c0) / (t2 - t0), w1, rtol=0, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 12. unit_py/test_simple_pendulum.py:662-750 -- flexibility joint + rotor inertia vs a series-elastic actuator
+def _flexible_pendulum(J, k, nu, inertia=1e-5):
+    r = _pendulum(J)
+    return M.add_flexibility_joints(r, [dict(frameName="PendulumJoint", stiffness=k * np.ones(3), damping=nu * np.ones(3),
+                                             inertia=inertia * np.ones(3))])
+
+
+def test_flexibility_model_like_the_reference_api_test():
+    """test_simple_pendulum.py:815-842: `robot.flexibility_joint_indices == [1]`, the mechanical joint moves to index 2."""
+    r = _flexible_pendulum(0.1, 1.0, 1.0, inertia=1.0)
+    assert r.joint_names == ["universe", "PendulumJointFlexibility", "PendulumJoint"]
+    assert [r.joint_index(n) for n in r.flexibility_joint_names] == [1]
+    assert (r.nq, r.nv) == (5, 4) and r.parent.tolist() == [0, 0, 1]
+    assert r.motors[0].joint == 2 and r.rotor_inertia.tolist() == [1.0, 1.0, 1.0, 0.1]
+    np.testing.assert_array_equal(r.placement[2], M.SE3().flat())
+    o = OracleBatch(r, _opt())
+    ts, qs, vs, _ = o.simulate(0.1, r.neutral(), np.zeros(4))
+    assert np.isfinite(qs).all()
+
+
+def test_flexibility_armature_vs_series_elastic_actuator_like_the_reference_test():
+    J, k, nu = 0.1, 20.0, 0.1
+    k_control, nu_control = 100.0, 1.0
+    r = _flexible_pendulum(J, k, nu)
+    opt = _opt(tolAbs=TOL * 0.1, tolRel=TOL * 0.1)
+    opt["world"]["gravity"] = [0.0] * 6
+    o = OracleBatch(r, opt)
+    o.set_callbacks(0, controller=lambda t, q, v, s, out: out.__setitem__(0, -k_control * q[4] - nu_control * v[3]))
+    v_init = 0.1
+    ts, qs, vs, _ = o.simulate(10.0, [0.0, 0.0, 0.0, 1.0, 0.0], [0.0, v_init, 0.0, 0.0])
+    # quaternion -> angle about y; no motion about the other axes
+    assert np.abs(qs[:, [0, 2]]).max() < 1e-12 and np.abs(vs[:, [0, 2]]).max() < 1e-12
+    flex_angle = 2.0 * np.arctan2(qs[:, 1], qs[:, 3])
+    x = np.c_[flex_angle, qs[:, 4], vs[:, 1], vs[:, 3]]
+    I = 5.0 * 1.0 ** 2
+    A = np.array([[0.0, 0.0, 1.0, 0.0],
+                  [0.0, 0.0, 0.0, 1.0],
+                  [-k * (1 / I + 1 / J), k_control / J, -nu * (1 / I + 1 / J), nu_control / J],
+                  [k / J, -k_control / J, nu / J, -nu_control / J]])
+    idx = np.linspace(0, len(ts) - 1, 80).astype(int)
+    xa = np.stack([scipy.linalg.expm(A * t) @ x[0] for t in ts[idx]])
+    np.testing.assert_allclose(x[idx], xa, atol=1e-4)       # the reference's own tolerance: the flexible element has inertia 1e-5, not 0
+
+
+def _flexible_arm_urdf(path, n_segments, mass=0.1, inertia=0.001, length=0.01):
+    """The procedural arm of unit_py/test_flexible_arm.py:32-79: one motorised revolute joint, then a chain of links held
+    by fixed joints."""
+    import xml.etree.ElementTree as ET
+    robot = ET.Element("robot", name="flexible_arm")
+    ET.SubElement(robot, "link", name="base")
+    for i in range(n_segments):
+        link = ET.SubElement(robot, "link", name=f"link{i}")
+        inertial = ET.SubElement(link, "inertial")
+        ET.SubElement(inertial, "origin", xyz=f"{length / 2} 0 0", rpy="0 0 0")
+        ET.SubElement(inertial, "mass", value=f"{mass}")
+        ET.SubElement(inertial, "inertia", ixx="0", ixy="0", ixz="0", iyy="0", iyz="0", izz=f"{inertia}")
+    motor = ET.SubElement(robot, "joint", name="base_to_link0", type="revolute")
+    ET.SubElement(motor, "parent", link="base")
+    ET.SubElement(motor, "child", link="link0")
+    ET.SubElement(motor, "origin", xyz="0 0 0", rpy=f"{np.pi / 2} 0 0")
+    ET.SubElement(motor, "axis", xyz="0 0 1")
+    ET.SubElement(motor, "limit", effort="100.0", lower=f"{-np.pi}", upper=f"{np.pi}", velocity="10.0")
+    for i in range(1, n_segments):
+        joint = ET.SubElement(robot, "joint", name=f"link{i - 1}_to_link{i}", type="fixed")
+        ET.SubElement(joint, "parent", link=f"link{i - 1}")
+        ET.SubElement(joint, "child", link=f"link{i}")
+        ET.SubElement(joint, "origin", xyz=f"{length} 0 0", rpy="0 0 0")
+    ET.ElementTree(robot).write(path)
+
+
+def test_rigid_vs_flexibility_at_fixed_frames_like_the_reference_test(tmp_path):
+    """unit_py/test_flexible_arm.py:178-259: with an extremely large flexibility inertia the arm split at its fixed frames
+    moves like the rigid one (1e-5), whatever the order in which the flexibility joints are inserted."""
+    n_flex = 12
+    urdf = str(tmp_path / "flexible_arm.urdf")
+    _flexible_arm_urdf(urdf, n_flex + 1)
+    rigid = M.build_robot_table(urdf, False)
+    M.attach_motor(rigid, "base_to_link0", "base_to_link0", enableVelocityLimit=False, enableEffortLimit=False)
+    opt = _opt(tolAbs=1e-9, tolRel=1e-9)
+    t_end = 1.0
+    o = OracleBatch(rigid, opt)
+    o.simulate(t_end, [0.0], [0.0], log=False)
+    q_rigid = o.get_state()[1][0]
+    assert abs(q_rigid[0]) > 0.1                    # the arm does fall
+    tables = []
+    for order in (range(n_flex), range(n_flex)[::-1]):
+        flex = M.add_flexibility_joints(rigid, [dict(frameName=f"link{i}_to_link{i + 1}", stiffness=np.zeros(3),
+                                                     damping=np.zeros(3), inertia=np.full(3, 1e6)) for i in order])
+        tables.append(flex)
+        assert flex.njoints == 2 + n_flex and flex.nq == 1 + 4 * n_flex
+        np.testing.assert_allclose(flex.mass, rigid.mass, rtol=1e-14)
+        of = OracleBatch(flex, opt)
+        of.simulate(t_end, flex.neutral(), np.zeros(flex.nv), log=False)
+        q = of.get_state()[1][0]
+        # get_theoretical_position_from_extended: the mechanical joint's coordinate
+        np.testing.assert_allclose(q[flex.idx_q[flex.joint_index("base_to_link0")]], q_rigid[0], atol=1e-5)
+    a, b = tables
+    assert a.joint_names == b.joint_names and a.parent.tolist() == b.parent.tolist()
+    np.testing.assert_allclose(a.inertia, b.inertia, atol=1e-12)
+    np.testing.assert_allclose(a.placement, b.placement, atol=1e-12)
