@@ -330,7 +330,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
     KParams& kp = b->kp;
     kp.n_env = n_env; kp.n_pad = b->n_pad;
     kp.L = P.L; kp.nrec = P.nrec; kp.ntrunk = P.ntrunk; kp.npool = P.npool; kp.ncslot = P.ncslot; kp.nimuslot = P.nimuslot;
-    kp.nfields = P.nfields; kp.pool_off = P.pool_off; kp.cslot_off = P.cslot_off; kp.imu_off = P.imu_off;
+    kp.nfields = P.nfields; kp.pool_off = P.pool_off; kp.cslot_off = P.cslot_off; kp.imu_off = P.imu_off; kp.sph_off = P.sph_off;
     kp.nq = m->nq; kp.nv = m->nv; kp.nmotors = m->nmotors; kp.njoints = m->njoints; kp.n_hist = (opt->ode_solver == JB_SOLVER_RUNGE_KUTTA_DOPRI) ? 7 : 0;
     kp.nimu = m->nimu; kp.nforce = m->nforce; kp.nenc = m->nencoder; kp.neff = m->neffort; kp.ncs = m->ncontact_sensor;
     for (int r = 0; r < P.nrec; ++r) { kp.rec_off[r] = P.rec_off[r]; kp.rec_free[r] = P.rec_free[r]; kp.trunk_reduce[r] = P.trunk_reduce[r]; }
@@ -421,11 +421,11 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
                 for (int s = 0; s < P.L; ++s) {
                     const RecInt& ri = P.rint[static_cast<size_t>(r) * P.L + s];
                     if (ri.kind == REC_PAD || ri.joint != j) continue;
-                    if (!found) { jm.rec = r; jm.sub = s; jm.kind = ri.kind; jm.nvj = ri.kind == REC_FREE ? 6 : 1; }
+                    if (!found) { jm.rec = r; jm.sub = s; jm.kind = ri.kind; jm.nvj = ri.kind == REC_FREE ? 6 : (ri.kind == REC_SPH ? 3 : 1); }
                     ++found;
                 }
             jm.trunk = found > 1;
-            if (m->joint_type[j] != JB_JOINT_FREEFLYER) { jc_of_joint[j] = static_cast<int32_t>(jc_joint.size()); jc_joint.push_back(j); }
+            if (m->joint_type[j] != JB_JOINT_FREEFLYER && m->joint_type[j] != JB_JOINT_SPHERICAL) { jc_of_joint[j] = static_cast<int32_t>(jc_joint.size()); jc_joint.push_back(j); }
         }
         std::vector<ContactMap> cmap(std::max(m->ncontacts, 1));
         for (int k = 0; k < m->ncontacts; ++k) {
@@ -440,7 +440,15 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
         }
         kp.n_jc = static_cast<int32_t>(jc_joint.size()); kp.n_cc = m->ncontacts;
         kp.m_max = kp.n_jc + 4 * kp.n_cc;
-        kp.cons_on = (m->nv <= 64) ? 1 : 0;
+        bool has_spherical = false;
+        for (int j = 1; j < m->njoints; ++j) has_spherical = has_spherical || m->joint_type[j] == JB_JOINT_SPHERICAL;
+        // the constraint solvers walk 1-dof and free-flyer records only: a model with flexibility joints has its joint
+        // bounds flagged (JB_ENV_JOINT_LIMIT), like one with more than 64 degrees of freedom
+        kp.cons_on = (m->nv <= 64 && !has_spherical) ? 1 : 0;
+        if (has_spherical && opt->contact_model == JB_CONTACT_CONSTRAINT) {
+            jb_batch_destroy(b);
+            return fail(JB_ERR_NOT_IMPLEMENTED, "contacts.model = 'constraint' is not available for a model with flexibility joints");
+        }
         kp.cons_off = P.nfields;
         kp.cq_off = P.nfields + 1;
         kp.cq_on = (kp.cons_on && opt->contact_model == JB_CONTACT_CONSTRAINT && cons_quadruped_matches(kp, P, *m) &&
@@ -582,6 +590,8 @@ int jb_set_options(JbBatch* b, const JbOptions* o) {
     if (rc) return rc;
     if (o->ode_solver == JB_SOLVER_RUNGE_KUTTA_DOPRI && b->kp.n_hist == 0)
         return fail(JB_ERR_BAD_CONTROL_FLOW, "switching to 'runge_kutta_dopri' changes the working-set layout: create a new batch");
+    if (o->contact_model == JB_CONTACT_CONSTRAINT && !b->kp.cons_on)
+        return fail(JB_ERR_NOT_IMPLEMENTED, "contacts.model = 'constraint' is not available for this robot (flexibility joints or more than 64 degrees of freedom)");
     apply_options(b, o);
     return JB_OK;
 }

@@ -9,7 +9,18 @@ namespace jb {
 JB_DI void load_record_state(const Ctx& c, const RecInt* ri, int base, const double* __restrict__ q,
                              const double* __restrict__ v, const double* __restrict__ a, size_t stride, size_t col) {
     double* const rp = jb_smem + base * 32 + c.lane;
-    if (ri->kind == REC_FREE) {
+    if (ri->kind == REC_SPH) {
+        // quaternion / angular velocity in the angular halves of the free-flyer layout, linear halves zero
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { RP(RF_Q + k) = 0.0; RP(RF_V + k) = 0.0; RP(RF_A + k) = 0.0; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) RP(RF_Q + 3 + k) = q[(ri->idx_q + k) * stride + col];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            RP(RF_V + 3 + k) = v[(ri->idx_v + k) * stride + col];
+            RP(RF_A + 3 + k) = a ? a[(ri->idx_v + k) * stride + col] : 0.0;
+        }
+    } else if (ri->kind == REC_FREE) {
 #pragma unroll
         for (int k = 0; k < 7; ++k) RP(RF_Q + k) = q[(ri->idx_q + k) * stride + col];
 #pragma unroll
@@ -31,7 +42,14 @@ JB_DI void load_record_state_aos(const Ctx& c, const RecInt* ri, int base, const
     double* const rp = jb_smem + base * 32 + c.lane;
     const double* qe = q + static_cast<size_t>(env) * KP->nq;
     const double* ve = v + static_cast<size_t>(env) * KP->nv;
-    if (ri->kind == REC_FREE) {
+    if (ri->kind == REC_SPH) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { RP(RF_Q + k) = 0.0; RP(RF_V + k) = 0.0; RP(RF_V + 3 + k) = ve[ri->idx_v + k]; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) RP(RF_Q + 3 + k) = qe[ri->idx_q + k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) RP(RF_A + k) = 0.0;
+    } else if (ri->kind == REC_FREE) {
 #pragma unroll
         for (int k = 0; k < 7; ++k) RP(RF_Q + k) = qe[ri->idx_q + k];
 #pragma unroll
@@ -47,7 +65,7 @@ JB_DI void load_record_state_aos(const Ctx& c, const RecInt* ri, int base, const
 // pinocchio::normalize on the record (Engine::start, engine.cc:1042-1043)
 JB_DI void normalize_record(const Ctx& c, const RecInt* ri, int base) {
     double* const rp = jb_smem + base * 32 + c.lane;
-    if (ri->kind == REC_FREE) {
+    if (rec_is_big(ri->kind)) {
         double n2 = 0.0;
 #pragma unroll
         for (int k = 3; k < 7; ++k) n2 += RP(RF_Q + k) * RP(RF_Q + k);
@@ -189,7 +207,26 @@ __device__ __noinline__ void store_outputs(const Ctx c) {
         const int base = KP->rec_off[r];
         double* const rp = jb_smem + base * 32 + c.lane;
         double* qv = KP->qv_out ? KP->qv_out + col * (KP->nq + KP->nv) : nullptr;
-        if (ri->kind == REC_FREE) {
+        if (ri->kind == REC_SPH) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const double x = RP(RF_Q + 3 + k); KP->q[(ri->idx_q + k) * N + col] = x; if (qv) qv[ri->idx_q + k] = x; }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double x = RP(RF_V + 3 + k);
+                KP->v[(ri->idx_v + k) * N + col] = x; if (qv) qv[KP->nq + ri->idx_v + k] = x;
+                KP->a[(ri->idx_v + k) * N + col] = RP(RF_A + 3 + k);
+            }
+            // RobotState.u: uInternal of the flexibility (engine.cc:3367-3391), rebuilt from the accepted state
+            if (KP->eff_u) {
+                const double qa[4] = {RP(RF_Q + 3), RP(RF_Q + 4), RP(RF_Q + 5), RP(RF_Q + 6)};
+                double angle;
+                const V3 aa = quat_log3(qa, angle);
+                const V3 t = jlog3_mul(angle, aa, mk(rd->motor[0] * aa.x, rd->motor[1] * aa.y, rd->motor[2] * aa.z));
+                KP->eff_u[col * KP->nv + ri->idx_v + 0] = (0.0 - t.x) - rd->motor[3] * RP(RF_V + 3);
+                KP->eff_u[col * KP->nv + ri->idx_v + 1] = (0.0 - t.y) - rd->motor[4] * RP(RF_V + 4);
+                KP->eff_u[col * KP->nv + ri->idx_v + 2] = (0.0 - t.z) - rd->motor[5] * RP(RF_V + 5);
+            }
+        } else if (ri->kind == REC_FREE) {
 #pragma unroll
             for (int k = 0; k < 7; ++k) { const double x = RP(RF_Q + k); KP->q[(ri->idx_q + k) * N + col] = x; if (qv) qv[ri->idx_q + k] = x; }
 #pragma unroll
@@ -252,7 +289,19 @@ __device__ __noinline__ void store_dynamics(const Ctx c) {
         const RecDbl* rd = JB_RDBL + (r * L + c.sub);
         const int base = KP->rec_off[r];
         double* const rp = jb_smem + base * 32 + c.lane;
-        if (ri->kind == REC_FREE) {
+        if (ri->kind == REC_SPH) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) KP->a_out[col * KP->nv + ri->idx_v + k] = RP(RF_A + 3 + k);
+            if (KP->u_out) {
+                const double qa[4] = {RP(RF_QS + 3), RP(RF_QS + 4), RP(RF_QS + 5), RP(RF_QS + 6)};
+                double angle;
+                const V3 aa = quat_log3(qa, angle);
+                const V3 t = jlog3_mul(angle, aa, mk(rd->motor[0] * aa.x, rd->motor[1] * aa.y, rd->motor[2] * aa.z));
+                KP->u_out[col * KP->nv + ri->idx_v + 0] = (0.0 - t.x) - rd->motor[3] * RP(RF_VS + 3);
+                KP->u_out[col * KP->nv + ri->idx_v + 1] = (0.0 - t.y) - rd->motor[4] * RP(RF_VS + 4);
+                KP->u_out[col * KP->nv + ri->idx_v + 2] = (0.0 - t.z) - rd->motor[5] * RP(RF_VS + 5);
+            }
+        } else if (ri->kind == REC_FREE) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
                 KP->a_out[col * KP->nv + ri->idx_v + k] = RP(RF_A + k);
@@ -327,7 +376,7 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
             load_record_state_aos(c, ri, base, KP->q_in, KP->v_in, c.env);
             if (mode == MODE_START) normalize_record(c, ri, base);
         }
-        if (ri->kind != REC_FREE) {
+        if (!rec_is_big(ri->kind)) {
             // torque command: the action itself, or (PD mode) the torque held since the last breakpoint
             const double* cmd_src = ((KP->pd_gains != nullptr || KP->pdf != nullptr) && mode == MODE_STEP) ? KP->cmd_torque
                                     : ((mode == MODE_DYNAMICS && la.command != nullptr) ? la.command : KP->command);

@@ -11,7 +11,7 @@
 
 namespace jb {
 
-static int joint_nv(int t) { return t == JB_JOINT_UNIVERSE ? 0 : (t == JB_JOINT_FREEFLYER ? 6 : 1); }
+static int joint_nv(int t) { return t == JB_JOINT_UNIVERSE ? 0 : (t == JB_JOINT_FREEFLYER ? 6 : (t == JB_JOINT_SPHERICAL ? 3 : 1)); }
 
 static int rec_kind(int t) {
     switch (t) {
@@ -19,7 +19,8 @@ static int rec_kind(int t) {
         case JB_JOINT_RUBX: case JB_JOINT_RUBY: case JB_JOINT_RUBZ: case JB_JOINT_RUBU: return REC_REVU;
         case JB_JOINT_PX: case JB_JOINT_PY: case JB_JOINT_PZ: case JB_JOINT_PU: return REC_PRISM;
         case JB_JOINT_FREEFLYER: return REC_FREE;
-        default: return REC_PAD;
+        case JB_JOINT_SPHERICAL: return REC_SPH;
+        default: throw std::invalid_argument("unknown joint type");
     }
 }
 
@@ -162,13 +163,16 @@ Plan build_plan(const JbModelDesc& m, int lanes, int n_hist) {
     P.trunk_reduce.assign(P.nrec, 0);
     int off = 0;
     for (int r = 0; r < P.nrec; ++r) {
-        bool any_free = false;
-        for (int s = 0; s < L; ++s)
+        bool any_free = false, any_sph = false;
+        for (int s = 0; s < L; ++s) {
             if (rec_joint[s][r] >= 0 && m.joint_type[rec_joint[s][r]] == JB_JOINT_FREEFLYER) any_free = true;
-        P.rec_free[r] = any_free;
+            if (rec_joint[s][r] >= 0 && m.joint_type[rec_joint[s][r]] == JB_JOINT_SPHERICAL) any_sph = true;
+        }
+        P.rec_free[r] = any_free || any_sph;
         P.rec_off[r] = off;
-        off += any_free ? (RF_KA + 6 * n_hist) : (R1_KA + n_hist);
+        off += (any_free || any_sph) ? (RF_KA + 6 * n_hist + (any_sph ? RS_EXTRA : 0)) : (R1_KA + n_hist);
     }
+    P.sph_off = RF_KA + 6 * n_hist;
     P.pool_off = off;
     off += POOL_SIZE * P.npool;
     P.cslot_off = off;
@@ -262,6 +266,9 @@ Plan build_plan(const JbModelDesc& m, int lanes, int n_hist) {
                 rd.armature = m.rotor_inertia[m.idx_v[j]];
                 rd.q_lo = m.q_lower[m.idx_q[j]];
                 rd.q_hi = m.q_upper[m.idx_q[j]];
+            } else if (m.joint_type[j] == JB_JOINT_SPHERICAL) {
+                for (int k = 0; k < 3; ++k) rd.axis[k] = m.rotor_inertia[m.idx_v[j] + k];
+                for (int k = 0; k < 6; ++k) rd.motor[k] = m.flexibility ? m.flexibility[6 * j + k] : 0.0;
             } else {
                 for (int k = 0; k < 6; ++k)
                     if (m.rotor_inertia[m.idx_v[j] + k] != 0.0)

@@ -23,7 +23,13 @@ namespace jb {
 
 // Record kinds (what the lane executes for this record)
 enum : int32_t { REC_PAD = 0, REC_REV = 1, REC_REVU = 2, REC_PRISM = 3, REC_FREE = 4,
-                 REC_REVX = 5 /* bounded revolute about +-x of the joint frame */ };
+                 REC_REVX = 5 /* bounded revolute about +-x of the joint frame */,
+                 REC_SPH = 6 /* spherical (flexibility) joint: lives in a free-flyer-sized record, see RS_* */ };
+// records with the free-flyer layout (RF_*)
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr bool rec_is_big(int kind) { return kind == REC_FREE || kind == REC_SPH; }
 
 constexpr int MAX_CONTACTS_PER_REC = 8;
 
@@ -117,7 +123,8 @@ struct Plan {
     int nimuslot = 0;          // IMU capture slots per lane
     int nfields = 0;           // doubles of shared memory per lane
     std::vector<int32_t> rec_off;       // [nrec] field offset of each record (lane-uniform)
-    std::vector<int32_t> rec_free;      // [nrec] 1 if the record slot is sized for a free-flyer
+    std::vector<int32_t> rec_free;      // [nrec] 1 if the record slot is sized for a free-flyer / spherical joint
+    int sph_off = 0;                    // RF_KA + 6 * n_hist: where the RS_* block of a spherical record starts
     std::vector<int32_t> trunk_reduce;  // [nrec] 1 if a trunk record all-reduces its pool accumulator
     int pool_off = 0, cslot_off = 0, imu_off = 0;
     std::vector<RecInt> rint;           // [nrec * L]
@@ -155,6 +162,16 @@ constexpr int RF_VS = 44;     // 6
 constexpr int RF_SV = 50;     // 6
 constexpr int RF_SA = 56;     // 6
 constexpr int RF_KA = 62;     // DOPRI history (7 x 6) starts here
+// spherical record = free-flyer layout with the linear halves of q / v / a / stage / accumulator / history slots held at
+// zero (every copy / accumulate loop of the steppers serves both kinds unchanged; only integrate, difference, the joint
+// transform and the articulated-body step are its own), followed by RS_EXTRA doubles at RF_KA + 6 * n_hist:
+constexpr int RS_BIAS = 0;    // 6 : a_gf bias v x vJ
+constexpr int RS_U = 6;       // 18: U = Ia S, three columns (linear, angular)
+constexpr int RS_DINV = 24;   // 6 : (S^T U + Im)^-1, symmetric (xx xy yy xz yz zz)
+constexpr int RS_TAU = 30;    // 3 : joint efforts (flexibility spring-damper), then u = tau - S^T f after the backward step
+constexpr int RS_EXTRA = 33;
+// RecDbl of a spherical record: axis[3] = armature-like rotor inertia of its three dofs, motor[0..2] = stiffness,
+// motor[3..5] = damping (JbModelDesc::flexibility)
 constexpr int POOL_SIZE = 27; // union { oMi 12 + v 6 | Y 21 + f 6 | a_gf 6 }
 constexpr int CSLOT_SIZE = 6; // cached contact wrench in the joint frame: force at the contact point (3), pure torque (3)
 constexpr int IMUSLOT_SIZE = 12; // v (6) captured in pass 1, a_gf (6) captured in pass 3

@@ -669,8 +669,10 @@ def robot_table_to_dict(robot: RobotTable) -> dict:
         "inertia": robot.inertia.tolist(), "rotor_inertia": robot.rotor_inertia.tolist(),
         "q_lower": robot.q_lower.tolist(), "q_upper": robot.q_upper.tolist(),
         "effort_limit": robot.effort_limit.tolist(), "velocity_limit": robot.velocity_limit.tolist(),
-        "frames": {n: {"joint": f.joint, "placement": f.placement.flat().tolist(), "kind": f.kind}
+        "frames": {n: {"joint": f.joint, "placement": f.placement.flat().tolist(), "kind": f.kind, "base": f.base}
                    for n, f in robot.frames.items()},
+        "flexibility": None if robot.flexibility is None else np.asarray(robot.flexibility).tolist(),
+        "flexibility_joint_names": list(robot.flexibility_joint_names),
         "motors": [vars(m) for m in robot.motors],
         "contact_frame_names": robot.contact_frame_names,
         "imu_names": robot.imu_names, "imu_frames": robot.imu_frames,
@@ -713,7 +715,7 @@ def robot_table_from_dict(d: dict) -> RobotTable:
     frames = {}
     for n, f in d["frames"].items():
         p = np.array(f["placement"], dtype=np.float64)
-        frames[n] = Frame(n, int(f["joint"]), SE3(p[:9].reshape(3, 3).copy(), p[9:].copy()), f["kind"])
+        frames[n] = Frame(n, int(f["joint"]), SE3(p[:9].reshape(3, 3).copy(), p[9:].copy()), f["kind"], f.get("base", ""))
     r = RobotTable(
         name=d["name"], has_freeflyer=bool(d["has_freeflyer"]), joint_names=list(d["joint_names"]),
         joint_type=np.array(d["joint_type"], dtype=np.int32), parent=np.array(d["parent"], dtype=np.int32),
@@ -729,6 +731,9 @@ def robot_table_from_dict(d: dict) -> RobotTable:
                 "encoder_names", "encoder_joints", "encoder_reduction", "effort_names", "effort_motors",
                 "contact_sensor_names", "contact_sensor_index"):
         setattr(r, key, list(d[key]))
+    if d.get("flexibility") is not None:
+        r.flexibility = np.array(d["flexibility"], dtype=np.float64)
+    r.flexibility_joint_names = list(d.get("flexibility_joint_names", []))
     return r
 
 
@@ -798,15 +803,17 @@ def add_flexibility_joints(robot: RobotTable, flexibility_config: Sequence[dict]
     if out.flexibility is None:
         out.flexibility = np.zeros((out.njoints, 6))
     for cfg in flexibility_config:
-        if cfg["frameName"] not in robot.frames:
+        if cfg["frameName"] not in robot.frames and cfg["frameName"] not in robot.joint_names:
             raise ValueError(f"Frame '{cfg['frameName']}' does not exists. Impossible to insert flexibility joint on it.")
     flex_names: List[str] = []
     for cfg in flexibility_config:
         frame_name = cfg["frameName"]
-        fr = out.frames[frame_name]
-        if fr.kind == "joint":
+        # a joint and a link may share a name (ANYmal's URDF): the joint frame is the one meant
+        is_joint = frame_name in out.joint_names[1:]
+        fr = out.frames.get(frame_name)
+        if is_joint:
             k = out.joint_index(frame_name)
-            if k == 0 or int(out.joint_type[k]) == JB_JOINT_FREEFLYER and frame_name == "root_joint":
+            if int(out.joint_type[k]) in (JB_JOINT_FREEFLYER, JB_JOINT_SPHERICAL):
                 raise ValueError("Flexible joint can only be inserted at fixed or joint frames.")
             flex_name = frame_name + FLEXIBLE_JOINT_SUFFIX
             parent, M = int(out.parent[k]), _se3_from_flat(out.placement[k])
@@ -814,8 +821,11 @@ def add_flexibility_joints(robot: RobotTable, flexibility_config: Sequence[dict]
             out.parent[k + 1] = k
             out.placement[k + 1] = SE3().flat()
             out.frames[flex_name] = Frame(flex_name, k, SE3(), "joint")
-        elif fr.kind == "fixed_joint":
+        elif fr is not None and fr.kind == "fixed_joint":
             flex_name = frame_name
+            if not out.urdf_path or not os.path.exists(out.urdf_path) or not out.links:
+                raise NotImplementedError("A flexibility at a fixed frame splits a composite body: it needs the URDF the table "
+                                          "was built from (`build_robot_table`), which a compiled table does not keep.")
             _, _, ujoints = parse_urdf(out.urdf_path)
             if frame_name not in ujoints or ujoints[frame_name].type != "fixed":
                 raise ValueError("Frame must be associated with fixed joint.")
@@ -870,6 +880,22 @@ def add_flexibility_joints(robot: RobotTable, flexibility_config: Sequence[dict]
                              f"for numerical stability: {diag}")
     out.flexibility_joint_names = list(out.flexibility_joint_names) + flex_names
     return out
+
+
+def extended_state_from_theoretical(flex: RobotTable, rigid: RobotTable, q: np.ndarray, v: Optional[np.ndarray] = None):
+    """`Model::getExtendedPositionFromTheoretical` / `getExtendedVelocityFromTheoretical` (model.cc): the state of the
+    rigid (theoretical) model laid over the model with flexibility joints -- undeformed flexibilities (unit quaternion,
+    no velocity), every other joint copied by name.  `q` [.., rigid.nq] -> [.., flex.nq] (and `v` likewise)."""
+    q = np.asarray(q, dtype=np.float64)
+    qe = np.broadcast_to(flex.neutral(), q.shape[:-1] + (flex.nq,)).copy()
+    ve = None if v is None else np.zeros(np.asarray(v).shape[:-1] + (flex.nv,))
+    for j in range(1, rigid.njoints):
+        k = flex.joint_index(rigid.joint_names[j])
+        t = int(rigid.joint_type[j])
+        qe[..., flex.idx_q[k]:flex.idx_q[k] + JOINT_NQ[t]] = q[..., rigid.idx_q[j]:rigid.idx_q[j] + JOINT_NQ[t]]
+        if ve is not None:
+            ve[..., flex.idx_v[k]:flex.idx_v[k] + JOINT_NV[t]] = np.asarray(v)[..., rigid.idx_v[j]:rigid.idx_v[j] + JOINT_NV[t]]
+    return qe if v is None else (qe, ve)
 
 
 def _op_base(robot: RobotTable, frame: Frame, moved: set) -> bool:

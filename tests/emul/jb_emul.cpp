@@ -11,7 +11,11 @@ thread_local int lane_id = 0;
 int current_L = 1;
 
 void launch(unsigned grid, unsigned block, size_t smem_bytes, int L, const std::function<void()>& body) {
-    std::vector<double> smem((smem_bytes + 7) / 8 + 1, 0.0);
+    // shared memory of a real launch holds whatever the previous block left there: JB_EMUL_SMEM_FILL=nan (or a number)
+    // poisons it so that a read-before-write shows up on the CPU
+    double fill = 0.0;
+    if (const char* e = std::getenv("JB_EMUL_SMEM_FILL")) fill = (e[0] == 'n' || e[0] == 'N') ? std::nan("") : std::atof(e);
+    std::vector<double> smem((smem_bytes + 7) / 8 + 1, fill);
     const unsigned nwarps = (block + 31) / 32;
     for (unsigned bi = 0; bi < grid; ++bi) {
         std::vector<Warp> warps(nwarps);

@@ -17,6 +17,11 @@ def random_states(robot, n, rng, base_height=0.45):
                 quat = rng.normal(size=4)
                 q[i, iq:iq + 3] = rng.normal(size=3) * 0.1 + [0, 0, base_height]
                 q[i, iq + 3:iq + 7] = quat / np.linalg.norm(quat)
+            elif t == 14:   # spherical (flexibility) joint: a moderate rotation
+                w = rng.normal(size=3) * 0.2
+                ang = np.linalg.norm(w)
+                q[i, iq:iq + 3] = np.sin(ang / 2) * w / ang
+                q[i, iq + 3] = np.cos(ang / 2)
             elif t in (5, 6, 7, 8):
                 a = rng.uniform(-3, 3)
                 q[i, iq], q[i, iq + 1] = np.cos(a), np.sin(a)

@@ -328,3 +328,14 @@ def test_model_variants_on_device():
     import test_kernel_emul as tke
     tke.test_model_variants_match_per_variant_oracles(None)
 
+
+
+def test_flexibility_joints_on_device():
+    """Flexibility joints (spherical records, Engine::computeInternalDynamics engine.cc:3367-3391): the reference's
+    series-elastic-actuator test on the CUDA path (closed form + oracle, adaptive steps), the flexible branched arm with
+    RK4 and Dormand-Prince, and ANYmal with a flexibility in every leg."""
+    import flexibility_common as fc
+    assert fc.series_elastic_actuator() < 1e-10
+    fc.branched_arm_parity()
+    fc.branched_arm_parity(solver="runge_kutta_dopri")
+    fc.flexible_anymal_parity(n_env=70, n_steps=2)

@@ -809,3 +809,37 @@ def test_model_variants_match_per_variant_oracles(api):
     other = scenarios.make("atlas", 1).robot
     with pytest.raises(Exception):
         eng.set_model_variants([other], np.zeros(4, dtype=np.int32))
+
+
+# ---- flexibility joints (Engine::computeInternalDynamics, engine.cc:3367-3391; spherical joints in the lane plan)
+def test_flexibility_branched_arm_matches_oracle(api):
+    import flexibility_common as fc
+    for lanes in (0, 1):
+        _lanes(lanes)
+        try:
+            fc.branched_arm_parity(api)
+        finally:
+            _lanes(0)
+
+
+def test_flexibility_dopri_matches_oracle(api):
+    import flexibility_common as fc
+    fc.branched_arm_parity(api, solver="runge_kutta_dopri")
+
+
+def test_flexibility_anymal_matches_oracle(api):
+    import flexibility_common as fc
+    fc.flexible_anymal_parity(api, n_env=8, n_steps=1)
+
+
+def test_flexibility_refuses_the_constraint_contact_model(api):
+    import flexibility_common as fc
+    robot, flex, opt = fc.flexible_branched_arm()
+    opt["contacts"]["model"] = "constraint"
+    with pytest.raises(NotImplementedError):
+        BatchedEngine(flex, opt, 2, api_=api)
+
+
+def test_flexibility_series_elastic_actuator_like_the_reference_test(api):
+    import flexibility_common as fc
+    assert fc.series_elastic_actuator(api) < 1e-11
