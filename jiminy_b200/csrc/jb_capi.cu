@@ -442,13 +442,9 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
         kp.m_max = kp.n_jc + 4 * kp.n_cc;
         bool has_spherical = false;
         for (int j = 1; j < m->njoints; ++j) has_spherical = has_spherical || m->joint_type[j] == JB_JOINT_SPHERICAL;
-        // the constraint solvers walk 1-dof and free-flyer records only: a model with flexibility joints has its joint
-        // bounds flagged (JB_ENV_JOINT_LIMIT), like one with more than 64 degrees of freedom
-        kp.cons_on = (m->nv <= 64 && !has_spherical) ? 1 : 0;
-        if (has_spherical && opt->contact_model == JB_CONTACT_CONSTRAINT) {
-            jb_batch_destroy(b);
-            return fail(JB_ERR_NOT_IMPLEMENTED, "contacts.model = 'constraint' is not available for a model with flexibility joints");
-        }
+        // the structured solvers (quadruped, body space, lane blocks) walk 1-dof and free-flyer records only: a model with
+        // flexibility joints goes through the generic solver (jb_constraints.cuh)
+        kp.cons_on = (m->nv <= 64) ? 1 : 0;
         kp.cons_off = P.nfields;
         kp.cq_off = P.nfields + 1;
         kp.cq_on = (kp.cons_on && opt->contact_model == JB_CONTACT_CONSTRAINT && cons_quadruped_matches(kp, P, *m) &&
@@ -464,7 +460,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
             body_of[k] = static_cast<int32_t>(bi);
         }
         const char* offb = std::getenv("JB_NO_BODY_CONS");
-        const bool bd_candidate = kp.cons_on && !kp.cq_on && P.L > 1 && P.L <= 8 && m->ncontacts > 0 && m->ncontacts <= BD_MAX_CONTACTS &&
+        const bool bd_candidate = kp.cons_on && !kp.cq_on && !has_spherical && P.L > 1 && P.L <= 8 && m->ncontacts > 0 && m->ncontacts <= BD_MAX_CONTACTS &&
                                   body_joint.size() <= BD_MAX_BODIES && opt->contact_model == JB_CONTACT_CONSTRAINT && !(offb && std::atoi(offb));
         kp.bd_off = b->base_fields; kp.bd_lsh = 0;
         while ((1 << kp.bd_lsh) < P.L) ++kp.bd_lsh;
@@ -492,7 +488,7 @@ int jb_batch_create(const JbModelDesc* m, const JbOptions* opt, int32_t n_env, i
             kp.cs_total = cs_fields; kp.cw_total = w.total;
             // lane-block solver: dof numbering inside the trunk block and each lane's private block, row budget per lane
             kp.lb_on = 0;
-            if (P.L > 1) {
+            if (P.L > 1 && !has_spherical) {
                 std::vector<int32_t> dof0(static_cast<size_t>(P.nrec) * P.L, 0);
                 int nt = 0, nl = 0, ml = 0;
                 for (int s = 0; s < P.L; ++s) {
@@ -591,7 +587,7 @@ int jb_set_options(JbBatch* b, const JbOptions* o) {
     if (o->ode_solver == JB_SOLVER_RUNGE_KUTTA_DOPRI && b->kp.n_hist == 0)
         return fail(JB_ERR_BAD_CONTROL_FLOW, "switching to 'runge_kutta_dopri' changes the working-set layout: create a new batch");
     if (o->contact_model == JB_CONTACT_CONSTRAINT && !b->kp.cons_on)
-        return fail(JB_ERR_NOT_IMPLEMENTED, "contacts.model = 'constraint' is not available for this robot (flexibility joints or more than 64 degrees of freedom)");
+        return fail(JB_ERR_NOT_IMPLEMENTED, "contacts.model = 'constraint' is not available for this robot (more than 64 degrees of freedom)");
     apply_options(b, o);
     return JB_OK;
 }

@@ -77,7 +77,8 @@ JB_DI Mot subspace_col(int kind, V3 ax, int d) {
     Mot s = mzero();
     if (kind == REC_FREE) {
         if (d < 3) s.l = mk(d == 0, d == 1, d == 2); else s.a = mk(d == 3, d == 4, d == 5);
-    } else if (kind == REC_PRISM) s.l = ax;
+    } else if (kind == REC_SPH) s.a = mk(d == 0, d == 1, d == 2);   // (`ax` holds the rotor inertias of a spherical record)
+    else if (kind == REC_PRISM) s.l = ax;
     else s.a = ax;
     return s;
 }
@@ -115,7 +116,7 @@ __device__ __noinline__ void cons_reset(const Ctx c) {
     for (int r = 0; r < KP->nrec; ++r) {
         const RecInt* ri = KP->rint + (r * L + c.sub);
         if (ri->kind == REC_PAD || !ri->owner) continue;
-        if (ri->kind != REC_FREE) {
+        if (!rec_is_big(ri->kind)) {
             const int k = KP->jc_of_joint[ri->joint];
             if (k >= 0) {
                 const double* rp = jb_smem + KP->rec_off[r] * 32 + c.lane;
@@ -147,7 +148,7 @@ __device__ __noinline__ void cons_load_count(const Ctx c) {
     for (int r = 0; r < KP->nrec; ++r) {
         const RecInt* ri = KP->rint + (r * L + c.sub);
         if (ri->kind == REC_PAD || !ri->owner) continue;
-        if (ri->kind != REC_FREE) {
+        if (!rec_is_big(ri->kind)) {
             const int k = KP->jc_of_joint[ri->joint];
             if (k >= 0 && CST(cs_joint(k)) != 0.0) count += CONS_BOUND_UNIT;
         }
@@ -165,7 +166,7 @@ __device__ __noinline__ void cons_update_bounds(const Ctx c, int* status) {
     const double eps = KP->opt.contact_transition_eps;
     for (int r = 0; r < KP->nrec; ++r) {
         const RecInt* ri = KP->rint + (r * L + c.sub);
-        if (ri->kind == REC_PAD || ri->kind == REC_FREE || !ri->owner || !ri->has_limit) continue;
+        if (ri->kind == REC_PAD || rec_is_big(ri->kind) || !ri->owner || !ri->has_limit) continue;
         const int k = KP->jc_of_joint[ri->joint];
         if (k < 0) continue;
         const RecDbl* rd = JB_RDBL + (r * L + c.sub);
@@ -338,7 +339,10 @@ __device__ __noinline__ void cons_refresh_accelerations(const Ctx c) {
         Xf li; sm_load_xf(c, base, li);
         Mot ag;
         if (kind == REC_FREE) ag = motion_act_inv(li, agc) + sm_load_mot(c, base + RF_A);
-        else {
+        else if (kind == REC_SPH) {
+            ag = sm_load_mot(c, base + KP->sph_off + RS_BIAS) + motion_act_inv(li, agc);
+            ag.a = ag.a + mk(RP(RF_A + 3), RP(RF_A + 4), RP(RF_A + 5));
+        } else {
             ag = sm_load_mot(c, base + R1_BIAS) + motion_act_inv(li, agc);
             const V3 ax = ld3(rd->axis);
             const double ddq = RP(R1_A);
@@ -369,7 +373,7 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
             const Xf li = ld_xf32(rq);
             const V3 ax = ld3(rd->axis);
             Mot vJ = mzero();
-            if (jm.kind == REC_FREE) vJ = ld_mot32(rq + RF_VS * 32);
+            if (rec_is_big(jm.kind)) vJ = ld_mot32(rq + RF_VS * 32);   // (spherical: linear half held at zero)
             else if (jm.kind == REC_PRISM) vJ.l = rq[R1_VS * 32] * ax;
             else vJ.a = rq[R1_VS * 32] * ax;
             Xf oM; Mot v, aD;
@@ -403,6 +407,7 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
             for (int k = 0; k < 9; ++k) CWK(w.YC + 21 * j + 6 + k) = Y.B[k];
             // unconstrained accelerations
             if (jm.kind == REC_FREE) { for (int d = 0; d < 6; ++d) CWK(w.DD + jm.idx_v + d) = rq[(RF_A + d) * 32]; }
+            else if (jm.kind == REC_SPH) { for (int d = 0; d < 3; ++d) CWK(w.DD + jm.idx_v + d) = rq[(RF_A + 3 + d) * 32]; }
             else CWK(w.DD + jm.idx_v) = rq[R1_A * 32];
         }
         for (int k = 0; k < nv * nv; ++k) CWK(w.MM + k) = 0.0;
@@ -433,7 +438,11 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
                     }
                 }
             }
-            if (jm.kind != REC_FREE) CWK(w.MM + jm.idx_v * nv + jm.idx_v) += rd->armature;
+            if (jm.kind == REC_SPH) {
+                CWK(w.MM + jm.idx_v * nv + jm.idx_v) += ax.x;
+                CWK(w.MM + (jm.idx_v + 1) * nv + jm.idx_v + 1) += ax.y;
+                CWK(w.MM + (jm.idx_v + 2) * nv + jm.idx_v + 2) += ax.z;
+            } else if (jm.kind != REC_FREE) CWK(w.MM + jm.idx_v * nv + jm.idx_v) += rd->armature;
             if (jm.parent > 0) {
                 SymY T;
                 sym_transform(ld_xf32(rec_of(c, jm)), Y, T);
@@ -583,6 +592,7 @@ __device__ __noinline__ bool constrained_solve(const Ctx c, int* status) {
             for (int s = (jm.trunk ? 0 : jm.sub); s < (jm.trunk ? L : jm.sub + 1); ++s) {
                 double* rq = rec_of_mut(c, jm, s);
                 if (jm.kind == REC_FREE) { for (int d = 0; d < 6; ++d) rq[(RF_A + d) * 32] = CWK(w.DD + jm.idx_v + d) + CWK(w.TT + jm.idx_v + d); }
+                else if (jm.kind == REC_SPH) { for (int d = 0; d < 3; ++d) rq[(RF_A + 3 + d) * 32] = CWK(w.DD + jm.idx_v + d) + CWK(w.TT + jm.idx_v + d); }
                 else rq[R1_A * 32] = CWK(w.DD + jm.idx_v) + CWK(w.TT + jm.idx_v);
             }
         }

@@ -135,10 +135,46 @@ def branched_arm_parity(api=None, device=0, solver="runge_kutta_4", n_steps=3, t
     return eng, orc
 
 
-def flexible_anymal_parity(api=None, device=0, n_env=8, n_steps=2, tol_state=1e-9, tol_sens=1e-7):
+def flexible_pendulum_on_its_bounds(api=None, device=0, model="spring_damper", n_steps=60):
+    """`parity_common.bounds_scenario` with a flexibility in front of the joint: the pendulum is thrown against its
+    position bounds, the JointConstraint of the mechanical joint is solved with a spherical joint in the tree (joint-space
+    inertia, Cholesky factor and M^-1 J^T over nv = 4), multiplier reported in u."""
+    r = M.build_robot_table(os.path.join(DATA, "simple_pendulum.urdf"), False)
+    M.attach_motor(r, "PendulumJoint", "PendulumJoint", enableVelocityLimit=False, enableEffortLimit=False)
+    r.q_upper[0], r.q_lower[0] = 0.5, -0.5
+    r = M.add_flexibility_joints(r, [dict(frameName="PendulumJoint", stiffness=[400.0, 300.0, 500.0], damping=[2.0, 3.0, 2.5],
+                                          inertia=[0.02, 0.03, 0.01])])
+    opt = _opt(odeSolver="runge_kutta_4", dtMax=1e-3, controllerUpdatePeriod=1e-3, sensorsUpdatePeriod=1e-3)
+    opt["contacts"]["model"] = model
+    eng, orc = BatchedEngine(r, opt, 3, device=device, api_=api), OracleBatch(r, opt, 3)
+    q0 = np.tile(r.neutral(), (3, 1))
+    q0[:, 4] = [0.3, 0.1, -0.45]
+    v0 = np.zeros((3, 4))
+    v0[:, 3] = [0.0, 1.0, -2.0]
+    for x in (eng, orc):
+        x.set_command(np.zeros((3, 1)))
+    eng.start(q0, v0)
+    assert not orc.start(q0, v0).any()
+    pc.compare(eng, orc, 1e-13, 1e-11)
+    hit = np.zeros(3, dtype=bool)
+    for _ in range(n_steps):
+        eng.step(0.01)
+        assert not orc.step(0.01).any()
+        pc.compare(eng, orc, 1e-9, 1e-7)
+        np.testing.assert_allclose(eng.get_efforts()[0], orc.get_efforts()[0], rtol=0, atol=1e-7)
+        hit |= (eng.get_status() & 8) != 0
+    assert hit.all()                                           # every env reached a bound (JB_ENV_JOINT_LIMIT)
+    assert np.abs(eng.get_state()[1][:, 4]).max() < 0.5 + 5e-3
+    return eng, orc
+
+
+def flexible_anymal_parity(api=None, device=0, n_env=8, n_steps=2, tol_state=1e-9, tol_sens=1e-7, contact_model=None):
     """ANYmal standing under its PD controller with a flexibility in front of a joint of every leg: the spherical
-    records sit inside the legs' private chains, four lanes per env, spring-damper ground."""
+    records sit inside the legs' private chains, four lanes per env; spring-damper ground, or (`contact_model`) the
+    reference's default `constraint` contacts through the generic constraint solver."""
     sc = scenarios.make("anymal", n_env, seed=3)
+    if contact_model is not None:
+        sc.options["contacts"]["model"] = contact_model
     rigid = sc.robot
     cfg = [dict(frameName=jn, stiffness=[5e3, 4e3, 6e3], damping=[20.0, 30.0, 25.0], inertia=[0.05, 0.04, 0.06])
            for jn in ("LF_HFE", "RF_KFE", "LH_HAA", "RH_HFE")]

@@ -339,3 +339,7 @@ def test_flexibility_joints_on_device():
     fc.branched_arm_parity()
     fc.branched_arm_parity(solver="runge_kutta_dopri")
     fc.flexible_anymal_parity(n_env=70, n_steps=2)
+    # ... and through the constraint path (generic solver): joint bounds behind a flexibility, constraint contacts
+    for model in ("spring_damper", "constraint"):
+        fc.flexible_pendulum_on_its_bounds(model=model)
+    fc.flexible_anymal_parity(n_env=40, n_steps=2, contact_model="constraint", tol_state=1e-8, tol_sens=1e-6)

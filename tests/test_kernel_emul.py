@@ -832,12 +832,15 @@ def test_flexibility_anymal_matches_oracle(api):
     fc.flexible_anymal_parity(api, n_env=8, n_steps=1)
 
 
-def test_flexibility_refuses_the_constraint_contact_model(api):
+@pytest.mark.parametrize("model", ["spring_damper", "constraint"])
+def test_flexibility_joint_bounds_constraint_path(api, model):
     import flexibility_common as fc
-    robot, flex, opt = fc.flexible_branched_arm()
-    opt["contacts"]["model"] = "constraint"
-    with pytest.raises(NotImplementedError):
-        BatchedEngine(flex, opt, 2, api_=api)
+    fc.flexible_pendulum_on_its_bounds(api, model=model)
+
+
+def test_flexibility_constraint_contacts_anymal(api):
+    import flexibility_common as fc
+    fc.flexible_anymal_parity(api, n_env=3, n_steps=1, contact_model="constraint", tol_state=1e-8, tol_sens=1e-6)
 
 
 def test_flexibility_series_elastic_actuator_like_the_reference_test(api):
