@@ -279,6 +279,15 @@ class RobotTable:
     def joint_index(self, name: str) -> int:
         return self.joint_names.index(name)
 
+    # ---- `robot.is_flexibility_enabled` / `robot.flexibility_joint_indices` (python/jiminy_pywrap/src/robot.cc)
+    @property
+    def is_flexibility_enabled(self) -> bool:
+        return bool(self.flexibility_joint_names)
+
+    @property
+    def flexibility_joint_indices(self) -> List[int]:
+        return [self.joint_index(n) for n in self.flexibility_joint_names]
+
     def neutral(self) -> np.ndarray:
         """`pinocchio::neutral`: zeros, (1, 0) for unbounded revolute, unit quaternion for free-flyer."""
         q = np.zeros(self.nq)

@@ -39,8 +39,10 @@ GLOBAL_TIME, TIME_UNIT = "Global.Time", "Global.TIME_UNIT"      # constants.h:14
 CONSTANT_DELIMITER, FIELDNAME_DELIMITER = "=", "."
 STEPPER_MIN_TIMESTEP = 1e-10                # constants.h:18 = Engine::getTelemetryTimeUnit (engine.cc:2902-2905)
 
-_POSITION_SUFFIXES = {"free": ("TransX", "TransY", "TransZ", "QuatX", "QuatY", "QuatZ", "QuatW"), "unbounded": ("Cos", "Sin"), "1dof": ("",)}
-_VELOCITY_SUFFIXES = {"free": ("LinX", "LinY", "LinZ", "AngX", "AngY", "AngZ"), "unbounded": ("",), "1dof": ("",)}
+_POSITION_SUFFIXES = {"free": ("TransX", "TransY", "TransZ", "QuatX", "QuatY", "QuatZ", "QuatW"), "unbounded": ("Cos", "Sin"), "1dof": ("",),
+                      "spherical": ("QuatX", "QuatY", "QuatZ", "QuatW")}      # utilities/pinocchio.cc:155-205
+_VELOCITY_SUFFIXES = {"free": ("LinX", "LinY", "LinZ", "AngX", "AngY", "AngZ"), "unbounded": ("",), "1dof": ("",),
+                      "spherical": ("AngX", "AngY", "AngZ")}
 SENSOR_FIELDS = {"ImuSensor": ("GyroX", "GyroY", "GyroZ", "AccelX", "AccelY", "AccelZ"),
                  "ForceSensor": ("FX", "FY", "FZ", "MX", "MY", "MZ"), "EncoderSensor": ("Q", "V"),
                  "EffortSensor": ("U",), "ContactSensor": ("FX", "FY", "FZ")}
@@ -58,6 +60,8 @@ def _circumfix(name: str, prefix: str) -> str:
 def _joint_class(joint_type: int) -> str:
     if joint_type == M.JB_JOINT_FREEFLYER:
         return "free"
+    if joint_type == M.JB_JOINT_SPHERICAL:
+        return "spherical"
     if joint_type in (M.JB_JOINT_RUBX, M.JB_JOINT_RUBY, M.JB_JOINT_RUBZ, M.JB_JOINT_RUBU):
         return "unbounded"
     return "1dof"

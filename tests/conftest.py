@@ -7,6 +7,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "emul"))
 DATA = os.path.join(ROOT, "tests", "data")
+# thread emulator of the CPU suite (tests/emul): a launch that makes no progress for this many seconds dumps what every
+# lane waits on and aborts, instead of hanging the suite
+os.environ.setdefault("JB_EMUL_WATCHDOG", "900")
 
 
 def pytest_configure(config):

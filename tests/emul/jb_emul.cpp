@@ -2,6 +2,8 @@
 // product's C ABI (jiminy_b200/csrc/jb_capi.cu + jb_plan.cpp, unchanged) on top of the thread
 // emulation of a warp.
 #include "jb_emul_shim.h"
+#include <chrono>
+#include <cstdio>
 
 thread_local EmulDim3 threadIdx, blockIdx, blockDim, gridDim;
 thread_local double* emul_smem = nullptr;
@@ -35,7 +37,23 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, int L, const std::
                 body();
             });
         }
+        std::atomic<bool> finished{false};
+        std::thread dog;
+        if (const char* e = std::getenv("JB_EMUL_WATCHDOG")) {
+            const int secs = std::atoi(e);
+            dog = std::thread([&, secs]() {
+                for (int k = 0; k < secs * 10 && !finished.load(); ++k) std::this_thread::sleep_for(std::chrono::milliseconds(100));
+                if (finished.load()) return;
+                std::fprintf(stderr, "[emul watchdog] block %u stuck (L = %d); lane: waiting mask syncs\n", bi, L);
+                for (auto& w : warps)
+                    for (int l = 0; l < 32; ++l)
+                        std::fprintf(stderr, "  lane %2d: %d %08x %lld\n", l, w.waiting[l], w.last_mask[l], w.n_sync[l]);
+                std::abort();
+            });
+        }
         for (auto& t : threads) t.join();
+        finished.store(true);
+        if (dog.joinable()) dog.join();
     }
 }
 }  // namespace emul

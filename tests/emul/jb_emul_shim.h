@@ -42,6 +42,10 @@ struct Warp {
     // kernels are contiguous aligned groups, so a barrier per (group size, group index) suffices.
     double dslot[32];
     int islot[32];
+    // watchdog (JB_EMUL_WATCHDOG=seconds): what every lane last waited on
+    unsigned last_mask[32] = {};
+    long long n_sync[32] = {};
+    int waiting[32] = {};
     std::vector<std::unique_ptr<std::barrier<>>> bars;   // indexed by group id for the current L
     std::unique_ptr<std::barrier<>> full;                 // whole-warp barrier (mask 0xffffffff)
     std::map<unsigned, std::unique_ptr<std::barrier<>>> other;   // any other mask (unions of groups: the scheduler's votes)
@@ -51,7 +55,13 @@ struct Warp {
 extern thread_local Warp* warp;
 extern thread_local int lane_id;
 inline int group_of(unsigned mask) { return __builtin_ctz(mask) / warp->L; }
+inline void sync_group_(unsigned mask);
 inline void sync_group(unsigned mask) {
+    warp->last_mask[lane_id] = mask; ++warp->n_sync[lane_id]; warp->waiting[lane_id] = 1;
+    sync_group_(mask);
+    warp->waiting[lane_id] = 0;
+}
+inline void sync_group_(unsigned mask) {
     if (mask == 0xffffffffu && warp->L < 32) { warp->full->arrive_and_wait(); return; }
     const int g = group_of(mask);
     const unsigned gm = warp->L >= 32 ? 0xffffffffu : (((1u << warp->L) - 1u) << (g * warp->L));

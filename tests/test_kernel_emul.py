@@ -846,3 +846,18 @@ def test_flexibility_constraint_contacts_anymal(api):
 def test_flexibility_series_elastic_actuator_like_the_reference_test(api):
     import flexibility_common as fc
     assert fc.series_elastic_actuator(api) < 1e-11
+
+
+def test_flexibility_engine_facade_like_the_reference_api_test(api):
+    """unit_py/test_simple_pendulum.py:815-842 through the single-env `Engine` facade: the flexibility API works, the
+    indices survive a simulation."""
+    import flexibility_common as fc
+    from jiminy_b200.core import Engine
+    robot = fc.flexible_pendulum(0.1, 1.0, 1.0, inertia=1.0)
+    assert robot.is_flexibility_enabled and robot.flexibility_joint_indices == [1]
+    engine = Engine(api_=api)
+    engine.add_robot(robot)
+    engine.simulate(0.1, np.array([0.0, 0.0, 0.0, 1.0, 0.0]), np.zeros(4))
+    assert engine.stepper_state.t >= 0.1 - 1e-9 and np.isfinite(engine.stepper_state.q).all()
+    assert abs(np.linalg.norm(engine.stepper_state.q[:4]) - 1.0) < 1e-9          # the quaternion stays on the sphere
+    assert robot.flexibility_joint_indices == [1]
