@@ -215,6 +215,7 @@ class Motor:
     friction_dry_negative: float = 0.0
     friction_dry_slope: float = 0.0
     armature: float = 0.0  # joint side (option * reduction^2)
+    backlash: float = 0.0  # transmission backlash (0 unless enableBacklash), abstract_motor.cc:347-355
 
 
 @dataclass
@@ -490,6 +491,8 @@ def attach_motor(robot: RobotTable, name: str, joint_name: str, **options) -> Mo
                      ("frictionDryPositive", m.friction_dry_positive)):
         if val > 0.0:
             raise ValueError(f"'{key}' must be negative.")
+    if options.get("enableBacklash", False):
+        m.backlash = float(options.get("backlash", 0.0))
     if options.get("enableArmature", False):
         m.armature = float(options.get("armature", 0.0)) * red ** 2
     robot.rotor_inertia[iv] += m.armature
@@ -760,38 +763,83 @@ def _se3_from_flat(x: np.ndarray) -> SE3:
     return SE3(np.array(x[:9], dtype=np.float64).reshape(3, 3), np.array(x[9:12], dtype=np.float64))
 
 
-def _insert_spherical_joint(robot: RobotTable, k: int, name: str, parent: int, placement: SE3, inertia: Inertia) -> None:
-    """Insert a spherical joint at joint index `k` (every joint >= k moves up by one: the succession of
-    `swapJointIndices` at the end of the reference's insertion routines), in place."""
+def _insert_joint(robot: RobotTable, k: int, name: str, jtype: int, parent: int, placement: SE3, inertia: Inertia,
+                  axis: Optional[np.ndarray] = None, lower: Optional[Sequence[float]] = None,
+                  upper: Optional[Sequence[float]] = None) -> None:
+    """Insert a joint at joint index `k` (every joint >= k moves up by one: the succession of `swapJointIndices` at the
+    end of the reference's insertion routines, utilities/pinocchio.cc:404-458), in place."""
     shift = lambda j: j + 1 if j >= k else j   # noqa: E731
     iq, iv = (int(robot.idx_q[k]), int(robot.idx_v[k])) if k < robot.njoints else (robot.nq, robot.nv)
+    nq, nv = JOINT_NQ[jtype], JOINT_NV[jtype]
     robot.joint_names.insert(k, name)
-    robot.joint_type = np.insert(robot.joint_type, k, JB_JOINT_SPHERICAL).astype(np.int32)
+    robot.joint_type = np.insert(robot.joint_type, k, jtype).astype(np.int32)
     par = [shift(int(p)) for p in robot.parent]
     par.insert(k, parent)
     robot.parent = np.array(par, dtype=np.int32)
     robot.placement = np.insert(robot.placement, k, placement.flat(), axis=0)
-    robot.axis = np.insert(robot.axis, k, np.zeros(3), axis=0)
+    robot.axis = np.insert(robot.axis, k, np.zeros(3) if axis is None else np.asarray(axis, dtype=np.float64), axis=0)
     robot.inertia = np.insert(robot.inertia, k, inertia.flat(), axis=0)
-    robot.rotor_inertia = np.insert(robot.rotor_inertia, iv, np.zeros(3))
-    robot.q_lower = np.insert(robot.q_lower, iq, np.full(4, -1.0 - EPS))   # model.cc:1379-1398
-    robot.q_upper = np.insert(robot.q_upper, iq, np.full(4, 1.0 + EPS))
-    robot.effort_limit = np.insert(robot.effort_limit, iv, np.full(3, INF))
-    robot.velocity_limit = np.insert(robot.velocity_limit, iv, np.full(3, INF))
+    robot.rotor_inertia = np.insert(robot.rotor_inertia, iv, np.zeros(nv))
+    robot.q_lower = np.insert(robot.q_lower, iq, np.full(nq, -1.0 - EPS) if lower is None else np.asarray(lower, dtype=np.float64))
+    robot.q_upper = np.insert(robot.q_upper, iq, np.full(nq, 1.0 + EPS) if upper is None else np.asarray(upper, dtype=np.float64))
+    robot.effort_limit = np.insert(robot.effort_limit, iv, np.full(nv, INF))
+    robot.velocity_limit = np.insert(robot.velocity_limit, iv, np.full(nv, INF))
     if robot.flexibility is not None:
         robot.flexibility = np.insert(robot.flexibility, k, np.zeros(6), axis=0)
-    idx_q, idx_v, nq, nv = [], [], 0, 0
+    idx_q, idx_v, nq_, nv_ = [], [], 0, 0
     for t in robot.joint_type:
-        idx_q.append(nq)
-        idx_v.append(nv)
-        nq += JOINT_NQ[int(t)]
-        nv += JOINT_NV[int(t)]
+        idx_q.append(nq_)
+        idx_v.append(nv_)
+        nq_ += JOINT_NQ[int(t)]
+        nv_ += JOINT_NV[int(t)]
     robot.idx_q, robot.idx_v = np.array(idx_q, dtype=np.int32), np.array(idx_v, dtype=np.int32)
     for f in robot.frames.values():
         f.joint = shift(f.joint)
     for m in robot.motors:
         m.joint = shift(m.joint)
     robot.encoder_joints = [shift(j) for j in robot.encoder_joints]
+
+
+def _insert_spherical_joint(robot: RobotTable, k: int, name: str, parent: int, placement: SE3, inertia: Inertia) -> None:
+    _insert_joint(robot, k, name, JB_JOINT_SPHERICAL, parent, placement, inertia)   # quaternion limits: model.cc:1379-1398
+
+
+BACKLASH_JOINT_SUFFIX = "Backlash"      # core/include/jiminy/core/robot/model.h:20
+
+
+def add_backlash_joints(robot: RobotTable) -> RobotTable:
+    """`Robot::initializeExtendedModel` (core/src/robot/robot.cc:582-629): for every motor with a transmission backlash
+    (`enableBacklash`, `backlash` motor options) a joint `<joint>Backlash` of the same model is inserted right after the
+    motorised joint (`addBacklashJointAfterMechanicalJoint`, utilities/pinocchio.cc:505-576): it takes over the body,
+    the children and the frames of the joint, which keeps the motor and its rotor inertia, and its position is bounded by
+    +- backlash / 2 -- a bound the engine enforces like any other (JointConstraint of the `boundJoints` registry).
+    Returns a new table; the argument is left alone."""
+    import copy
+    out = copy.deepcopy(robot)
+    for mi in range(len(out.motors)):
+        m = out.motors[mi]
+        if m.backlash < EPS:
+            continue
+        j = m.joint
+        t = int(out.joint_type[j])
+        if JOINT_NV[t] != 1:
+            raise ValueError("Backlash can only be associated with a 1-dof linear or rotary joint.")
+        name = out.joint_names[j] + BACKLASH_JOINT_SUFFIX
+        if name in out.joint_names:
+            raise ValueError(f"A joint with name '{name}' already exists.")
+        k = j + 1
+        body = _inertia_from_flat(out.inertia[j])
+        lo, hi = ([-m.backlash / 2.0], [m.backlash / 2.0]) if JOINT_NQ[t] == 1 else (None, None)
+        _insert_joint(out, k, name, t, j, SE3(), body, axis=out.axis[j].copy(), lower=lo, upper=hi)
+        out.inertia[j] = Inertia().flat()
+        for c in range(k + 1, out.njoints):
+            if int(out.parent[c]) == j:
+                out.parent[c] = k
+        for f in out.frames.values():
+            if f.joint == j and f.kind != "joint":
+                f.joint = k
+        out.frames[name] = Frame(name, k, SE3(), "joint")
+    return out
 
 
 def add_flexibility_joints(robot: RobotTable, flexibility_config: Sequence[dict]) -> RobotTable:

@@ -3,6 +3,7 @@
 // emulation of a warp.
 #include "jb_emul_shim.h"
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 
 thread_local EmulDim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -37,13 +38,16 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, int L, const std::
                 body();
             });
         }
-        std::atomic<bool> finished{false};
+        // watchdog: woken as soon as the block is done (a condition variable, not a polling sleep: a launch must stay cheap)
+        std::mutex dog_mutex;
+        std::condition_variable dog_cv;
+        bool finished = false;
         std::thread dog;
         if (const char* e = std::getenv("JB_EMUL_WATCHDOG")) {
             const int secs = std::atoi(e);
-            dog = std::thread([&, secs]() {
-                for (int k = 0; k < secs * 10 && !finished.load(); ++k) std::this_thread::sleep_for(std::chrono::milliseconds(100));
-                if (finished.load()) return;
+            if (secs > 0) dog = std::thread([&, secs]() {
+                std::unique_lock<std::mutex> lock(dog_mutex);
+                if (dog_cv.wait_for(lock, std::chrono::seconds(secs), [&] { return finished; })) return;
                 std::fprintf(stderr, "[emul watchdog] block %u stuck (L = %d); lane: waiting mask syncs\n", bi, L);
                 for (auto& w : warps)
                     for (int l = 0; l < 32; ++l)
@@ -52,8 +56,11 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, int L, const std::
             });
         }
         for (auto& t : threads) t.join();
-        finished.store(true);
-        if (dog.joinable()) dog.join();
+        if (dog.joinable()) {
+            { std::lock_guard<std::mutex> lock(dog_mutex); finished = true; }
+            dog_cv.notify_all();
+            dog.join();
+        }
     }
 }
 }  // namespace emul

@@ -199,3 +199,33 @@ def flexible_anymal_parity(api=None, device=0, n_env=8, n_steps=2, tol_state=1e-
     iq = flex.idx_q[flex.joint_index("LF_HFEFlexibility")]
     assert np.abs(qf[:, iq:iq + 3]).max() > 1e-6          # the flexibilities deform under the robot's weight
     return eng, orc
+
+
+def backlash_pendulum_parity(api=None, device=0, n_steps=120):
+    """Transmission backlash (`Robot::initializeExtendedModel`, robot.cc:582-629; `model.add_backlash_joints`): the
+    reference's `test_backlash` system -- a motorised pendulum with rotor inertia and a backlash joint behind the motor --
+    driven by a constant torque through the free play and onto the limit, device vs oracle.  The extra joint is an
+    ordinary bounded joint for the engine: the bound is a JointConstraint of the constraint path."""
+    J, B, TAU = 1.0, 1.1, 5.0
+    r = M.build_robot_table(os.path.join(DATA, "simple_pendulum.urdf"), False)
+    M.attach_motor(r, "PendulumJoint", "PendulumJoint", enableVelocityLimit=False, enableEffortLimit=False,
+                   enableArmature=True, armature=J, enableBacklash=True, backlash=2 * B)
+    r = M.add_backlash_joints(r)
+    opt = _opt(odeSolver="runge_kutta_4", dtMax=1e-3, controllerUpdatePeriod=1e-3, sensorsUpdatePeriod=1e-3)
+    opt["constraints"]["regularization"] = 0.0
+    n = 3
+    eng, orc = BatchedEngine(r, opt, n, device=device, api_=api), OracleBatch(r, opt, n)
+    cmd = np.array([[-TAU], [TAU], [-0.5 * TAU]])
+    q0 = np.array([[0.0, 0.1], [0.0, -0.2], [0.1, 0.0]])
+    for x in (eng, orc):
+        x.set_command(cmd)
+    eng.start(q0, np.zeros((n, 2)))
+    assert not orc.start(q0, np.zeros((n, 2))).any()
+    pc.compare(eng, orc, 1e-13, 1e-11)
+    for _ in range(n_steps):
+        eng.step(0.01)
+        assert not orc.step(0.01).any()
+        pc.compare(eng, orc, 1e-9, 1e-7)
+    q = eng.get_state()[1]
+    assert (np.abs(q[:2, 1]) > B - 1e-2).all() and (eng.get_status()[:2] & 8).all()      # on the limit: the bound has been active
+    return eng, orc

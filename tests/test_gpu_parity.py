@@ -343,3 +343,10 @@ def test_flexibility_joints_on_device():
     for model in ("spring_damper", "constraint"):
         fc.flexible_pendulum_on_its_bounds(model=model)
     fc.flexible_anymal_parity(n_env=40, n_steps=2, contact_model="constraint", tol_state=1e-8, tol_sens=1e-6)
+
+
+def test_backlash_joints_on_device():
+    """Transmission backlash (robot.cc:582-629): free play, impact and locked motion of the reference's `test_backlash`
+    system on the CUDA path against the oracle."""
+    import flexibility_common as fc
+    fc.backlash_pendulum_parity()

@@ -861,3 +861,8 @@ def test_flexibility_engine_facade_like_the_reference_api_test(api):
     assert engine.stepper_state.t >= 0.1 - 1e-9 and np.isfinite(engine.stepper_state.q).all()
     assert abs(np.linalg.norm(engine.stepper_state.q[:4]) - 1.0) < 1e-9          # the quaternion stays on the sphere
     assert robot.flexibility_joint_indices == [1]
+
+
+def test_backlash_joints_match_oracle(api):
+    import flexibility_common as fc
+    fc.backlash_pendulum_parity(api)

@@ -615,3 +615,52 @@ def test_rigid_vs_flexibility_at_fixed_frames_like_the_reference_test(tmp_path):
     assert a.joint_names == b.joint_names and a.parent.tolist() == b.parent.tolist()
     np.testing.assert_allclose(a.inertia, b.inertia, atol=1e-12)
     np.testing.assert_allclose(a.placement, b.placement, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 13. unit_py/test_simple_pendulum.py:269-333 -- transmission backlash: free play, then one body with the rotor
+def _backlash_pendulum(J=1.0, backlash=1.1):
+    r = M.build_robot_table(os.path.join(DATA, "simple_pendulum.urdf"), False)
+    M.attach_motor(r, "PendulumJoint", "PendulumJoint", enableVelocityLimit=False, enableEffortLimit=False,
+                   enableArmature=True, armature=J, enableBacklash=True, backlash=2 * backlash)
+    return M.add_backlash_joints(r)
+
+
+def _rk_reference(times, x0, dynamics):
+    sol = scipy.integrate.solve_ivp(dynamics, (times[0], times[-1]), x0, t_eval=times, method="DOP853", rtol=1e-12, atol=1e-12)
+    return sol.y.T
+
+
+def test_backlash_like_the_reference_test():
+    J, B, TAU, g, l, m = 1.0, 1.1, 5.0, 9.81, 1.0, 5.0
+    r = _backlash_pendulum(J, B)
+    assert r.joint_names == ["universe", "PendulumJoint", "PendulumJointBacklash"] and r.motors[0].joint == 1
+    assert (r.q_lower[1], r.q_upper[1]) == (-B, B) and r.inertia[1, 0] == 0.0 and r.inertia[2, 0] == m
+    opt = _opt(tolAbs=1e-9, tolRel=1e-9)
+    opt["constraints"]["regularization"] = 0.0
+    o = OracleBatch(r, opt)
+    o.set_command(np.array([[-TAU]]))
+    x0 = np.array([0.0, 0.1, 0.0, 0.0])
+    ts, qs, vs, _ = o.simulate(5.0, x0[:2], x0[2:])
+    x = np.c_[qs, vs]
+    # phase 1: inside the backlash the rotor spins up alone and the pendulum falls freely (its angle is q0 + q1)
+    # (the fixture's pendulum is the inverted one -- mass above the joint -- so it falls into the backlash earlier than the
+    # reference's hanging pendulum, whose impact time is sqrt(2 B J / TAU): the impact is read off the trajectory)
+    t_impact = ts[np.argmax(np.abs(qs[:, 1]) >= B - 1e-6)]
+    assert 0.2 < t_impact < np.sqrt(B / (TAU / J) * 2)
+    t1, t2 = np.searchsorted(ts, [t_impact - 0.02, t_impact + 0.4])
+
+    def free(t, y):
+        return np.array([y[2], y[3], -TAU / J, g / l * np.sin(y[0] + y[1]) + TAU / J])
+    np.testing.assert_allclose(x[:t1], _rk_reference(ts[:t1], x0, free), atol=TOL)
+    # phase 2: on the backlash limit both move as one body, rotor and body inertia summed up
+    I_total = m * l ** 2 + J
+    G = m * g * l / I_total
+
+    def locked(t, y):
+        return np.array([y[2], y[3], G * np.sin(y[0] + y[1]) - TAU / I_total, 0.0])
+    # (as long as the transmission stays on its limit: the falling inverted pendulum eventually pulls it off again)
+    off = np.nonzero(np.abs(qs[t2:, 1]) < B - 1e-4)[0]
+    t3 = t2 + (off[0] if off.size else len(ts) - t2) - 3        # (the multiplier fades out over the last samples before the release)
+    assert ts[t3 - 1] - ts[t2] > 0.25
+    np.testing.assert_allclose(x[t2:t3], _rk_reference(ts[t2:t3] - ts[t2], x[t2], locked), atol=1e-5)
