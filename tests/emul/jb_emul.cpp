@@ -27,6 +27,12 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, int L, const std::
             for (int g = 0; g < 32 / L; ++g) w.bars.emplace_back(new std::barrier<>(L));
             w.full.reset(new std::barrier<>(32));
         }
+        // The lanes of a block start together, like the threads of a real block do.  Without this the first lanes can be
+        // through a whole (small-robot) step before the last ones are even created -- and the padding groups of the last
+        // warp, which re-read the state of the last real env, would then read what that env has already written back
+        // (different values on the two lanes of a group -> different trip counts -> a deadlock that no GPU can show:
+        // there the loads of all 32 lanes are issued before any lane gets anywhere near the store phase).
+        std::barrier<> start_line(block);
         std::vector<std::thread> threads;
         threads.reserve(block);
         for (unsigned ti = 0; ti < block; ++ti) {
@@ -35,6 +41,7 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, int L, const std::
                 emul_smem = smem.data();
                 warp = &warps[ti / 32];
                 lane_id = static_cast<int>(ti % 32);
+                start_line.arrive_and_wait();
                 body();
             });
         }
