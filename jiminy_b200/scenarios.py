@@ -111,8 +111,25 @@ def standing_posture(name: str, robot: RobotTable) -> np.ndarray:
     return q
 
 
+# flexibilities of the "anymal_flexible" scenario (`modelOptions["dynamics"]["flexibilityConfig"]` of the reference)
+FLEXIBLE_ANYMAL_CONFIG = [dict(frameName=jn, stiffness=[5e3, 4e3, 6e3], damping=[20.0, 30.0, 25.0], inertia=[0.05, 0.04, 0.06])
+                          for jn in ("LF_HFE", "RF_KFE", "LH_HAA", "RH_HFE")]
+
+
 def make(name: str, n_env: int, seed: int = 0, dt_max: Optional[float] = None, solver: Optional[str] = None,
          contact_model: Optional[str] = None, action: str = "pd", flagged_fraction: float = 0.0) -> Scenario:
+    if name == "anymal_flexible":
+        # the ANYmal scenario with `dynamics.enableFlexibility`: a flexibility joint in front of a joint of every leg
+        # (Model::addFlexibilityJointsToExtendedModel), undeformed at the start
+        from . import model as M
+        sc = make("anymal", n_env, seed=seed, dt_max=dt_max, solver=solver, contact_model=contact_model, action=action,
+                  flagged_fraction=flagged_fraction)
+        rigid = sc.robot
+        sc.robot = M.add_flexibility_joints(rigid, FLEXIBLE_ANYMAL_CONFIG)
+        sc.q0, sc.v0 = M.extended_state_from_theoretical(sc.robot, rigid, sc.q0, sc.v0)
+        sc._motor_q = np.array([sc.robot.idx_q[m.joint] for m in sc.robot.motors])
+        sc.name, sc.description = name, sc.description.replace("anymal:", "anymal with 4 flexibility joints:")
+        return sc
     robot, base = R.load_robot(name)
     opt = R.baseline_options(name, copy.deepcopy(base))
     if dt_max is not None:

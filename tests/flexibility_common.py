@@ -172,14 +172,8 @@ def flexible_anymal_parity(api=None, device=0, n_env=8, n_steps=2, tol_state=1e-
     """ANYmal standing under its PD controller with a flexibility in front of a joint of every leg: the spherical
     records sit inside the legs' private chains, four lanes per env; spring-damper ground, or (`contact_model`) the
     reference's default `constraint` contacts through the generic constraint solver."""
-    sc = scenarios.make("anymal", n_env, seed=3)
-    if contact_model is not None:
-        sc.options["contacts"]["model"] = contact_model
-    rigid = sc.robot
-    cfg = [dict(frameName=jn, stiffness=[5e3, 4e3, 6e3], damping=[20.0, 30.0, 25.0], inertia=[0.05, 0.04, 0.06])
-           for jn in ("LF_HFE", "RF_KFE", "LH_HAA", "RH_HFE")]
-    flex = M.add_flexibility_joints(rigid, cfg)
-    q0, v0 = M.extended_state_from_theoretical(flex, rigid, sc.q0, sc.v0)
+    sc = scenarios.make("anymal_flexible", n_env, seed=3, contact_model=contact_model)
+    flex, q0, v0 = sc.robot, sc.q0, sc.v0
     eng = BatchedEngine(flex, sc.options, n_env, device=device, api_=api)
     orc = OracleBatch(flex, sc.options, n_env)
     for e in (eng, orc):

@@ -21,7 +21,7 @@ from conftest import ROOT
 import parity_common as pc
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-NAMES = ("double_pendulum", "cartpole", "anymal", "atlas")
+NAMES = ("double_pendulum", "cartpole", "anymal", "atlas", "anymal_flexible")
 NORTH_STAR_REL = 1e-10
 
 

@@ -34,6 +34,9 @@ CONFIGS = {   # name -> (urdf relative to --data, has_freeflyer, number of env-s
     "cartpole": ("toys_models/cartpole/cartpole.urdf", False, 100),
     "anymal": ("quadrupedal_robots/anymal/anymal.urdf", True, 250),
     "atlas": ("bipedal_robots/atlas/atlas.urdf", True, 50),
+    # ANYmal with `dynamics.enableFlexibility` (scenarios.FLEXIBLE_ANYMAL_CONFIG): pins the flexibility joints
+    # (Engine::computeInternalDynamics, engine.cc:3367-3391) and the joint order of the extended model
+    "anymal_flexible": ("quadrupedal_robots/anymal/anymal.urdf", True, 50),
 }
 
 
@@ -61,6 +64,13 @@ def dump(name: str, data_dir: str, out_dir: str) -> str:
     if name == "atlas":   # the env's contact-point clean-up (gym_jiminy/envs/atlas.py:95-111), needed for equal contact sets
         from gym_jiminy.envs.atlas import _cleanup_contact_points
         _cleanup_contact_points(robot)
+    if name == "anymal_flexible":
+        model_options = robot.get_model_options()
+        model_options["dynamics"]["enableFlexibility"] = True
+        model_options["dynamics"]["flexibilityConfig"] = [
+            {k: (np.asarray(v, dtype=np.float64) if k != "frameName" else v) for k, v in cfg.items()}
+            for cfg in scenarios.FLEXIBLE_ANYMAL_CONFIG]
+        robot.set_model_options(model_options)
     opts = engine.get_options()
     _set_nested(opts, sc.options)
     engine.set_options(opts)
