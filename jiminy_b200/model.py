@@ -996,6 +996,11 @@ def biased_robot(robot: RobotTable, rng: np.random.Generator, *, mass_std: float
     for j in range(1, robot.njoints):
         if int(robot.joint_type[j]) == JB_JOINT_FREEFLYER:
             continue
+        # `mechanicalJointNames_` only: the joints of the theoretical model, not the flexibility joints inserted into the
+        # extended one.  Order of the reference (Model / Robot::initializeExtendedModel): flexibilities, then the biases,
+        # then the backlash joints -- call `add_backlash_joints` on the biased table, not before.
+        if robot.joint_names[j] in robot.flexibility_joint_names:
+            continue
         if com_std > EPS:
             out.inertia[j, 1:4] *= normal(3, 1.0, com_std)
         if mass_std > EPS:
