@@ -337,7 +337,7 @@ def run_gpu(args):
     bytes_per_launch = sc.algorithmic_bytes_per_env_step() * n_env
     # `traffic` and the FP64-pipe figure come from the committed ncu capture of THIS device code (profiles/ncu_traffic.json is
     # written by tools/ncu_traffic.py with the hash of jiminy_b200/csrc): a stale capture reports null, never an old number
-    traffic, fp64_pct, prof_src = None, None, None
+    traffic, fp64_pct, prof_src, stale_capture = None, None, None, None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
             default = (args.contact_model in (None, "spring_damper") and args.ode_solver is None and args.dt_max is None and
@@ -345,6 +345,12 @@ def run_gpu(args):
             rec = json.load(fh).get(args.workload) if default else None
         if rec and rec["n_env"] == n_env and rec.get("kernel_source_sha") == kernel_source_sha():
             traffic, fp64_pct, prof_src = rec["traffic_bytes"], rec["fp64_pipe_active_pct"], rec.get("source")
+        elif rec and rec["n_env"] == n_env:
+            # the device sources changed since the capture: the figures above stay null; what the last capture of this
+            # workload measured is reported apart, labelled with the device code it belongs to
+            stale_capture = {"traffic": rec["traffic_bytes"], "fp64_pipe_active_pct": rec["fp64_pipe_active_pct"],
+                             "ncu_capture": rec.get("source"), "kernel_source_sha": rec.get("kernel_source_sha"),
+                             "note": "taken on an earlier version of the device sources (hash above), not on the code timed here"}
     except Exception:
         pass
     achieved_gbs = bytes_per_launch / (step_ms_dev * 1e-3) / 1e9
@@ -379,6 +385,7 @@ def run_gpu(args):
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
                      "fp64_pipe_active_pct_ncu": fp64_pct, "ncu_capture": prof_src, "kernel_source_sha": kernel_source_sha(),
+                     "last_capture": stale_capture,
                      "kernel": "env_step_kernel", "kernel_ms": step_ms_dev,
                      "algorithmic_bytes_per_launch": bytes_per_launch,
                      "note": "fp64-pipe / latency bound by construction (state stays on chip for the whole "
@@ -400,7 +407,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="jiminy_b200", choices=["jiminy_b200", "reference"])
-    ap.add_argument("--workload", default="anymal", choices=["anymal", "atlas", "cartpole", "double_pendulum"])
+    ap.add_argument("--workload", default="anymal", choices=["anymal", "atlas", "cartpole", "double_pendulum", "anymal_flexible"])
     ap.add_argument("--ode-solver", default=None, choices=["euler_explicit", "runge_kutta_4", "runge_kutta_dopri"],
                     help="override stepper.odeSolver of the scenario")
     ap.add_argument("--dt-max", type=float, default=None, help="override stepper.dtMax of the scenario")
