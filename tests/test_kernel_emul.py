@@ -866,3 +866,22 @@ def test_flexibility_engine_facade_like_the_reference_api_test(api):
 def test_backlash_joints_match_oracle(api):
     import flexibility_common as fc
     fc.backlash_pendulum_parity(api)
+
+
+def test_flexibility_batched_env(api):
+    """The gym-style batched env over the flexible ANYmal (`scenarios.make("anymal_flexible")`): extended state in the
+    observation, restart of the finished envs with undeformed flexibilities."""
+    from jiminy_b200.envs import BatchedJiminyEnv
+    sc = scenarios.make("anymal_flexible", 3)
+    assert sc.robot.is_flexibility_enabled and sc.robot.nq == 19 + 4 * 4
+    env = BatchedJiminyEnv(sc, api_=api, simulation_duration_max=0.08)
+    obs, _ = env.reset()
+    assert obs["states"]["agent"]["q"].shape == (3, 35) and obs["states"]["agent"]["v"].shape == (3, 30)
+    obs, rew, term, trunc, info = env.step(sc.sample_targets(0))
+    assert not term.any() and not trunc.any()
+    iq = sc.robot.idx_q[sc.robot.joint_index("LF_HFEFlexibility")]
+    assert np.abs(obs["states"]["agent"]["q"][:, iq:iq + 3]).max() > 1e-7      # deformed under load
+    obs, rew, term, trunc, info = env.step(sc.sample_targets(1))
+    assert trunc.all()                                                          # duration limit -> restarted ...
+    np.testing.assert_allclose(obs["states"]["agent"]["q"][:, iq:iq + 4], [[0.0, 0.0, 0.0, 1.0]] * 3)   # ... undeformed
+    env.close()
