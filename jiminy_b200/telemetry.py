@@ -26,7 +26,7 @@ from __future__ import annotations
 
 import json
 import struct
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -202,6 +202,53 @@ class TelemetryRecorder:
     def log_data(self) -> dict:
         """`Engine.log_data`-like dict: constants, times (s) and one array per variable."""
         return read_log_bytes(self.to_bytes())
+
+
+class BatchTelemetryRecorder:
+    """Telemetry of a batched rollout: one reference-format log per recorded env of a `BatchedEngine`, so that
+    `jiminy_py.log` / `plot` / `viewer.replay` keep working on the rollouts of the batched path.  The batch is
+    read once per snapshot (state, efforts, sensors, energies: one device-to-host copy each, whatever the number of
+    recorded envs), not once per env."""
+
+    def __init__(self, engine, envs: Optional[Sequence[int]] = None, options: Optional[dict] = None,
+                 constants: Optional[Dict[str, str]] = None):
+        self.engine = engine
+        self.envs = list(range(engine.n_env)) if envs is None else [int(e) for e in envs]
+        for e in self.envs:
+            if not 0 <= e < engine.n_env:
+                raise ValueError(f"env index {e} out of range")
+        self.recorders = {e: TelemetryRecorder(engine.robot, options, constants) for e in self.envs}
+
+    def snapshot(self) -> None:
+        """Append the current state of every recorded env (call after `start` and after every `step`)."""
+        eng = self.engine
+        t, q, v, a = eng.get_state()
+        keys = {k for k, _ in next(iter(self.recorders.values()))._groups} if self.recorders else set()
+        uu = cc = energies = sensors = None
+        if keys & {"effort", "command"}:
+            uu, _, cc, _ = eng.get_efforts()
+        if "energy" in keys:
+            energies = eng.get_extra_terms()[0].sum(axis=1)
+        if "sensors" in keys:
+            sensors = eng.get_sensors()
+        for e, rec in self.recorders.items():
+            rec.append(float(t[e]), q[e], v[e], a[e], sensors=None if sensors is None else sensors[e],
+                       u=None if uu is None else uu[e], command=None if cc is None else cc[e],
+                       energy=None if energies is None else float(energies[e]))
+
+    def write_logs(self, directory: str, prefix: str = "env") -> List[str]:
+        """One `<prefix>_<env>.data` per recorded env (`Engine.write_log(path, format="binary")`); returns the paths."""
+        import os
+        os.makedirs(directory, exist_ok=True)
+        paths = []
+        for e, rec in self.recorders.items():
+            path = os.path.join(directory, f"{prefix}_{e:06d}.data")
+            rec.write_log(path)
+            paths.append(path)
+        return paths
+
+    def log_data(self, env: int) -> dict:
+        return self.recorders[int(env)].log_data
 
 
 def read_log_bytes(buf: bytes) -> dict:

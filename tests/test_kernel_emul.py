@@ -885,3 +885,35 @@ def test_flexibility_batched_env(api):
     assert trunc.all()                                                          # duration limit -> restarted ...
     np.testing.assert_allclose(obs["states"]["agent"]["q"][:, iq:iq + 4], [[0.0, 0.0, 0.0, 1.0]] * 3)   # ... undeformed
     env.close()
+
+
+def test_batched_rollout_telemetry_logs(api, tmp_path):
+    """One reference-format log per recorded env of a batched rollout (`telemetry.BatchTelemetryRecorder`), read back with the
+    restated reference reader: times, states and sensors of the chosen envs, the batch read once per snapshot."""
+    from jiminy_b200 import telemetry as T
+    sc = scenarios.make("anymal", 5, seed=2)
+    opt = dict(sc.options)
+    opt["telemetry"] = {"enableConfiguration": True, "enableVelocity": True, "enableAcceleration": True, "enableEnergy": True}
+    eng = BatchedEngine(sc.robot, opt, sc.n_env, api_=api)
+    eng.set_pd_controller(sc.kp, sc.kd)
+    eng.set_command(sc.target0)
+    eng.start(sc.q0, sc.v0)
+    rec = T.BatchTelemetryRecorder(eng, envs=[0, 3, 4], options=opt)
+    rec.snapshot()
+    states = [eng.get_state()]
+    for k in range(2):
+        eng.set_command(sc.sample_targets(k))
+        eng.step(sc.step_dt)
+        rec.snapshot()
+        states.append(eng.get_state())
+    paths = rec.write_logs(str(tmp_path), prefix="rollout")
+    assert [os.path.basename(p) for p in paths] == ["rollout_000000.data", "rollout_000003.data", "rollout_000004.data"]
+    for e, path in zip((0, 3, 4), paths):
+        var = T.read_log(path)["variables"]
+        np.testing.assert_allclose(var["Global.Time"], [0.0, 0.04, 0.08], rtol=0, atol=1e-10)
+        for k, (t, q, v, a) in enumerate(states):
+            assert var["currentFreeflyerPositionTransZ"][k] == q[e, 2]
+            assert var["currentVelocityRH_KFE"][k] == v[e, sc.robot.idx_v[sc.robot.joint_index("RH_KFE")]]
+        assert np.isfinite(var["energy"]).all() and f"ImuSensor.{sc.robot.imu_names[0]}.GyroX" in var
+    with pytest.raises(ValueError):
+        T.BatchTelemetryRecorder(eng, envs=[7])
