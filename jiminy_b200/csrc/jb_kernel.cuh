@@ -337,6 +337,16 @@ __device__ __noinline__ void store_dynamics(const Ctx c) {
 // FAST = true: the product hot path only (MODE_STEP, Euler / RK4, spring-damper contacts, no external forces,
 // no enabled constraint).  An env that needs anything else leaves untouched (needs_full raised) and is stepped by the
 // full body right behind, inside the same launch (`only_flagged`).
+// (host emulation of the CPU test suite only, tests/emul/jb_emul_shim.h: "this lane is through / leaves before the loads
+// of its env state"; nothing in the device build)
+#ifdef JB_HOST_EMUL
+#define JB_EMUL_LOADS_DONE(pass) emul::load_fence_wait(pass)
+#define JB_EMUL_LEAVES_EARLY(pass) emul::load_fence_drop(pass)
+#else
+#define JB_EMUL_LOADS_DONE(pass)
+#define JB_EMUL_LEAVES_EARLY(pass)
+#endif
+
 template <bool FAST>
 __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool only_flagged) {
     Ctx c;
@@ -355,10 +365,13 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
 
     const bool masked_out = (mode == MODE_START) && la.mask != nullptr && la.mask[c.env] == 0;
     if (masked_out) return;   // whole env (all its lanes) leaves: group masks keep the others safe
-    if (mode == MODE_STEP && (status & (JB_ENV_NOT_STARTED | JB_ENV_NAN | JB_ENV_ITER_FAILED | JB_ENV_DT_UNDERFLOW | JB_ENV_SOLVER_FAILED))) return;
+    if (mode == MODE_STEP && (status & (JB_ENV_NOT_STARTED | JB_ENV_NAN | JB_ENV_ITER_FAILED | JB_ENV_DT_UNDERFLOW | JB_ENV_SOLVER_FAILED))) {
+        JB_EMUL_LEAVES_EARLY(FAST ? 0 : 1);
+        return;
+    }
     int32_t* const needs_full = KP->needs_full + (blockIdx.x * epw + c.lane / L);   // own row, also for padding envs
-    if constexpr (FAST) { if (*needs_full != 0) return; }
-    else if (mode == MODE_STEP && only_flagged && *needs_full == 0) return;
+    if constexpr (FAST) { if (*needs_full != 0) { JB_EMUL_LEAVES_EARLY(0); return; } }
+    else if (mode == MODE_STEP && only_flagged && *needs_full == 0) { JB_EMUL_LEAVES_EARLY(1); return; }
 
     // The stateful device blocks (PDController targets, MahonyFilter) advance inside the launch; an env handed over to
     // the full body is replayed from the top of the step, so the fast body keeps a copy to put back.
@@ -456,6 +469,7 @@ __device__ __forceinline__ void env_step_body(const LaunchArgs& la, const bool o
         dtLargest = KP->sched[SCH_DTLARGEST * N + col]; dtLargestPrev = KP->sched[SCH_DTLARGESTPREV * N + col];
         tError = KP->sched[SCH_TERROR * N + col]; tPrev = KP->sched[SCH_TPREV * N + col];
         iter = KP->iters[col]; iterFailed = KP->iters[N + col];
+        JB_EMUL_LOADS_DONE(FAST ? 0 : 1);
 
         // ------------- Engine::step (engine.cc:1724-2417)
         const JbOptions& opt = KP->opt;

@@ -26,6 +26,7 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, int L, const std::
             w.L = L;
             for (int g = 0; g < 32 / L; ++g) w.bars.emplace_back(new std::barrier<>(L));
             w.full.reset(new std::barrier<>(32));
+            for (auto& f : w.load_fence) f.reset(new std::barrier<>(32));
         }
         // The lanes of a block start together, like the threads of a real block do.  Without this the first lanes can be
         // through a whole (small-robot) step before the last ones are even created -- and the padding groups of the last

@@ -49,6 +49,9 @@ struct Warp {
     std::vector<std::unique_ptr<std::barrier<>>> bars;   // indexed by group id for the current L
     std::unique_ptr<std::barrier<>> full;                 // whole-warp barrier (mask 0xffffffff)
     std::map<unsigned, std::unique_ptr<std::barrier<>>> other;   // any other mask (unions of groups: the scheduler's votes)
+    // "every lane of the warp has loaded its env state": one per pass of the step body (hot-path pass, full pass), see
+    // load_fence_wait() below
+    std::unique_ptr<std::barrier<>> load_fence[2];
     std::mutex other_mutex;
     int L = 1;
 };
@@ -75,6 +78,18 @@ inline void sync_group_(unsigned mask) {
     }
     b->arrive_and_wait();
 }
+}  // namespace emul
+
+// The padding env groups of the last warp re-read the state of the last real env (c.env = n_env - 1), which that env
+// writes back at the end of its step.  On the GPU the loads of all the lanes of a warp are one instruction, issued long
+// before any lane reaches the store phase; here the lanes are OS threads that can be descheduled for longer than a whole
+// step, so two lanes of a padding group could load different values of (t, dt, ...) and run different numbers of loop
+// iterations -- a deadlock of the emulation only.  The step body therefore tells the emulator when a lane is through its
+// loads (wait: nobody goes on to compute, let alone store, before every lane has loaded) or leaves the body before them
+// (drop).  Both are no-ops in the device build.
+namespace emul {
+inline void load_fence_wait(int pass) { warp->load_fence[pass]->arrive_and_wait(); }
+inline void load_fence_drop(int pass) { warp->load_fence[pass]->arrive_and_drop(); }
 }  // namespace emul
 
 inline void __syncwarp(unsigned mask = 0xffffffffu) { emul::sync_group(mask); }

@@ -917,3 +917,32 @@ def test_batched_rollout_telemetry_logs(api, tmp_path):
         assert np.isfinite(var["energy"]).all() and f"ImuSensor.{sc.robot.imu_names[0]}.GyroX" in var
     with pytest.raises(ValueError):
         T.BatchTelemetryRecorder(eng, envs=[7])
+
+
+def test_centroidal_terms_of_a_massless_subtree_are_finite(api):
+    """A flexibility at a fixed frame whose bodies are massless leaves a joint with a massless subtree: its centre of mass
+    is the joint origin (InertiaTpl::__pequ__ divides by max(mass, eps)), not 0 / 0; everything else matches the oracle."""
+    import flexibility_common as fc
+    robot, _, opt = fc.flexible_branched_arm()
+    flex = M.add_flexibility_joints(robot, [dict(frameName="b_sole_fixed", stiffness=[300.0] * 3, damping=[2.0] * 3, inertia=[0.01] * 3)])
+    j = flex.joint_index("b_sole_fixed")
+    assert flex.inertia[j, 0] == 0.0
+    rng = np.random.default_rng(1)
+    q, v = pc.random_states(flex, 2, rng, base_height=0.55)
+    eng, orc = BatchedEngine(flex, opt, 2, api_=api), OracleBatch(flex, opt, 2)
+    cmd = np.zeros((2, flex.nmotors))
+    for x in (eng, orc):
+        x.set_command(cmd)
+    eng.start(q, v)
+    assert not orc.start(q, v).any()
+    eng.step(4e-3)
+    orc.step(4e-3)
+    ycrb, com, vcom, hg, dhg = [np.asarray(x) for x in eng.get_centroidal()]
+    yo, co, vo, hgo, dhgo = [np.asarray(x) for x in orc.get_centroidal()]
+    assert np.isfinite(ycrb).all() and np.isfinite(com).all()
+    np.testing.assert_array_equal(com[:, j], 0.0)
+    keep = np.arange(flex.njoints) != j          # (the reference keeps the meaningless lever of its inertia bookkeeping there)
+    np.testing.assert_allclose(ycrb[:, keep], yo[:, keep], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(com[:, keep], co[:, keep], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(hg, hgo, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(dhg, dhgo, rtol=1e-8, atol=1e-7)
