@@ -609,6 +609,8 @@ class Engine:
     def add_robot(self, robot: M.RobotTable, controller: Optional[FunctionalController] = None) -> None:
         if self.robots:
             raise NotImplementedError("Multi-robot engines are outside the accelerated path.")
+        if isinstance(robot, M.Robot):       # the engine simulates the extended model (flexibilities, biases, backlash)
+            robot = robot.extended
         self.robots.append(robot)
         self._controller = controller
         self.robot_states = [RobotState(robot.nq, robot.nv, robot.nmotors, robot.njoints)]

@@ -955,6 +955,115 @@ def extended_state_from_theoretical(flex: RobotTable, rigid: RobotTable, q: np.n
     return qe if v is None else (qe, ve)
 
 
+def default_model_options() -> dict:
+    """`Model::getDefaultModelOptions` (core/include/jiminy/core/robot/model.h:136-178)."""
+    return {"dynamics": {"inertiaBodiesBiasStd": 0.0, "massBodiesBiasStd": 0.0, "centerOfMassPositionBodiesBiasStd": 0.0,
+                         "relativePositionBodiesBiasStd": 0.0, "enableFlexibility": True, "flexibilityConfig": []},
+            "joints": {"positionLimitFromUrdf": True, "positionLimitLower": np.zeros(0), "positionLimitUpper": np.zeros(0)},
+            "collisions": {"contactPointsPerBodyMax": 5}}
+
+
+class Robot:
+    """The model-option surface of `jiminy.Robot` (`get_model_options` / `set_model_options`, the theoretical and the
+    extended model) over `RobotTable`s: `theoretical` is what the URDF and the hardware description gave,
+    `extended` what the engine simulates -- rebuilt at every `set_model_options` in the reference's order
+    (`Model::initializeExtendedModel`, model.cc:1047-1085, then `Robot::initializeExtendedModel`, robot.cc:582-629):
+    flexibility joints, biases of the body inertias and joint placements, position limits of the mechanical joints,
+    backlash joints.  Pass `robot.extended` (or the `Robot` itself) to `Engine.add_robot` / `BatchedEngine`."""
+
+    def __init__(self, theoretical: RobotTable, seed: int = 0):
+        self.theoretical = theoretical
+        self._options = default_model_options()
+        self._seed = seed
+        self.extended = self._build()
+
+    # ---- options
+    def get_model_options(self) -> dict:
+        import copy
+        return copy.deepcopy(self._options)
+
+    def set_model_options(self, options: dict) -> None:
+        import copy
+        opts = copy.deepcopy(options)
+        dyn, joints = opts["dynamics"], opts["joints"]
+        if not joints["positionLimitFromUrdf"]:
+            n_mech = sum(1 for j in range(1, self.theoretical.njoints) if int(self.theoretical.joint_type[j]) != JB_JOINT_FREEFLYER
+                         for _ in range(JOINT_NQ[int(self.theoretical.joint_type[j])]))
+            for key in ("positionLimitLower", "positionLimitUpper"):
+                if len(np.atleast_1d(joints[key])) != n_mech:       # model.cc:1557-1570
+                    raise ValueError(f"Wrong vector size for '{key}'.")
+        names = [c["frameName"] for c in dyn["flexibilityConfig"]]
+        if len(set(names)) != len(names):                            # model.cc:1596-1611
+            raise ValueError("Each flexibility frame name must be unique.")
+        for key in ("inertiaBodiesBiasStd", "massBodiesBiasStd", "centerOfMassPositionBodiesBiasStd", "relativePositionBodiesBiasStd"):
+            if dyn[key] < 0.0:
+                raise ValueError(f"'{key}' must be positive.")
+        previous, self._options = self._options, opts
+        try:
+            self.extended = self._build()
+        except Exception:
+            self._options = previous
+            raise
+
+    def _build(self) -> RobotTable:
+        import copy
+        dyn, joints = self._options["dynamics"], self._options["joints"]
+        out = copy.deepcopy(self.theoretical)
+        if dyn["enableFlexibility"] and len(dyn["flexibilityConfig"]):
+            out = add_flexibility_joints(out, dyn["flexibilityConfig"])
+        if any(dyn[k] > EPS for k in ("inertiaBodiesBiasStd", "massBodiesBiasStd", "centerOfMassPositionBodiesBiasStd",
+                                      "relativePositionBodiesBiasStd")):
+            out = biased_robot(out, np.random.default_rng(self._seed), mass_std=dyn["massBodiesBiasStd"],
+                               com_std=dyn["centerOfMassPositionBodiesBiasStd"], inertia_std=dyn["inertiaBodiesBiasStd"],
+                               relative_position_std=dyn["relativePositionBodiesBiasStd"])
+        if not joints["positionLimitFromUrdf"]:
+            # model.cc:1426-1434: one entry per position coordinate of the mechanical joints, in the theoretical model's order
+            lo, hi, k = np.atleast_1d(joints["positionLimitLower"]), np.atleast_1d(joints["positionLimitUpper"]), 0
+            out.q_lower, out.q_upper = out.q_lower.copy(), out.q_upper.copy()
+            for j in range(1, self.theoretical.njoints):
+                t = int(self.theoretical.joint_type[j])
+                if t == JB_JOINT_FREEFLYER:
+                    continue
+                iq = int(out.idx_q[out.joint_index(self.theoretical.joint_names[j])])
+                for c in range(JOINT_NQ[t]):
+                    out.q_lower[iq + c], out.q_upper[iq + c] = lo[k], hi[k]
+                    k += 1
+        return add_backlash_joints(out)
+
+    # ---- what the envs and the tests of the reference read
+    @property
+    def is_flexibility_enabled(self) -> bool:
+        return self.extended.is_flexibility_enabled
+
+    @property
+    def flexibility_joint_names(self) -> List[str]:
+        return list(self.extended.flexibility_joint_names)
+
+    @property
+    def flexibility_joint_indices(self) -> List[int]:
+        return self.extended.flexibility_joint_indices
+
+    @property
+    def backlash_joint_names(self) -> List[str]:
+        return [n for n in self.extended.joint_names if n.endswith(BACKLASH_JOINT_SUFFIX)]
+
+    def get_extended_position_from_theoretical(self, q: np.ndarray) -> np.ndarray:
+        return extended_state_from_theoretical(self.extended, self.theoretical, q)
+
+    def get_extended_velocity_from_theoretical(self, v: np.ndarray) -> np.ndarray:
+        q = np.broadcast_to(self.theoretical.neutral(), np.asarray(v).shape[:-1] + (self.theoretical.nq,))
+        return extended_state_from_theoretical(self.extended, self.theoretical, q, v)[1]
+
+    def get_theoretical_position_from_extended(self, q: np.ndarray) -> np.ndarray:
+        q = np.asarray(q, dtype=np.float64)
+        out = np.zeros(q.shape[:-1] + (self.theoretical.nq,))
+        for j in range(1, self.theoretical.njoints):
+            k = self.extended.joint_index(self.theoretical.joint_names[j])
+            n = JOINT_NQ[int(self.theoretical.joint_type[j])]
+            out[..., self.theoretical.idx_q[j]:self.theoretical.idx_q[j] + n] = q[..., self.extended.idx_q[k]:self.extended.idx_q[k] + n]
+        return out
+
+
 def _op_base(robot: RobotTable, frame: Frame, moved: set) -> bool:
     """An operational frame added with `add_frame` follows the frame it was attached to."""
     seen = set()

@@ -853,7 +853,14 @@ def test_flexibility_engine_facade_like_the_reference_api_test(api):
     indices survive a simulation."""
     import flexibility_common as fc
     from jiminy_b200.core import Engine
-    robot = fc.flexible_pendulum(0.1, 1.0, 1.0, inertia=1.0)
+    th = M.build_robot_table(os.path.join(DATA, "simple_pendulum.urdf"), False)
+    M.attach_motor(th, "PendulumJoint", "PendulumJoint", enableVelocityLimit=False, enableEffortLimit=False)
+    robot = M.Robot(th)
+    model_options = robot.get_model_options()
+    model_options["dynamics"]["enableFlexibility"] = True
+    model_options["dynamics"]["flexibilityConfig"] = [{"frameName": "PendulumJoint", "stiffness": np.ones(3),
+                                                       "damping": np.ones(3), "inertia": np.ones(3)}]
+    robot.set_model_options(model_options)
     assert robot.is_flexibility_enabled and robot.flexibility_joint_indices == [1]
     engine = Engine(api_=api)
     engine.add_robot(robot)

@@ -120,3 +120,43 @@ def test_option_validation():
     opt["stepper"]["sensorsUpdatePeriod"] = 0.005
     with pytest.raises(ValueError):
         M.validate_options(opt)
+
+
+def test_robot_model_options_like_the_reference_tests():
+    """`jiminy.Robot.get_model_options / set_model_options` over the tables: the flexibility API test
+    (unit_py/test_simple_pendulum.py:815-842), the joint-limit options of unit_py/test_dense_pole.py:38-43, backlash from
+    the motor options (test_simple_pendulum.py:276-284), theoretical <-> extended state maps."""
+    import os
+    import numpy as np
+    from jiminy_b200 import model as M
+    from conftest import DATA
+    th = M.build_robot_table(os.path.join(DATA, "simple_pendulum.urdf"), False)
+    M.attach_motor(th, "PendulumJoint", "PendulumJoint", enableVelocityLimit=False, enableEffortLimit=False,
+                   enableArmature=True, armature=0.1, enableBacklash=True, backlash=0.4)
+    robot = M.Robot(th)
+    assert not robot.is_flexibility_enabled and robot.backlash_joint_names == ["PendulumJointBacklash"]
+    opts = robot.get_model_options()
+    assert opts["dynamics"]["enableFlexibility"] is True and opts["joints"]["positionLimitFromUrdf"] is True
+    opts["dynamics"]["flexibilityConfig"] = [{"frameName": "PendulumJoint", "stiffness": np.ones(3), "damping": np.ones(3),
+                                              "inertia": np.ones(3)}]
+    opts["joints"]["positionLimitFromUrdf"] = False
+    opts["joints"]["positionLimitLower"], opts["joints"]["positionLimitUpper"] = [-0.002], [0.002]
+    robot.set_model_options(opts)
+    ext = robot.extended
+    assert robot.flexibility_joint_indices == [1]
+    assert ext.joint_names == ["universe", "PendulumJointFlexibility", "PendulumJoint", "PendulumJointBacklash"]
+    iq = ext.idx_q[ext.joint_index("PendulumJoint")]
+    assert (ext.q_lower[iq], ext.q_upper[iq]) == (-0.002, 0.002) and (ext.q_lower[iq + 1], ext.q_upper[iq + 1]) == (-0.2, 0.2)
+    assert th.njoints == 2 and robot.theoretical is th                      # the theoretical model is left alone
+    qe = robot.get_extended_position_from_theoretical(np.array([0.3]))
+    np.testing.assert_allclose(qe, [0.0, 0.0, 0.0, 1.0, 0.3, 0.0])
+    np.testing.assert_allclose(robot.get_theoretical_position_from_extended(qe), [0.3])
+    np.testing.assert_allclose(robot.get_extended_velocity_from_theoretical(np.array([2.0])), [0.0, 0.0, 0.0, 2.0, 0.0])
+    bad = robot.get_model_options()
+    bad["joints"]["positionLimitLower"] = [0.0, 1.0]
+    with pytest.raises(ValueError):
+        robot.set_model_options(bad)
+    assert robot.flexibility_joint_indices == [1]                            # a refused update changes nothing
+    opts["dynamics"]["enableFlexibility"] = False
+    robot.set_model_options(opts)
+    assert not robot.is_flexibility_enabled and robot.extended.joint_names == ["universe", "PendulumJoint", "PendulumJointBacklash"]
