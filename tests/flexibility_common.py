@@ -223,3 +223,44 @@ def backlash_pendulum_parity(api=None, device=0, n_steps=120):
     q = eng.get_state()[1]
     assert (np.abs(q[:2, 1]) > B - 1e-2).all() and (eng.get_status()[:2] & 8).all()      # on the limit: the bound has been active
     return eng, orc
+
+
+def flexible_atlas_trunk_parity(api=None, device=0, n_env=3):
+    """Atlas with flexibilities in front of a back joint (a TRUNK joint of the lane plan: the spherical record is walked by
+    all the lanes and its articulated inertia all-reduced), a knee and a shoulder, deformed and moving at the start:
+    single evaluation and one PD env-step against the oracle."""
+    sc = scenarios.make("atlas", n_env, seed=1)
+    rigid = sc.robot
+    cfg = [dict(frameName=jn, stiffness=[8e3, 9e3, 7e3], damping=[40.0, 30.0, 35.0], inertia=[0.2, 0.3, 0.25])
+           for jn in ("back_bky", "l_leg_kny", "r_arm_shx")]
+    flex = M.add_flexibility_joints(rigid, cfg)
+    q0, v0 = M.extended_state_from_theoretical(flex, rigid, sc.q0, sc.v0)
+    rng = np.random.default_rng(0)
+    for name in flex.flexibility_joint_names:
+        j = flex.joint_index(name)
+        iq, iv = flex.idx_q[j], flex.idx_v[j]
+        w = rng.normal(size=(n_env, 3)) * 0.05
+        ang = np.linalg.norm(w, axis=1, keepdims=True)
+        q0[:, iq:iq + 3], q0[:, iq + 3] = np.sin(ang / 2) * w / ang, np.cos(ang / 2)[:, 0]
+        v0[:, iv:iv + 3] = rng.normal(size=(n_env, 3)) * 0.3
+    eng = BatchedEngine(flex, sc.options, n_env, device=device, api_=api)
+    orc = OracleBatch(flex, sc.options, n_env)
+    assert "ntrunk=5" in eng.describe()                     # pelvis, the three back joints and the flexibility
+    cmd = rng.uniform(-20, 20, size=(n_env, flex.nmotors))
+    a0, f0, u0 = orc.compute_dynamics(q0, v0, cmd)
+    a1, f1, u1 = eng.compute_dynamics(q0, v0, cmd)
+    np.testing.assert_allclose(a1, a0, rtol=0, atol=1e-11 * max(1.0, np.abs(a0).max()))
+    np.testing.assert_allclose(u1, u0, rtol=0, atol=1e-11 * max(1.0, np.abs(u0).max()))
+    for e in (eng, orc):
+        e.set_pd_controller(sc.kp, sc.kd)
+        e.set_command(sc.target0)
+    eng.start(q0, v0)
+    assert not orc.start(q0, v0).any()
+    pc.compare(eng, orc, 1e-12, 1e-10)
+    act = sc.sample_targets(0)
+    eng.set_command(act)
+    orc.set_command(act)
+    eng.step(sc.step_dt)
+    assert not orc.step(sc.step_dt, parallel=True).any()
+    pc.compare(eng, orc, 1e-8, 1e-6)
+    return eng, orc

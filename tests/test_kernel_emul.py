@@ -953,3 +953,8 @@ def test_centroidal_terms_of_a_massless_subtree_are_finite(api):
     np.testing.assert_allclose(com[:, keep], co[:, keep], rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(hg, hgo, rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(dhg, dhgo, rtol=1e-8, atol=1e-7)
+
+
+def test_flexibility_on_a_trunk_joint_of_atlas(api):
+    import flexibility_common as fc
+    fc.flexible_atlas_trunk_parity(api)
